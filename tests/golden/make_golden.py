@@ -1,0 +1,199 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the reference's own regression cases (run in the build container only).
+
+For every hot-path deck under /root/reference/test/dynamics this script stores, in one compressed npz:
+  * the mesh read from <case>.g (NetCDF-3 / Exodus II; read with scipy.io.netcdf_file),
+  * the deck text (<case>.in),
+  * the reference's gold results <case>.gold.e (times, nodal and element variables, by name)
+    -- these pin the oracle at the reference's own exodiff tolerance (1e-6 * max|gold|),
+  * `ref_*`: snapshots produced HERE by the reference's serial code (oracle/_ref/libnimble_ref.so) on the
+    same deck -- these pin the GPU path at the north-star tolerances when /root/reference is absent.
+Decomposed pieces (<case>.g.<P>.<r>) are stored for the multi-rank shared-node tests.
+
+Usage:  python tests/golden/make_golden.py [/root/reference]
+"""
+import glob
+import os
+import sys
+
+import numpy as np
+from scipy.io import netcdf_file
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+CASES = [
+    ("wave_in_bar", "wave_in_bar", "wave_in_bar"),
+    ("notched_plate_native_neohookean", "notched_plate_native_neohookean", "notched_plate_native_neohookean"),
+    ("notched_plate_native_hypoelastic", "notched_plate_native_hypoelastic", "notched_plate_native_hypoelastic"),
+    ("brick_with_fibers", "brick_with_fibers", "brick_with_fibers"),
+    ("simple_deformation_modes", "simple_deformation_modes", "simple_deformation_modes"),
+    ("rigid_body_motion", "rigid_body_motion", "rigid_body_motion"),
+    ("single_elem_complex_displacement", "single_elem_complex_displacement", "single_elem_complex_displacement"),
+    ("single_elem_complex_displacement", "single_elem_native_neohookean", "single_elem"),
+]
+
+
+def _names(var):
+    out = []
+    for row in var.data:
+        s = b"".join(row).split(b"\x00")[0].decode().strip()
+        out.append(s)
+    return out
+
+
+def read_genesis(path):
+    """-> mesh dict: x,y,z, node_gid (0-based), block_ids, conn{b}[ne,8] 0-based, elem_gid{b}, node_sets{id}."""
+    f = netcdf_file(path, "r", mmap=False)
+    v = f.variables
+    n_nodes = f.dimensions["num_nodes"]
+    if "coordx" in v:
+        x, y, z = (np.array(v[k].data, dtype=np.float64) for k in ("coordx", "coordy", "coordz"))
+    else:
+        c = np.array(v["coord"].data, dtype=np.float64)
+        x, y, z = c[0], c[1], c[2]
+    node_gid = (np.array(v["node_num_map"].data, dtype=np.int32) - 1 if "node_num_map" in v
+                else np.arange(n_nodes, dtype=np.int32))
+    # decomp's original_global_id_map wins (src/nimble_genesis_mesh.cc:123-149)
+    if "nmap_names" in v:
+        for i, nm in enumerate(_names(v["nmap_names"])):
+            if nm == "original_global_id_map":
+                node_gid = np.array(v["node_map%d" % (i + 1)].data, dtype=np.int32) - 1
+    n_elem = f.dimensions["num_elem"]
+    elem_gid_all = (np.array(v["elem_num_map"].data, dtype=np.int32) - 1 if "elem_num_map" in v
+                    else np.arange(n_elem, dtype=np.int32))
+    block_ids = [int(b) for b in v["eb_prop1"].data]
+    conn, elem_gid = {}, {}
+    off = 0
+    local_blocks = []
+    for i, b in enumerate(block_ids):
+        key = "connect%d" % (i + 1)
+        if key not in v:
+            continue
+        c = np.array(v[key].data, dtype=np.int32) - 1
+        conn[b] = np.ascontiguousarray(c)
+        elem_gid[b] = elem_gid_all[off:off + len(c)].copy()
+        off += len(c)
+        local_blocks.append(b)
+    node_sets = {}
+    if "ns_prop1" in v:
+        for i, sid in enumerate(v["ns_prop1"].data):
+            key = "node_ns%d" % (i + 1)
+            node_sets[int(sid)] = (np.array(v[key].data, dtype=np.int32) - 1 if key in v
+                                   else np.zeros(0, np.int32))
+    f.close()
+    return dict(x=x, y=y, z=z, node_gid=node_gid, block_ids=local_blocks, all_block_ids=block_ids, conn=conn,
+                elem_gid=elem_gid, node_sets=node_sets)
+
+
+def read_results(path):
+    f = netcdf_file(path, "r", mmap=False)
+    v = f.variables
+    times = np.array(v["time_whole"].data, dtype=np.float64)
+    nod = {}
+    if "name_nod_var" in v:
+        for k, nm in enumerate(_names(v["name_nod_var"])):
+            nod[nm] = np.array(v["vals_nod_var%d" % (k + 1)].data, dtype=np.float64)
+    elem = {}
+    if "name_elem_var" in v:
+        nblk = f.dimensions["num_el_blk"]
+        for k, nm in enumerate(_names(v["name_elem_var"])):
+            for b in range(nblk):
+                key = "vals_elem_var%deb%d" % (k + 1, b + 1)
+                if key in v:
+                    elem[(nm, b)] = np.array(v[key].data, dtype=np.float64)
+    f.close()
+    return times, nod, elem
+
+
+def pack_mesh(prefix, m, out):
+    out[prefix + "x"], out[prefix + "y"], out[prefix + "z"] = m["x"], m["y"], m["z"]
+    out[prefix + "node_gid"] = m["node_gid"]
+    out[prefix + "block_ids"] = np.array(m["block_ids"], dtype=np.int32)
+    out[prefix + "all_block_ids"] = np.array(m["all_block_ids"], dtype=np.int32)
+    for b in m["block_ids"]:
+        out[prefix + "conn_%d" % b] = m["conn"][b]
+        out[prefix + "elem_gid_%d" % b] = m["elem_gid"][b]
+    out[prefix + "ns_ids"] = np.array(list(m["node_sets"].keys()), dtype=np.int32)
+    for sid, nodes in m["node_sets"].items():
+        out[prefix + "ns_%d" % sid] = nodes
+
+
+def unpack_mesh(prefix, z):
+    m = dict(x=z[prefix + "x"], y=z[prefix + "y"], z=z[prefix + "z"], node_gid=z[prefix + "node_gid"],
+             block_ids=[int(b) for b in z[prefix + "block_ids"]],
+             all_block_ids=[int(b) for b in z[prefix + "all_block_ids"]], conn={}, elem_gid={}, node_sets={})
+    for b in m["block_ids"]:
+        m["conn"][b] = z[prefix + "conn_%d" % b]
+        m["elem_gid"][b] = z[prefix + "elem_gid_%d" % b]
+    for sid in z[prefix + "ns_ids"]:
+        m["node_sets"][int(sid)] = z[prefix + "ns_%d" % sid]
+    return m
+
+
+def load_case(name):
+    """Loader used by the tests: -> (deck_text, mesh, gold dict, ref dict, pieces dict)."""
+    z = np.load(os.path.join(HERE, name + ".npz"), allow_pickle=False)
+    mesh = unpack_mesh("mesh_", z)
+    gold = {"times": z["gold_times"], "nod": {}, "elem": {}}
+    for k in z.files:
+        if k.startswith("gold_nod_"):
+            gold["nod"][k[len("gold_nod_"):]] = z[k]
+        elif k.startswith("gold_elem_"):
+            nm, b = k[len("gold_elem_"):].rsplit("_eb", 1)
+            gold["elem"][(nm, int(b))] = z[k]
+    ref = {k[len("ref_"):]: z[k] for k in z.files if k.startswith("ref_")}
+    pieces = {}
+    for k in z.files:
+        if k.startswith("piece_") and k.endswith("_x"):
+            tag = k[len("piece_"):-2]  # "P.r"
+            P, r = tag.split(".")
+            pieces[(int(P), int(r))] = unpack_mesh("piece_%s_" % tag, z)
+    return str(z["deck"]), mesh, gold, ref, pieces
+
+
+def main():
+    refroot = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    from oracle import refdrive
+
+    for d, deck, g in CASES:
+        base = os.path.join(refroot, "test", "dynamics", d)
+        out = {}
+        mesh = read_genesis(os.path.join(base, g + ".g"))
+        pack_mesh("mesh_", mesh, out)
+        out["deck"] = np.array(open(os.path.join(base, deck + ".in")).read())
+        times, nod, elem = read_results(os.path.join(base, deck + ".gold.e"))
+        out["gold_times"] = times
+        for k, a in nod.items():
+            out["gold_nod_" + k] = a
+        for (k, b), a in elem.items():
+            out["gold_elem_%s_eb%d" % (k, b)] = a
+        for p in sorted(glob.glob(os.path.join(base, g + ".g.*.*"))):
+            tag = p.split(".g.")[1]
+            pack_mesh("piece_%s_" % tag, read_genesis(p), out)
+        # reference-code snapshots at the deck's output steps (tight oracle when /root/reference is absent)
+        run = refdrive.RefRun(str(out["deck"]), mesh, keep_snapshots=True)
+        out["ref_critical_dt"] = np.array(run.begin())
+        import re
+        nsteps = int(re.search(r"number of load steps:\s*(\d+)", str(out["deck"])).group(1))
+        run.advance(nsteps)
+        snaps = run.snapshots()
+        out["ref_times"] = np.array([s["time"] for s in snaps])
+        for lbl in snaps[0]["node"]:
+            out["ref_node_" + lbl] = np.stack([s["node"][lbl] for s in snaps])
+        for b in mesh["block_ids"]:
+            # full per-ipt F/sigma only at the final output step (keeps the fixture small)
+            out["ref_elem_last_%d" % b] = snaps[-1]["elem"][b]
+            for lbl in snaps[0]["derived"][b]:
+                out["ref_derived_%d_%s" % (b, lbl)] = np.stack([s["derived"][b][lbl] for s in snaps])
+        run.close()
+        path = os.path.join(HERE, deck + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-40s %8.1f kB  nodes=%d elems=%d times=%d" % (
+            deck + ".npz", os.path.getsize(path) / 1e3, len(mesh["x"]),
+            sum(len(c) for c in mesh["conn"].values()), len(times)))
+
+
+if __name__ == "__main__":
+    main()
