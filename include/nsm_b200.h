@@ -1,0 +1,199 @@
+/* include/nsm_b200.h — C ABI of the B200-native hex8 explicit-dynamics path.
+ *
+ * This is the drop-in boundary: plain C types, caller-owned host buffers, no torch /
+ * Kokkos types.  The C++ host classes in nimblesm_b200/host (B200ModelData, B200Block,
+ * B200BlockMaterialInterface, ...) and the ctypes mirror nimblesm_b200/capi.py call exactly these
+ * entry points.  Every entry point names the reference interface (path:line under /root/reference)
+ * that it replaces.  All work is issued on one CUDA stream owned by the context; calls are
+ * synchronous unless stated.  There is no CPU fallback: every call fails with NSM_ERR_CUDA when no
+ * sm_100 device is usable.
+ *
+ * Conventions
+ *   - status: 0 = NSM_OK, otherwise an nsm_status; nsm_b200_last_error() gives the message.
+ *     Nothing throws across this boundary (reference: NIMBLE_ABORT / std::invalid_argument,
+ *     src/nimble_macros.h:49-72, src/nimble.cc:129-137 — the C++ wrappers convert).
+ *   - host nodal VECTOR fields are AoS [n_nodes][3] doubles exactly as nimble::Viewify<2> with
+ *     strides {3,1} presents them (src/nimble_model_data.cc:540-546); SCALAR fields are [n_nodes].
+ *     On the device everything is SoA fp64 (x[], y[], z[] separately).
+ *   - connectivity is int32 [n_elem][8], 0-based local node ids, Exodus hex8 ordering
+ *     (src/nimble_element.cc:113-120).
+ *   - integration-point data is [n_elem][8][15]: F in storage order xx,yy,zz,xy,yz,zx,yx,zy,xz then
+ *     sigma xx,yy,zz,xy,yz,zx (src/nimble_block.cc:84-108, src/nimble_utils.h:86-110).
+ */
+#ifndef NSM_B200_H
+#define NSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsm_b200_ctx nsm_b200_ctx;
+
+typedef enum {
+  NSM_OK          = 0,
+  NSM_ERR_ARG     = 1, /* bad argument / call order                                       */
+  NSM_ERR_CUDA    = 2, /* CUDA runtime error or no usable sm_100 device                   */
+  NSM_ERR_JACOBIAN = 3, /* non-positive Jacobian determinant met (src/nimble_utils.h:1253) */
+  NSM_ERR_MATERIAL = 4, /* unknown material model / parameter                              */
+  NSM_ERR_COMM    = 5  /* peer exchange not set up / peer failure                         */
+} nsm_status;
+
+/* nimble material models on the path (src/nimble_material.cc:60,218; both carry 0 state variables). */
+typedef enum { NSM_MAT_ELASTIC = 0, NSM_MAT_NEOHOOKEAN = 1 } nsm_material_kind;
+
+/* nodal fields allocated by DataManager::Initialize (src/nimble_data_manager.cc:135-158). */
+typedef enum {
+  NSM_FIELD_LUMPED_MASS          = 0, /* scalar */
+  NSM_FIELD_REFERENCE_COORDINATE = 1,
+  NSM_FIELD_DISPLACEMENT         = 2,
+  NSM_FIELD_VELOCITY             = 3,
+  NSM_FIELD_ACCELERATION         = 4,
+  NSM_FIELD_INTERNAL_FORCE       = 5,
+  NSM_FIELD_EXTERNAL_FORCE       = 6,
+  NSM_FIELD_COUNT                = 7
+} nsm_field;
+
+/* boundary-condition kinds applied inside the step (src/nimble_boundary_condition.h:62-69). */
+typedef enum { NSM_BC_PRESCRIBED_VELOCITY = 0, NSM_BC_PRESCRIBED_DISPLACEMENT = 1 } nsm_bc_kind;
+
+/* force assembly (SURVEY.md §2b "scatter-add"):
+ *   ATOMIC  : red.global.add.f64 per nodal component, order of the <=8 element contributions per node
+ *             is not fixed (run-to-run noise ~1e-16 relative).
+ *   ORDERED : element kernel stores per-element nodal forces, the node kernel sums them through a
+ *             node->element adjacency in ascending (block id, element) order == the summation order
+ *             of the reference's serial loop (src/nimble_model_data.cc:636-659, src/nimble_block.cc:434),
+ *             so nodal forces are bit-reproducible and bit-identical to the serial reference. */
+typedef enum { NSM_ASSEMBLY_ATOMIC = 0, NSM_ASSEMBLY_ORDERED = 1 } nsm_assembly;
+
+/* nsm_b200_finalize flags */
+#define NSM_FLAG_STORE_IPT_EVERY_STEP 0x1 /* write F/sigma each step as the reference does (960 B/elem);     \
+                                             default: only when a call asks for it (output steps)          */
+#define NSM_FLAG_CACHE_REF_JACOBIAN 0x2   /* keep inverse reference Jacobians (576 B/elem) instead of      \
+                                             recomputing them each step; bit-identical either way          */
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Creates a context bound to CUDA device `device` (one context per GPU, one host thread drives it:
+ * the reference is single-threaded per rank, src/nimble.cc:139-143). */
+int nsm_b200_create(int device, nsm_b200_ctx** out);
+void nsm_b200_destroy(nsm_b200_ctx* ctx);
+/* Message of the last failure on ctx (ctx may be NULL: creation failures). */
+const char* nsm_b200_last_error(const nsm_b200_ctx* ctx);
+/* Library build info: "nsm_b200 <version> sm_100a fmad=off ...". */
+const char* nsm_b200_version(void);
+
+/* ---- model definition (replaces ModelData::SetReferenceCoordinates + InitializeBlocks/EmplaceBlocks,
+ *      src/nimble_model_data.cc:416-493, src/nimble_kokkos_model_data.cc:893-961) ------------------ */
+int nsm_b200_set_nodes(nsm_b200_ctx* ctx, int64_t n_nodes, const double* x, const double* y, const double* z);
+/* Blocks may be added in any order; they are processed in ascending block_id like the reference's
+ * std::map (src/nimble_model_data.cc:636).  Material = MaterialFactory::create result
+ * (src/nimble_material_factory.cc:56-69): bulk_modulus, shear_modulus, density. */
+int nsm_b200_add_block(nsm_b200_ctx* ctx, int block_id, int64_t n_elem, const int32_t* conn, int material_kind,
+                       double bulk_modulus, double shear_modulus, double density);
+/* Uploads the mesh, builds assembly tables, allocates fields (zeroed; F = identity, sigma = 0 like
+ * Block::InitializeElementData, src/nimble_block.cc:148-207). */
+int nsm_b200_finalize(nsm_b200_ctx* ctx, int assembly, unsigned flags);
+
+int64_t nsm_b200_num_nodes(const nsm_b200_ctx* ctx);
+int64_t nsm_b200_num_elements(const nsm_b200_ctx* ctx, int block_id); /* block_id < 0: all blocks */
+int64_t nsm_b200_device_bytes(const nsm_b200_ctx* ctx);               /* HBM held by the context  */
+
+/* ---- nodal fields (replaces ModelData::GetNodeData / UpdateWithNewVelocity / UpdateWithNewDisplacement
+ *      host<->device deep copies, src/nimble_kokkos_model_data.cc:1730-1740,1282) ------------------ */
+int nsm_b200_upload_field(nsm_b200_ctx* ctx, int field, const double* host);
+int nsm_b200_download_field(nsm_b200_ctx* ctx, int field, double* host);
+/* Asynchronous variants on the context stream (host memory should be pinned); pair with nsm_b200_sync. */
+int nsm_b200_upload_field_async(nsm_b200_ctx* ctx, int field, const double* host);
+int nsm_b200_download_field_async(nsm_b200_ctx* ctx, int field, double* host);
+int nsm_b200_sync(nsm_b200_ctx* ctx);
+/* Pinned host allocation helpers for callers without a CUDA runtime of their own. */
+void* nsm_b200_host_alloc(int64_t bytes);
+void  nsm_b200_host_free(void* p);
+
+/* ---- setup kernels ---------------------------------------------------------------------------- */
+/* ModelData::ComputeLumpedMass (src/nimble_model_data.cc:495-530 -> src/nimble_block.cc:110-146 ->
+ * src/nimble_element.h:266-309) and BlockBase::ComputeCriticalTimeStep (src/nimble_block_base.cc:51-84,
+ * min over blocks/elements; informational).  Includes the shared-node sum when peers are attached. */
+int nsm_b200_compute_lumped_mass(nsm_b200_ctx* ctx, double* critical_dt);
+
+/* ---- internal force (replaces ModelDataBase::ComputeInternalForce, src/nimble_model_data.cc:620-667,
+ *      src/nimble_kokkos_model_data.cc:1154-1286: gather -> F -> stress -> Bt.sigma.detJ.w -> scatter ->
+ *      shared-node sum) --------------------------------------------------------------------------- */
+/* From the device-resident displacement into the device-resident internal_force. store_ipt != 0 also
+ * writes F/sigma of every integration point (is_output_step of the reference). */
+int nsm_b200_internal_force(nsm_b200_ctx* ctx, int store_ipt);
+/* Same through host views: uploads displacement [n][3], computes, downloads internal_force [n][3]
+ * (the exact shape of the reference call with Viewify<2> arguments). */
+int nsm_b200_internal_force_host(nsm_b200_ctx* ctx, const double* displacement, double* internal_force,
+                                 int store_ipt);
+
+/* ---- stress seam (replaces BlockMaterialInterface::ComputeStress, the MDRange(elem, ipt) loop of
+ *      src/nimble_kokkos_block_material_interface.cc:65-119 -> Material::GetStress,
+ *      src/nimble_material.cc:95-126, 252-310) ----------------------------------------------------- */
+/* Host arrays: def_grad [n_points][9] -> stress [n_points][6], evaluated on the device. */
+int nsm_b200_compute_stress(nsm_b200_ctx* ctx, int material_kind, double bulk_modulus, double shear_modulus,
+                            int64_t n_points, const double* def_grad, double* stress);
+
+/* ---- boundary conditions (replaces BoundaryConditionManager::ApplyKinematicBC,
+ *      src/nimble_boundary_condition_manager.h:136-204) -------------------------------------------- */
+/* Flattened table in deck order: entry k constrains velocity(node[k], comp[k]).  When a (node, comp)
+ * pair appears more than once the later entry wins, as in the reference's sequential loop.
+ * value[k] = prescribed velocity, or prescribed displacement d for which v = (d - u)/dt when dt > 0. */
+int nsm_b200_set_bc_table(nsm_b200_ctx* ctx, int64_t n, const int32_t* node, const int32_t* comp,
+                          const int32_t* kind);
+/* Host-evaluated magnitudes (constants or expression(x,y,z,t) results) for the NEXT steps. */
+int nsm_b200_set_bc_values(nsm_b200_ctx* ctx, int64_t n, const double* value);
+/* Applies the table once at (time_current, time_previous) to the device velocity. */
+int nsm_b200_apply_kinematic_bc(nsm_b200_ctx* ctx, double time_current, double time_previous);
+
+/* ---- the explicit step (replaces the loop body of ExplicitTimeIntegrator::Integrate,
+ *      src/integrators/explicit_time_integrator.cc:177-278, contact disabled) ----------------------
+ * Advances n_steps steps from *time (in/out): per step t_prev = t; t += dt_user; dt = t - t_prev;
+ * v += dt/2 a; BC; u += dt v; BC; f_int(u); a = (1/m)(f_int + f_ext); v += dt/2 a.
+ * BC magnitudes are those of the last nsm_b200_set_bc_values call (time-dependent expressions: call
+ * with n_steps = 1).  store_ipt_last != 0 writes F/sigma on the final step and re-applies the BCs after
+ * it, which is what the reference does on an output step (:266-275). */
+int nsm_b200_step(nsm_b200_ctx* ctx, int n_steps, double* time, double dt_user, int store_ipt_last);
+
+/* ---- element data / derived output (replaces ModelData::GetElementDataNew + Block::ComputeDerivedElementData,
+ *      src/nimble_block.cc:438-497; HexElement::ComputeVolumeAverage, src/nimble_element.h:343-392) --- */
+int nsm_b200_get_element_data(nsm_b200_ctx* ctx, int block_id, double* out /*[n_elem][8][15]*/);
+/* out [16][n_elem]: volume, then volume averages of F (9) and sigma (6) in storage order. */
+int nsm_b200_derived_element_data(nsm_b200_ctx* ctx, int block_id, double* out);
+
+/* ---- shared-node exchange over NVLink peer memory (replaces VectorCommunicator::VectorReduction /
+ *      ReductionClique_t MPI_Iallreduce, src/nimble_vector_communicator.h:104-157,
+ *      src/nimble.mpi.rank_clique_reducer.h:130-257) -----------------------------------------------
+ * One context per rank (process-per-GPU or thread-per-GPU).  The host layer discovers the nodes this rank
+ * shares with each other rank from the global node ids, exactly as GenerateReductionInfo does
+ * (src/nimble.mpi.reduction.cc:50-123), and passes, for every peer rank, the LOCAL ids of the nodes shared
+ * with that peer sorted by GLOBAL id (both sides sort alike, :114-120).  Receive buffers are exported as
+ * opaque blobs that the host layer passes between ranks by any transport (torch.distributed, MPI, files,
+ * or a plain memcpy between threads).  Sums are formed in ascending rank order on every holder, so all
+ * replicas of a shared node carry bit-identical values. */
+#define NSM_COMM_HANDLE_BYTES 192
+int nsm_b200_comm_init(nsm_b200_ctx* ctx, int rank, int world_size, int n_peers, const int32_t* peer_ranks,
+                       const int64_t* pair_offsets /*[n_peers+1]*/, const int32_t* pair_local_nodes);
+int nsm_b200_comm_export(nsm_b200_ctx* ctx, unsigned char handle[NSM_COMM_HANDLE_BYTES]);
+int nsm_b200_comm_attach(nsm_b200_ctx* ctx, int peer_rank, const unsigned char handle[NSM_COMM_HANDLE_BYTES]);
+/* All peers attached: build the device tables; from here on lumped mass and internal force include the
+ * shared-node sum.  Every rank must be past comm_attach of all its peers before any rank steps. */
+int nsm_b200_comm_ready(nsm_b200_ctx* ctx);
+
+/* ---- measurement helpers (CUDA events on the context stream) ---------------------------------- */
+int nsm_b200_timer_start(nsm_b200_ctx* ctx);
+int nsm_b200_timer_stop(nsm_b200_ctx* ctx, float* milliseconds);
+/* Kernels launched by this context since creation (bench.py reports the delta as gpu_launches). */
+int64_t nsm_b200_launch_count(const nsm_b200_ctx* ctx);
+/* Average device time of the element (internal-force) kernel launches since the last reset, measured
+ * with CUDA events around each launch when profiling is switched on. */
+int nsm_b200_profile(nsm_b200_ctx* ctx, int enable);
+int nsm_b200_profile_read(nsm_b200_ctx* ctx, double* elem_kernel_ms_avg, double* node_kernel_ms_avg, int64_t* n_launches);
+/* FP64 pipe micro-benchmark: sustained DADD+DMUL (no FMA) and DFMA issue rates in 1e12 lane-ops/s. */
+int nsm_b200_fp64_peak(nsm_b200_ctx* ctx, double* dadd_dmul_tops, double* dfma_tops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSM_B200_H */

@@ -1,0 +1,630 @@
+// nimblesm_b200/csrc/hex8_kernels.cuh — CUDA kernels of the hex8 explicit step (sm_100a, fp64, no FMA
+// contraction).  See DESIGN.md §3 for the execution plan; in short:
+//
+//   element kernel  (hot; FP64-issue bound)   8 lanes = 1 element, lane q owns Gauss point q.
+//       gather   lane j loads node j (conn coalesced, SoA coordinates), stages X / x through shared memory
+//       compute  gradient operator a, b at the lane's point -> b^-1 -> F -> stress -> a^-1 -> per-node
+//                Bt.sigma.detJ shares (24 values per lane), all in registers
+//       reduce   shares are transposed through (per-warp) shared memory; lane n sums node n over the Gauss
+//                points 0..7 in the reference's order (src/nimble_element.h:575-612)
+//       assemble red.global.add.f64 into the SoA nodal force (ATOMIC) or a coalesced store of the
+//                element's [8][3] forces for the ordered node-side gather (ORDERED)
+//   node kernels    (HBM bound)   a = (1/m)(f+f_ext), v += dt/2 a | v += dt/2 a, BC, u += dt v, BC
+//   setup kernels   lumped mass, critical time step, volume averages (thread per element; not hot)
+#pragma once
+#include <stdint.h>
+
+#include "hex8_math.cuh"
+
+namespace nsm {
+
+constexpr int kElemThreads     = 256;                    // 8 warps, 32 elements per CTA
+constexpr int kElemsPerWarp    = 4;
+constexpr int kCoordStride     = 4;                      // [c*8+j][e_w]
+constexpr int kCoordDoubles    = 3 * 24 * kCoordStride;  // X, cc (F path), cur (force path)
+constexpr int kShareStride     = 43;                     // 3*43 = 1 (mod 16): conflict-free transpose
+constexpr int kShareDoubles    = 24 * kShareStride;
+constexpr int kWarpSmemDoubles = kShareDoubles;          // coords alias the share buffer
+static_assert(kCoordDoubles <= kShareDoubles, "coordinate staging must fit in the aliased share buffer");
+
+struct ElemArgs
+{
+  int64_t       n_elem;
+  const int*    conn;        // [n_elem][8]
+  const double* X[3];        // reference coordinates, SoA
+  const double* u[3];        // displacement, SoA
+  double*       f[3];        // nodal internal force, SoA (ATOMIC)
+  double*       ef;          // [n_elem][8][3] element nodal forces (ORDERED), already offset to the block
+  double*       ipt;         // [n_elem][8][15] or nullptr
+  double*       binv_cache;  // [n_elem][8][9] or nullptr
+  double        bulk, shear;
+  int*          flags;       // bit 0: non-positive Jacobian seen
+};
+
+template <int J>
+__device__ __forceinline__ void
+load_node(const double* sm, int ew, double& x0, double& x1, double& x2)
+{
+  x0 = sm[(0 * 8 + J) * kCoordStride + ew];
+  x1 = sm[(1 * 8 + J) * kCoordStride + ew];
+  x2 = sm[(2 * 8 + J) * kCoordStride + ew];
+}
+
+template <int J>
+__device__ __forceinline__ void
+accumulate_pair(const ShapeAtPoint& sh, const double* sX, const double* sC, int ew, double (&a)[3][3],
+                double (&b)[3][3])
+{
+  double x0, x1, x2;
+  load_node<J>(sC, ew, x0, x1, x2);
+  grad_accumulate<J>(sh, x0, x1, x2, a);
+  load_node<J>(sX, ew, x0, x1, x2);
+  grad_accumulate<J>(sh, x0, x1, x2, b);
+}
+
+template <int J>
+__device__ __forceinline__ void
+accumulate_one(const ShapeAtPoint& sh, const double* sC, int ew, double (&a)[3][3])
+{
+  double x0, x1, x2;
+  load_node<J>(sC, ew, x0, x1, x2);
+  grad_accumulate<J>(sh, x0, x1, x2, a);
+}
+
+template <int N>
+__device__ __forceinline__ void
+store_share(const ShapeAtPoint& sh, const double (&ai)[3][3], double det, const double (&s)[6], double* share,
+            int lane)
+{
+  double f1, f2, f3;
+  node_force_at_point<N>(sh, ai, det, s, f1, f2, f3);
+  share[(N * 3 + 0) * kShareStride + lane] = f1;
+  share[(N * 3 + 1) * kShareStride + lane] = f2;
+  share[(N * 3 + 2) * kShareStride + lane] = f3;
+}
+
+// MAT: nsm_material_kind; ORDERED: store element forces instead of atomics; MODE bit0: store F/sigma,
+// bit1: read cached b^-1 (filled once by binv_cache_kernel).
+enum { kModeStoreIpt = 1, kModeReadBinv = 2 };
+
+template <int MAT, bool ORDERED, int MODE>
+__global__ void __launch_bounds__(kElemThreads)
+element_force_kernel(const ElemArgs p)
+{
+  extern __shared__ double smem[];
+  const int     lane = threadIdx.x & 31;
+  const int     warp = threadIdx.x >> 5;
+  const int     q    = lane & 7;   // Gauss point (compute) == local node (gather / assemble)
+  const int     ew   = lane >> 3;  // element within the warp
+  double*       wsm  = smem + warp * kWarpSmemDoubles;
+  const int64_t e    = (int64_t)blockIdx.x * (kElemThreads / 8) + warp * kElemsPerWarp + ew;
+  const bool    live = e < p.n_elem;
+
+  // ---- gather: lane j <- node j -----------------------------------------------------------------
+  int    node = 0;
+  double X0 = 0.0, X1 = 0.0, X2 = 0.0, u0 = 0.0, u1 = 0.0, u2 = 0.0;
+  if (live) {
+    node = p.conn[e * 8 + q];
+    X0 = p.X[0][node], X1 = p.X[1][node], X2 = p.X[2][node];
+    u0 = p.u[0][node], u1 = p.u[1][node], u2 = p.u[2][node];
+  } else {
+    // dead lanes of a tail warp get a unit cube so that no NaN/inf work (and no flag) is produced
+    X0 = ((q & 3) == 1 || (q & 3) == 2) ? 1.0 : 0.0;
+    X1 = (q & 2) ? 1.0 : 0.0;
+    X2 = (q & 4) ? 1.0 : 0.0;
+  }
+  // current coordinates: the block functor forms cur = ref + disp (src/nimble_block.cc:309-316); the
+  // serial F wrapper then passes disp' = cur - ref and the kernel re-adds it (src/nimble_element.cc:341-344,
+  // src/nimble_element.h:455-457); the force wrapper uses cur itself (src/nimble_element.cc:462-463).
+  const double c0 = X0 + u0, c1 = X1 + u1, c2 = X2 + u2;
+  const double k0 = X0 + (c0 - X0), k1 = X1 + (c1 - X1), k2 = X2 + (c2 - X2);
+  const bool   differs = (k0 != c0) || (k1 != c1) || (k2 != c2);
+  double*      sX      = wsm;
+  double*      sK      = wsm + 24 * kCoordStride;
+  double*      sC      = wsm + 48 * kCoordStride;
+  sX[(0 * 8 + q) * kCoordStride + ew] = X0;
+  sX[(1 * 8 + q) * kCoordStride + ew] = X1;
+  sX[(2 * 8 + q) * kCoordStride + ew] = X2;
+  sK[(0 * 8 + q) * kCoordStride + ew] = k0;
+  sK[(1 * 8 + q) * kCoordStride + ew] = k1;
+  sK[(2 * 8 + q) * kCoordStride + ew] = k2;
+  sC[(0 * 8 + q) * kCoordStride + ew] = c0;
+  sC[(1 * 8 + q) * kCoordStride + ew] = c1;
+  sC[(2 * 8 + q) * kCoordStride + ew] = c2;
+  // The F-path and force-path Jacobians coincide unless ref + ((ref+d) - ref) != ref + d for some node of
+  // the warp's elements (possible only when |d| is comparable to |ref|); decided warp-uniformly.
+  const bool recompute_a = __any_sync(0xffffffffu, differs);
+  __syncwarp();
+
+  // ---- per-Gauss-point kinematics ---------------------------------------------------------------
+  ShapeAtPoint sh;
+  sh.init(q);
+  double a[3][3], binv[3][3], F[9], sig[6];
+  zero33(a);
+  if (MODE & kModeReadBinv) {
+    accumulate_one<0>(sh, sK, ew, a);
+    accumulate_one<1>(sh, sK, ew, a);
+    accumulate_one<2>(sh, sK, ew, a);
+    accumulate_one<3>(sh, sK, ew, a);
+    accumulate_one<4>(sh, sK, ew, a);
+    accumulate_one<5>(sh, sK, ew, a);
+    accumulate_one<6>(sh, sK, ew, a);
+    accumulate_one<7>(sh, sK, ew, a);
+    const double* bc = p.binv_cache + ((live ? e : 0) * 8 + q) * 9;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) binv[i][k] = bc[3 * i + k];
+  } else {
+    double b[3][3];
+    zero33(b);
+    accumulate_pair<0>(sh, sX, sK, ew, a, b);
+    accumulate_pair<1>(sh, sX, sK, ew, a, b);
+    accumulate_pair<2>(sh, sX, sK, ew, a, b);
+    accumulate_pair<3>(sh, sX, sK, ew, a, b);
+    accumulate_pair<4>(sh, sX, sK, ew, a, b);
+    accumulate_pair<5>(sh, sX, sK, ew, a, b);
+    accumulate_pair<6>(sh, sX, sK, ew, a, b);
+    accumulate_pair<7>(sh, sX, sK, ew, a, b);
+    const double detb = invert3x3(b, binv);
+    if (live && !(detb > 0.0)) atomicOr(p.flags, 1);
+  }
+  def_grad_from(a, binv, F);
+
+  if (MAT == 0)
+    stress_elastic(p.bulk, p.shear, F, sig);
+  else
+    stress_neohookean(p.bulk, p.shear, F, sig);
+
+  if ((MODE & kModeStoreIpt) && live) {
+    double* d = p.ipt + (e * 8 + q) * 15;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) d[i] = F[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d[9 + i] = sig[i];
+  }
+
+  // ---- force-path Jacobian ----------------------------------------------------------------------
+  if (recompute_a) {
+    zero33(a);
+    accumulate_one<0>(sh, sC, ew, a);
+    accumulate_one<1>(sh, sC, ew, a);
+    accumulate_one<2>(sh, sC, ew, a);
+    accumulate_one<3>(sh, sC, ew, a);
+    accumulate_one<4>(sh, sC, ew, a);
+    accumulate_one<5>(sh, sC, ew, a);
+    accumulate_one<6>(sh, sC, ew, a);
+    accumulate_one<7>(sh, sC, ew, a);
+  }
+  double       ai[3][3];
+  const double det = invert3x3(a, ai);
+  if (live && !(det > 0.0)) atomicOr(p.flags, 1);
+
+  // ---- per-node shares -> shared memory (aliases the coordinate staging) ---------------------------
+  __syncwarp();
+  store_share<0>(sh, ai, det, sig, wsm, lane);
+  store_share<1>(sh, ai, det, sig, wsm, lane);
+  store_share<2>(sh, ai, det, sig, wsm, lane);
+  store_share<3>(sh, ai, det, sig, wsm, lane);
+  store_share<4>(sh, ai, det, sig, wsm, lane);
+  store_share<5>(sh, ai, det, sig, wsm, lane);
+  store_share<6>(sh, ai, det, sig, wsm, lane);
+  store_share<7>(sh, ai, det, sig, wsm, lane);
+  __syncwarp();
+
+  // ---- lane n: node n, Gauss points in ascending order: force -= share (src/nimble_element.h:609-611)
+  double        fx = 0.0, fy = 0.0, fz = 0.0;
+  const double* col = wsm + (q * 3) * kShareStride + ew * 8;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    fx -= col[0 * kShareStride + g];
+    fy -= col[1 * kShareStride + g];
+    fz -= col[2 * kShareStride + g];
+  }
+  if (live) {
+    if (ORDERED) {
+      double* o = p.ef + (e * 8 + q) * 3;
+      o[0] = fx, o[1] = fy, o[2] = fz;
+    } else {
+      atomicAdd(p.f[0] + node, fx);
+      atomicAdd(p.f[1] + node, fy);
+      atomicAdd(p.f[2] + node, fz);
+    }
+  }
+}
+
+// Inverse reference Jacobians b^-1 of every Gauss point, computed once (NSM_FLAG_CACHE_REF_JACOBIAN):
+// the same arithmetic as the in-kernel path, so the cached values are the bits the step would recompute.
+__global__ void __launch_bounds__(kElemThreads)
+binv_cache_kernel(const ElemArgs p)
+{
+  const int64_t t = (int64_t)blockIdx.x * kElemThreads + threadIdx.x;
+  const int64_t e = t >> 3;
+  const int     q = (int)(t & 7);
+  if (e >= p.n_elem) return;
+  ShapeAtPoint sh;
+  sh.init(q);
+  double b[3][3], binv[3][3], x[8][3];
+  zero33(b);
+  for (int j = 0; j < 8; ++j) {
+    const int nd = p.conn[e * 8 + j];
+    x[j][0] = p.X[0][nd], x[j][1] = p.X[1][nd], x[j][2] = p.X[2][nd];
+  }
+  grad_accumulate<0>(sh, x[0][0], x[0][1], x[0][2], b);
+  grad_accumulate<1>(sh, x[1][0], x[1][1], x[1][2], b);
+  grad_accumulate<2>(sh, x[2][0], x[2][1], x[2][2], b);
+  grad_accumulate<3>(sh, x[3][0], x[3][1], x[3][2], b);
+  grad_accumulate<4>(sh, x[4][0], x[4][1], x[4][2], b);
+  grad_accumulate<5>(sh, x[5][0], x[5][1], x[5][2], b);
+  grad_accumulate<6>(sh, x[6][0], x[6][1], x[6][2], b);
+  grad_accumulate<7>(sh, x[7][0], x[7][1], x[7][2], b);
+  const double detb = invert3x3(b, binv);
+  if (!(detb > 0.0)) atomicOr(p.flags, 1);
+  double* bc = p.binv_cache + (e * 8 + q) * 9;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bc[3 * i + k] = binv[i][k];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stress seam: one thread per integration point, F[9] -> sigma[6]
+// (BlockMaterialInterface::ComputeStress, src/nimble_kokkos_block_material_interface.cc:65-119)
+// ---------------------------------------------------------------------------------------------------
+template <int MAT>
+__global__ void __launch_bounds__(128)
+stress_kernel(int64_t n, const double* __restrict__ Fin, double* __restrict__ sout, double bulk, double shear)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double F[9], s[6];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) F[k] = Fin[i * 9 + k];
+  if (MAT == 0)
+    stress_elastic(bulk, shear, F, s);
+  else
+    stress_neohookean(bulk, shear, F, s);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) sout[i * 6 + k] = s[k];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// node kernels
+// ---------------------------------------------------------------------------------------------------
+struct NodeArgs
+{
+  int64_t         n_nodes;
+  double*         u[3];
+  double*         v[3];
+  double*         a[3];
+  double*         f[3];
+  const double*   fext[3];   // nullptr: external force is identically zero (src/nimble_model_data.cc:609-618)
+  const double*   mass;
+  const int*      bc_of_dof[3];  // entry index or -1; nullptr when the deck has no kinematic BC
+  const int*      bc_kind;
+  const double*   bc_value;
+  // ORDERED assembly
+  const double*   ef;         // [slots][3]
+  const int64_t*  adj_off;    // [n_nodes+1]
+  const uint32_t* adj_slot;   // slot = global element * 8 + local node, ascending per node
+};
+
+__device__ __forceinline__ double
+bc_velocity(int kind, double value, double u, double dt, double v_old)
+{
+  // BoundaryConditionManager::ApplyKinematicBC (src/nimble_boundary_condition_manager.h:146-201)
+  if (kind == 0) return value;
+  if (dt > 0.0) return (value - u) / dt;
+  return v_old;
+}
+
+// first half of a step (src/integrators/explicit_time_integrator.cc:199-216):
+//   v += (dt/2) a ; BC ; u += dt v ; BC ; and the nodal force is cleared for the coming assembly.
+template <bool HAS_BC, bool ZERO_F>
+__global__ void __launch_bounds__(256)
+node_predict_kernel(const NodeArgs p, double hdt, double dt)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_nodes) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double v = p.v[c][i];
+    double u = p.u[c][i];
+    v        = v + hdt * p.a[c][i];  // Viewify += AXPYResult: prod = alpha*1.0; data += prod*rhs (src/nimble_view.h:194-200)
+    int bc   = -1;
+    if (HAS_BC) {
+      bc = p.bc_of_dof[c][i];
+      if (bc >= 0) v = bc_velocity(p.bc_kind[bc], p.bc_value[bc], u, dt, v);
+    }
+    u = u + dt * v;
+    if (HAS_BC) {
+      if (bc >= 0) v = bc_velocity(p.bc_kind[bc], p.bc_value[bc], u, dt, v);
+    }
+    p.v[c][i] = v;
+    p.u[c][i] = u;
+    if (ZERO_F) p.f[c][i] = 0.0;
+  }
+}
+
+// second half (src/integrators/explicit_time_integrator.cc:250-262): a = (1/m)(f_int + f_ext); v += (dt/2) a.
+// ORDERED: f_int is first summed from the element forces in ascending (block, element) order.
+template <bool ORDERED, bool HAS_FEXT>
+__global__ void __launch_bounds__(256)
+node_correct_kernel(const NodeArgs p, double hdt, int update_velocity)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_nodes) return;
+  double f0, f1, f2;
+  if (ORDERED) {
+    f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    const int64_t b = p.adj_off[i], e = p.adj_off[i + 1];
+    for (int64_t k = b; k < e; ++k) {
+      const double* s = p.ef + (int64_t)p.adj_slot[k] * 3;
+      f0 += s[0];
+      f1 += s[1];
+      f2 += s[2];
+    }
+    p.f[0][i] = f0, p.f[1][i] = f1, p.f[2][i] = f2;
+  } else {
+    f0 = p.f[0][i], f1 = p.f[1][i], f2 = p.f[2][i];
+  }
+  if (!update_velocity) return;
+  const double rm = 1.0 / p.mass[i];
+  const double a0 = rm * (f0 + (HAS_FEXT ? p.fext[0][i] : 0.0));
+  const double a1 = rm * (f1 + (HAS_FEXT ? p.fext[1][i] : 0.0));
+  const double a2 = rm * (f2 + (HAS_FEXT ? p.fext[2][i] : 0.0));
+  p.a[0][i] = a0, p.a[1][i] = a1, p.a[2][i] = a2;
+  p.v[0][i] = p.v[0][i] + hdt * a0;
+  p.v[1][i] = p.v[1][i] + hdt * a1;
+  p.v[2][i] = p.v[2][i] + hdt * a2;
+}
+
+// BoundaryConditionManager::ApplyKinematicBC alone (output steps, t = 0): table entries in deck order;
+// duplicates of a dof were resolved to the last entry when the dof map was built.
+__global__ void __launch_bounds__(256)
+apply_bc_kernel(const NodeArgs p, double dt)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_nodes) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int bc = p.bc_of_dof[c][i];
+    if (bc >= 0) p.v[c][i] = bc_velocity(p.bc_kind[bc], p.bc_value[bc], p.u[c][i], dt, p.v[c][i]);
+  }
+}
+
+// host AoS [n][3] staging <-> device SoA
+__global__ void __launch_bounds__(256)
+aos_to_soa_kernel(int64_t n, const double* __restrict__ aos, double* x, double* y, double* z)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  x[i] = aos[3 * i], y[i] = aos[3 * i + 1], z[i] = aos[3 * i + 2];
+}
+
+__global__ void __launch_bounds__(256)
+soa_to_aos_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                  double* aos)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  aos[3 * i] = x[i], aos[3 * i + 1] = y[i], aos[3 * i + 2] = z[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// setup / output kernels: one thread per element, plain loops over a constant shape table.
+// ---------------------------------------------------------------------------------------------------
+struct ShapeTables
+{
+  double N[64];    // [q][j]
+  double dN[192];  // [q][j][3]
+};
+__constant__ ShapeTables c_shape;
+
+__device__ __forceinline__ void
+param_gradient_tbl(const double (&x)[24], int q, double (&J)[3][3])
+{
+  zero33(J);
+  for (int j = 0; j < 8; ++j) {
+    const double* d = &c_shape.dN[24 * q + 3 * j];
+    for (int i = 0; i < 3; ++i) {
+      J[i][0] += x[3 * j + i] * d[0];
+      J[i][1] += x[3 * j + i] * d[1];
+      J[i][2] += x[3 * j + i] * d[2];
+    }
+  }
+}
+
+struct SetupArgs
+{
+  int64_t         n_elem;
+  const int*      conn;
+  const double*   X[3];
+  const double*   u[3];
+  double          density, bulk;
+  double*         mass;        // ATOMIC: nodal lumped mass (atomic add)
+  double*         em;          // ORDERED: [n_elem][8] element lumped masses
+  unsigned long long* min_dt_bits;
+  int*            flags;
+};
+
+// HexElement::ComputeLumpedMass (src/nimble_element.cc:173-193 / src/nimble_element.h:266-309) and
+// HexElement::ComputeCharacteristicLength (src/nimble_element.cc:221-260) + BlockBase::ComputeCriticalTimeStep
+// (src/nimble_block_base.cc:51-84).
+template <bool ORDERED>
+__global__ void __launch_bounds__(128)
+lumped_mass_kernel(const SetupArgs p)
+{
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.n_elem) return;
+  int    nd[8];
+  double X[24], x[24];
+  for (int j = 0; j < 8; ++j) {
+    nd[j] = p.conn[e * 8 + j];
+    for (int i = 0; i < 3; ++i) {
+      X[3 * j + i] = p.X[i][nd[j]];
+      x[3 * j + i] = X[3 * j + i] + p.u[i][nd[j]];
+    }
+  }
+  double det[8];
+  for (int q = 0; q < 8; ++q) {
+    double a[3][3], ai[3][3];
+    param_gradient_tbl(X, q, a);
+    det[q] = invert3x3(a, ai);
+    if (!(det[q] > 0.0)) atomicOr(p.flags, 1);
+  }
+  for (int i = 0; i < 8; ++i) {
+    double mi = 0.0;
+    for (int j = 0; j < 8; ++j) {
+      double mij = 0.0;
+      for (int q = 0; q < 8; ++q) mij += 1.0 * p.density * c_shape.N[8 * q + i] * c_shape.N[8 * q + j] * det[q];
+      mi += mij;
+    }
+    if (ORDERED)
+      p.em[e * 8 + i] = mi;
+    else
+      atomicAdd(p.mass + nd[i], mi);
+  }
+  // characteristic length on the current configuration, including the reference's quirk that the box
+  // maxima start at 0.0 (src/nimble_element.cc:230)
+  double xmax = 0.0, ymax = 0.0, zmax = 0.0;
+  double xmin = 1.7976931348623157e308, ymin = xmin, zmin = xmin, dmin2 = xmin;
+  for (int n = 0; n < 8; ++n) {
+    const double nx = x[3 * n], ny = x[3 * n + 1], nz = x[3 * n + 2];
+    if (nx < xmin) xmin = nx;
+    if (nx > xmax) xmax = nx;
+    if (ny < ymin) ymin = ny;
+    if (ny > ymax) ymax = ny;
+    if (nz < zmin) zmin = nz;
+    if (nz > zmax) zmax = nz;
+    for (int m = n + 1; m < 8; ++m) {
+      const double mx = x[3 * m], my = x[3 * m + 1], mz = x[3 * m + 2];
+      const double d2 = (nx - mx) * (nx - mx) + (ny - my) * (ny - my) + (nz - mz) * (nz - mz);
+      if (d2 < dmin2) dmin2 = d2;
+    }
+  }
+  double len = sqrt(dmin2);
+  double box = xmax - xmin;
+  if (ymax - ymin < box) box = ymax - ymin;
+  if (zmax - zmin < box) box = zmax - zmin;
+  if (box < len) len = box;
+  const double dt = len / sqrt(p.bulk / p.density);
+  // non-negative doubles order like their bit patterns
+  if (dt >= 0.0) atomicMin(p.min_dt_bits, (unsigned long long)__double_as_longlong(dt));
+}
+
+// ordered nodal sum of element scalars (lumped mass), ascending (block, element)
+__global__ void __launch_bounds__(256)
+node_gather_scalar_kernel(int64_t n_nodes, const double* __restrict__ es, const int64_t* __restrict__ adj_off,
+                          const uint32_t* __restrict__ adj_slot, double* out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  double s = 0.0;
+  for (int64_t k = adj_off[i]; k < adj_off[i + 1]; ++k) s += es[adj_slot[k]];
+  out[i] = s;
+}
+
+// Block::ComputeDerivedElementData (src/nimble_block.cc:438-497) -> HexElement::ComputeVolumeAverage
+// (src/nimble_element.cc:262-282, src/nimble_element.h:343-392): volume = sum detJ (unit weights) on the
+// current configuration; averages of the 15 integration-point fields.  out [16][n_elem].
+__global__ void __launch_bounds__(128)
+derived_kernel(int64_t n_elem, const int* __restrict__ conn, const double* X0, const double* X1, const double* X2,
+               const double* u0, const double* u1, const double* u2, const double* __restrict__ ipt, double* out)
+{
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  const double* Xs[3] = {X0, X1, X2};
+  const double* us[3] = {u0, u1, u2};
+  double        x[24];
+  for (int j = 0; j < 8; ++j) {
+    const int nd = conn[e * 8 + j];
+    for (int i = 0; i < 3; ++i) x[3 * j + i] = (Xs[i][nd] + us[i][nd]) + 0.0;
+  }
+  double vol = 0.0, avg[15];
+  for (int i = 0; i < 15; ++i) avg[i] = 0.0;
+  const double* qd = ipt + e * 120;
+  for (int g = 0; g < 8; ++g) {
+    double a[3][3], ai[3][3];
+    param_gradient_tbl(x, g, a);
+    const double det = invert3x3(a, ai);
+    vol += det;
+    for (int i = 0; i < 15; ++i) avg[i] += qd[g * 15 + i] * 1.0 * det;
+  }
+  out[e] = vol;
+  for (int i = 0; i < 15; ++i) out[(int64_t)(i + 1) * n_elem + e] = avg[i] / vol;
+}
+
+// F = identity, sigma = 0 (Block::InitializeElementData, src/nimble_block.cc:148-207)
+__global__ void __launch_bounds__(256)
+init_ipt_kernel(int64_t n_points, double* ipt)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  double* d = ipt + i * 15;
+#pragma unroll
+  for (int k = 0; k < 15; ++k) d[k] = (k < 3) ? 1.0 : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// node -> element adjacency (ORDERED assembly), built on the device
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adj_count_kernel(int64_t n_slots, const int* __restrict__ conn, unsigned long long* counts)
+{
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  atomicAdd(counts + conn[s], 1ULL);
+}
+
+__global__ void __launch_bounds__(256)
+adj_fill_kernel(int64_t n_slots, int64_t slot_base, const int* __restrict__ conn, const int64_t* __restrict__ off,
+                unsigned long long* cursor, uint32_t* slots)
+{
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const int                n = conn[s];
+  const unsigned long long k = atomicAdd(cursor + n, 1ULL);
+  slots[off[n] + (int64_t)k] = (uint32_t)(slot_base + s);
+}
+
+__global__ void __launch_bounds__(256)
+adj_sort_kernel(int64_t n_nodes, const int64_t* __restrict__ off, uint32_t* slots)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const int64_t b = off[i], e = off[i + 1];
+  for (int64_t k = b + 1; k < e; ++k) {  // insertion sort; lists hold ~8 entries
+    const uint32_t key = slots[k];
+    int64_t        j   = k - 1;
+    while (j >= b && slots[j] > key) {
+      slots[j + 1] = slots[j];
+      --j;
+    }
+    slots[j + 1] = key;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FP64 pipe micro-benchmark (roofline denominator for an FP64-issue-bound kernel)
+// ---------------------------------------------------------------------------------------------------
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double* out, int iters, double seed)
+{
+  double x0 = seed + threadIdx.x, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
+  double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    if (FUSED) {
+      x0 = fma(x0, m, c), x1 = fma(x1, m, c), x2 = fma(x2, m, c), x3 = fma(x3, m, c);
+      x4 = fma(x4, m, c), x5 = fma(x5, m, c), x6 = fma(x6, m, c), x7 = fma(x7, m, c);
+    } else {  // -fmad=false keeps these as DMUL + DADD
+      x0 = x0 * m, x1 = x1 + c, x2 = x2 * m, x3 = x3 + c;
+      x4 = x4 * m, x5 = x5 + c, x6 = x6 * m, x7 = x7 + c;
+    }
+  }
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace nsm

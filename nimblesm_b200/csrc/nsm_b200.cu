@@ -1,0 +1,1095 @@
+// nimblesm_b200/csrc/nsm_b200.cu — context and C ABI (include/nsm_b200.h) of the B200 hex8 path.
+//
+// One context owns one GPU's share of the model: SoA fp64 nodal fields, per-block connectivity and
+// material, optional integration-point storage, assembly tables, a CUDA stream and the peer-exchange
+// state.  Host code (nimblesm_b200/host, C++; nimblesm_b200/capi.py, ctypes) reaches the kernels only
+// through the extern "C" functions at the bottom.  No CPU fallback exists anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/nsm_b200.h"
+#include "hex8_kernels.cuh"
+#include "peer_exchange.cuh"
+
+using namespace nsm;
+
+namespace {
+
+struct Block
+{
+  int              id       = 0;
+  int64_t          n_elem   = 0;
+  int              material = 0;
+  double           bulk = 0, shear = 0, density = 0;
+  std::vector<int> conn_host;  // dropped after finalize
+  int*             conn      = nullptr;
+  int64_t          elem_base = 0;  // first global element (ascending block id order)
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct nsm_b200_ctx
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;
+  std::string  err;
+
+  int64_t n_nodes = 0;
+  bool    finalized = false;
+  int     assembly  = NSM_ASSEMBLY_ATOMIC;
+  unsigned flags_   = 0;
+
+  std::vector<double> hx, hy, hz;  // host copies until finalize
+  std::map<int, Block> blocks;     // ascending id == reference processing order
+  int64_t              n_elem_total = 0;
+
+  // nodal fields, SoA
+  double* X[3]    = {nullptr, nullptr, nullptr};
+  double* u[3]    = {nullptr, nullptr, nullptr};
+  double* v[3]    = {nullptr, nullptr, nullptr};
+  double* a[3]    = {nullptr, nullptr, nullptr};
+  double* f[3]    = {nullptr, nullptr, nullptr};
+  double* fext[3] = {nullptr, nullptr, nullptr};
+  double* mass    = nullptr;
+  double* staging = nullptr;  // [n][3] AoS bounce buffer for host views
+  bool    has_fext = false;
+
+  // element data
+  double* ipt  = nullptr;  // [n_elem_total][8][15], lazily allocated
+  double* binv = nullptr;  // [n_elem_total][8][9]
+  double* ef   = nullptr;  // ORDERED: [n_elem_total][8][3]
+  int64_t*  adj_off  = nullptr;
+  uint32_t* adj_slot = nullptr;
+
+  // boundary conditions
+  int64_t n_bc = 0;
+  int*    bc_of_dof[3] = {nullptr, nullptr, nullptr};
+  int*    bc_kind  = nullptr;
+  double* bc_value = nullptr;
+
+  int*                d_flags  = nullptr;
+  unsigned long long* d_min_dt = nullptr;
+
+  int64_t launches     = 0;
+  int64_t device_bytes = 0;
+
+  // per-launch profiling (CUDA events on the stream)
+  bool                     profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t                   ev_used = 0;
+  double                   prof_elem_ms = 0, prof_node_ms = 0;
+  int64_t                  prof_steps   = 0;
+
+  PeerExchange comm;
+};
+
+namespace {
+
+int
+fail(nsm_b200_ctx* c, int code, const char* fmt, ...)
+{
+  char    buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define NSM_CUDA(c, call)                                                                               \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail((c), NSM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define NSM_REQUIRE(c, cond, msg) \
+  do {                            \
+    if (!(cond)) return fail((c), NSM_ERR_ARG, "%s", msg); \
+  } while (0)
+
+template <class T>
+int
+dev_alloc(nsm_b200_ctx* c, T** p, int64_t count)
+{
+  *p = nullptr;
+  if (count <= 0) count = 1;
+  NSM_CUDA(c, cudaMalloc((void**)p, (size_t)count * sizeof(T)));
+  c->device_bytes += count * (int64_t)sizeof(T);
+  return NSM_OK;
+}
+
+inline unsigned
+grid_for(int64_t n, int block)
+{
+  return (unsigned)((n + block - 1) / block);
+}
+
+ShapeTables
+make_shape_tables()
+{
+  // HexElement::HexElement / ShapeFunctionValues / ShapeFunctionDerivatives (src/nimble_element.cc:55-171)
+  ShapeTables  t;
+  const double g = 0.577350269189626;
+  const double c = 1.0 / 8.0;
+  for (int q = 0; q < 8; ++q) {
+    const double r = sgn_x(q) * g, s = sgn_y(q) * g, tt = sgn_z(q) * g;
+    for (int j = 0; j < 8; ++j) {
+      const double fr = 1.0 + sgn_x(j) * r, fs = 1.0 + sgn_y(j) * s, ft = 1.0 + sgn_z(j) * tt;
+      t.N[8 * q + j]            = c * fr * fs * ft;
+      t.dN[24 * q + 3 * j + 0] = (sgn_x(j) * c) * fs * ft;
+      t.dN[24 * q + 3 * j + 1] = (sgn_y(j) * c) * fr * ft;
+      t.dN[24 * q + 3 * j + 2] = (sgn_z(j) * c) * fr * fs;
+    }
+  }
+  return t;
+}
+
+NodeArgs
+node_args(nsm_b200_ctx* c)
+{
+  NodeArgs p{};
+  p.n_nodes = c->n_nodes;
+  for (int i = 0; i < 3; ++i) {
+    p.u[i] = c->u[i], p.v[i] = c->v[i], p.a[i] = c->a[i], p.f[i] = c->f[i];
+    p.fext[i]      = c->has_fext ? c->fext[i] : nullptr;
+    p.bc_of_dof[i] = c->bc_of_dof[i];
+  }
+  p.mass     = c->mass;
+  p.bc_kind  = c->bc_kind;
+  p.bc_value = c->bc_value;
+  p.ef       = c->ef;
+  p.adj_off  = c->adj_off;
+  p.adj_slot = c->adj_slot;
+  return p;
+}
+
+ElemArgs
+elem_args(nsm_b200_ctx* c, const Block& b)
+{
+  ElemArgs p{};
+  p.n_elem = b.n_elem;
+  p.conn   = b.conn;
+  for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.f[i] = c->f[i];
+  p.ef         = c->ef ? c->ef + b.elem_base * 24 : nullptr;
+  p.ipt        = c->ipt ? c->ipt + b.elem_base * 120 : nullptr;
+  p.binv_cache = c->binv ? c->binv + b.elem_base * 72 : nullptr;
+  p.bulk       = b.bulk;
+  p.shear      = b.shear;
+  p.flags      = c->d_flags;
+  return p;
+}
+
+constexpr size_t kElemSmemBytes = (size_t)(kElemThreads / 32) * kWarpSmemDoubles * sizeof(double);
+
+template <int MAT, bool ORDERED, int MODE>
+cudaError_t
+launch_element(const ElemArgs& p, cudaStream_t s)
+{
+  static bool configured = false;
+  auto        k          = element_force_kernel<MAT, ORDERED, MODE>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kElemSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  k<<<grid_for(p.n_elem, kElemThreads / 8), kElemThreads, kElemSmemBytes, s>>>(p);
+  return cudaGetLastError();
+}
+
+template <int MAT, bool ORDERED>
+cudaError_t
+launch_element_mode(const ElemArgs& p, int mode, cudaStream_t s)
+{
+  switch (mode) {
+    case 0: return launch_element<MAT, ORDERED, 0>(p, s);
+    case 1: return launch_element<MAT, ORDERED, 1>(p, s);
+    case 2: return launch_element<MAT, ORDERED, 2>(p, s);
+    default: return launch_element<MAT, ORDERED, 3>(p, s);
+  }
+}
+
+cudaError_t
+launch_element_any(const ElemArgs& p, int material, bool ordered, int mode, cudaStream_t s)
+{
+  if (material == NSM_MAT_ELASTIC)
+    return ordered ? launch_element_mode<0, true>(p, mode, s) : launch_element_mode<0, false>(p, mode, s);
+  return ordered ? launch_element_mode<1, true>(p, mode, s) : launch_element_mode<1, false>(p, mode, s);
+}
+
+int
+ensure_ipt(nsm_b200_ctx* c)
+{
+  if (c->ipt) return NSM_OK;
+  int rc = dev_alloc(c, &c->ipt, c->n_elem_total * 120);
+  if (rc) return rc;
+  const int64_t np = c->n_elem_total * 8;
+  if (np > 0) {
+    init_ipt_kernel<<<grid_for(np, 256), 256, 0, c->stream>>>(np, c->ipt);
+    c->launches++;
+    NSM_CUDA(c, cudaGetLastError());
+  }
+  return NSM_OK;
+}
+
+// element kernels of all blocks, ascending block id (src/nimble_model_data.cc:636-659)
+int
+enqueue_element_kernels(nsm_b200_ctx* c, bool store_ipt)
+{
+  const bool ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
+  int        mode    = 0;
+  if (store_ipt) {
+    int rc = ensure_ipt(c);
+    if (rc) return rc;
+    mode |= kModeStoreIpt;
+  }
+  if (c->binv) mode |= kModeReadBinv;
+  for (auto& kv : c->blocks) {
+    const Block& b = kv.second;
+    if (b.n_elem == 0) continue;
+    NSM_CUDA(c, launch_element_any(elem_args(c, b), b.material, ordered, mode, c->stream));
+    c->launches++;
+  }
+  return NSM_OK;
+}
+
+int
+check_flags(nsm_b200_ctx* c)
+{
+  int h = 0;
+  NSM_CUDA(c, cudaMemcpyAsync(&h, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (h & 1) {
+    NSM_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+    return fail(c, NSM_ERR_JACOBIAN, "non-positive Jacobian determinant in Invert3x3 (singular or inverted element)");
+  }
+  if (c->comm.poll_error(c->stream)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  return NSM_OK;
+}
+
+cudaEvent_t
+prof_event(nsm_b200_ctx* c)
+{
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  cudaEvent_t e = c->ev_pool[c->ev_used++];
+  cudaEventRecord(e, c->stream);
+  return e;
+}
+
+void
+prof_resolve(nsm_b200_ctx* c)
+{
+  // events come in triples: before the element kernels, after them, after the node-side work of the step
+  cudaStreamSynchronize(c->stream);
+  for (size_t i = 0; i + 2 < c->ev_used; i += 3) {
+    float m1 = 0, m2 = 0;
+    cudaEventElapsedTime(&m1, c->ev_pool[i], c->ev_pool[i + 1]);
+    cudaEventElapsedTime(&m2, c->ev_pool[i + 1], c->ev_pool[i + 2]);
+    c->prof_elem_ms += m1;
+    c->prof_node_ms += m2;
+    c->prof_steps++;
+  }
+  c->ev_used = 0;
+}
+
+// internal force of the current device displacement into the device force field (+ shared-node sum)
+int
+enqueue_internal_force(nsm_b200_ctx* c, bool store_ipt)
+{
+  const bool ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
+  if (!ordered) {
+    for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->f[i], 0, (size_t)c->n_nodes * sizeof(double), c->stream));
+  }
+  int rc = enqueue_element_kernels(c, store_ipt);
+  if (rc) return rc;
+  if (ordered) {
+    node_correct_kernel<true, false><<<grid_for(c->n_nodes, 256), 256, 0, c->stream>>>(node_args(c), 0.0, 0);
+    c->launches++;
+    NSM_CUDA(c, cudaGetLastError());
+  }
+  if (c->comm.active()) {
+    rc = c->comm.reduce(c->stream, c->f, 3, &c->launches);
+    if (rc) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  }
+  return NSM_OK;
+}
+
+int
+field_ptrs(nsm_b200_ctx* c, int field, double** p, int* ncomp)
+{
+  *ncomp = 3;
+  switch (field) {
+    case NSM_FIELD_LUMPED_MASS:
+      p[0]   = c->mass;
+      *ncomp = 1;
+      return NSM_OK;
+    case NSM_FIELD_REFERENCE_COORDINATE: p[0] = c->X[0], p[1] = c->X[1], p[2] = c->X[2]; return NSM_OK;
+    case NSM_FIELD_DISPLACEMENT: p[0] = c->u[0], p[1] = c->u[1], p[2] = c->u[2]; return NSM_OK;
+    case NSM_FIELD_VELOCITY: p[0] = c->v[0], p[1] = c->v[1], p[2] = c->v[2]; return NSM_OK;
+    case NSM_FIELD_ACCELERATION: p[0] = c->a[0], p[1] = c->a[1], p[2] = c->a[2]; return NSM_OK;
+    case NSM_FIELD_INTERNAL_FORCE: p[0] = c->f[0], p[1] = c->f[1], p[2] = c->f[2]; return NSM_OK;
+    case NSM_FIELD_EXTERNAL_FORCE: p[0] = c->fext[0], p[1] = c->fext[1], p[2] = c->fext[2]; return NSM_OK;
+  }
+  return fail(c, NSM_ERR_ARG, "unknown field id %d", field);
+}
+
+int
+upload_field(nsm_b200_ctx* c, int field, const double* host, bool sync)
+{
+  NSM_REQUIRE(c, c && c->finalized, "upload_field: context not finalized");
+  NSM_REQUIRE(c, host != nullptr, "upload_field: null host pointer");
+  double* p[3];
+  int     nc;
+  int     rc = field_ptrs(c, field, p, &nc);
+  if (rc) return rc;
+  const int64_t n = c->n_nodes;
+  if (nc == 1) {
+    NSM_CUDA(c, cudaMemcpyAsync(p[0], host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    NSM_CUDA(c, cudaMemcpyAsync(c->staging, host, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (n > 0) {
+      aos_to_soa_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, c->staging, p[0], p[1], p[2]);
+      c->launches++;
+      NSM_CUDA(c, cudaGetLastError());
+    }
+    if (field == NSM_FIELD_EXTERNAL_FORCE) c->has_fext = true;
+  }
+  if (sync) NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
+download_field(nsm_b200_ctx* c, int field, double* host, bool sync)
+{
+  NSM_REQUIRE(c, c && c->finalized, "download_field: context not finalized");
+  NSM_REQUIRE(c, host != nullptr, "download_field: null host pointer");
+  double* p[3];
+  int     nc;
+  int     rc = field_ptrs(c, field, p, &nc);
+  if (rc) return rc;
+  const int64_t n = c->n_nodes;
+  if (nc == 1) {
+    NSM_CUDA(c, cudaMemcpyAsync(host, p[0], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    if (n > 0) {
+      soa_to_aos_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, p[0], p[1], p[2], c->staging);
+      c->launches++;
+      NSM_CUDA(c, cudaGetLastError());
+    }
+    NSM_CUDA(c, cudaMemcpyAsync(host, c->staging, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (sync) NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char*
+nsm_b200_version(void)
+{
+  return "nsm_b200 0.1.0 sm_100a fp64 fmad=off"
+#ifdef NSM_SHARED_DIVISOR
+         " shared-divisor"
+#endif
+      ;
+}
+
+const char*
+nsm_b200_last_error(const nsm_b200_ctx* ctx)
+{
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int
+nsm_b200_create(int device, nsm_b200_ctx** out)
+{
+  if (!out) return fail(nullptr, NSM_ERR_ARG, "nsm_b200_create: null out pointer");
+  *out  = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, NSM_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= n) return fail(nullptr, NSM_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  cudaDeviceProp prop;
+  NSM_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, NSM_ERR_CUDA, "device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major,
+                prop.minor);
+  NSM_CUDA(nullptr, cudaSetDevice(device));
+  auto* c   = new nsm_b200_ctx;
+  c->device = device;
+  NSM_CUDA(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  NSM_CUDA(nullptr, cudaEventCreate(&c->ev_start));
+  NSM_CUDA(nullptr, cudaEventCreate(&c->ev_stop));
+  static const ShapeTables tables = make_shape_tables();
+  NSM_CUDA(nullptr, cudaMemcpyToSymbol(c_shape, &tables, sizeof tables));
+  *out = c;
+  return NSM_OK;
+}
+
+void
+nsm_b200_destroy(nsm_b200_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->comm.destroy();
+  auto fr = [](void* p) {
+    if (p) cudaFree(p);
+  };
+  for (int i = 0; i < 3; ++i) {
+    fr(c->X[i]), fr(c->u[i]), fr(c->v[i]), fr(c->a[i]), fr(c->f[i]), fr(c->fext[i]), fr(c->bc_of_dof[i]);
+  }
+  fr(c->mass), fr(c->staging), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
+  fr(c->bc_kind), fr(c->bc_value), fr(c->d_flags), fr(c->d_min_dt);
+  for (auto& kv : c->blocks) fr(kv.second.conn);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_start);
+  cudaEventDestroy(c->ev_stop);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int
+nsm_b200_set_nodes(nsm_b200_ctx* c, int64_t n_nodes, const double* x, const double* y, const double* z)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_REQUIRE(c, !c->finalized, "set_nodes after finalize");
+  NSM_REQUIRE(c, n_nodes >= 0 && n_nodes < (int64_t)2147483647, "node count must fit int32 local ids");
+  NSM_REQUIRE(c, n_nodes == 0 || (x && y && z), "null coordinate pointer");
+  c->n_nodes = n_nodes;
+  c->hx.assign(x, x + n_nodes);
+  c->hy.assign(y, y + n_nodes);
+  c->hz.assign(z, z + n_nodes);
+  return NSM_OK;
+}
+
+int
+nsm_b200_add_block(nsm_b200_ctx* c, int block_id, int64_t n_elem, const int32_t* conn, int material_kind,
+                   double bulk_modulus, double shear_modulus, double density)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_REQUIRE(c, !c->finalized, "add_block after finalize");
+  NSM_REQUIRE(c, n_elem >= 0 && (n_elem == 0 || conn), "bad element count / null connectivity");
+  NSM_REQUIRE(c, c->blocks.find(block_id) == c->blocks.end(), "duplicate block id");
+  if (material_kind != NSM_MAT_ELASTIC && material_kind != NSM_MAT_NEOHOOKEAN)
+    return fail(c, NSM_ERR_MATERIAL, "unknown material kind %d (0 = elastic, 1 = neohookean)", material_kind);
+  for (int64_t i = 0; i < n_elem * 8; ++i)
+    if (conn[i] < 0 || conn[i] >= c->n_nodes)
+      return fail(c, NSM_ERR_ARG, "block %d: connectivity entry %lld = %d outside [0, %lld)", block_id, (long long)i,
+                  conn[i], (long long)c->n_nodes);
+  Block b;
+  b.id = block_id, b.n_elem = n_elem, b.material = material_kind;
+  b.bulk = bulk_modulus, b.shear = shear_modulus, b.density = density;
+  b.conn_host.assign(conn, conn + n_elem * 8);
+  c->blocks[block_id] = std::move(b);
+  return NSM_OK;
+}
+
+int
+nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_REQUIRE(c, !c->finalized, "finalize called twice");
+  NSM_REQUIRE(c, assembly == NSM_ASSEMBLY_ATOMIC || assembly == NSM_ASSEMBLY_ORDERED, "unknown assembly mode");
+  NSM_CUDA(c, cudaSetDevice(c->device));
+  c->assembly = assembly;
+  c->flags_   = flags;
+  const int64_t n = c->n_nodes;
+  int           rc;
+  for (int i = 0; i < 3; ++i) {
+    if ((rc = dev_alloc(c, &c->X[i], n))) return rc;
+    if ((rc = dev_alloc(c, &c->u[i], n))) return rc;
+    if ((rc = dev_alloc(c, &c->v[i], n))) return rc;
+    if ((rc = dev_alloc(c, &c->a[i], n))) return rc;
+    if ((rc = dev_alloc(c, &c->f[i], n))) return rc;
+    if ((rc = dev_alloc(c, &c->fext[i], n))) return rc;
+    for (double* p : {c->u[i], c->v[i], c->a[i], c->f[i], c->fext[i]})
+      NSM_CUDA(c, cudaMemsetAsync(p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->stream));
+  }
+  if ((rc = dev_alloc(c, &c->mass, n))) return rc;
+  NSM_CUDA(c, cudaMemsetAsync(c->mass, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->stream));
+  if ((rc = dev_alloc(c, &c->staging, n * 3))) return rc;
+  if ((rc = dev_alloc(c, &c->d_flags, 1))) return rc;
+  if ((rc = dev_alloc(c, &c->d_min_dt, 1))) return rc;
+  NSM_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+  NSM_CUDA(c, cudaMemcpyAsync(c->X[0], c->hx.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemcpyAsync(c->X[1], c->hy.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemcpyAsync(c->X[2], c->hz.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+
+  int64_t base = 0;
+  for (auto& kv : c->blocks) {
+    Block& b    = kv.second;
+    b.elem_base = base;
+    base += b.n_elem;
+    if ((rc = dev_alloc(c, &b.conn, b.n_elem * 8))) return rc;
+    NSM_CUDA(c, cudaMemcpyAsync(b.conn, b.conn_host.data(), (size_t)b.n_elem * 8 * sizeof(int), cudaMemcpyHostToDevice,
+                                c->stream));
+  }
+  c->n_elem_total = base;
+  NSM_REQUIRE(c, base * 8 < (int64_t)4294967295LL, "too many elements for 32-bit assembly slots on one GPU");
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& kv : c->blocks) std::vector<int>().swap(kv.second.conn_host);
+  std::vector<double>().swap(c->hx), std::vector<double>().swap(c->hy), std::vector<double>().swap(c->hz);
+
+  if (assembly == NSM_ASSEMBLY_ORDERED) {
+    // node -> (element, local node) adjacency, ascending slot == ascending (block id, element)
+    if ((rc = dev_alloc(c, &c->ef, c->n_elem_total * 24))) return rc;
+    NSM_CUDA(c, cudaMemsetAsync(c->ef, 0, (size_t)std::max<int64_t>(c->n_elem_total * 24, 1) * sizeof(double), c->stream));
+    if ((rc = dev_alloc(c, &c->adj_off, n + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->adj_slot, c->n_elem_total * 8))) return rc;
+    unsigned long long* counts = nullptr;
+    NSM_CUDA(c, cudaMalloc((void**)&counts, (size_t)(n + 1) * sizeof(unsigned long long)));
+    NSM_CUDA(c, cudaMemsetAsync(counts, 0, (size_t)(n + 1) * sizeof(unsigned long long), c->stream));
+    for (auto& kv : c->blocks) {
+      const Block& b = kv.second;
+      if (b.n_elem == 0) continue;
+      adj_count_kernel<<<grid_for(b.n_elem * 8, 256), 256, 0, c->stream>>>(b.n_elem * 8, b.conn, counts);
+      c->launches++;
+    }
+    void*  tmp      = nullptr;
+    size_t tmp_size = 0;
+    NSM_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_size, (const long long*)counts, (long long*)c->adj_off,
+                                               (int)(n + 1), c->stream));
+    NSM_CUDA(c, cudaMalloc(&tmp, tmp_size ? tmp_size : 1));
+    NSM_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp, tmp_size, (const long long*)counts, (long long*)c->adj_off,
+                                               (int)(n + 1), c->stream));
+    c->launches++;
+    NSM_CUDA(c, cudaMemsetAsync(counts, 0, (size_t)(n + 1) * sizeof(unsigned long long), c->stream));
+    for (auto& kv : c->blocks) {
+      const Block& b = kv.second;
+      if (b.n_elem == 0) continue;
+      adj_fill_kernel<<<grid_for(b.n_elem * 8, 256), 256, 0, c->stream>>>(b.n_elem * 8, b.elem_base * 8, b.conn,
+                                                                          c->adj_off, counts, c->adj_slot);
+      c->launches++;
+    }
+    if (n > 0) {
+      adj_sort_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, c->adj_off, c->adj_slot);
+      c->launches++;
+    }
+    NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    NSM_CUDA(c, cudaGetLastError());
+    cudaFree(tmp);
+    cudaFree(counts);
+  }
+
+  c->finalized = true;
+  if (flags & NSM_FLAG_STORE_IPT_EVERY_STEP) {
+    if ((rc = ensure_ipt(c))) return rc;
+  }
+  if (flags & NSM_FLAG_CACHE_REF_JACOBIAN) {
+    if ((rc = dev_alloc(c, &c->binv, c->n_elem_total * 72))) return rc;
+    for (auto& kv : c->blocks) {
+      const Block& b = kv.second;
+      if (b.n_elem == 0) continue;
+      binv_cache_kernel<<<grid_for(b.n_elem * 8, kElemThreads), kElemThreads, 0, c->stream>>>(elem_args(c, b));
+      c->launches++;
+      NSM_CUDA(c, cudaGetLastError());
+    }
+    if ((rc = check_flags(c))) return rc;
+  }
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int64_t
+nsm_b200_num_nodes(const nsm_b200_ctx* c)
+{
+  return c ? c->n_nodes : -1;
+}
+
+int64_t
+nsm_b200_num_elements(const nsm_b200_ctx* c, int block_id)
+{
+  if (!c) return -1;
+  if (block_id < 0) {
+    int64_t n = 0;
+    for (auto& kv : c->blocks) n += kv.second.n_elem;
+    return n;
+  }
+  auto it = c->blocks.find(block_id);
+  return it == c->blocks.end() ? -1 : it->second.n_elem;
+}
+
+int64_t
+nsm_b200_device_bytes(const nsm_b200_ctx* c)
+{
+  return c ? c->device_bytes : -1;
+}
+
+int
+nsm_b200_upload_field(nsm_b200_ctx* c, int field, const double* host)
+{
+  return upload_field(c, field, host, true);
+}
+int
+nsm_b200_download_field(nsm_b200_ctx* c, int field, double* host)
+{
+  return download_field(c, field, host, true);
+}
+int
+nsm_b200_upload_field_async(nsm_b200_ctx* c, int field, const double* host)
+{
+  return upload_field(c, field, host, false);
+}
+int
+nsm_b200_download_field_async(nsm_b200_ctx* c, int field, double* host)
+{
+  // the AoS bounce buffer is shared: serialise with earlier async transfers through the stream order
+  return download_field(c, field, host, false);
+}
+
+int
+nsm_b200_sync(nsm_b200_ctx* c)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+void*
+nsm_b200_host_alloc(int64_t bytes)
+{
+  void* p = nullptr;
+  if (cudaMallocHost(&p, (size_t)(bytes > 0 ? bytes : 1)) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void
+nsm_b200_host_free(void* p)
+{
+  if (p) cudaFreeHost(p);
+}
+
+int
+nsm_b200_compute_lumped_mass(nsm_b200_ctx* c, double* critical_dt)
+{
+  NSM_REQUIRE(c, c && c->finalized, "compute_lumped_mass: context not finalized");
+  const bool ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
+  const int64_t n    = c->n_nodes;
+  const unsigned long long inf_bits = 0x7ff0000000000000ULL;
+  NSM_CUDA(c, cudaMemcpyAsync(c->d_min_dt, &inf_bits, sizeof inf_bits, cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemsetAsync(c->mass, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->stream));
+  double* em = nullptr;
+  if (ordered) NSM_CUDA(c, cudaMalloc((void**)&em, (size_t)std::max<int64_t>(c->n_elem_total * 8, 1) * sizeof(double)));
+  for (auto& kv : c->blocks) {
+    const Block& b = kv.second;
+    if (b.n_elem == 0) continue;
+    SetupArgs p{};
+    p.n_elem = b.n_elem, p.conn = b.conn;
+    for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i];
+    p.density = b.density, p.bulk = b.bulk;
+    p.mass        = c->mass;
+    p.em          = ordered ? em + b.elem_base * 8 : nullptr;
+    p.min_dt_bits = c->d_min_dt;
+    p.flags       = c->d_flags;
+    if (ordered)
+      lumped_mass_kernel<true><<<grid_for(b.n_elem, 128), 128, 0, c->stream>>>(p);
+    else
+      lumped_mass_kernel<false><<<grid_for(b.n_elem, 128), 128, 0, c->stream>>>(p);
+    c->launches++;
+    NSM_CUDA(c, cudaGetLastError());
+  }
+  if (ordered && n > 0) {
+    node_gather_scalar_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, em, c->adj_off, c->adj_slot, c->mass);
+    c->launches++;
+    NSM_CUDA(c, cudaGetLastError());
+  }
+  if (c->comm.active()) {
+    double* m1[3] = {c->mass, nullptr, nullptr};
+    if (c->comm.reduce(c->stream, m1, 1, &c->launches)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  }
+  unsigned long long bits = 0;
+  NSM_CUDA(c, cudaMemcpyAsync(&bits, c->d_min_dt, sizeof bits, cudaMemcpyDeviceToHost, c->stream));
+  int rc = check_flags(c);
+  if (em) cudaFree(em);
+  if (rc) return rc;
+  if (critical_dt) memcpy(critical_dt, &bits, sizeof bits);
+  return NSM_OK;
+}
+
+int
+nsm_b200_internal_force(nsm_b200_ctx* c, int store_ipt)
+{
+  NSM_REQUIRE(c, c && c->finalized, "internal_force: context not finalized");
+  int rc = enqueue_internal_force(c, store_ipt != 0 || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP));
+  if (rc) return rc;
+  return check_flags(c);
+}
+
+int
+nsm_b200_internal_force_host(nsm_b200_ctx* c, const double* displacement, double* internal_force, int store_ipt)
+{
+  int rc = upload_field(c, NSM_FIELD_DISPLACEMENT, displacement, false);
+  if (rc) return rc;
+  rc = enqueue_internal_force(c, store_ipt != 0 || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP));
+  if (rc) return rc;
+  rc = download_field(c, NSM_FIELD_INTERNAL_FORCE, internal_force, false);
+  if (rc) return rc;
+  return check_flags(c);
+}
+
+int
+nsm_b200_compute_stress(nsm_b200_ctx* c, int material_kind, double bulk, double shear, int64_t n_points,
+                        const double* def_grad, double* stress)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_REQUIRE(c, n_points >= 0 && (n_points == 0 || (def_grad && stress)), "compute_stress: bad arguments");
+  if (material_kind != NSM_MAT_ELASTIC && material_kind != NSM_MAT_NEOHOOKEAN)
+    return fail(c, NSM_ERR_MATERIAL, "unknown material kind %d", material_kind);
+  if (n_points == 0) return NSM_OK;
+  NSM_CUDA(c, cudaSetDevice(c->device));
+  double *dF = nullptr, *dS = nullptr;
+  NSM_CUDA(c, cudaMalloc((void**)&dF, (size_t)n_points * 9 * sizeof(double)));
+  NSM_CUDA(c, cudaMalloc((void**)&dS, (size_t)n_points * 6 * sizeof(double)));
+  NSM_CUDA(c, cudaMemcpyAsync(dF, def_grad, (size_t)n_points * 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (material_kind == NSM_MAT_ELASTIC)
+    stress_kernel<0><<<grid_for(n_points, 128), 128, 0, c->stream>>>(n_points, dF, dS, bulk, shear);
+  else
+    stress_kernel<1><<<grid_for(n_points, 128), 128, 0, c->stream>>>(n_points, dF, dS, bulk, shear);
+  c->launches++;
+  NSM_CUDA(c, cudaGetLastError());
+  NSM_CUDA(c, cudaMemcpyAsync(stress, dS, (size_t)n_points * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dF);
+  cudaFree(dS);
+  return NSM_OK;
+}
+
+int
+nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int32_t* comp, const int32_t* kind)
+{
+  NSM_REQUIRE(c, c && c->finalized, "set_bc_table: context not finalized");
+  NSM_REQUIRE(c, n >= 0 && (n == 0 || (node && comp && kind)), "set_bc_table: bad arguments");
+  for (int i = 0; i < 3; ++i) {
+    if (c->bc_of_dof[i]) cudaFree(c->bc_of_dof[i]);
+    c->bc_of_dof[i] = nullptr;
+  }
+  if (c->bc_kind) cudaFree(c->bc_kind);
+  if (c->bc_value) cudaFree(c->bc_value);
+  c->bc_kind = nullptr, c->bc_value = nullptr;
+  c->n_bc = n;
+  if (n == 0) return NSM_OK;
+  // dof -> last table entry constraining it (later entries win, like the reference's sequential loop)
+  std::vector<int> map[3];
+  for (int i = 0; i < 3; ++i) map[i].assign((size_t)c->n_nodes, -1);
+  for (int64_t k = 0; k < n; ++k) {
+    if (node[k] < 0 || node[k] >= c->n_nodes || comp[k] < 0 || comp[k] > 2 ||
+        (kind[k] != NSM_BC_PRESCRIBED_VELOCITY && kind[k] != NSM_BC_PRESCRIBED_DISPLACEMENT))
+      return fail(c, NSM_ERR_ARG, "set_bc_table: entry %lld invalid (node %d comp %d kind %d)", (long long)k, node[k],
+                  comp[k], kind[k]);
+    map[comp[k]][node[k]] = (int)k;
+  }
+  int rc;
+  for (int i = 0; i < 3; ++i) {
+    if ((rc = dev_alloc(c, &c->bc_of_dof[i], c->n_nodes))) return rc;
+    NSM_CUDA(c, cudaMemcpyAsync(c->bc_of_dof[i], map[i].data(), (size_t)c->n_nodes * sizeof(int), cudaMemcpyHostToDevice,
+                                c->stream));
+  }
+  if ((rc = dev_alloc(c, &c->bc_kind, n))) return rc;
+  if ((rc = dev_alloc(c, &c->bc_value, n))) return rc;
+  NSM_CUDA(c, cudaMemcpyAsync(c->bc_kind, kind, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemsetAsync(c->bc_value, 0, (size_t)n * sizeof(double), c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
+nsm_b200_set_bc_values(nsm_b200_ctx* c, int64_t n, const double* value)
+{
+  NSM_REQUIRE(c, c && c->finalized, "set_bc_values: context not finalized");
+  NSM_REQUIRE(c, n == c->n_bc, "set_bc_values: length differs from the BC table");
+  if (n == 0) return NSM_OK;
+  NSM_CUDA(c, cudaMemcpyAsync(c->bc_value, value, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));  // `value` may be reused by the caller right away
+  return NSM_OK;
+}
+
+int
+nsm_b200_apply_kinematic_bc(nsm_b200_ctx* c, double time_current, double time_previous)
+{
+  NSM_REQUIRE(c, c && c->finalized, "apply_kinematic_bc: context not finalized");
+  if (c->n_bc == 0 || c->n_nodes == 0) return NSM_OK;
+  const double dt = time_current - time_previous;
+  apply_bc_kernel<<<grid_for(c->n_nodes, 256), 256, 0, c->stream>>>(node_args(c), dt);
+  c->launches++;
+  NSM_CUDA(c, cudaGetLastError());
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
+nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int store_ipt_last)
+{
+  NSM_REQUIRE(c, c && c->finalized, "step: context not finalized");
+  NSM_REQUIRE(c, time != nullptr && n_steps >= 0, "step: bad arguments");
+  const bool     ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
+  const bool     has_bc  = c->n_bc > 0;
+  const int64_t  n       = c->n_nodes;
+  const unsigned ngrid   = grid_for(n, 256);
+  double         t       = *time;
+  double         dt      = 0.0;
+  for (int s = 0; s < n_steps; ++s) {
+    // explicit_time_integrator.cc:192-195: dt is re-derived from the accumulated time every step
+    const double t_prev = t;
+    t += dt_user;
+    dt               = t - t_prev;
+    const double hdt = 0.5 * dt;
+    const bool   store =
+        (store_ipt_last && s == n_steps - 1) || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP);
+    if (n > 0) {
+      const NodeArgs na = node_args(c);
+      if (has_bc) {
+        if (ordered)
+          node_predict_kernel<true, false><<<ngrid, 256, 0, c->stream>>>(na, hdt, dt);
+        else
+          node_predict_kernel<true, true><<<ngrid, 256, 0, c->stream>>>(na, hdt, dt);
+      } else {
+        if (ordered)
+          node_predict_kernel<false, false><<<ngrid, 256, 0, c->stream>>>(na, hdt, dt);
+        else
+          node_predict_kernel<false, true><<<ngrid, 256, 0, c->stream>>>(na, hdt, dt);
+      }
+      c->launches++;
+    }
+    if (c->profiling) prof_event(c);
+    int rc = enqueue_element_kernels(c, store);
+    if (rc) return rc;
+    if (c->profiling) prof_event(c);
+    if (n > 0) {
+      const NodeArgs na = node_args(c);
+      if (c->comm.active()) {
+        if (ordered) {
+          node_correct_kernel<true, false><<<ngrid, 256, 0, c->stream>>>(na, 0.0, 0);
+          c->launches++;
+        }
+        if (c->comm.reduce(c->stream, c->f, 3, &c->launches)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+        if (c->has_fext)
+          node_correct_kernel<false, true><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
+        else
+          node_correct_kernel<false, false><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
+      } else if (ordered) {
+        if (c->has_fext)
+          node_correct_kernel<true, true><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
+        else
+          node_correct_kernel<true, false><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
+      } else {
+        if (c->has_fext)
+          node_correct_kernel<false, true><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
+        else
+          node_correct_kernel<false, false><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
+      }
+      c->launches++;
+    }
+    if (c->profiling) {
+      prof_event(c);
+      if (c->ev_used >= 3 * 256) prof_resolve(c);
+    }
+    NSM_CUDA(c, cudaGetLastError());
+  }
+  if (store_ipt_last && n_steps > 0 && has_bc && n > 0) {
+    // output step: ApplyKinematicConditions once more before the data is read (explicit_time_integrator.cc:266-269)
+    apply_bc_kernel<<<ngrid, 256, 0, c->stream>>>(node_args(c), dt);
+    c->launches++;
+  }
+  *time = t;
+  if (c->profiling) prof_resolve(c);
+  return check_flags(c);
+}
+
+int
+nsm_b200_get_element_data(nsm_b200_ctx* c, int block_id, double* out)
+{
+  NSM_REQUIRE(c, c && c->finalized, "get_element_data: context not finalized");
+  auto it = c->blocks.find(block_id);
+  NSM_REQUIRE(c, it != c->blocks.end(), "get_element_data: unknown block id");
+  int rc = ensure_ipt(c);
+  if (rc) return rc;
+  const Block& b = it->second;
+  NSM_CUDA(c, cudaMemcpyAsync(out, c->ipt + b.elem_base * 120, (size_t)b.n_elem * 120 * sizeof(double),
+                              cudaMemcpyDeviceToHost, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
+nsm_b200_derived_element_data(nsm_b200_ctx* c, int block_id, double* out)
+{
+  NSM_REQUIRE(c, c && c->finalized, "derived_element_data: context not finalized");
+  auto it = c->blocks.find(block_id);
+  NSM_REQUIRE(c, it != c->blocks.end(), "derived_element_data: unknown block id");
+  int rc = ensure_ipt(c);
+  if (rc) return rc;
+  const Block& b = it->second;
+  if (b.n_elem == 0) return NSM_OK;
+  double* d = nullptr;
+  NSM_CUDA(c, cudaMalloc((void**)&d, (size_t)b.n_elem * 16 * sizeof(double)));
+  derived_kernel<<<grid_for(b.n_elem, 128), 128, 0, c->stream>>>(b.n_elem, b.conn, c->X[0], c->X[1], c->X[2], c->u[0],
+                                                                 c->u[1], c->u[2], c->ipt + b.elem_base * 120, d);
+  c->launches++;
+  NSM_CUDA(c, cudaGetLastError());
+  NSM_CUDA(c, cudaMemcpyAsync(out, d, (size_t)b.n_elem * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  return NSM_OK;
+}
+
+// ---- peer exchange ---------------------------------------------------------------------------------
+int
+nsm_b200_comm_init(nsm_b200_ctx* c, int rank, int world_size, int n_peers, const int32_t* peer_ranks,
+                   const int64_t* pair_offsets, const int32_t* pair_local_nodes)
+{
+  NSM_REQUIRE(c, c && c->finalized, "comm_init: context not finalized");
+  NSM_REQUIRE(c, n_peers >= 0 && (n_peers == 0 || (peer_ranks && pair_offsets)), "comm_init: bad arguments");
+  NSM_CUDA(c, cudaSetDevice(c->device));
+  static const int64_t zero = 0;
+  if (n_peers == 0) pair_offsets = &zero;
+  for (int64_t k = 0; k < pair_offsets[n_peers]; ++k)
+    if (pair_local_nodes[k] < 0 || pair_local_nodes[k] >= c->n_nodes)
+      return fail(c, NSM_ERR_ARG, "comm_init: shared node id out of range");
+  if (c->comm.init(c->device, rank, world_size, n_peers, peer_ranks, pair_offsets, pair_local_nodes))
+    return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  return NSM_OK;
+}
+
+int
+nsm_b200_comm_export(nsm_b200_ctx* c, unsigned char handle[NSM_COMM_HANDLE_BYTES])
+{
+  NSM_REQUIRE(c, c && c->finalized, "comm_export: context not finalized");
+  NSM_CUDA(c, cudaSetDevice(c->device));
+  if (c->comm.export_handle(handle)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  return NSM_OK;
+}
+
+int
+nsm_b200_comm_attach(nsm_b200_ctx* c, int peer_rank, const unsigned char handle[NSM_COMM_HANDLE_BYTES])
+{
+  NSM_REQUIRE(c, c && c->finalized, "comm_attach: context not finalized");
+  NSM_CUDA(c, cudaSetDevice(c->device));
+  if (c->comm.attach(peer_rank, handle)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  return NSM_OK;
+}
+
+int
+nsm_b200_comm_ready(nsm_b200_ctx* c)
+{
+  NSM_REQUIRE(c, c && c->finalized, "comm_ready: context not finalized");
+  NSM_CUDA(c, cudaSetDevice(c->device));
+  if (c->comm.ready(c->stream)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  return NSM_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------------------
+int
+nsm_b200_timer_start(nsm_b200_ctx* c)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  NSM_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+  return NSM_OK;
+}
+
+int
+nsm_b200_timer_stop(nsm_b200_ctx* c, float* ms)
+{
+  NSM_REQUIRE(c, c != nullptr && ms != nullptr, "timer_stop: bad arguments");
+  NSM_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
+  NSM_CUDA(c, cudaEventSynchronize(c->ev_stop));
+  NSM_CUDA(c, cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
+  return NSM_OK;
+}
+
+int64_t
+nsm_b200_launch_count(const nsm_b200_ctx* c)
+{
+  return c ? c->launches : -1;
+}
+
+int
+nsm_b200_profile(nsm_b200_ctx* c, int enable)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  c->profiling    = enable != 0;
+  c->prof_elem_ms = c->prof_node_ms = 0;
+  c->prof_steps   = 0;
+  c->ev_used      = 0;
+  return NSM_OK;
+}
+
+int
+nsm_b200_profile_read(nsm_b200_ctx* c, double* elem_ms, double* node_ms, int64_t* n)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  prof_resolve(c);
+  const double k = c->prof_steps ? 1.0 / (double)c->prof_steps : 0.0;
+  if (elem_ms) *elem_ms = c->prof_elem_ms * k;
+  if (node_ms) *node_ms = c->prof_node_ms * k;
+  if (n) *n = c->prof_steps;
+  return NSM_OK;
+}
+
+int
+nsm_b200_fp64_peak(nsm_b200_ctx* c, double* dadd_dmul_tops, double* dfma_tops)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_CUDA(c, cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  NSM_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double*   out = nullptr;
+  NSM_CUDA(c, cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  double res[2] = {0, 0};
+  for (int fused = 0; fused < 2; ++fused) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      cudaEventRecord(e0, c->stream);
+      if (fused)
+        fp64_peak_kernel<true><<<blocks, threads, 0, c->stream>>>(out, iters, 1.0);
+      else
+        fp64_peak_kernel<false><<<blocks, threads, 0, c->stream>>>(out, iters, 1.0);
+      cudaEventRecord(e1, c->stream);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < best) best = ms;
+      c->launches++;
+    }
+    res[fused] = (double)blocks * threads * (double)iters * 8.0 / (best * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  cudaFree(out);
+  NSM_CUDA(c, cudaGetLastError());
+  if (dadd_dmul_tops) *dadd_dmul_tops = res[0];
+  if (dfma_tops) *dfma_tops = res[1];
+  return NSM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (oracle/hex8_oracle.c,
+itself pinned bit-for-bit to the reference's compiled serial code in tests/test_oracle.py).
+
+Bars (BASELINE.json north_star): nodal internal force within 1e-12 (max-norm relative) per step; u, v, sigma, F
+after N steps within 1e-9 * max|oracle| (exodiff-style).  Integer-free path, so "bit-exact" is asserted where the
+summation order is fixed (per-integration-point F and sigma, ORDERED assembly, lumped mass in ORDERED mode).
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import load_golden, perturbed_cube
+
+pytestmark = pytest.mark.gpu
+
+RHO, K, G = 7.8, 1.6e12, 0.8e12
+
+
+def _ctx(mesh, material, assembly, flags=0, blocks=None):
+    from nimblesm_b200 import capi
+
+    c = capi.Context(0)
+    c.set_nodes(mesh["x"], mesh["y"], mesh["z"])
+    for b in mesh["block_ids"]:
+        mat, k, g, rho = blocks[b] if blocks else (material, K, G, RHO)
+        c.add_block(b, mesh["conn"][b], mat, k, g, rho)
+    c.finalize(assembly, flags)
+    return c
+
+
+def _rel(a, b):
+    s = np.abs(b).max()
+    return np.abs(a - b).max() / (s if s > 0 else 1.0)
+
+
+@pytest.mark.parametrize("material", ["elastic", "neohookean"])
+@pytest.mark.parametrize("eps", [1e-6, 1e-4, 1e-3, 1e-2, 1e-1])
+def test_stress_seam_bitwise(oracle, material, eps):
+    """BlockMaterialInterface::ComputeStress seam: F -> sigma bit-identical to the oracle at every strain level."""
+    from nimblesm_b200 import capi
+
+    rng = np.random.default_rng(7)
+    n = 20000
+    F = np.zeros((n, 9))
+    F[:, :3] = 1.0
+    F += eps * (2.0 * rng.random((n, 9)) - 1.0)
+    L = oracle.lib()
+    want = np.empty((n, 6))
+    fn = L.h8o_stress_elastic if material == "elastic" else L.h8o_stress_neohookean
+    for i in range(n):
+        fn(K, G, F[i], want[i])
+    with capi.Context(0) as c:
+        got = c.compute_stress(material, K, G, F)
+    assert np.array_equal(got.view(np.int64), want.view(np.int64)), "max rel diff %.3e" % _rel(got, want)
+
+
+def test_stress_seam_degenerate_inputs(oracle):
+    """Identity, pure dilatation and repeated-eigenvalue F hit the eigen-solver's degenerate branches
+    (src/nimble_utils.h:836-854)."""
+    from nimblesm_b200 import capi
+
+    F = np.zeros((6, 9))
+    F[:, :3] = 1.0
+    F[1, :3] = 1.1
+    F[2, :3] = (1.2, 1.2, 0.9)
+    F[3, :3] = (2.0, 0.5, 1.0)
+    F[4, 3] = 0.3  # simple shear xy
+    F[5, :] = (1.05, 0.97, 1.01, 0.02, -0.01, 0.03, 0.02, -0.01, 0.03)  # symmetric stretch
+    L = oracle.lib()
+    want = np.empty((6, 6))
+    for i in range(6):
+        L.h8o_stress_neohookean(K, G, F[i], want[i])
+    with capi.Context(0) as c:
+        got = c.compute_stress("neohookean", K, G, F)
+    assert np.array_equal(got.view(np.int64), want.view(np.int64))
+
+
+@pytest.mark.parametrize("material", ["elastic", "neohookean"])
+@pytest.mark.parametrize("eps", [0.0, 1e-6, 1e-3, 1e-1])
+def test_internal_force_vs_oracle(oracle, material, eps):
+    from nimblesm_b200 import capi
+
+    mesh, ref, disp = perturbed_cube(12, eps)
+    conn = mesh["conn"][1]
+    mk = oracle.ELASTIC if material == "elastic" else oracle.NEOHOOKEAN
+    f_want, ed_want = oracle.internal_force(mk, K, G, ref, disp, conn)
+    for assembly in (capi.ASSEMBLY_ORDERED, capi.ASSEMBLY_ATOMIC):
+        for flags in (0, capi.FLAG_CACHE_REF_JACOBIAN):
+            with _ctx(mesh, material, assembly, flags) as c:
+                f = c.internal_force_host(disp, store_ipt=True)
+                ed = c.element_data(1)
+            # per-integration-point F and sigma: fixed operation order -> identical bits
+            assert np.array_equal(ed.view(np.int64), ed_want.view(np.int64)), "ipt data differ: %.3e" % _rel(ed, ed_want)
+            if assembly == capi.ASSEMBLY_ORDERED:
+                assert np.array_equal(f.view(np.int64), f_want.view(np.int64)), "ordered assembly must be bit-exact"
+            else:
+                assert _rel(f, f_want) <= 1e-12
+
+
+def test_internal_force_large_displacement_path(oracle):
+    """|d| >> |ref| makes ref + ((ref+d) - ref) != ref + d: the kernel must then rebuild the force-path
+    Jacobian from cur (src/nimble_element.cc:341-344 vs :462-463) and stay bit-exact."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, _ = perturbed_cube(5, 0.0)
+    shift = np.array([3.0e3, -7.0e5, 1.1e4])
+    ref2 = ref * 1e-3
+    mesh["x"], mesh["y"], mesh["z"] = (np.ascontiguousarray(ref2[:, i]) for i in range(3))
+    rng = np.random.default_rng(3)
+    disp = shift + 1e-5 * rng.random(ref.shape)
+    conn = mesh["conn"][1]
+    f_want, ed_want = oracle.internal_force(oracle.NEOHOOKEAN, K, G, ref2, disp, conn)
+    with _ctx(mesh, "neohookean", capi.ASSEMBLY_ORDERED) as c:
+        f = c.internal_force_host(disp, store_ipt=True)
+        ed = c.element_data(1)
+    assert np.array_equal(ed.view(np.int64), ed_want.view(np.int64))
+    assert np.array_equal(f.view(np.int64), f_want.view(np.int64))
+
+
+def test_ragged_and_tiny_blocks(oracle):
+    """1, 3, 31, 33 elements: tail warps / partially filled CTAs; empty block is accepted."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, disp = perturbed_cube(4, 1e-2)
+    conn_all = mesh["conn"][1]
+    for ne in (1, 3, 31, 33):
+        conn = np.ascontiguousarray(conn_all[:ne])
+        f_want, _ = oracle.internal_force(oracle.NEOHOOKEAN, K, G, ref, disp, conn)
+        m = dict(mesh, conn={1: conn})
+        with _ctx(m, "neohookean", capi.ASSEMBLY_ORDERED) as c:
+            f = c.internal_force_host(disp)
+        assert np.array_equal(f.view(np.int64), f_want.view(np.int64)), ne
+    m = dict(mesh, conn={1: np.zeros((0, 8), np.int32)})
+    with _ctx(m, "elastic", capi.ASSEMBLY_ATOMIC) as c:
+        f = c.internal_force_host(disp)
+    assert np.all(f == 0.0)
+
+
+def test_lumped_mass_and_critical_dt(oracle):
+    from nimblesm_b200 import capi
+
+    mesh, ref, _ = perturbed_cube(9, 0.0)
+    conn = mesh["conn"][1]
+    m_want = oracle.lumped_mass(RHO, ref, conn)
+    dt_want = oracle.critical_dt(K, RHO, ref, np.zeros_like(ref), conn)
+    with _ctx(mesh, "neohookean", capi.ASSEMBLY_ORDERED) as c:
+        dt = c.compute_lumped_mass()
+        m = c.download("lumped_mass")
+    assert np.array_equal(m.view(np.int64), m_want.view(np.int64))
+    assert dt == dt_want
+    with _ctx(mesh, "neohookean", capi.ASSEMBLY_ATOMIC) as c:
+        dt = c.compute_lumped_mass()
+        m = c.download("lumped_mass")
+    assert _rel(m, m_want) <= 1e-14 and dt == dt_want
+
+
+def test_inverted_element_is_reported():
+    """The serial reference aborts on det <= 0 (src/nimble_utils.h:1253); the ABI returns NSM_ERR_JACOBIAN."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, _ = perturbed_cube(3, 0.0)
+    disp = np.zeros_like(ref)
+    disp[:, 0] = -2.5 * ref[:, 0]  # mirror in x: negative Jacobian everywhere
+    with _ctx(mesh, "elastic", capi.ASSEMBLY_ATOMIC) as c:
+        with pytest.raises(capi.NsmError) as e:
+            c.internal_force_host(disp)
+        assert e.value.code == capi.ERR_JACOBIAN
+
+
+@pytest.mark.parametrize("assembly", ["ordered", "atomic"])
+def test_explicit_steps_vs_oracle(oracle, assembly):
+    """40 whole steps on a 10^3 cube with a fixed face: per-step force 1e-12, fields 1e-9 after N steps."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, _ = perturbed_cube(10, 0.0)
+    conn = mesh["conn"][1]
+    n = 10
+    dt = 0.2 * (1.0 / n) / np.sqrt(K / RHO)
+    face = mesh["node_sets"][2]
+    v0 = np.zeros_like(ref)
+    v0[:, 0] = 1000.0 * ref[:, 0]
+    # oracle loop (explicit_time_integrator.cc:177-278 with prescribed_velocity 0 on the face)
+    L = oracle.lib()
+    m = oracle.lumped_mass(RHO, ref, conn)
+    u, v, a = np.zeros_like(ref), v0.copy(), np.zeros_like(ref)
+    v[face] = 0.0
+    c = _ctx(mesh, "neohookean", capi.ASSEMBLY_ORDERED if assembly == "ordered" else capi.ASSEMBLY_ATOMIC)
+    c.compute_lumped_mass()
+    c.upload("velocity", v0)
+    c.set_bc_table(np.repeat(face, 3), np.tile(np.arange(3, dtype=np.int32), len(face)), np.zeros(3 * len(face), np.int32))
+    c.set_bc_values(np.zeros(3 * len(face)))
+    c.apply_kinematic_bc(0.0, 0.0)
+    t = 0.0
+    worst_f = 0.0
+    for s in range(40):
+        t_prev, t = t, t + dt
+        d = t - t_prev
+        L.h8o_axpy(u.size, 0.5 * d, a.ravel(), v.ravel())
+        v[face] = 0.0
+        L.h8o_axpy(u.size, d, v.ravel(), u.ravel())
+        v[face] = 0.0
+        f, _ = oracle.internal_force(oracle.NEOHOOKEAN, K, G, ref, u, conn, False)
+        L.h8o_accel(len(ref), m, f, None, a)
+        L.h8o_axpy(u.size, 0.5 * d, a.ravel(), v.ravel())
+        tg = c.step(1, t_prev, dt)
+        assert tg == t
+        worst_f = max(worst_f, _rel(c.download("internal_force"), f))
+    assert worst_f <= 1e-12, worst_f
+    for lbl, want in (("displacement", u), ("velocity", v), ("acceleration", a)):
+        got = c.download(lbl)
+        assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max(), lbl
+        if assembly == "ordered":
+            assert np.array_equal(got.view(np.int64), want.view(np.int64)), lbl + " not bit-exact in ORDERED mode"
+    c.close()
+
+
+@pytest.mark.parametrize("case", ["wave_in_bar", "notched_plate_native_neohookean", "notched_plate_native_hypoelastic",
+                                  "brick_with_fibers", "single_elem_complex_displacement",
+                                  "single_elem_native_neohookean", "rigid_body_motion", "simple_deformation_modes"])
+def test_reference_decks_vs_reference_snapshots(case):
+    """The reference's own regression decks end to end (deck parse -> BCs -> N steps -> output-step data) against
+    (1) snapshots the reference's serial code produced on the same deck (tests/golden, ref_*: bar 1e-9 * max) and
+    (2) the reference's gold Exodus files (exodiff bar of the reference: 1e-6 * max)."""
+    from nimblesm_b200 import capi
+    from nimblesm_b200.model import ExplicitModel
+
+    deck, mesh, gold, ref, _ = load_golden(case)
+    m = ExplicitModel(deck, mesh, assembly=capi.ASSEMBLY_ORDERED)
+    crit = m.begin(keep_snapshots=True)
+    assert crit == float(ref["critical_dt"])
+    m.advance(m.deck.num_load_steps)
+    snaps = m.snapshots
+    assert np.allclose([s["time"] for s in snaps], ref["times"], rtol=0, atol=0)
+    for lbl in ("lumped_mass", "displacement", "velocity", "acceleration", "internal_force"):
+        want = ref["node_" + lbl]
+        got = np.stack([s["node"][lbl] for s in snaps])
+        tol = 1e-9 * max(np.abs(want).max(), 1e-300)
+        assert np.abs(got - want).max() <= tol, "%s: %.3e > %.3e" % (lbl, np.abs(got - want).max(), tol)
+    for b in mesh["block_ids"]:
+        want = ref["elem_last_%d" % b]
+        got = snaps[-1]["elem"][b]
+        for k0, k1, nm in ((0, 9, "F"), (9, 15, "sigma")):
+            tol = 1e-9 * np.abs(want[..., k0:k1]).max()
+            assert np.abs(got[..., k0:k1] - want[..., k0:k1]).max() <= tol, nm
+        for key in ref:
+            pre = "derived_%d_" % b
+            if key.startswith(pre):
+                lab = key[len(pre):]
+                w = ref[key]
+                g = np.stack([s["derived"][b][lab] for s in snaps])
+                scale = np.abs(w).max()
+                if lab.startswith("stress"):
+                    scale = max(scale, np.abs(want[..., 9:15]).max())  # analytically-zero components
+                assert np.abs(g - w).max() <= 1e-9 * max(scale, 1e-300), lab
+    # gold Exodus file of the reference, at the reference's own exodiff tolerance
+    nod = gold["nod"]
+    comp = {"x": 0, "y": 1, "z": 2}
+    for nm, arr in nod.items():
+        base, _, cx = nm.rpartition("_")
+        if base in ("displacement", "velocity", "acceleration", "internal_force") and cx in comp:
+            got = np.stack([s["node"][base][:, comp[cx]] for s in snaps])
+            field_scale = max(np.abs(nod[base + "_" + q]).max() for q in "xyz")
+            assert np.abs(got - arr).max() <= 1e-6 * max(field_scale, 1e-300), nm
+    m.close()
+
+
+def test_full_size_properties():
+    """BASELINE-sized mesh (200^3 = 8 M elements, elastic): size-independent properties instead of an oracle run.
+    (a) zero displacement -> zero force; (b) rigid translation -> zero force (relative to the stiffness scale);
+    (c) linearity of the elastic force in u; (d) total internal force sums to ~0 (self-equilibrated);
+    (e) ORDERED and ATOMIC assembly agree to 1e-12."""
+    from nimblesm_b200 import capi
+    from nimblesm_b200.mesh import structured_cube
+
+    n = 200
+    mesh = structured_cube(n)
+    nn = len(mesh["x"])
+    h = 1.0 / n
+    x = np.stack([mesh["x"], mesh["y"], mesh["z"]], 1)
+    rng = np.random.default_rng(5)
+    u1 = 1e-3 * h * (2 * rng.random((nn, 3)) - 1)
+    with _ctx(mesh, "elastic", capi.ASSEMBLY_ATOMIC) as c:
+        assert c.n_elements == n ** 3
+        f0 = c.internal_force_host(np.zeros((nn, 3)))
+        assert np.all(f0 == 0.0)
+        f1 = c.internal_force_host(u1)
+        f2 = c.internal_force_host(2.0 * u1)
+        scale = np.abs(f1).max()
+        assert scale > 0
+        ft = c.internal_force_host(np.broadcast_to(np.array([1e-4, -2e-4, 3e-4]), (nn, 3)).copy())
+        assert np.abs(ft).max() <= 1e-9 * K * h * h  # translation: F = I up to rounding of x + d
+        assert np.abs(f2 - 2.0 * f1).max() <= 1e-10 * scale
+        assert np.abs(f1.sum(0)).max() <= 1e-9 * np.abs(f1).sum()
+    with _ctx(mesh, "elastic", capi.ASSEMBLY_ORDERED) as c:
+        f1o = c.internal_force_host(u1)
+    assert np.abs(f1o - f1).max() <= 1e-12 * scale
