@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnsm_b200.so")
+# NSM_B200_LIB selects another build of the SAME library (kernel-variant experiments); never a fallback.
+LIB_PATH = os.environ.get("NSM_B200_LIB") or os.path.join(_HERE, "lib", "libnsm_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_JACOBIAN, ERR_MATERIAL, ERR_COMM = range(6)
 MAT_ELASTIC, MAT_NEOHOOKEAN = 0, 1

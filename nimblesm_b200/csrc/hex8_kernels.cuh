@@ -87,8 +87,12 @@ store_share(const ShapeAtPoint& sh, const double (&ai)[3][3], double det, const 
 // bit1: read cached b^-1 (filled once by binv_cache_kernel).
 enum { kModeStoreIpt = 1, kModeReadBinv = 2 };
 
+#ifndef NSM_ELEM_MIN_BLOCKS
+#define NSM_ELEM_MIN_BLOCKS 2
+#endif
+
 template <int MAT, bool ORDERED, int MODE>
-__global__ void __launch_bounds__(kElemThreads)
+__global__ void __launch_bounds__(kElemThreads, NSM_ELEM_MIN_BLOCKS)
 element_force_kernel(const ElemArgs p)
 {
   extern __shared__ double smem[];

@@ -175,3 +175,30 @@ class ExplicitModel:
 
     def close(self):
         self.ctx.close()
+
+
+def exodus_variables(snaps, mesh):
+    """Snapshots -> Exodus variable dictionaries named as ModelData::SpecifyOutputFields / ExodusOutput write them
+    (src/nimble_model_data.cc:215-368, src/nimble_exodus_output.cc:259-272): nodal `<field>_{x,y,z}` and
+    `lumped_mass`; element `iptNN_deformation_gradient_<c>`, `iptNN_stress_<c>` and the volume-averaged
+    `deformation_gradient_<c>`, `stress_<c>`, `volume`, keyed (name, 0-based block index)."""
+    out = {"times": np.array([s["time"] for s in snaps]), "nod": {}, "elem": {}}
+    for lbl in snaps[0]["node"]:
+        a = np.stack([s["node"][lbl] for s in snaps])
+        if a.ndim == 2:
+            out["nod"][lbl] = a
+        else:
+            for i, c in enumerate("xyz"):
+                out["nod"]["%s_%s" % (lbl, c)] = a[:, :, i]
+    for bi, b in enumerate(mesh["all_block_ids"] if "all_block_ids" in mesh else mesh["block_ids"]):
+        if b not in snaps[0]["elem"]:
+            continue
+        ed = np.stack([s["elem"][b] for s in snaps])  # [T, ne, 8, 15]
+        for q in range(8):
+            for i, c in enumerate(IPT_F_LABELS):
+                out["elem"][("ipt%02d_deformation_gradient_%s" % (q + 1, c), bi)] = ed[:, :, q, i]
+            for i, c in enumerate(IPT_S_LABELS):
+                out["elem"][("ipt%02d_stress_%s" % (q + 1, c), bi)] = ed[:, :, q, 9 + i]
+        for lab in snaps[0]["derived"][b]:
+            out["elem"][(lab, bi)] = np.stack([s["derived"][b][lab] for s in snaps])
+    return out

@@ -150,6 +150,7 @@ def load_case(name):
             tag = k[len("piece_"):-2]  # "P.r"
             P, r = tag.split(".")
             pieces[(int(P), int(r))] = unpack_mesh("piece_%s_" % tag, z)
+    gold["exodiff"] = str(z["exodiff"]) if "exodiff" in z.files else ""
     return str(z["deck"]), mesh, gold, ref, pieces
 
 
@@ -163,6 +164,8 @@ def main():
         mesh = read_genesis(os.path.join(base, g + ".g"))
         pack_mesh("mesh_", mesh, out)
         out["deck"] = np.array(open(os.path.join(base, deck + ".in")).read())
+        # the reference's own per-variable tolerances for this case (exodiff -f <case>.exodiff)
+        out["exodiff"] = np.array(open(os.path.join(base, deck + ".exodiff")).read())
         times, nod, elem = read_results(os.path.join(base, deck + ".gold.e"))
         out["gold_times"] = times
         for k, a in nod.items():

@@ -203,7 +203,15 @@ def test_explicit_steps_vs_oracle(oracle, assembly):
         L.h8o_axpy(u.size, 0.5 * d, a.ravel(), v.ravel())
         tg = c.step(1, t_prev, dt)
         assert tg == t
-        worst_f = max(worst_f, _rel(c.download("internal_force"), f))
+        fg = c.download("internal_force")
+        if assembly == "ordered":
+            worst_f = max(worst_f, _rel(fg, f))
+        else:
+            # atomics fix no summation order, so the two trajectories drift apart by rounding noise that the
+            # small-strain cancellation amplifies; the per-step force bar is therefore checked
+            # on the SAME displacement: oracle force of the GPU's own u
+            f_same, _ = oracle.internal_force(oracle.NEOHOOKEAN, K, G, ref, c.download("displacement"), conn, False)
+            worst_f = max(worst_f, _rel(fg, f_same))
     assert worst_f <= 1e-12, worst_f
     for lbl, want in (("displacement", u), ("velocity", v), ("acceleration", a)):
         got = c.download(lbl)
@@ -251,15 +259,12 @@ def test_reference_decks_vs_reference_snapshots(case):
                 if lab.startswith("stress"):
                     scale = max(scale, np.abs(want[..., 9:15]).max())  # analytically-zero components
                 assert np.abs(g - w).max() <= 1e-9 * max(scale, 1e-300), lab
-    # gold Exodus file of the reference, at the reference's own exodiff tolerance
-    nod = gold["nod"]
-    comp = {"x": 0, "y": 1, "z": 2}
-    for nm, arr in nod.items():
-        base, _, cx = nm.rpartition("_")
-        if base in ("displacement", "velocity", "acceleration", "internal_force") and cx in comp:
-            got = np.stack([s["node"][base][:, comp[cx]] for s in snaps])
-            field_scale = max(np.abs(nod[base + "_" + q]).max() for q in "xyz")
-            assert np.abs(got - arr).max() <= 1e-6 * max(field_scale, 1e-300), nm
+    # gold Exodus file of the reference under the reference's own exodiff command file for this case
+    from nimblesm_b200 import exodiff
+    from nimblesm_b200.model import exodus_variables
+
+    fails = exodiff.compare(gold["exodiff"], gold, exodus_variables(snaps, mesh))
+    assert not fails, fails[:5]
     m.close()
 
 
