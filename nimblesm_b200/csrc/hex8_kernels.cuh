@@ -18,7 +18,10 @@
 
 namespace nsm {
 
-constexpr int kElemThreads     = 256;                    // 8 warps, 32 elements per CTA
+#ifndef NSM_ELEM_THREADS
+#define NSM_ELEM_THREADS 256
+#endif
+constexpr int kElemThreads     = NSM_ELEM_THREADS;       // 8 warps, 32 elements per CTA
 constexpr int kElemsPerWarp    = 4;
 constexpr int kCoordStride     = 4;                      // [c*8+j][e_w]
 constexpr int kCoordDoubles    = 3 * 24 * kCoordStride;  // X, cc (F path), cur (force path)

@@ -413,8 +413,8 @@ const char*
 nsm_b200_version(void)
 {
   return "nsm_b200 0.1.0 sm_100a fp64 fmad=off"
-#ifdef NSM_SHARED_DIVISOR
-         " shared-divisor"
+#ifdef NSM_PLAIN_DIVISION
+         " plain-division"
 #endif
       ;
 }

@@ -270,7 +270,7 @@ def test_reference_decks_vs_reference_snapshots(case):
 
 def test_full_size_properties():
     """BASELINE-sized mesh (200^3 = 8 M elements, elastic): size-independent properties instead of an oracle run.
-    (a) zero displacement -> zero force; (b) rigid translation -> zero force (relative to the stiffness scale);
+    (a) zero displacement -> zero force (to rounding); (b) rigid translation -> zero force (relative to the stiffness scale);
     (c) linearity of the elastic force in u; (d) total internal force sums to ~0 (self-equilibrated);
     (e) ORDERED and ATOMIC assembly agree to 1e-12."""
     from nimblesm_b200 import capi
@@ -286,7 +286,9 @@ def test_full_size_properties():
     with _ctx(mesh, "elastic", capi.ASSEMBLY_ATOMIC) as c:
         assert c.n_elements == n ** 3
         f0 = c.internal_force_host(np.zeros((nn, 3)))
-        assert np.all(f0 == 0.0)
+        # F = a.b^-1 with a == b is the identity only up to rounding (coordinates i*h are not exact), so the
+        # elastic force of the undeformed mesh is rounding noise on the K*h^2 scale, as in the reference
+        assert np.abs(f0).max() <= 1e-12 * K * h * h
         f1 = c.internal_force_host(u1)
         f2 = c.internal_force_host(2.0 * u1)
         scale = np.abs(f1).max()
