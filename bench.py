@@ -27,7 +27,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RHO, BULK, SHEAR = 7.8, 1.6e12, 0.8e12  # test/dynamics/notched_plate_native_neohookean deck constants
-DP_INSTR_PER_ELEMENT = {"neohookean": 13760, "elastic": 8100}  # SASS count of DADD+DMUL+DFMA+DSETP x 8 lanes
+# executed DADD+DMUL+DFMA+DSETP lane-instructions per element, from the ncu source page of the profiled kernel
+# (scripts/ncu_sass_mix.py on profiles/r01g_*): [flags & 2 == 0 (b^-1 recomputed), flags & 2 (b^-1 cached)]
+DP_INSTR_PER_ELEMENT = {"neohookean": (10730, 9072), "elastic": (6080, 4424)}
+# dram__bytes_read.sum + dram__bytes_write.sum of one element-kernel launch / elements, same captures (200^3 cube)
+DRAM_TRAFFIC_PER_ELEMENT = {"neohookean": (128.2, 705.6), "elastic": (128.2, 705.6)}
 
 
 def env_int(k, d):
@@ -169,7 +173,7 @@ def main():
     ap.add_argument("--material", default="neohookean", choices=["neohookean", "elastic"])
     ap.add_argument("--assembly", default="atomic", choices=["atomic", "ordered"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--flags", type=int, default=2, help="nsm_b200_finalize flags (2 = cache the reference Jacobians)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -324,9 +328,14 @@ def main():
     step_bytes = 32.0 + 200.0 * r  # + node kernel: f 24, m 8, v 24, u 24 read, v 24, u 24 write (SURVEY §8d B_min)
     ach = elem_bytes * n_elem / (elem_ms * 1e-3) / 1e9 if elem_ms > 0 else None
     dadd, dfma = c.fp64_peak()
-    dp = DP_INSTR_PER_ELEMENT[args.material]
+    dp = DP_INSTR_PER_ELEMENT[args.material][1 if args.flags & 2 else 0]
     roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": (ach / peaks["hbm_gbs"]) if ach else None, "traffic": None, "peak_source": how,
+            "frac": (ach / peaks["hbm_gbs"]) if ach else None,
+            "traffic": DRAM_TRAFFIC_PER_ELEMENT[args.material][1 if args.flags & 2 else 0] * n_elem,
+            "traffic_source": "ncu --set full capture of the same kernel on a 200^3 cube (profiles/), scaled per element; "
+                              "flags & 2 adds the cached inverse reference Jacobians (576 B/element) to the 105 B/element "
+                              "of algorithmic traffic",
+            "peak_source": how,
             "kernel": "element_force_kernel", "kernel_ms": elem_ms, "kernel_share_of_step": elem_ms * nprof / ms if ms else None,
             "algorithmic_bytes_per_element": elem_bytes,
             "whole_step": {"bytes_per_element_update": step_bytes,
@@ -343,6 +352,7 @@ def main():
         "config": dict(workload_config(args, n), grid=[px, py, pz], nodes_per_gpu=n_nodes, dt=dt_user,
                        critical_dt=crit, device_bytes=c.device_bytes),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "fp64": fp64, "node_kernels_ms": node_ms,
+        "cold_points": c.cold_points,
     }
     if e2e:
         out["e2e"] = e2e

@@ -144,7 +144,12 @@ int nsm_b200_set_bc_table(nsm_b200_ctx* ctx, int64_t n, const int32_t* node, con
                           const int32_t* kind);
 /* Host-evaluated magnitudes (constants or expression(x,y,z,t) results) for the NEXT steps. */
 int nsm_b200_set_bc_values(nsm_b200_ctx* ctx, int64_t n, const double* value);
-/* Applies the table once at (time_current, time_previous) to the device velocity. */
+/* Time-dependent magnitudes for a run of steps: value[r][k] is entry k's magnitude at the time of step r of the
+ * next nsm_b200_step call (r = 0 .. n_rows-1; that call must not ask for more steps than rows).  The host
+ * evaluates expression(x,y,z,t) exactly where the reference does (src/nimble_boundary_condition_manager.h:166-201)
+ * and uploads the table, so that runs of steps stay on the device.  nsm_b200_set_bc_values returns to one row. */
+int nsm_b200_set_bc_values_steps(nsm_b200_ctx* ctx, int n_rows, int64_t n, const double* value);
+/* Applies the table once at (time_current, time_previous) to the device velocity (row 0 of the magnitudes). */
 int nsm_b200_apply_kinematic_bc(nsm_b200_ctx* ctx, double time_current, double time_previous);
 
 /* ---- the explicit step (replaces the loop body of ExplicitTimeIntegrator::Integrate,
@@ -190,6 +195,9 @@ int64_t nsm_b200_launch_count(const nsm_b200_ctx* ctx);
  * with CUDA events around each launch when profiling is switched on. */
 int nsm_b200_profile(nsm_b200_ctx* ctx, int enable);
 int nsm_b200_profile_read(nsm_b200_ctx* ctx, double* elem_kernel_ms_avg, double* node_kernel_ms_avg, int64_t* n_launches);
+/* Integration points that left the branch-free arithmetic window since creation and were recomputed with the
+ * plain IEEE operators (same bits, slower; see csrc/hex8_math.cuh).  Wraps at 2^32. */
+int64_t nsm_b200_cold_points(nsm_b200_ctx* ctx);
 /* FP64 pipe micro-benchmark: sustained DADD+DMUL (no FMA) and DFMA issue rates in 1e12 lane-ops/s. */
 int nsm_b200_fp64_peak(nsm_b200_ctx* ctx, double* dadd_dmul_tops, double* dfma_tops);
 

@@ -39,7 +39,7 @@ SYMBOLS = [
     "nsm_b200_step", "nsm_b200_get_element_data", "nsm_b200_derived_element_data", "nsm_b200_comm_init",
     "nsm_b200_comm_export", "nsm_b200_comm_attach", "nsm_b200_comm_ready", "nsm_b200_timer_start",
     "nsm_b200_timer_stop", "nsm_b200_launch_count", "nsm_b200_profile", "nsm_b200_profile_read",
-    "nsm_b200_fp64_peak",
+    "nsm_b200_fp64_peak", "nsm_b200_cold_points", "nsm_b200_set_bc_values_steps",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
         "nsm_b200_compute_stress": (i32, [vp, i32, dbl, dbl, i64, dp, dp]),
         "nsm_b200_set_bc_table": (i32, [vp, i64, ip, ip, ip]),
         "nsm_b200_set_bc_values": (i32, [vp, i64, dp]),
+        "nsm_b200_set_bc_values_steps": (i32, [vp, i32, i64, dp]),
         "nsm_b200_apply_kinematic_bc": (i32, [vp, dbl, dbl]),
         "nsm_b200_step": (i32, [vp, i32, dp, dbl, i32]),
         "nsm_b200_get_element_data": (i32, [vp, i32, dp]),
@@ -107,6 +108,7 @@ def lib():
         "nsm_b200_profile": (i32, [vp, i32]),
         "nsm_b200_profile_read": (i32, [vp, dp, dp, lp]),
         "nsm_b200_fp64_peak": (i32, [vp, dp, dp]),
+        "nsm_b200_cold_points": (i64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -273,6 +275,12 @@ class Context:
         value = np.ascontiguousarray(value, dtype=np.float64)
         self._ck(self._L.nsm_b200_set_bc_values(self._h, len(value), _dptr(value)))
 
+    def set_bc_values_steps(self, values):
+        """values[r][k]: magnitude of table entry k at the time of step r of the next step() call."""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        assert values.ndim == 2
+        self._ck(self._L.nsm_b200_set_bc_values_steps(self._h, values.shape[0], values.shape[1], _dptr(values)))
+
     def apply_kinematic_bc(self, time_current, time_previous):
         self._ck(self._L.nsm_b200_apply_kinematic_bc(self._h, time_current, time_previous))
 
@@ -330,6 +338,10 @@ class Context:
         e, n, k = C.c_double(), C.c_double(), C.c_int64()
         self._ck(self._L.nsm_b200_profile_read(self._h, C.byref(e), C.byref(n), C.byref(k)))
         return e.value, n.value, k.value
+
+    @property
+    def cold_points(self):
+        return int(self._L.nsm_b200_cold_points(self._h))
 
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()

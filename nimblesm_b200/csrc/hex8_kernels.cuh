@@ -21,14 +21,23 @@ namespace nsm {
 #ifndef NSM_ELEM_THREADS
 #define NSM_ELEM_THREADS 256
 #endif
-constexpr int kElemThreads     = NSM_ELEM_THREADS;       // 8 warps, 32 elements per CTA
-constexpr int kElemsPerWarp    = 4;
-constexpr int kCoordStride     = 4;                      // [c*8+j][e_w]
-constexpr int kCoordDoubles    = 3 * 24 * kCoordStride;  // X, cc (F path), cur (force path)
-constexpr int kShareStride     = 43;                     // 3*43 = 1 (mod 16): conflict-free transpose
-constexpr int kShareDoubles    = 24 * kShareStride;
-constexpr int kWarpSmemDoubles = kShareDoubles;          // coords alias the share buffer
-static_assert(kCoordDoubles <= kShareDoubles, "coordinate staging must fit in the aliased share buffer");
+#ifndef NSM_ELEM_MIN_BLOCKS
+#define NSM_ELEM_MIN_BLOCKS 2
+#endif
+constexpr int kElemThreads   = NSM_ELEM_THREADS;  // 8 warps; a warp owns 4 elements ("group") per pass
+constexpr int kElemWarps     = kElemThreads / 32;
+constexpr int kElemsPerWarp  = 4;
+#ifndef NSM_TICKET_CHUNK
+#define NSM_TICKET_CHUNK 8
+#endif
+constexpr int kTicketChunk   = NSM_TICKET_CHUNK;   // groups per work ticket
+constexpr int kCoordStride   = 4;                    // [c*8+j][e_w]
+constexpr int kCoordDoubles  = 24 * kCoordStride;    // one [3][8] coordinate set of the warp's 4 elements
+constexpr int kStageDoubles  = 2 * kCoordDoubles;    // X and u of one group, filled by cp.async
+constexpr int kShareStride   = 33;                   // odd: the 8x8 transpose is bank-conflict free
+constexpr int kShareDoubles  = 24 * kShareStride;
+constexpr int kBinvGroupDoubles = 9 * 32;            // cached b^-1 of one group: [9][32 lanes]
+constexpr int kWarpSmemDoubles = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDoubles + kBinvGroupDoubles;  // stages, K, C, shares, b^-1
 
 struct ElemArgs
 {
@@ -39,10 +48,43 @@ struct ElemArgs
   double*       f[3];        // nodal internal force, SoA (ATOMIC)
   double*       ef;          // [n_elem][8][3] element nodal forces (ORDERED), already offset to the block
   double*       ipt;         // [n_elem][8][15] or nullptr
-  double*       binv_cache;  // [n_elem][8][9] or nullptr
+  double*       binv_cache;  // [n_groups][9][32] or nullptr, already offset to the block
   double        bulk, shear;
-  int*          flags;       // bit 0: non-positive Jacobian seen
+  unsigned long long* ticket;  // next unclaimed 4-element group of this launch (zeroed by the host)
+  int           zero;        // always 0: keeps ptxas from proving the ticket address warp-uniform (see draw_ticket)
+  int*          flags;       // [0] bit 0: non-positive Jacobian seen; [1]: integration points redone in IEEE mode
 };
+
+__device__ __forceinline__ void
+cp_async8(double* smem_dst, const double* gsrc)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// Same copy, ordered after the value `dep` is available (a register dependence the compiler cannot hoist
+// the copy above): used to overwrite a staging slot only once its previous content has been consumed.
+__device__ __forceinline__ void
+cp_async8_after(double* smem_dst, const double* gsrc, double dep)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("{ .reg .b64 t; mov.b64 t, %2; cp.async.ca.shared.global [%0], [%1], 8; }" ::"r"(d), "l"(gsrc), "d"(dep) : "memory");
+}
+__device__ __forceinline__ void
+cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void
+cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void
+prefetch_l2(const void* g)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+}
 
 template <int J>
 __device__ __forceinline__ void
@@ -74,81 +116,54 @@ accumulate_one(const ShapeAtPoint& sh, const double* sC, int ew, double (&a)[3][
   grad_accumulate<J>(sh, x0, x1, x2, a);
 }
 
+// MAT: nsm_material_kind; ORDERED: store element forces instead of atomics; MODE bit0: store F/sigma,
+// bit1: read cached b^-1 (filled once by binv_cache_kernel).
+enum { kModeStoreIpt = 1, kModeReadBinv = 2 };
+
+// How the cached b^-1 reaches the lane.  Neohookean passes are long (~1130 DP instructions per lane), so the
+// next group's values are staged in shared memory by cp.async while the stress is computed.  Elastic passes
+// are half as long and the nine extra LDGSTS per lane saturate the LSU queue (profiles/r01g: mio_throttle 2.7
+// stalls per issue), so there the values are loaded straight from the L2-prefetched cache line.
+template <int MAT, int MODE>
+struct BinvStaged
+{
+  static constexpr bool value = (MODE & kModeReadBinv) && MAT == 1;
+};
+
 template <int N>
 __device__ __forceinline__ void
-store_share(const ShapeAtPoint& sh, const double (&ai)[3][3], double det, const double (&s)[6], double* share,
-            int lane)
+store_share(const GradProducts& gp, double det, const double (&s)[6], double* share, int lane)
 {
   double f1, f2, f3;
-  node_force_at_point<N>(sh, ai, det, s, f1, f2, f3);
+  node_force_at_point<N>(gp, det, s, f1, f2, f3);
   share[(N * 3 + 0) * kShareStride + lane] = f1;
   share[(N * 3 + 1) * kShareStride + lane] = f2;
   share[(N * 3 + 2) * kShareStride + lane] = f3;
 }
 
-// MAT: nsm_material_kind; ORDERED: store element forces instead of atomics; MODE bit0: store F/sigma,
-// bit1: read cached b^-1 (filled once by binv_cache_kernel).
-enum { kModeStoreIpt = 1, kModeReadBinv = 2 };
-
-#ifndef NSM_ELEM_MIN_BLOCKS
-#define NSM_ELEM_MIN_BLOCKS 2
-#endif
-
-template <int MAT, bool ORDERED, int MODE>
-__global__ void __launch_bounds__(kElemThreads, NSM_ELEM_MIN_BLOCKS)
-element_force_kernel(const ElemArgs p)
+// Everything one lane does for its integration point: gradient operators -> b^-1 -> F -> stress -> a^-1 ->
+// the 24 nodal-force shares (stored to the warp's share buffer).  Returns bit 0: a fast-path operand left
+// its window (FAST only; the caller reruns the point with FAST = false), bit 1: non-positive Jacobian.
+//   FAST = true : branch-free arithmetic (hex8_math.cuh) in ONE basic block; the force-path Jacobian reuses
+//                 the F-path one (the caller sends the warp to FAST = false when they differ)
+//   FAST = false: plain IEEE operators, force-path Jacobian always rebuilt from the cur coordinates
+template <int MAT, int MODE, bool FAST>
+__device__ __forceinline__ unsigned
+integration_point(const ShapeAtPoint& sh, const double* sX, const double* sK, const double* sC, int ew, int lane,
+                  const double* binv_row, double* binv_slot, const double* binv_next, double bulk, double shear,
+                  double* share, double (&F)[9], double (&sig)[6])
 {
-  extern __shared__ double smem[];
-  const int     lane = threadIdx.x & 31;
-  const int     warp = threadIdx.x >> 5;
-  const int     q    = lane & 7;   // Gauss point (compute) == local node (gather / assemble)
-  const int     ew   = lane >> 3;  // element within the warp
-  double*       wsm  = smem + warp * kWarpSmemDoubles;
-  const int64_t e    = (int64_t)blockIdx.x * (kElemThreads / 8) + warp * kElemsPerWarp + ew;
-  const bool    live = e < p.n_elem;
-
-  // ---- gather: lane j <- node j -----------------------------------------------------------------
-  int    node = 0;
-  double X0 = 0.0, X1 = 0.0, X2 = 0.0, u0 = 0.0, u1 = 0.0, u2 = 0.0;
-  if (live) {
-    node = p.conn[e * 8 + q];
-    X0 = p.X[0][node], X1 = p.X[1][node], X2 = p.X[2][node];
-    u0 = p.u[0][node], u1 = p.u[1][node], u2 = p.u[2][node];
-  } else {
-    // dead lanes of a tail warp get a unit cube so that no NaN/inf work (and no flag) is produced
-    X0 = ((q & 3) == 1 || (q & 3) == 2) ? 1.0 : 0.0;
-    X1 = (q & 2) ? 1.0 : 0.0;
-    X2 = (q & 4) ? 1.0 : 0.0;
-  }
-  // current coordinates: the block functor forms cur = ref + disp (src/nimble_block.cc:309-316); the
-  // serial F wrapper then passes disp' = cur - ref and the kernel re-adds it (src/nimble_element.cc:341-344,
-  // src/nimble_element.h:455-457); the force wrapper uses cur itself (src/nimble_element.cc:462-463).
-  const double c0 = X0 + u0, c1 = X1 + u1, c2 = X2 + u2;
-  const double k0 = X0 + (c0 - X0), k1 = X1 + (c1 - X1), k2 = X2 + (c2 - X2);
-  const bool   differs = (k0 != c0) || (k1 != c1) || (k2 != c2);
-  double*      sX      = wsm;
-  double*      sK      = wsm + 24 * kCoordStride;
-  double*      sC      = wsm + 48 * kCoordStride;
-  sX[(0 * 8 + q) * kCoordStride + ew] = X0;
-  sX[(1 * 8 + q) * kCoordStride + ew] = X1;
-  sX[(2 * 8 + q) * kCoordStride + ew] = X2;
-  sK[(0 * 8 + q) * kCoordStride + ew] = k0;
-  sK[(1 * 8 + q) * kCoordStride + ew] = k1;
-  sK[(2 * 8 + q) * kCoordStride + ew] = k2;
-  sC[(0 * 8 + q) * kCoordStride + ew] = c0;
-  sC[(1 * 8 + q) * kCoordStride + ew] = c1;
-  sC[(2 * 8 + q) * kCoordStride + ew] = c2;
-  // The F-path and force-path Jacobians coincide unless ref + ((ref+d) - ref) != ref + d for some node of
-  // the warp's elements (possible only when |d| is comparable to |ref|); decided warp-uniformly.
-  const bool recompute_a = __any_sync(0xffffffffu, differs);
-  __syncwarp();
-
-  // ---- per-Gauss-point kinematics ---------------------------------------------------------------
-  ShapeAtPoint sh;
-  sh.init(q);
-  double a[3][3], binv[3][3], F[9], sig[6];
+  unsigned bad = 0u, jac = 0u;
+  double   a[3][3], binv[3][3];
   zero33(a);
   if (MODE & kModeReadBinv) {
+    // FAST: this lane's nine values were staged in shared memory by cp.async during the previous pass;
+    // IEEE redo: the staging slot may already be refilling, read the cache itself
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        binv[i][k] = (FAST && BinvStaged<MAT, MODE>::value) ? binv_slot[(3 * i + k) * 32] : __ldcs(binv_row + (3 * i + k) * 32);
     accumulate_one<0>(sh, sK, ew, a);
     accumulate_one<1>(sh, sK, ew, a);
     accumulate_one<2>(sh, sK, ew, a);
@@ -157,11 +172,6 @@ element_force_kernel(const ElemArgs p)
     accumulate_one<5>(sh, sK, ew, a);
     accumulate_one<6>(sh, sK, ew, a);
     accumulate_one<7>(sh, sK, ew, a);
-    const double* bc = p.binv_cache + ((live ? e : 0) * 8 + q) * 9;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) binv[i][k] = bc[3 * i + k];
   } else {
     double b[3][3];
     zero33(b);
@@ -173,26 +183,21 @@ element_force_kernel(const ElemArgs p)
     accumulate_pair<5>(sh, sX, sK, ew, a, b);
     accumulate_pair<6>(sh, sX, sK, ew, a, b);
     accumulate_pair<7>(sh, sX, sK, ew, a, b);
-    const double detb = invert3x3(b, binv);
-    if (live && !(detb > 0.0)) atomicOr(p.flags, 1);
+    const double detb = invert3x3<FAST>(b, binv, bad);
+    jac |= !(detb > 0.0) ? 2u : 0u;
   }
   def_grad_from(a, binv, F);
-
-  if (MAT == 0)
-    stress_elastic(p.bulk, p.shear, F, sig);
-  else
-    stress_neohookean(p.bulk, p.shear, F, sig);
-
-  if ((MODE & kModeStoreIpt) && live) {
-    double* d = p.ipt + (e * 8 + q) * 15;
+  if (FAST && BinvStaged<MAT, MODE>::value) {
+    // F is formed, so the staged values have been consumed: refill this lane's slots with the next group's
+    // b^-1 (lane-private slots: no cross-lane hazard; the copy lands while the stress is computed)
+    if (binv_next) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) d[i] = F[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) d[9 + i] = sig[i];
+      for (int i = 0; i < 9; ++i) cp_async8_after(binv_slot + i * 32, binv_next + i * 32, F[i]);
+    }
+    cp_async_commit();
   }
 
-  // ---- force-path Jacobian ----------------------------------------------------------------------
-  if (recompute_a) {
+  if (!FAST) {  // force-path Jacobian from cur = ref + disp (src/nimble_element.cc:462-463)
     zero33(a);
     accumulate_one<0>(sh, sC, ew, a);
     accumulate_one<1>(sh, sC, ew, a);
@@ -204,58 +209,242 @@ element_force_kernel(const ElemArgs p)
     accumulate_one<7>(sh, sC, ew, a);
   }
   double       ai[3][3];
-  const double det = invert3x3(a, ai);
-  if (live && !(det > 0.0)) atomicOr(p.flags, 1);
+  const double det = invert3x3<FAST>(a, ai, bad);
+  jac |= !(det > 0.0) ? 2u : 0u;
 
-  // ---- per-node shares -> shared memory (aliases the coordinate staging) ---------------------------
-  __syncwarp();
-  store_share<0>(sh, ai, det, sig, wsm, lane);
-  store_share<1>(sh, ai, det, sig, wsm, lane);
-  store_share<2>(sh, ai, det, sig, wsm, lane);
-  store_share<3>(sh, ai, det, sig, wsm, lane);
-  store_share<4>(sh, ai, det, sig, wsm, lane);
-  store_share<5>(sh, ai, det, sig, wsm, lane);
-  store_share<6>(sh, ai, det, sig, wsm, lane);
-  store_share<7>(sh, ai, det, sig, wsm, lane);
-  __syncwarp();
+  if (MAT == 0)
+    stress_elastic(bulk, shear, F, sig);
+  else
+    stress_neohookean<FAST>(bulk, shear, F, sig, bad);
 
-  // ---- lane n: node n, Gauss points in ascending order: force -= share (src/nimble_element.h:609-611)
-  double        fx = 0.0, fy = 0.0, fz = 0.0;
-  const double* col = wsm + (q * 3) * kShareStride + ew * 8;
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    fx -= col[0 * kShareStride + g];
-    fy -= col[1 * kShareStride + g];
-    fz -= col[2 * kShareStride + g];
+  GradProducts gp;
+  gp.init(sh, ai);
+  store_share<0>(gp, det, sig, share, lane);
+  store_share<1>(gp, det, sig, share, lane);
+  store_share<2>(gp, det, sig, share, lane);
+  store_share<3>(gp, det, sig, share, lane);
+  store_share<4>(gp, det, sig, share, lane);
+  store_share<5>(gp, det, sig, share, lane);
+  store_share<6>(gp, det, sig, share, lane);
+  store_share<7>(gp, det, sig, share, lane);
+  return bad | jac;
+}
+
+// One ticket from the grid-wide work counter, drawn by lane 0.  ptxas rewrites an atomic on a provably
+// warp-uniform address into its warp-aggregated form, whose shuffle waits for the L2 round trip on the spot
+// (profiles/r01f: 0.66 long-scoreboard stalls per issue); `lane * zero` (a kernel argument that is always 0)
+// hides the uniformity, so a plain ATOMG is issued and its result is not touched until the caller needs it.
+__device__ __forceinline__ unsigned long long*
+ticket_address(unsigned long long* ticket, int lane, int zero)
+{
+  int opaque = lane;
+  asm volatile("" : "+r"(opaque));  // the compiler must not fold `lane` to 0 under `if (lane == 0)`
+  return ticket + opaque * zero;
+}
+
+__device__ __forceinline__ int64_t
+claim_group(unsigned long long* address, int lane)
+{
+  unsigned long long t = 0;
+  if (lane == 0) t = atomicAdd(address, 1ULL);
+  return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+}
+
+// Node id of this lane's (element, local node) in group g, or -1 beyond the block's last element.
+__device__ __forceinline__ int
+group_node(const ElemArgs& p, int64_t g, int ew, int q)
+{
+  const int64_t e = g * kElemsPerWarp + ew;
+  return e < p.n_elem ? __ldg(p.conn + e * 8 + q) : -1;
+}
+
+// Asynchronous gather of one group's X and u into a stage buffer: lane j <- node j of its element, global ->
+// shared without passing through registers.  Lanes beyond the last element stage a unit cube at rest, so
+// the tail of the last group computes finite values (and raises no Jacobian flag).
+__device__ __forceinline__ void
+stage_gather(const ElemArgs& p, double* st, int node, int q, int ew)
+{
+  double* sx = st + q * kCoordStride + ew;
+  double* su = sx + kCoordDoubles;
+  if (node >= 0) {
+    cp_async8(sx + 0 * 8 * kCoordStride, p.X[0] + node);
+    cp_async8(sx + 1 * 8 * kCoordStride, p.X[1] + node);
+    cp_async8(sx + 2 * 8 * kCoordStride, p.X[2] + node);
+    cp_async8(su + 0 * 8 * kCoordStride, p.u[0] + node);
+    cp_async8(su + 1 * 8 * kCoordStride, p.u[1] + node);
+    cp_async8(su + 2 * 8 * kCoordStride, p.u[2] + node);
+  } else {
+    sx[0 * 8 * kCoordStride] = ((q & 3) == 1 || (q & 3) == 2) ? 1.0 : 0.0;
+    sx[1 * 8 * kCoordStride] = (q & 2) ? 1.0 : 0.0;
+    sx[2 * 8 * kCoordStride] = (q & 4) ? 1.0 : 0.0;
+    su[0 * 8 * kCoordStride] = 0.0, su[1 * 8 * kCoordStride] = 0.0, su[2 * 8 * kCoordStride] = 0.0;
   }
-  if (live) {
-    if (ORDERED) {
-      double* o = p.ef + (e * 8 + q) * 3;
-      o[0] = fx, o[1] = fy, o[2] = fz;
-    } else {
-      atomicAdd(p.f[0] + node, fx);
-      atomicAdd(p.f[1] + node, fy);
-      atomicAdd(p.f[2] + node, fz);
+}
+
+// Persistent: every warp walks the block's groups with the grid-wide warp stride.  While group g is computed
+// (FP64-pipe bound, ~10 k DP lane-ops per element) the gather of group g+W is in flight (cp.async, double
+// buffered), the connectivity of group g+2W is being loaded and the cached b^-1 of group g+W is pulled into L2.
+template <int MAT, bool ORDERED, int MODE>
+__global__ void __launch_bounds__(kElemThreads, NSM_ELEM_MIN_BLOCKS)
+element_force_kernel(const ElemArgs p)
+{
+  extern __shared__ double smem[];
+  const int     lane = threadIdx.x & 31;
+  const int     warp = threadIdx.x >> 5;
+  const int     q    = lane & 7;   // Gauss point (compute) == local node (gather / assemble)
+  const int     ew   = lane >> 3;  // element within the group
+  double*       wsm  = smem + warp * kWarpSmemDoubles;
+  double*       sK    = wsm + 2 * kStageDoubles;  // ref + ((ref + disp) - ref): F-path coordinates
+  double*       sC    = sK + kCoordDoubles;         // ref + disp: force-path coordinates
+  double*       share = sC + kCoordDoubles;         // [24][kShareStride] nodal-force shares of the 32 points
+  double*       sB    = share + kShareDoubles + lane;  // [9][32] staged b^-1: this lane's column
+  const int64_t n_groups = (p.n_elem + kElemsPerWarp - 1) / kElemsPerWarp;
+
+  ShapeAtPoint sh;
+  sh.init(q);
+
+  // Groups are claimed from a grid-wide ticket counter in chunks of kTicketChunk consecutive groups: warps of
+  // one scheduler advance at different rates, and a static stride left the slow ones to finish alone
+  // (profiles/r01e: 14 of 16 warps active on average).  The next chunk's ticket is drawn when the current chunk
+  // is entered and first read kTicketChunk passes later, so the atomic's round trip (which queues behind every
+  // other warp's on the one counter) never shows; groups are looked up two passes ahead (connectivity load).
+  unsigned long long* const ticket_at = ticket_address(p.ticket, lane, p.zero);
+  int64_t chunk_base = claim_group(ticket_at, lane) * kTicketChunk;  // chunk that holds the group two passes ahead
+  int     chunk_off  = 0;
+  unsigned long long ticket = 0;                                     // lane 0: the chunk after that one
+  if (lane == 0) ticket = atomicAdd(ticket_at, 1ULL);
+  auto next_group = [&]() -> int64_t {
+    if (++chunk_off == kTicketChunk) {
+      chunk_base = (int64_t)__shfl_sync(0xffffffffu, ticket, 0) * kTicketChunk;
+      chunk_off  = 0;
+      if (lane == 0 && chunk_base < n_groups) ticket = atomicAdd(ticket_at, 1ULL);
     }
+    const int64_t gg = chunk_base + chunk_off;
+    return gg < n_groups ? gg : n_groups;
+  };
+  int64_t g = chunk_base < n_groups ? chunk_base : n_groups, g_next = next_group();
+  if (g >= n_groups) return;
+  int node      = group_node(p, g, ew, q);
+  int node_next = (g_next < n_groups) ? group_node(p, g_next, ew, q) : -1;
+  stage_gather(p, wsm, node, q, ew);
+  cp_async_commit();
+  if (BinvStaged<MAT, MODE>::value) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cp_async8(sB + i * 32, p.binv_cache + g * kBinvGroupDoubles + lane + i * 32);
+    cp_async_commit();
+  }
+  int stage = 0;
+
+  while (g < n_groups) {
+    const bool has_next = g_next < n_groups;
+    if (has_next) stage_gather(p, wsm + (stage ^ 1) * kStageDoubles, node_next, q, ew);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
+    const int64_t e    = g * kElemsPerWarp + ew;
+    const bool    live = node >= 0;
+    const double* sX   = wsm + stage * kStageDoubles;
+    const double* sU   = sX + kCoordDoubles;
+    const double* binv_row  = (MODE & kModeReadBinv) ? p.binv_cache + g * kBinvGroupDoubles + lane : nullptr;
+    const double* binv_next = ((MODE & kModeReadBinv) && has_next) ? p.binv_cache + g_next * kBinvGroupDoubles + lane : nullptr;
+
+    // current coordinates: the block functor forms cur = ref + disp (src/nimble_block.cc:309-316); the
+    // serial F wrapper then passes disp' = cur - ref and the kernel re-adds it (src/nimble_element.cc:341-344,
+    // src/nimble_element.h:455-457); the force wrapper uses cur itself (src/nimble_element.cc:462-463).
+    const double X0 = sX[(0 * 8 + q) * kCoordStride + ew], X1 = sX[(1 * 8 + q) * kCoordStride + ew],
+                 X2 = sX[(2 * 8 + q) * kCoordStride + ew];
+    const double u0 = sU[(0 * 8 + q) * kCoordStride + ew], u1 = sU[(1 * 8 + q) * kCoordStride + ew],
+                 u2 = sU[(2 * 8 + q) * kCoordStride + ew];
+    const double c0 = X0 + u0, c1 = X1 + u1, c2 = X2 + u2;
+    const double k0 = X0 + (c0 - X0), k1 = X1 + (c1 - X1), k2 = X2 + (c2 - X2);
+    const bool   differs = (k0 != c0) || (k1 != c1) || (k2 != c2);
+    sK[(0 * 8 + q) * kCoordStride + ew] = k0;
+    sK[(1 * 8 + q) * kCoordStride + ew] = k1;
+    sK[(2 * 8 + q) * kCoordStride + ew] = k2;
+    sC[(0 * 8 + q) * kCoordStride + ew] = c0;
+    sC[(1 * 8 + q) * kCoordStride + ew] = c1;
+    sC[(2 * 8 + q) * kCoordStride + ew] = c2;
+    // The F-path and force-path Jacobians coincide unless ref + ((ref+d) - ref) != ref + d for some node of
+    // the warp's elements (possible only when |d| is comparable to |ref|); decided warp-uniformly.
+    const bool jacobians_differ = __any_sync(0xffffffffu, differs);
+    __syncwarp();
+
+    double   F[9], sig[6];
+    // (the fast pass always runs: it also refills the b^-1 staging slots and closes their copy group)
+    unsigned st = integration_point<MAT, MODE, true>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear,
+                                                     share, F, sig);
+    if (jacobians_differ) st |= 1u;
+    if (st & 1u) {  // cold: some operand outside the fast window (or distinct Jacobians): plain IEEE operators
+      atomicAdd(p.flags + 1, 1);  // statistics: integration points redone (nsm_b200_cold_points)
+      st = integration_point<MAT, MODE, false>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear, share,
+                                               F, sig);
+    }
+    if (live && (st & 2u)) atomicOr(p.flags, 1);
+
+    if ((MODE & kModeStoreIpt) && live) {
+      double* d = p.ipt + (e * 8 + q) * 15;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) d[i] = F[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) d[9 + i] = sig[i];
+    }
+    __syncwarp();
+
+    // ---- lane n: node n, Gauss points in ascending order: force -= share (src/nimble_element.h:609-611)
+    double        fx = 0.0, fy = 0.0, fz = 0.0;
+    const double* col = share + (q * 3) * kShareStride + ew * 8;
+#pragma unroll
+    for (int gq = 0; gq < 8; ++gq) {
+      fx -= col[0 * kShareStride + gq];
+      fy -= col[1 * kShareStride + gq];
+      fz -= col[2 * kShareStride + gq];
+    }
+    if (live) {
+      if (ORDERED) {
+        double* o = p.ef + (e * 8 + q) * 3;
+        o[0] = fx, o[1] = fy, o[2] = fz;
+      } else {
+        atomicAdd(p.f[0] + node, fx);
+        atomicAdd(p.f[1] + node, fy);
+        atomicAdd(p.f[2] + node, fz);
+      }
+    }
+    // roll the pipeline
+    const int64_t g_nn = has_next ? next_group() : n_groups;
+    node               = node_next;
+    node_next          = (g_nn < n_groups) ? group_node(p, g_nn, ew, q) : -1;
+    if ((MODE & kModeReadBinv) && g_nn < n_groups && lane < (kBinvGroupDoubles * 8) / 128)
+      prefetch_l2(p.binv_cache + g_nn * kBinvGroupDoubles + lane * 16);  // DRAM -> L2 a full pass before the cp.async
+    g                  = g_next;
+    g_next             = g_nn;
+    stage ^= 1;
   }
 }
 
 // Inverse reference Jacobians b^-1 of every Gauss point, computed once (NSM_FLAG_CACHE_REF_JACOBIAN):
 // the same arithmetic as the in-kernel path, so the cached values are the bits the step would recompute.
+// Layout [group][9][32 lanes]: every load of the element kernel is one fully coalesced 256-byte row.
 __global__ void __launch_bounds__(kElemThreads)
 binv_cache_kernel(const ElemArgs p)
 {
-  const int64_t t = (int64_t)blockIdx.x * kElemThreads + threadIdx.x;
-  const int64_t e = t >> 3;
-  const int     q = (int)(t & 7);
-  if (e >= p.n_elem) return;
+  const int64_t t    = (int64_t)blockIdx.x * kElemThreads + threadIdx.x;
+  const int64_t g    = t >> 5;
+  const int     lane = (int)(t & 31);
+  const int     q = lane & 7, ew = lane >> 3;
+  const int64_t e = g * kElemsPerWarp + ew;
+  if (g >= (p.n_elem + kElemsPerWarp - 1) / kElemsPerWarp) return;
   ShapeAtPoint sh;
   sh.init(q);
   double b[3][3], binv[3][3], x[8][3];
   zero33(b);
   for (int j = 0; j < 8; ++j) {
-    const int nd = p.conn[e * 8 + j];
-    x[j][0] = p.X[0][nd], x[j][1] = p.X[1][nd], x[j][2] = p.X[2][nd];
+    if (e < p.n_elem) {
+      const int nd = p.conn[e * 8 + j];
+      x[j][0] = p.X[0][nd], x[j][1] = p.X[1][nd], x[j][2] = p.X[2][nd];
+    } else {
+      x[j][0] = ((j & 3) == 1 || (j & 3) == 2) ? 1.0 : 0.0, x[j][1] = (j & 2) ? 1.0 : 0.0, x[j][2] = (j & 4) ? 1.0 : 0.0;
+    }
   }
   grad_accumulate<0>(sh, x[0][0], x[0][1], x[0][2], b);
   grad_accumulate<1>(sh, x[1][0], x[1][1], x[1][2], b);
@@ -265,13 +454,14 @@ binv_cache_kernel(const ElemArgs p)
   grad_accumulate<5>(sh, x[5][0], x[5][1], x[5][2], b);
   grad_accumulate<6>(sh, x[6][0], x[6][1], x[6][2], b);
   grad_accumulate<7>(sh, x[7][0], x[7][1], x[7][2], b);
-  const double detb = invert3x3(b, binv);
-  if (!(detb > 0.0)) atomicOr(p.flags, 1);
-  double* bc = p.binv_cache + (e * 8 + q) * 9;
+  unsigned     unused = 0u;
+  const double detb   = invert3x3<false>(b, binv, unused);
+  if (e < p.n_elem && !(detb > 0.0)) atomicOr(p.flags, 1);
+  double* bc = p.binv_cache + g * kBinvGroupDoubles + lane;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) bc[3 * i + k] = binv[i][k];
+    for (int k = 0; k < 3; ++k) bc[(3 * i + k) * 32] = binv[i][k];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -287,10 +477,13 @@ stress_kernel(int64_t n, const double* __restrict__ Fin, double* __restrict__ so
   double F[9], s[6];
 #pragma unroll
   for (int k = 0; k < 9; ++k) F[k] = Fin[i * 9 + k];
-  if (MAT == 0)
+  if (MAT == 0) {
     stress_elastic(bulk, shear, F, s);
-  else
-    stress_neohookean(bulk, shear, F, s);
+  } else {  // the element kernel's pattern: branch-free fast path, IEEE redo when an operand left its window
+    unsigned bad = 0u;
+    stress_neohookean<true>(bulk, shear, F, s, bad);
+    if (bad) stress_neohookean<false>(bulk, shear, F, s, bad);
+  }
 #pragma unroll
   for (int k = 0; k < 6; ++k) sout[i * 6 + k] = s[k];
 }
@@ -386,6 +579,53 @@ node_correct_kernel(const NodeArgs p, double hdt, int update_velocity)
   p.v[2][i] = p.v[2][i] + hdt * a2;
 }
 
+// Second half of step s fused with the first half of step s+1 (one pass over the nodes per interior step of a
+// multi-step call): a = (1/m)(f_int + f_ext); v += (dt_s/2) a | v += (dt_{s+1}/2) a; BC; u += dt_{s+1} v; BC.
+// Per node this is the operation sequence of node_correct_kernel followed by node_predict_kernel, so the
+// results are bit-identical; a and the integer-time velocity are not written (nothing reads them before
+// the next pass overwrites them), and the force field is cleared for the coming atomic assembly.
+template <bool ORDERED, bool HAS_FEXT, bool HAS_BC, bool ZERO_F>
+__global__ void __launch_bounds__(256)
+node_fused_kernel(const NodeArgs p, double hdt, double hdt_next, double dt_next)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_nodes) return;
+  double f[3];
+  if (ORDERED) {
+    f[0] = 0.0, f[1] = 0.0, f[2] = 0.0;
+    const int64_t b = p.adj_off[i], e = p.adj_off[i + 1];
+    for (int64_t k = b; k < e; ++k) {
+      const double* s = p.ef + (int64_t)p.adj_slot[k] * 3;
+      f[0] += s[0];
+      f[1] += s[1];
+      f[2] += s[2];
+    }
+  } else {
+    f[0] = p.f[0][i], f[1] = p.f[1][i], f[2] = p.f[2][i];
+  }
+  const double rm = 1.0 / p.mass[i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double a = rm * (f[c] + (HAS_FEXT ? p.fext[c][i] : 0.0));
+    double       v = p.v[c][i];
+    double       u = p.u[c][i];
+    v              = v + hdt * a;
+    v              = v + hdt_next * a;
+    int bc         = -1;
+    if (HAS_BC) {
+      bc = p.bc_of_dof[c][i];
+      if (bc >= 0) v = bc_velocity(p.bc_kind[bc], p.bc_value[bc], u, dt_next, v);
+    }
+    u = u + dt_next * v;
+    if (HAS_BC) {
+      if (bc >= 0) v = bc_velocity(p.bc_kind[bc], p.bc_value[bc], u, dt_next, v);
+    }
+    p.v[c][i] = v;
+    p.u[c][i] = u;
+    if (ZERO_F) p.f[c][i] = 0.0;
+  }
+}
+
 // BoundaryConditionManager::ApplyKinematicBC alone (output steps, t = 0): table entries in deck order;
 // duplicates of a dof were resolved to the last entry when the dof map was built.
 __global__ void __launch_bounds__(256)
@@ -477,7 +717,8 @@ lumped_mass_kernel(const SetupArgs p)
   for (int q = 0; q < 8; ++q) {
     double a[3][3], ai[3][3];
     param_gradient_tbl(X, q, a);
-    det[q] = invert3x3(a, ai);
+    unsigned unused = 0u;
+    det[q]          = invert3x3<false>(a, ai, unused);
     if (!(det[q] > 0.0)) atomicOr(p.flags, 1);
   }
   for (int i = 0; i < 8; ++i) {
@@ -554,7 +795,8 @@ derived_kernel(int64_t n_elem, const int* __restrict__ conn, const double* X0, c
   for (int g = 0; g < 8; ++g) {
     double a[3][3], ai[3][3];
     param_gradient_tbl(x, g, a);
-    const double det = invert3x3(a, ai);
+    unsigned     unused = 0u;
+    const double det    = invert3x3<false>(a, ai, unused);
     vol += det;
     for (int i = 0; i < 15; ++i) avg[i] += qd[g * 15 + i] * 1.0 * det;
   }

@@ -33,6 +33,7 @@ struct Block
   std::vector<int> conn_host;  // dropped after finalize
   int*             conn      = nullptr;
   int64_t          elem_base = 0;  // first global element (ascending block id order)
+  int64_t          group_base = 0; // first 4-element group of the block in the b^-1 cache
 };
 
 thread_local std::string g_create_error;
@@ -75,11 +76,13 @@ struct nsm_b200_ctx
 
   // boundary conditions
   int64_t n_bc = 0;
+  int64_t bc_rows = 1, bc_rows_cap = 0;  // per-step magnitude rows held in bc_value ([bc_rows][n_bc])
   int*    bc_of_dof[3] = {nullptr, nullptr, nullptr};
   int*    bc_kind  = nullptr;
   double* bc_value = nullptr;
 
   int*                d_flags  = nullptr;
+  unsigned long long* d_ticket = nullptr;  // element-kernel work counter
   unsigned long long* d_min_dt = nullptr;
 
   int64_t launches     = 0;
@@ -162,7 +165,7 @@ make_shape_tables()
 }
 
 NodeArgs
-node_args(nsm_b200_ctx* c)
+node_args(nsm_b200_ctx* c, int64_t bc_row = 0)
 {
   NodeArgs p{};
   p.n_nodes = c->n_nodes;
@@ -173,7 +176,7 @@ node_args(nsm_b200_ctx* c)
   }
   p.mass     = c->mass;
   p.bc_kind  = c->bc_kind;
-  p.bc_value = c->bc_value;
+  p.bc_value = c->bc_value ? c->bc_value + (c->bc_rows > 1 ? bc_row : 0) * c->n_bc : nullptr;
   p.ef       = c->ef;
   p.adj_off  = c->adj_off;
   p.adj_slot = c->adj_slot;
@@ -189,27 +192,41 @@ elem_args(nsm_b200_ctx* c, const Block& b)
   for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.f[i] = c->f[i];
   p.ef         = c->ef ? c->ef + b.elem_base * 24 : nullptr;
   p.ipt        = c->ipt ? c->ipt + b.elem_base * 120 : nullptr;
-  p.binv_cache = c->binv ? c->binv + b.elem_base * 72 : nullptr;
+  p.binv_cache = c->binv ? c->binv + b.group_base * kBinvGroupDoubles : nullptr;
   p.bulk       = b.bulk;
   p.shear      = b.shear;
   p.flags      = c->d_flags;
+  p.ticket     = c->d_ticket;
   return p;
 }
 
-constexpr size_t kElemSmemBytes = (size_t)(kElemThreads / 32) * kWarpSmemDoubles * sizeof(double);
+constexpr size_t kElemSmemBytes = (size_t)kElemWarps * kWarpSmemDoubles * sizeof(double);
 
+inline int64_t
+groups_of(int64_t n_elem)
+{
+  return (n_elem + kElemsPerWarp - 1) / kElemsPerWarp;
+}
+
+// Persistent launch: one wave of CTAs (SM count x resident CTAs per SM), fewer when the block is small.
 template <int MAT, bool ORDERED, int MODE>
 cudaError_t
 launch_element(const ElemArgs& p, cudaStream_t s)
 {
-  static bool configured = false;
-  auto        k          = element_force_kernel<MAT, ORDERED, MODE>;
-  if (!configured) {
+  static int  wave = 0;
+  auto        k    = element_force_kernel<MAT, ORDERED, MODE>;
+  if (wave == 0) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kElemSmemBytes);
     if (e != cudaSuccess) return e;
-    configured = true;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kElemThreads, kElemSmemBytes)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    wave = sms * per_sm;
   }
-  k<<<grid_for(p.n_elem, kElemThreads / 8), kElemThreads, kElemSmemBytes, s>>>(p);
+  const int64_t need = (groups_of(p.n_elem) + kElemWarps - 1) / kElemWarps;
+  k<<<(unsigned)std::min<int64_t>(need, wave), kElemThreads, kElemSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -263,6 +280,7 @@ enqueue_element_kernels(nsm_b200_ctx* c, bool store_ipt)
   for (auto& kv : c->blocks) {
     const Block& b = kv.second;
     if (b.n_elem == 0) continue;
+    NSM_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned long long), c->stream));
     NSM_CUDA(c, launch_element_any(elem_args(c, b), b.material, ordered, mode, c->stream));
     c->launches++;
   }
@@ -467,7 +485,7 @@ nsm_b200_destroy(nsm_b200_ctx* c)
     fr(c->X[i]), fr(c->u[i]), fr(c->v[i]), fr(c->a[i]), fr(c->f[i]), fr(c->fext[i]), fr(c->bc_of_dof[i]);
   }
   fr(c->mass), fr(c->staging), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
-  fr(c->bc_kind), fr(c->bc_value), fr(c->d_flags), fr(c->d_min_dt);
+  fr(c->bc_kind), fr(c->bc_value), fr(c->d_flags), fr(c->d_min_dt), fr(c->d_ticket);
   for (auto& kv : c->blocks) fr(kv.second.conn);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_start);
@@ -536,18 +554,21 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
   if ((rc = dev_alloc(c, &c->mass, n))) return rc;
   NSM_CUDA(c, cudaMemsetAsync(c->mass, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->stream));
   if ((rc = dev_alloc(c, &c->staging, n * 3))) return rc;
-  if ((rc = dev_alloc(c, &c->d_flags, 1))) return rc;
+  if ((rc = dev_alloc(c, &c->d_flags, 2))) return rc;
   if ((rc = dev_alloc(c, &c->d_min_dt, 1))) return rc;
-  NSM_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+  if ((rc = dev_alloc(c, &c->d_ticket, 1))) return rc;
+  NSM_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(int), c->stream));
   NSM_CUDA(c, cudaMemcpyAsync(c->X[0], c->hx.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemcpyAsync(c->X[1], c->hy.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemcpyAsync(c->X[2], c->hz.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 
-  int64_t base = 0;
+  int64_t base = 0, gbase = 0;
   for (auto& kv : c->blocks) {
     Block& b    = kv.second;
     b.elem_base = base;
+    b.group_base = gbase;
     base += b.n_elem;
+    gbase += groups_of(b.n_elem);
     if ((rc = dev_alloc(c, &b.conn, b.n_elem * 8))) return rc;
     NSM_CUDA(c, cudaMemcpyAsync(b.conn, b.conn_host.data(), (size_t)b.n_elem * 8 * sizeof(int), cudaMemcpyHostToDevice,
                                 c->stream));
@@ -604,11 +625,13 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
     if ((rc = ensure_ipt(c))) return rc;
   }
   if (flags & NSM_FLAG_CACHE_REF_JACOBIAN) {
-    if ((rc = dev_alloc(c, &c->binv, c->n_elem_total * 72))) return rc;
+    int64_t n_groups = 0;
+    for (auto& kv : c->blocks) n_groups += groups_of(kv.second.n_elem);
+    if ((rc = dev_alloc(c, &c->binv, n_groups * kBinvGroupDoubles))) return rc;
     for (auto& kv : c->blocks) {
       const Block& b = kv.second;
       if (b.n_elem == 0) continue;
-      binv_cache_kernel<<<grid_for(b.n_elem * 8, kElemThreads), kElemThreads, 0, c->stream>>>(elem_args(c, b));
+      binv_cache_kernel<<<grid_for(groups_of(b.n_elem) * 32, kElemThreads), kElemThreads, 0, c->stream>>>(elem_args(c, b));
       c->launches++;
       NSM_CUDA(c, cudaGetLastError());
     }
@@ -814,6 +837,7 @@ nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int
   }
   if ((rc = dev_alloc(c, &c->bc_kind, n))) return rc;
   if ((rc = dev_alloc(c, &c->bc_value, n))) return rc;
+  c->bc_rows = 1, c->bc_rows_cap = 1;
   NSM_CUDA(c, cudaMemcpyAsync(c->bc_kind, kind, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemsetAsync(c->bc_value, 0, (size_t)n * sizeof(double), c->stream));
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -826,8 +850,29 @@ nsm_b200_set_bc_values(nsm_b200_ctx* c, int64_t n, const double* value)
   NSM_REQUIRE(c, c && c->finalized, "set_bc_values: context not finalized");
   NSM_REQUIRE(c, n == c->n_bc, "set_bc_values: length differs from the BC table");
   if (n == 0) return NSM_OK;
+  c->bc_rows = 1;
   NSM_CUDA(c, cudaMemcpyAsync(c->bc_value, value, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));  // `value` may be reused by the caller right away
+  return NSM_OK;
+}
+
+int
+nsm_b200_set_bc_values_steps(nsm_b200_ctx* c, int n_rows, int64_t n, const double* value)
+{
+  NSM_REQUIRE(c, c && c->finalized, "set_bc_values_steps: context not finalized");
+  NSM_REQUIRE(c, n == c->n_bc && n_rows >= 1, "set_bc_values_steps: bad arguments");
+  if (n == 0) return NSM_OK;
+  if (n_rows > c->bc_rows_cap) {
+    NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->bc_value) cudaFree(c->bc_value);
+    c->bc_value = nullptr;
+    int rc      = dev_alloc(c, &c->bc_value, (int64_t)n_rows * n);
+    if (rc) return rc;
+    c->bc_rows_cap = n_rows;
+  }
+  c->bc_rows = n_rows;
+  NSM_CUDA(c, cudaMemcpyAsync(c->bc_value, value, (size_t)n_rows * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   return NSM_OK;
 }
 
@@ -849,12 +894,14 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
 {
   NSM_REQUIRE(c, c && c->finalized, "step: context not finalized");
   NSM_REQUIRE(c, time != nullptr && n_steps >= 0, "step: bad arguments");
+  NSM_REQUIRE(c, c->bc_rows <= 1 || n_steps <= c->bc_rows, "step: more steps than per-step boundary-condition rows");
   const bool     ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
   const bool     has_bc  = c->n_bc > 0;
   const int64_t  n       = c->n_nodes;
   const unsigned ngrid   = grid_for(n, 256);
   double         t       = *time;
   double         dt      = 0.0;
+  const bool     gather_in_node_kernel = ordered && !c->comm.active();
   for (int s = 0; s < n_steps; ++s) {
     // explicit_time_integrator.cc:192-195: dt is re-derived from the accumulated time every step
     const double t_prev = t;
@@ -863,8 +910,8 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     const double hdt = 0.5 * dt;
     const bool   store =
         (store_ipt_last && s == n_steps - 1) || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP);
-    if (n > 0) {
-      const NodeArgs na = node_args(c);
+    if (n > 0 && s == 0) {  // later first halves ride in the previous step's fused node pass
+      const NodeArgs na = node_args(c, 0);
       if (has_bc) {
         if (ordered)
           node_predict_kernel<true, false><<<ngrid, 256, 0, c->stream>>>(na, hdt, dt);
@@ -883,18 +930,40 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     if (rc) return rc;
     if (c->profiling) prof_event(c);
     if (n > 0) {
-      const NodeArgs na = node_args(c);
+      const NodeArgs na = node_args(c, s + 1);  // boundary-condition magnitudes of the step the fused pass opens
       if (c->comm.active()) {
         if (ordered) {
           node_correct_kernel<true, false><<<ngrid, 256, 0, c->stream>>>(na, 0.0, 0);
           c->launches++;
         }
         if (c->comm.reduce(c->stream, c->f, 3, &c->launches)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
-        if (c->has_fext)
-          node_correct_kernel<false, true><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
-        else
-          node_correct_kernel<false, false><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
-      } else if (ordered) {
+      }
+      if (s + 1 < n_steps) {
+        const double dt_next  = (t + dt_user) - t;
+        const double hdt_next = 0.5 * dt_next;
+        const int    variant  = (gather_in_node_kernel ? 4 : 0) | (c->has_fext ? 2 : 0) | (has_bc ? 1 : 0);
+#define NSM_FUSED(O, FE, BC, Z) node_fused_kernel<O, FE, BC, Z><<<ngrid, 256, 0, c->stream>>>(na, hdt, hdt_next, dt_next)
+        if (ordered) {  // element forces are gathered, nothing to clear
+          switch (variant) {
+            case 0: NSM_FUSED(false, false, false, false); break;
+            case 1: NSM_FUSED(false, false, true, false); break;
+            case 2: NSM_FUSED(false, true, false, false); break;
+            case 3: NSM_FUSED(false, true, true, false); break;
+            case 4: NSM_FUSED(true, false, false, false); break;
+            case 5: NSM_FUSED(true, false, true, false); break;
+            case 6: NSM_FUSED(true, true, false, false); break;
+            default: NSM_FUSED(true, true, true, false); break;
+          }
+        } else {
+          switch (variant) {
+            case 0: NSM_FUSED(false, false, false, true); break;
+            case 1: NSM_FUSED(false, false, true, true); break;
+            case 2: NSM_FUSED(false, true, false, true); break;
+            default: NSM_FUSED(false, true, true, true); break;
+          }
+        }
+#undef NSM_FUSED
+      } else if (gather_in_node_kernel) {
         if (c->has_fext)
           node_correct_kernel<true, true><<<ngrid, 256, 0, c->stream>>>(na, hdt, 1);
         else
@@ -915,7 +984,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
   }
   if (store_ipt_last && n_steps > 0 && has_bc && n > 0) {
     // output step: ApplyKinematicConditions once more before the data is read (explicit_time_integrator.cc:266-269)
-    apply_bc_kernel<<<ngrid, 256, 0, c->stream>>>(node_args(c), dt);
+    apply_bc_kernel<<<ngrid, 256, 0, c->stream>>>(node_args(c, n_steps - 1), dt);
     c->launches++;
   }
   *time = t;
@@ -1052,6 +1121,16 @@ nsm_b200_profile_read(nsm_b200_ctx* c, double* elem_ms, double* node_ms, int64_t
   if (node_ms) *node_ms = c->prof_node_ms * k;
   if (n) *n = c->prof_steps;
   return NSM_OK;
+}
+
+int64_t
+nsm_b200_cold_points(nsm_b200_ctx* c)
+{
+  if (!c || !c->finalized) return -1;
+  int h = 0;
+  if (cudaMemcpyAsync(&h, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+  return (int64_t)(unsigned)h;
 }
 
 int

@@ -1,0 +1,230 @@
+// nimblesm_b200/host/host_c_api.cc — plain-C entry points over the host classes, bound with ctypes by the CPU
+// tests (tests/test_host_cpp.py).  Nothing here computes on the device; every function returns 0 on success
+// and writes a message into `err` otherwise (exceptions never cross the boundary).
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <thread>
+
+#include "boundary_condition.h"
+#include "data_manager.h"
+#include "exodus_output.h"
+#include "expression.h"
+#include "genesis_mesh.h"
+#include "material.h"
+#include "parser.h"
+
+using namespace nimble_b200;
+
+namespace {
+int
+fail(char* err, int errlen, const std::string& m)
+{
+  if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", m.c_str());
+  return 1;
+}
+int
+put(char* out, int outlen, const std::string& s, char* err, int errlen)
+{
+  if ((int)s.size() + 1 > outlen) return fail(err, errlen, "output buffer too small");
+  memcpy(out, s.c_str(), s.size() + 1);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int
+nsmh_expression_eval(const char* text, double x, double y, double z, double t, double* out, char* err, int errlen)
+{
+  try {
+    *out = Expression(text).eval(x, y, z, t);
+    return 0;
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
+int
+nsmh_io_file_name(const char* serial, const char* ext, const char* label, int rank, int nranks, char* out, int outlen)
+{
+  return put(out, outlen, IOFileName(serial, ext, label, rank, nranks), nullptr, 0);
+}
+
+// deck text -> JSON summary of what the Parser holds
+int
+nsmh_deck_summary(const char* deck_text, const int* block_ids, int n_blocks, char* out, int outlen, char* err, int errlen)
+{
+  try {
+    Parser p;
+    p.InitializeFromString(deck_text);
+    std::ostringstream j;
+    j.precision(17);
+    j << "{\"genesis\":\"" << p.GenesisFileName() << "\",\"exodus\":\"" << p.ExodusFileName() << "\",\"scheme\":\""
+      << p.TimeIntegrationScheme() << "\",\"initial_time\":" << p.InitialTime() << ",\"final_time\":" << p.FinalTime()
+      << ",\"num_load_steps\":" << p.NumLoadSteps() << ",\"output_frequency\":" << p.OutputFrequency() << ",\"output_fields\":\""
+      << p.GetOutputFieldString() << "\",\"n_bc\":" << p.GetBoundaryConditionStrings().size() << ",\"materials\":{";
+    MaterialFactory factory;
+    for (int i = 0; i < n_blocks; ++i) {
+      const std::string mp = p.GetModelMaterialParameters(block_ids[i]);
+      j << (i ? "," : "") << "\"" << block_ids[i] << "\":";
+      if (mp == "none") {
+        j << "null";
+        continue;
+      }
+      factory.parse_and_create(mp);
+      auto m = factory.get_material();
+      j << "{\"model\":\"" << m->Parameters().GetMaterialName() << "\",\"density\":" << m->GetDensity() << ",\"bulk_modulus\":"
+        << m->GetBulkModulus() << ",\"shear_modulus\":" << m->GetShearModulus() << ",\"num_state\":" << m->NumStateVariables() << "}";
+    }
+    j << "}}";
+    return put(out, outlen, j.str(), err, errlen);
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
+// Genesis file -> JSON summary (counts, id maps, checksums) for comparison with an independent reader
+int
+nsmh_mesh_summary(const char* path, char* out, int outlen, char* err, int errlen)
+{
+  try {
+    GenesisMesh m;
+    m.ReadFile(path);
+    std::ostringstream j;
+    j.precision(17);
+    double sx = 0, sy = 0, sz = 0;
+    for (unsigned i = 0; i < m.GetNumNodes(); ++i) sx += m.GetCoordinatesX()[i], sy += m.GetCoordinatesY()[i], sz += m.GetCoordinatesZ()[i];
+    long long gsum = 0;
+    for (unsigned i = 0; i < m.GetNumNodes(); ++i) gsum += m.GetNodeGlobalIds()[i];
+    j << "{\"dim\":" << m.GetDim() << ",\"num_nodes\":" << m.GetNumNodes() << ",\"num_elements\":" << m.GetNumElements()
+      << ",\"sum_x\":" << sx << ",\"sum_y\":" << sy << ",\"sum_z\":" << sz << ",\"node_gid_sum\":" << gsum << ",\"blocks\":{";
+    bool first = true;
+    for (int id : m.GetAllBlockIds()) {
+      long long csum = 0;
+      int       ne   = 0;
+      bool      local = false;
+      for (int b : m.GetBlockIds()) local |= b == id;
+      if (local) {
+        ne = m.GetNumElementsInBlock(id);
+        for (long i = 0; i < (long)ne * m.GetNumNodesPerElement(id); ++i) csum += (long long)(i % 7 + 1) * m.GetConnectivity(id)[i];
+      }
+      j << (first ? "" : ",") << "\"" << id << "\":{\"name\":\"" << m.GetBlockName(id) << "\",\"num_elements\":" << ne << ",\"conn_checksum\":" << csum
+        << "}";
+      first = false;
+    }
+    j << "},\"node_sets\":{";
+    first      = true;
+    auto sets  = m.GetNodeSets();
+    auto names = m.GetNodeSetNames();
+    for (int id : m.GetNodeSetIds()) {
+      long long s = 0;
+      for (int n : sets[id]) s += n;
+      j << (first ? "" : ",") << "\"" << id << "\":{\"name\":\"" << names[id] << "\",\"size\":" << sets[id].size() << ",\"sum\":" << s << "}";
+      first = false;
+    }
+    j << "}}";
+    return put(out, outlen, j.str(), err, errlen);
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
+// reads a Genesis file and writes an Exodus file with `n_steps` planes of synthetic data through ExodusOutput:
+// nodal displacement_{x,y,z} = (step+1) * coordinate, element "volume" = element index + step, per-point
+// "ipt01_stress_xx" = 10 * element index + step.  The test reads the file back with scipy.
+int
+nsmh_exodus_roundtrip(const char* genesis_path, const char* out_path, int n_steps, char* err, int errlen)
+{
+  try {
+    GenesisMesh m;
+    m.ReadFile(genesis_path);
+    ExodusOutput ex;
+    ex.Initialize(out_path, m);
+    std::map<int, std::vector<std::string>> elem_names, derived_names;
+    for (int id : m.GetBlockIds()) {
+      elem_names[id]    = {"ipt01_stress_xx"};
+      derived_names[id] = {"volume"};
+    }
+    ex.InitializeDatabase(m, {}, {"displacement_x", "displacement_y", "displacement_z"}, elem_names, derived_names);
+    const int n = (int)m.GetNumNodes();
+    for (int s = 0; s < n_steps; ++s) {
+      std::vector<std::vector<double>> node(3, std::vector<double>(n));
+      for (int i = 0; i < n; ++i) {
+        node[0][i] = (s + 1) * m.GetCoordinatesX()[i];
+        node[1][i] = (s + 1) * m.GetCoordinatesY()[i];
+        node[2][i] = (s + 1) * m.GetCoordinatesZ()[i];
+      }
+      std::map<int, std::vector<std::vector<double>>> elem, derived;
+      for (int id : m.GetBlockIds()) {
+        const int ne = m.GetNumElementsInBlock(id);
+        elem[id].assign(1, std::vector<double>(ne));
+        derived[id].assign(1, std::vector<double>(ne));
+        for (int e = 0; e < ne; ++e) elem[id][0][e] = 10.0 * e + s, derived[id][0][e] = e + s;
+      }
+      ex.WriteStep(0.25 * s, {}, node, elem_names, elem, derived_names, derived);
+    }
+    ex.Close();
+    return 0;
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
+// boundary-condition manager on a Genesis file: device table size, time dependence, magnitudes at time t
+int
+nsmh_bc_table(const char* genesis_path, const char* deck_text, double t, int max_entries, int* n_entries, int* node, int* comp,
+              int* kind, double* value, int* time_dependent, char* err, int errlen)
+{
+  try {
+    GenesisMesh m;
+    m.ReadFile(genesis_path);
+    Parser p;
+    p.InitializeFromString(deck_text);
+    BoundaryConditionManager bc;
+    bc.Initialize(m.GetNodeSetNames(), m.GetNodeSets(), {}, {}, p.GetBoundaryConditionStrings(), m.GetDim(), p.TimeIntegrationScheme());
+    const auto& tb = bc.GetDeviceTable();
+    *n_entries     = (int)tb.node.size();
+    *time_dependent = bc.HasTimeDependentMagnitudes() ? 1 : 0;
+    if (*n_entries > max_entries) return fail(err, errlen, "too many entries");
+    std::vector<double> X((size_t)m.GetNumNodes() * 3);
+    for (unsigned i = 0; i < m.GetNumNodes(); ++i)
+      X[3 * i] = m.GetCoordinatesX()[i], X[3 * i + 1] = m.GetCoordinatesY()[i], X[3 * i + 2] = m.GetCoordinatesZ()[i];
+    Viewify<2> Xv(X.data(), {(int)m.GetNumNodes(), 3}, {3, 1});
+    bc.EvaluateMagnitudes(t, Xv, value);
+    for (int k = 0; k < *n_entries; ++k) node[k] = tb.node[k], comp[k] = tb.comp[k], kind[k] = tb.kind[k];
+    return 0;
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
+// VectorCommunicator::Initialize on `n_ranks` threads: rank r holds global ids gids[off[r] .. off[r+1]).
+// Returns, for rank `query_rank`, its peers and shared local node lists (flattened).
+int
+nsmh_shared_node_tables(int n_ranks, const int* gids, const int* off, int query_rank, int max_out, int* n_peers, int* peer_ranks,
+                        long long* pair_off, int* pair_nodes, char* err, int errlen)
+{
+  try {
+    auto group = std::make_shared<RankGroup>(n_ranks);
+    std::vector<std::shared_ptr<VectorCommunicator>> comms(n_ranks);
+    std::vector<std::thread>                         th;
+    for (int r = 0; r < n_ranks; ++r)
+      th.emplace_back([&, r] {
+        comms[r] = std::make_shared<VectorCommunicator>(3, (unsigned)(off[r + 1] - off[r]), group, r);
+        comms[r]->Initialize(std::vector<int>(gids + off[r], gids + off[r + 1]));
+      });
+    for (auto& t : th) t.join();
+    const VectorCommunicator& c = *comms[query_rank];
+    *n_peers = (int)c.PeerRanks().size();
+    if ((int)c.PairLocalNodes().size() > max_out) return fail(err, errlen, "output too small");
+    for (int i = 0; i < *n_peers; ++i) peer_ranks[i] = c.PeerRanks()[i];
+    for (int i = 0; i <= *n_peers; ++i) pair_off[i] = c.PairOffsets()[i];
+    for (size_t i = 0; i < c.PairLocalNodes().size(); ++i) pair_nodes[i] = c.PairLocalNodes()[i];
+    return 0;
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+// nimblesm_b200/host/integrator.cc — see integrator.h.
+#include "integrator.h"
+
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <thread>
+
+namespace nimble_b200 {
+
+namespace {
+
+thread_local int t_rank = 0;
+
+// Viewify::operator+=(alpha * w) of the reference (src/nimble_view.h:181-214): prod = alpha * 1.0; data += prod * rhs
+void
+axpy(Viewify<2> dest, double alpha, const Viewify<2>& rhs)
+{
+  const double prod = alpha * 1.0;
+  const long   n    = (long)dest.size()[0] * dest.stride()[0];
+  double*      d    = dest.data();
+  const double* r   = rhs.data();
+  for (long i = 0; i < n; ++i) d[i] += prod * r[i];
+}
+
+// BlockMaterialInterfaceFactory of the B200 build: stress through the device seam on host arrays
+class B200BlockMaterialInterfaceFactory : public BlockMaterialInterfaceFactoryBase
+{
+ public:
+  std::shared_ptr<BlockMaterialInterfaceBase>
+  create(double time_n, double time_np1, const FieldIds&, const std::vector<BlockData>& blocks, ModelDataBase* model_data_ptr) const override
+  {
+    auto* md = dynamic_cast<ModelData*>(model_data_ptr);
+    if (!md) throw std::invalid_argument("BlockMaterialInterfaceFactory::create needs a nimble_b200::ModelData");
+    return std::make_shared<BlockMaterialInterface>(time_n, time_np1, blocks, std::map<int, BlockMaterialInterface::Arrays>(), md->Device());
+  }
+};
+
+}  // namespace
+
+int
+ExplicitTimeIntegrator::Integrate()
+{
+  DataManager&  data_manager = GetDataManager();
+  const Parser& parser       = data_manager.GetParser();
+  const int     my_rank      = App().Rank();
+  const bool    talk         = my_rank == 0 && !App().Options().quiet;
+  auto          model_base   = data_manager.GetModelData();
+  auto*         model_data   = dynamic_cast<ModelData*>(model_base.get());
+  if (!model_data) throw std::runtime_error("ExplicitTimeIntegrator needs a nimble_b200::ModelData");
+  const int num_nodes = (int)Mesh().GetNumNodes();
+
+  auto displacement   = model_data->GetVectorNodeData("displacement");
+  auto velocity       = model_data->GetVectorNodeData("velocity");
+  auto acceleration   = model_data->GetVectorNodeData("acceleration");
+  auto internal_force = model_data->GetVectorNodeData("internal_force");
+  auto external_force = model_data->GetVectorNodeData("external_force");
+
+  model_data->ComputeLumpedMass(data_manager);
+  double critical_time_step = model_data->GetCriticalTimeStep();
+  auto   group              = data_manager.GetVectorCommunicator()->Group();
+  if (group && group->NumRanks() > 1) critical_time_step = group->MinAll(my_rank, critical_time_step);
+  auto lumped_mass = model_data->GetScalarNodeData("lumped_mass");
+
+  const double initial_time = parser.InitialTime(), final_time = parser.FinalTime();
+  double       time_current = initial_time, time_previous = initial_time;
+  const int    num_load_steps = parser.NumLoadSteps(), output_frequency = parser.OutputFrequency();
+  const double user_specified_time_step = (final_time - initial_time) / num_load_steps;
+  if (final_time < initial_time)
+    throw std::invalid_argument("Final time: " + std::to_string(final_time) + " is less than initial time: " + std::to_string(initial_time) + "\n");
+
+  model_data->ApplyInitialConditions(data_manager);
+  model_data->ApplyKinematicConditions(data_manager, 0.0, 0.0);
+  model_data->PushNodalFields();
+  data_manager.WriteOutput(time_current);
+
+  if (talk) {
+    std::cout << "\nUser specified time step:              " << user_specified_time_step << std::endl;
+    std::cout << "Approximate maximum stable time step:  " << critical_time_step << "\n" << std::endl;
+    if (user_specified_time_step > critical_time_step)
+      std::cout << "**** WARNING:  The user specified time step exceeds the computed maximum stable time step.\n" << std::endl;
+    std::cout << "Explicit time integration:\n    0% complete" << std::endl;
+  }
+  auto is_output = [&](int step) { return output_frequency != 0 && (step % output_frequency == 0 || step == num_load_steps - 1); };
+  auto progress  = [&](int step) {
+    if (!talk) return;
+    if (10 * (step + 1) % num_load_steps == 0 && step != num_load_steps - 1)
+      std::cout << "   " << (int)(100.0 * (double)(step + 1) / num_load_steps) << "% complete" << std::endl;
+    else if (step == num_load_steps - 1)
+      std::cout << "  100% complete\n" << std::endl;
+  };
+
+  const auto t0 = std::chrono::steady_clock::now();
+  if (!reference_sequence_) {
+    // ---- fused: one device call per run of steps that ends at an output step (or at a 10 % progress mark)
+    int step = 0;
+    while (step < num_load_steps) {
+      int  run = 0;
+      bool out = false;
+      while (step + run < num_load_steps) {
+        out = is_output(step + run);
+        const bool mark = 10 * (step + run + 1) % num_load_steps == 0;
+        ++run;
+        if (out || mark || run >= 4096) break;
+      }
+      model_data->AdvanceOnDevice(data_manager, run, time_current, user_specified_time_step, out);
+      for (int s = 0; s < run; ++s) progress(step + s);
+      step += run;
+      if (out) {
+        model_data->PullNodalFields();
+        data_manager.WriteOutput(time_current);
+      }
+    }
+    model_data->PullNodalFields();
+  } else {
+    // ---- reference sequence (explicit_time_integrator.cc:177-278), host-sequenced through the ModelData virtuals
+    for (int step = 0; step < num_load_steps; ++step) {
+      progress(step);
+      const bool is_output_step = is_output(step);
+      time_previous             = time_current;
+      time_current += user_specified_time_step;
+      const double delta_time = time_current - time_previous, half_delta_time = 0.5 * delta_time;
+      axpy(velocity, half_delta_time, acceleration);
+      model_data->UpdateWithNewVelocity(data_manager, half_delta_time);
+      model_data->ApplyKinematicConditions(data_manager, time_current, time_previous);
+      axpy(displacement, delta_time, velocity);
+      model_data->UpdateWithNewDisplacement(data_manager, delta_time);
+      model_data->ApplyKinematicConditions(data_manager, time_current, time_previous);
+      model_data->ComputeExternalForce(data_manager, time_previous, time_current, is_output_step);
+      model_data->ComputeInternalForce(data_manager, time_previous, time_current, is_output_step, displacement, internal_force);
+      for (int i = 0; i < num_nodes; ++i) {
+        const double one_over_m = 1.0 / lumped_mass(i);
+        for (int c = 0; c < 3; ++c) acceleration(i, c) = one_over_m * (internal_force(i, c) + external_force(i, c));
+      }
+      axpy(velocity, half_delta_time, acceleration);
+      model_data->UpdateWithNewVelocity(data_manager, half_delta_time);
+      if (is_output_step) {
+        model_data->ApplyKinematicConditions(data_manager, time_current, time_previous);
+        data_manager.WriteOutput(time_current);
+      }
+      model_data->UpdateStates(data_manager);
+    }
+  }
+  step_loop_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (group) group->Barrier();
+  if (talk) {
+    const double upd = (double)Mesh().GetNumElements() * num_load_steps / (step_loop_seconds_ > 0 ? step_loop_seconds_ : 1.0);
+    std::cout << " Total step time = " << step_loop_seconds_ << " s (" << upd << " element-updates/s on rank 0, output included)\n";
+  }
+  return 0;
+}
+
+std::shared_ptr<BlockMaterialInterfaceFactoryBase>
+NimbleApplication::CreateBlockMaterialInterfaceFactory()
+{
+  return std::make_shared<B200BlockMaterialInterfaceFactory>();
+}
+
+std::unique_ptr<IntegratorBase>
+NimbleApplication::CreateIntegrator(GenesisMesh& mesh, DataManager& data_manager)
+{
+  return std::unique_ptr<IntegratorBase>(new ExplicitTimeIntegrator(*this, mesh, data_manager, options_.reference_sequence));
+}
+
+int
+NimbleApplication::Rank() const
+{
+  return t_rank;
+}
+
+int
+NimbleApplication::Run(int argc, char** argv)
+{
+  RunOptions o;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "--gpus" && i + 1 < argc)
+      o.num_ranks = std::atoi(argv[++i]);
+    else if (a == "--assembly" && i + 1 < argc)
+      o.assembly = std::string(argv[++i]) == "atomic" ? NSM_ASSEMBLY_ATOMIC : NSM_ASSEMBLY_ORDERED;
+    else if (a == "--flags" && i + 1 < argc)
+      o.flags = (unsigned)std::atoi(argv[++i]);
+    else if (a == "--reference_sequence")
+      o.reference_sequence = true;
+    else if (a == "--quiet")
+      o.quiet = true;
+    else if (a == "--use_tpetra" || a == "--use_vt" || a == "--use_uq") {
+      std::cerr << "NimbleSM_b200: option " << a << " belongs to reference subsystems outside the B200 hex8 explicit path\n";
+      return 1;
+    } else if (!a.empty() && a[0] == '-') {
+      std::cerr << "NimbleSM_b200: unknown option " << a << "\n";
+      return 1;
+    } else
+      o.input_file = a;
+  }
+  if (o.input_file.empty()) {
+    std::cerr << "Usage: NimbleSM_b200 [--gpus N] [--assembly atomic|ordered] [--reference_sequence] [--quiet] <input deck>\n";
+    return 1;
+  }
+  return Run(o);
+}
+
+int
+NimbleApplication::Run(const RunOptions& options)
+{
+  options_ = options;
+  if (options_.num_ranks < 1) options_.num_ranks = 1;
+  auto             group = std::make_shared<RankGroup>(options_.num_ranks);
+  std::vector<int> status(options_.num_ranks, 0);
+  if (options_.num_ranks == 1) {
+    status[0] = ExecRank(0, group);
+  } else {
+    std::vector<std::thread> threads;
+    for (int r = 0; r < options_.num_ranks; ++r) threads.emplace_back([&, r] { status[r] = ExecRank(r, group); });
+    for (auto& t : threads) t.join();
+  }
+  for (int s : status)
+    if (s) return s;
+  return 0;
+}
+
+int
+NimbleApplication::ExecRank(int rank, std::shared_ptr<RankGroup> group)
+{
+  t_rank = rank;
+  try {
+    // InitializeSubsystems / MainLoop (src/nimble.cc:176-237, 323-372)
+    auto parser = CreateParser();
+    parser->SetInputFilename(options_.input_file);
+    parser->SetRankID(rank);
+    parser->SetNumRanks(options_.num_ranks);
+    parser->Initialize();
+    if (rank == 0 && !options_.quiet)
+      std::cout << "\n-- NimbleSM_b200 (" << nsm_b200_version() << ")\n-- input deck " << options_.input_file << ", " << options_.num_ranks
+                << " rank(s), one B200 each\n";
+    GenesisMesh mesh;
+    mesh.ReadFile(IOFileName(parser->GenesisFileName(), "g", "", rank, options_.num_ranks));
+    DataManager data_manager(*parser, mesh, rank, options_.assembly, options_.flags, group);
+    data_manager.SetBlockMaterialInterfaceFactory(CreateBlockMaterialInterfaceFactory());
+    data_manager.GetModelData()->InitializeBlocks(data_manager, CreateMaterialFactory());
+    data_manager.InitializeOutput(IOFileName(parser->ExodusFileName(), "e", "out", rank, options_.num_ranks));
+    auto integrator = CreateIntegrator(mesh, data_manager);
+    const int status = integrator->Integrate();
+    data_manager.GetExodusOutput()->Close();
+    return status;
+  } catch (std::exception const& e) {
+    std::cerr << "Standard exception: " << e.what() << std::endl;
+    // a rank that dies leaves the others waiting in a collective: this build runs all ranks in one process
+    if (options_.num_ranks > 1) std::exit(1);
+    return 1;
+  }
+}
+
+}  // namespace nimble_b200

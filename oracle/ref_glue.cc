@@ -10,6 +10,7 @@
 //     that TU hard-wires nimble_kokkos::ModelData, :113)
 // All arithmetic (element, material, utils, block, BC manager, expression parser) is the reference's.
 // Nothing under nimblesm_b200/ may include or link this file.
+#include "nimble_expression_parser.h"
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -547,6 +548,22 @@ nsmref_bench_steps(
   }
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+
+// The reference's own expression parser on one point (src/nimble_expression_parser.h:694-760): pins
+// nimblesm_b200/host/expression.cc.  Returns 0 and the value, or 1 when the reference throws.
+int
+nsmref_expression_eval(const char* text, double x, double y, double z, double t, double* out)
+{
+  try {
+    ExpressionParsing::BoundaryConditionFunctor f{std::string(text)};
+    f.x = x, f.y = y, f.z = z, f.t = t;
+    *out = f.eval();
+    return 0;
+  } catch (...) {
+    return 1;
+  }
 }
 
 }  // extern "C"

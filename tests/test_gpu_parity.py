@@ -221,6 +221,48 @@ def test_explicit_steps_vs_oracle(oracle, assembly):
     c.close()
 
 
+@pytest.mark.parametrize("flags", [0, 2])
+@pytest.mark.parametrize("with_bc", [False, True])
+def test_multi_step_call_equals_single_steps(flags, with_bc):
+    """One nsm_b200_step(n) call (interior steps run the fused node pass) == n calls of one step, bit for bit in
+    ORDERED mode, on a two-block mesh whose block sizes are not multiples of the 4-element warp group (tail
+    lanes) with and without the cached reference Jacobians (flags = NSM_FLAG_CACHE_REF_JACOBIAN)."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, _ = perturbed_cube(7, 0.0)
+    conn = mesh["conn"][1]
+    mesh["block_ids"] = [3, 9]
+    mesh["conn"] = {3: np.ascontiguousarray(conn[:101]), 9: np.ascontiguousarray(conn[101:])}
+    blocks = {3: ("neohookean", K, G, RHO), 9: ("elastic", 0.9 * K, 1.1 * G, 2.0 * RHO)}
+    dt = 0.2 * (1.0 / 7) / np.sqrt(K / RHO)
+    v0 = np.zeros_like(ref)
+    v0[:, 0] = 1000.0 * ref[:, 0]
+    face = mesh["node_sets"][2]
+    out = []
+    for chunks in ([1] * 12, [12], [5, 1, 6]):
+        c = _ctx(mesh, None, capi.ASSEMBLY_ORDERED, flags, blocks)
+        c.compute_lumped_mass()
+        c.upload("velocity", v0)
+        if with_bc:
+            kinds = np.zeros(3 * len(face), np.int32)
+            kinds[2::3] = capi.BC_PRESCRIBED_DISPLACEMENT
+            c.set_bc_table(np.repeat(face, 3), np.tile(np.arange(3, dtype=np.int32), len(face)), kinds)
+            vals = np.zeros(3 * len(face))
+            vals[2::3] = 1e-7
+            c.set_bc_values(vals)
+            c.apply_kinematic_bc(0.0, 0.0)
+        t = 0.0
+        for k in chunks:
+            t = c.step(k, t, dt)
+        out.append((t, [c.download(l) for l in ("displacement", "velocity", "acceleration", "internal_force")]))
+        c.close()
+    for t, fields in out[1:]:
+        assert t == out[0][0]
+        for a, b in zip(fields, out[0][1]):
+            assert np.array_equal(a.view(np.int64), b.view(np.int64))
+    assert np.abs(out[0][1][0]).max() > 0
+
+
 @pytest.mark.parametrize("case", ["wave_in_bar", "notched_plate_native_neohookean", "notched_plate_native_hypoelastic",
                                   "brick_with_fibers", "single_elem_complex_displacement",
                                   "single_elem_native_neohookean", "rigid_body_motion", "simple_deformation_modes"])
@@ -271,7 +313,7 @@ def test_reference_decks_vs_reference_snapshots(case):
 def test_full_size_properties():
     """BASELINE-sized mesh (200^3 = 8 M elements, elastic): size-independent properties instead of an oracle run.
     (a) zero displacement -> zero force (to rounding); (b) rigid translation -> zero force (relative to the stiffness scale);
-    (c) linearity of the elastic force in u; (d) total internal force sums to ~0 (self-equilibrated);
+    (c) first-order linearity of the elastic force in u; (d) total internal force sums to ~0 (self-equilibrated);
     (e) ORDERED and ATOMIC assembly agree to 1e-12."""
     from nimblesm_b200 import capi
     from nimblesm_b200.mesh import structured_cube
@@ -295,7 +337,9 @@ def test_full_size_properties():
         assert scale > 0
         ft = c.internal_force_host(np.broadcast_to(np.array([1e-4, -2e-4, 3e-4]), (nn, 3)).copy())
         assert np.abs(ft).max() <= 1e-9 * K * h * h  # translation: F = I up to rounding of x + d
-        assert np.abs(f2 - 2.0 * f1).max() <= 1e-10 * scale
+        # the force is assembled on the CURRENT configuration (B and detJ of x = X + u), so it is linear in u only
+        # to first order: |f(2u) - 2 f(u)| = O(strain) * |f|, strain = 2e-3 here
+        assert np.abs(f2 - 2.0 * f1).max() <= 1e-2 * scale
         assert np.abs(f1.sum(0)).max() <= 1e-9 * np.abs(f1).sum()
     with _ctx(mesh, "elastic", capi.ASSEMBLY_ORDERED) as c:
         f1o = c.internal_force_host(u1)

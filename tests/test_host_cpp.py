@@ -1,0 +1,259 @@
+"""CPU tests of the C++ host layer (nimblesm_b200/host) through its C shim (lib/libnsm_host_c.so): deck parser,
+Genesis reader, Exodus writer, expression evaluator, boundary-condition tables and shared-node discovery — the
+reference-facing surfaces either side of the hot path.  No device work happens here."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, load_golden
+
+LIB = os.path.join(ROOT, "nimblesm_b200", "lib", "libnsm_host_c.so")
+CASES = ["wave_in_bar", "notched_plate_native_neohookean", "notched_plate_native_hypoelastic", "brick_with_fibers",
+         "simple_deformation_modes", "rigid_body_motion", "single_elem_complex_displacement", "single_elem_native_neohookean"]
+
+
+@pytest.fixture(scope="module")
+def host():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+
+        g.build()
+    return C.CDLL(LIB)
+
+
+def _call_json(fn, *args):
+    out, err = C.create_string_buffer(1 << 20), C.create_string_buffer(2048)
+    rc = fn(*args, out, len(out), err, len(err))
+    assert rc == 0, err.value.decode()
+    return json.loads(out.value.decode())
+
+
+EXPRESSIONS = [" 0.0635 * (-0.5*cos(t*3.141592653589793/2.0e-4) + 0.5)", "-0.0635 * (-0.5*cos(t*3.141592653589793/2.0e-4) + 0.5)",
+               " 0.01 * t", "-0.01 * t", "0.0005 * (-0.5*cos(t*3.141592653589793/2.0e-6) + 0.5)", "exp(0.2*t)", "exp(-0.2*t)",
+               "1000.0*x", "x*y/z*t", "x+y-z+t", "x-y+z", "2*x/3*y", "x^2 + y*z - 3", "-(x+1)^2", "sqrt(x*x+y*y)+abs(-z)",
+               "t>0.5?x:y", "x*(y+z)^3/2", "sin(x)*cos(y)+tan(z)-log(t+2)", "1.5e-3*x", "PI*x", "x % 0.3", "floor(10*x)+ceil(y)+round(z)",
+               "cbrt(x)+erf(y)-erfc(z)+log10(t+1)+asin(x)+acos(y)+atan(z)", "e^x"]
+POINTS = [(0.3, 0.7, 1.1, 1.0e-4), (1.25, -0.5, 2.0, 0.75), (0.0, 0.0, 0.5, 0.0), (0.9, 0.1, 3.3, 2.0e-6)]
+
+
+def test_expression_tree_matches_the_reference_parser(host, refdrive):
+    """Same value, bit for bit, as ExpressionParsing::BoundaryConditionFunctor of the reference (compiled into
+    oracle/_ref) on expressions that exercise its association rules (a*b/c = a*(b/c), a+b-c = a+(b-c), ...)."""
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libnimble_ref.so"))
+    ref.nsmref_expression_eval.argtypes = [C.c_char_p] + [C.c_double] * 4 + [C.POINTER(C.c_double)]
+    host.nsmh_expression_eval.argtypes = [C.c_char_p] + [C.c_double] * 4 + [C.POINTER(C.c_double), C.c_char_p, C.c_int]
+    for ex in EXPRESSIONS:
+        for p in POINTS:
+            a, b = C.c_double(), C.c_double()
+            err = C.create_string_buffer(512)
+            ra = host.nsmh_expression_eval(ex.encode(), *p, C.byref(a), err, 512)
+            rb = ref.nsmref_expression_eval(ex.encode(), *p, C.byref(b))
+            assert ra == rb, (ex, err.value)
+            if ra == 0:
+                assert np.float64(a.value).view(np.int64) == np.float64(b.value).view(np.int64) or (
+                    np.isnan(a.value) and np.isnan(b.value)), (ex, p, a.value, b.value)
+
+
+def test_expression_known_answers(host):
+    """Runs everywhere (no reference needed): values of the reference decks' BC expressions at fixed points,
+    generated with the reference parser in the build container."""
+    host.nsmh_expression_eval.argtypes = [C.c_char_p] + [C.c_double] * 4 + [C.POINTER(C.c_double), C.c_char_p, C.c_int]
+    known = json.load(open(os.path.join(ROOT, "tests", "golden", "expressions.json")))
+    assert len(known) >= 40
+    for ex, p, bits in known:
+        a = C.c_double()
+        err = C.create_string_buffer(512)
+        assert host.nsmh_expression_eval(ex.encode(), *p, C.byref(a), err, 512) == 0, err.value
+        assert int(np.float64(a.value).view(np.int64)) == bits, (ex, p)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_parser_and_material_factory_on_reference_decks(host, case):
+    from nimblesm_b200.deck import parse_deck
+
+    deck, mesh, _gold, _ref, _pieces = load_golden(case)
+    ids = (C.c_int * len(mesh["all_block_ids"]))(*mesh["all_block_ids"])
+    s = _call_json(host.nsmh_deck_summary, deck.encode(), ids, len(mesh["all_block_ids"]))
+    d = parse_deck(deck)
+    assert s["scheme"] == "explicit" and s["num_load_steps"] == d.num_load_steps and s["output_frequency"] == d.output_frequency
+    assert s["final_time"] == d.final_time and s["initial_time"] == d.initial_time
+    assert s["genesis"] == d.genesis_file and s["exodus"] == d.exodus_file
+    assert s["n_bc"] == len(d.boundary_conditions)
+    for b in mesh["block_ids"]:
+        m, want = s["materials"][str(b)], d.block_material(b)
+        assert (m["model"], m["density"], m["bulk_modulus"], m["shear_modulus"], m["num_state"]) == (
+            want.model, want.density, want.bulk_modulus, want.shear_modulus, 0)
+
+
+def test_parser_errors_like_the_reference(host):
+    ids = (C.c_int * 1)(1)
+    out, err = C.create_string_buffer(4096), C.create_string_buffer(2048)
+    base = "genesis input file: a.g\nexodus output file: a.e\nfinal time: 1.0\nnumber of load steps: 1\noutput fields: displacement\n"
+    rc = host.nsmh_deck_summary((base + "no such key: 1\n").encode(), ids, 1, out, 4096, err, 2048)
+    assert rc != 0 and b"unknown key no such key" in err.value
+    rc = host.nsmh_deck_summary((base + "material parameters: m neohookean density 1 youngs 3\nelement block: block_1 m\n").encode(),
+                                ids, 1, out, 4096, err, 2048)
+    assert rc != 0 and b"Invalid material parameter encountered: 'youngs'" in err.value
+    rc = host.nsmh_deck_summary((base + "material parameters: m plastic density 1 bulk_modulus 2 shear_modulus 3\nelement block: block_1 m\n").encode(),
+                                ids, 1, out, 4096, err, 2048)
+    assert rc != 0 and b"invalid material model name" in err.value
+    rc = host.nsmh_deck_summary("genesis input file: a.g\n".encode(), ids, 1, out, 4096, err, 2048)
+    assert rc != 0 and b"output fields not found" in err.value
+
+
+def test_io_file_name(host):
+    out = C.create_string_buffer(512)
+    for args, want in ((("wave.g", "g", "", 0, 1), "wave.g"), (("wave.g", "g", "", 3, 16), "wave.g.16.03"),
+                       (("wave.e", "e", "out", 0, 1), "wave.out.e"), (("wave.e", "e", "out", 1, 2), "wave.out.e.2.1"),
+                       (("none", "e", "out", 1, 2), "none")):
+        assert host.nsmh_io_file_name(args[0].encode(), args[1].encode(), args[2].encode(), args[3], args[4], out, 512) == 0
+        assert out.value.decode() == want
+
+
+def _mesh_checks(s, mesh):
+    assert s["dim"] == 3 and s["num_nodes"] == len(mesh["x"])
+    assert s["num_elements"] == sum(len(mesh["conn"][b]) for b in mesh["block_ids"])
+    assert s["sum_x"] == float(np.sum(np.cumsum(mesh["x"])[-1:])) or np.isclose(s["sum_x"], mesh["x"].sum(), rtol=1e-13)
+    assert s["node_gid_sum"] == int(np.asarray(mesh["node_gid"], dtype=np.int64).sum())
+    for b in mesh["block_ids"]:
+        c = np.asarray(mesh["conn"][b], dtype=np.int64).ravel()
+        w = (np.arange(len(c)) % 7 + 1)
+        assert s["blocks"][str(b)]["num_elements"] == len(mesh["conn"][b])
+        assert s["blocks"][str(b)]["conn_checksum"] == int((w * c).sum())
+        assert s["blocks"][str(b)]["name"] == "block_%d" % b
+    for sid, nodes in mesh["node_sets"].items():
+        e = s["node_sets"][str(sid)]
+        assert e["size"] == len(nodes) and e["sum"] == int(np.asarray(nodes, dtype=np.int64).sum())
+        assert e["name"] == "nodelist_%d" % sid
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_genesis_reader_on_fixture_meshes_and_pieces(host, case, tmp_path):
+    """The mesh of every fixture (and every decomposed piece) is written as a NetCDF-3 Genesis file and read back
+    by the C++ reader: counts, id maps, connectivity checksums, node-set contents, default names."""
+    from nimblesm_b200.exodus_py import write_genesis
+
+    _deck, mesh, _gold, _ref, pieces = load_golden(case)
+    p = str(tmp_path / "m.g")
+    write_genesis(p, mesh)
+    _mesh_checks(_call_json(host.nsmh_mesh_summary, p.encode()), mesh)
+    for (P, r), piece in list(pieces.items())[:6]:
+        pp = str(tmp_path / ("m.g.%d.%d" % (P, r)))
+        write_genesis(pp, piece)
+        _mesh_checks(_call_json(host.nsmh_mesh_summary, pp.encode()), piece)
+
+
+def test_genesis_reader_on_the_reference_files(host):
+    """The cubit / SEACAS-written files of the reference themselves (only where /root/reference exists)."""
+    base = "/root/reference/test/dynamics"
+    if not os.path.isdir(base):
+        pytest.skip("reference tree not present")
+    from tests.golden.make_golden import read_genesis
+
+    n = 0
+    for d in sorted(os.listdir(base)):
+        if not os.path.isdir(os.path.join(base, d)):
+            continue
+        for fn in sorted(os.listdir(os.path.join(base, d))):
+            if fn.endswith(".g") or ".g." in fn:
+                path = os.path.join(base, d, fn)
+                _mesh_checks(_call_json(host.nsmh_mesh_summary, path.encode()), read_genesis(path))
+                n += 1
+    assert n >= 20
+
+
+def test_exodus_writer_round_trip(host, tmp_path):
+    from nimblesm_b200.exodus_py import read_results, write_genesis
+
+    _deck, mesh, _gold, _ref, _pieces = load_golden("brick_with_fibers")
+    g, e = str(tmp_path / "b.g"), str(tmp_path / "b.out.e")
+    write_genesis(g, mesh)
+    err = C.create_string_buffer(2048)
+    assert host.nsmh_exodus_roundtrip(g.encode(), e.encode(), 3, err, 2048) == 0, err.value
+    r = read_results(e)
+    assert np.array_equal(r["times"], [0.0, 0.25, 0.5])
+    for k, c in enumerate("xyz"):
+        want = np.stack([(s + 1) * np.asarray(mesh[c]) for s in range(3)])
+        assert np.array_equal(r["nod"]["displacement_" + c], want)
+    assert r["block_ids"] == mesh["all_block_ids"]
+    for bi, b in enumerate(mesh["all_block_ids"]):
+        ne = len(mesh["conn"][b])
+        assert np.array_equal(r["elem"][("volume", bi)], np.stack([np.arange(ne) + s for s in range(3)]))
+        assert np.array_equal(r["elem"][("ipt01_stress_xx", bi)], np.stack([10.0 * np.arange(ne) + s for s in range(3)]))
+    assert np.array_equal(r["node_gid"], mesh["node_gid"])
+    # the file is a well-formed Exodus database for scipy's independent NetCDF reader: mesh payload intact
+    from scipy.io import netcdf_file
+
+    f = netcdf_file(e, "r", mmap=False)
+    assert f.variables["coordx"].data.shape == (len(mesh["x"]),) and np.array_equal(f.variables["coordx"].data, mesh["x"])
+    for bi, b in enumerate(mesh["all_block_ids"]):
+        assert np.array_equal(f.variables["connect%d" % (bi + 1)].data - 1, mesh["conn"][b])
+    names = [b"".join(row).split(b"\x00")[0].decode() for row in f.variables["name_elem_var"].data]
+    assert names == sorted(names) == ["ipt01_stress_xx", "volume"]
+    f.close()
+
+
+def test_boundary_condition_tables(host, tmp_path):
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, _gold, _ref, _pieces = load_golden("notched_plate_native_neohookean")
+    g = str(tmp_path / "n.g")
+    write_genesis(g, mesh)
+    cap = 100000
+    n, td = C.c_int(), C.c_int()
+    node, comp, kind = (C.c_int * cap)(), (C.c_int * cap)(), (C.c_int * cap)()
+    val = (C.c_double * cap)()
+    err = C.create_string_buffer(2048)
+    t = 7.0e-7
+    assert host.nsmh_bc_table(g.encode(), deck.encode(), C.c_double(t), cap, C.byref(n), node, comp, kind, val, C.byref(td), err, 2048) == 0, err.value
+    from nimblesm_b200.deck import parse_deck
+
+    d = parse_deck(deck)
+    want_nodes, want_comp, want_kind = [], [], []
+    for bc in d.boundary_conditions:
+        if bc.kind == "initial_velocity":
+            continue
+        ns = mesh["node_sets"][bc.node_set_id]
+        want_nodes += list(ns)
+        want_comp += [bc.coordinate] * len(ns)
+        want_kind += [0 if bc.kind == "prescribed_velocity" else 1] * len(ns)
+    assert n.value == len(want_nodes) and list(node[:n.value]) == want_nodes
+    assert list(comp[:n.value]) == want_comp and list(kind[:n.value]) == want_kind
+    assert td.value == 0  # constants only
+    assert np.array_equal(np.array(val[:n.value]), np.zeros(n.value))
+    # a prescribed displacement that depends on t and x is flagged time dependent and evaluated per entry
+    deck2 = deck + '\nboundary condition: prescribed_displacement nodelist_1 y "0.5*x*cos(t*3.0/2.0e-6)"\n'
+    assert host.nsmh_bc_table(g.encode(), deck2.encode(), C.c_double(t), cap, C.byref(n), node, comp, kind, val, C.byref(td), err, 2048) == 0, err.value
+    ns1 = mesh["node_sets"][1]
+    assert td.value == 1 and n.value == len(want_nodes) + len(ns1)
+    tail_nodes = np.array(node[len(want_nodes):n.value])
+    assert np.array_equal(tail_nodes, ns1) and set(kind[len(want_nodes):n.value]) == {1}
+    want = np.array([0.5 * x * np.cos(t * (3.0 / 2.0e-6)) for x in mesh["x"][ns1]])
+    assert np.allclose(np.array(val[len(want_nodes):n.value]), want, rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("case,P", [("wave_in_bar", 2), ("wave_in_bar", 4), ("brick_with_fibers", 4)])
+def test_vector_communicator_tables_match_python(host, case, P):
+    """VectorCommunicator::Initialize on P rank threads == mesh.shared_node_tables (used by bench.py): for every
+    peer the shared nodes in ascending GLOBAL id order."""
+    from nimblesm_b200.mesh import shared_node_tables
+
+    _deck, _mesh, _gold, _ref, pieces = load_golden(case)
+    parts = [pieces[(P, r)] for r in range(P)]
+    gids = np.concatenate([np.asarray(p["node_gid"], dtype=np.int32) for p in parts])
+    off = np.concatenate([[0], np.cumsum([len(p["node_gid"]) for p in parts])]).astype(np.int32)
+    cap = 1 << 16
+    for r in range(P):
+        npeers = C.c_int()
+        peers, poff, pnodes = (C.c_int * 64)(), (C.c_longlong * 65)(), (C.c_int * cap)()
+        err = C.create_string_buffer(2048)
+        rc = host.nsmh_shared_node_tables(P, gids.ctypes.data_as(C.POINTER(C.c_int)), off.ctypes.data_as(C.POINTER(C.c_int)), r, cap,
+                                          C.byref(npeers), peers, poff, pnodes, err, 2048)
+        assert rc == 0, err.value
+        wp, wo, wn = shared_node_tables(r, [np.asarray(p["node_gid"]) for p in parts], np.asarray(parts[r]["node_gid"]))
+        assert list(peers[:npeers.value]) == list(wp)
+        assert list(poff[:npeers.value + 1]) == list(wo)
+        assert list(pnodes[:poff[npeers.value]]) == list(wn)
