@@ -1,5 +1,5 @@
 #!/bin/bash
-# scripts/build_variants.sh — A/B builds of libnsm_b200.so (CTA size / resident CTAs / division strategy) into
+# scripts/build_variants.sh — A/B builds of libnsm_b200.so (CTA size / resident CTAs / ticket chunk) into
 # nimblesm_b200/lib/variants/; select one at run time with NSM_B200_LIB=<path>.
 set -e
 cd "$(dirname "$0")/../nimblesm_b200/csrc"
@@ -9,11 +9,9 @@ build() { # name, extra flags
      -Xcompiler -fPIC -ccbin /usr/bin/g++ $2 -shared -o ../lib/variants/libnsm_b200_$1.so nsm_b200.cu \
      -Xptxas -v 2> ../lib/variants/ptxas_$1.log &
 }
-
-build t256b1 "-DNSM_ELEM_THREADS=256 -DNSM_ELEM_MIN_BLOCKS=1"
-build t192b2 "-DNSM_ELEM_THREADS=192 -DNSM_ELEM_MIN_BLOCKS=2"
+build chunk1 "-DNSM_TICKET_CHUNK=1"
+build chunk4 "-DNSM_TICKET_CHUNK=4"
+build chunk32 "-DNSM_TICKET_CHUNK=32"
 build t128b4 "-DNSM_ELEM_THREADS=128 -DNSM_ELEM_MIN_BLOCKS=4"
-build t384b1 "-DNSM_ELEM_THREADS=384 -DNSM_ELEM_MIN_BLOCKS=1"
-build t320b1 "-DNSM_ELEM_THREADS=320 -DNSM_ELEM_MIN_BLOCKS=1"
 wait
 for f in ../lib/variants/ptxas_*.log; do echo $f; grep -A2 "element_force_kernelILi1ELb0ELi2E" $f | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores"; done

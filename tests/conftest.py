@@ -23,7 +23,9 @@ def pytest_configure(config):
 def _native_built():
     """Checker libraries (oracle/_ref) and the product library are built once per session if missing."""
     need = [os.path.join(ROOT, "oracle", "_ref", "libhex8_oracle.so"),
-            os.path.join(ROOT, "nimblesm_b200", "lib", "libnsm_b200.so")]
+            os.path.join(ROOT, "nimblesm_b200", "lib", "libnsm_b200.so"),
+            os.path.join(ROOT, "nimblesm_b200", "lib", "libnsm_host_c.so"),
+            os.path.join(ROOT, "nimblesm_b200", "lib", "NimbleSM_b200")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__ as g
 
