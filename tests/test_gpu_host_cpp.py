@@ -99,3 +99,58 @@ def test_driver_errors_like_the_reference(tmp_path):
     assert r.returncode == 1 and "unknown key no such key" in r.stderr
     r = subprocess.run([EXE], cwd=tmp_path, capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "Usage" in r.stderr
+
+
+def _num_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+def _join_pieces(tmp_path, stem, P, pieces, mesh):
+    """epu: per-rank results -> global arrays by global node / element id (shared nodes must agree bit for bit)."""
+    from nimblesm_b200.exodus_py import read_results
+
+    parts = [read_results(str(tmp_path / ("%s.out.e.%d.%d" % (stem, P, r)))) for r in range(P)]
+    out = {"times": parts[0]["times"], "nod": {}, "elem": {}}
+    n_nodes = len(mesh["x"])
+    gid_to_local = {int(g): i for i, g in enumerate(mesh["node_gid"])}
+    for k in parts[0]["nod"]:
+        a = np.full((len(out["times"]), n_nodes), np.nan)
+        for r, pr in enumerate(parts):
+            idx = np.array([gid_to_local[int(g)] for g in pieces[(P, r)]["node_gid"]])
+            prev = a[:, idx]
+            new = pr["nod"][k]
+            seen = ~np.isnan(prev)
+            assert np.array_equal(prev[seen].view(np.int64), new[seen].view(np.int64)), "replicas of a shared node differ: " + k
+            a[:, idx] = new
+        out["nod"][k] = a
+    for bi, b in enumerate(mesh["all_block_ids"]):
+        egid_to_local = {int(g): i for i, g in enumerate(mesh["elem_gid"][b])} if b in mesh["elem_gid"] else {}
+        keys = set(k for pr in parts for k in pr["elem"] if k[1] == bi)
+        for k in keys:
+            a = np.full((len(out["times"]), len(egid_to_local)), np.nan)
+            for r, pr in enumerate(parts):
+                if k in pr["elem"] and b in pieces[(P, r)]["elem_gid"]:
+                    idx = np.array([egid_to_local[int(g)] for g in pieces[(P, r)]["elem_gid"][b]])
+                    a[:, idx] = pr["elem"][k]
+            out["elem"][k] = a
+    return out
+
+
+@pytest.mark.parametrize("case,P", [("wave_in_bar", 2), ("brick_with_fibers", 2), ("wave_in_bar", 4), ("notched_plate_native_neohookean", 4)])
+def test_driver_on_decomposed_meshes(case, P, tmp_path):
+    """The reference's -np2 / -np4 regression runs: one rank (thread + GPU) per Nemesis piece, shared-node forces
+    summed over NVLink peer memory, per-rank outputs joined by global id and compared with the SERIAL gold file and
+    the serial reference snapshots.  Needs P GPUs (gpurun --gpus P)."""
+    if _num_gpus() < P:
+        pytest.skip("needs %d GPUs" % P)
+    import re
+
+    deck, mesh, gold, ref, pieces, _out = _run(tmp_path, case, extra=("--gpus", str(P)), pieces=P)
+    out = re.search(r"exodus output file:\s*(\S+)", deck).group(1)
+    stem = out[:-2] if out.endswith(".e") else out
+    res = _join_pieces(tmp_path, stem, P, pieces, mesh)
+    _check_against_reference(mesh, gold, ref, res)
