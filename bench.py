@@ -169,7 +169,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=400, help="cube edge in elements per GPU (400 -> 64 M elements)")
+    ap.add_argument("--n", "--edge", dest="n", type=int, default=400,
+                    help="cube edge in elements per GPU (400 -> 64 M elements); spell it --edge under torchrun")
     ap.add_argument("--material", default="neohookean", choices=["neohookean", "elastic"])
     ap.add_argument("--assembly", default="atomic", choices=["atomic", "ordered"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -52,6 +52,14 @@ struct ElemArgs
   double        bulk, shear;
   unsigned long long* ticket;  // next unclaimed 4-element group of this launch (zeroed by the host)
   int           zero;        // always 0: keeps ptxas from proving the ticket address warp-uniform (see draw_ticket)
+  // Element schedule of this launch (multi-GPU overlap, nsm_b200_step): kSchedAll walks every group;
+  // kSchedList walks group_list[0 .. n_list) (the groups that touch a node shared with another rank, run first so
+  // that their forces can travel while the rest computes); kSchedSkipFlagged walks every group whose
+  // group_flag byte is 0 (the rest).
+  int                  sched;
+  const unsigned char* group_flag;  // [n_groups rounded up to kTicketChunk], 1 = touches a shared node
+  const int*           group_list;
+  int64_t              n_list;
   int*          flags;       // [0] bit 0: non-positive Jacobian seen; [1]: integration points redone in IEEE mode
 };
 
@@ -115,6 +123,9 @@ accumulate_one(const ShapeAtPoint& sh, const double* sC, int ew, double (&a)[3][
   load_node<J>(sC, ew, x0, x1, x2);
   grad_accumulate<J>(sh, x0, x1, x2, a);
 }
+
+enum { kSchedAll = 0, kSchedList = 1, kSchedSkipFlagged = 2 };
+static_assert(kTicketChunk == 8, "the skip-flag mask packs one chunk of 8 group flags into 64 bits");
 
 // MAT: nsm_material_kind; ORDERED: store element forces instead of atomics; MODE bit0: store F/sigma,
 // bit1: read cached b^-1 (filled once by binv_cache_kernel).
@@ -309,20 +320,29 @@ element_force_kernel(const ElemArgs p)
   // is entered and first read kTicketChunk passes later, so the atomic's round trip (which queues behind every
   // other warp's on the one counter) never shows; groups are looked up two passes ahead (connectivity load).
   unsigned long long* const ticket_at = ticket_address(p.ticket, lane, p.zero);
-  int64_t chunk_base = claim_group(ticket_at, lane) * kTicketChunk;  // chunk that holds the group two passes ahead
-  int     chunk_off  = 0;
-  unsigned long long ticket = 0;                                     // lane 0: the chunk after that one
+  const int64_t n_tickets  = p.sched == kSchedList ? p.n_list : n_groups;  // positions the counter hands out
+  int64_t       chunk_base = claim_group(ticket_at, lane) * kTicketChunk;  // chunk that holds the position two passes ahead
+  int           chunk_off  = -1;
+  unsigned long long ticket = 0;                                           // lane 0: the chunk after that one
   if (lane == 0) ticket = atomicAdd(ticket_at, 1ULL);
+  unsigned long long skip_mask = 0;  // kSchedSkipFlagged: the 8 flag bytes of the current chunk
+  if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets) skip_mask = *(const unsigned long long*)(p.group_flag + chunk_base);
   auto next_group = [&]() -> int64_t {
-    if (++chunk_off == kTicketChunk) {
-      chunk_base = (int64_t)__shfl_sync(0xffffffffu, ticket, 0) * kTicketChunk;
-      chunk_off  = 0;
-      if (lane == 0 && chunk_base < n_groups) ticket = atomicAdd(ticket_at, 1ULL);
+    for (;;) {
+      if (++chunk_off == kTicketChunk) {
+        chunk_base = (int64_t)__shfl_sync(0xffffffffu, ticket, 0) * kTicketChunk;
+        chunk_off  = 0;
+        if (lane == 0 && chunk_base < n_tickets) ticket = atomicAdd(ticket_at, 1ULL);
+        if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets)
+          skip_mask = *(const unsigned long long*)(p.group_flag + chunk_base);
+      }
+      const int64_t pos = chunk_base + chunk_off;
+      if (pos >= n_tickets) return n_groups;
+      if (p.sched == kSchedSkipFlagged && ((skip_mask >> (8 * chunk_off)) & 0xffULL)) continue;
+      return p.sched == kSchedList ? (int64_t)__ldg(p.group_list + pos) : pos;
     }
-    const int64_t gg = chunk_base + chunk_off;
-    return gg < n_groups ? gg : n_groups;
   };
-  int64_t g = chunk_base < n_groups ? chunk_base : n_groups, g_next = next_group();
+  int64_t g = next_group(), g_next = g < n_groups ? next_group() : n_groups;
   if (g >= n_groups) return;
   int node      = group_node(p, g, ew, q);
   int node_next = (g_next < n_groups) ? group_node(p, g_next, ew, q) : -1;
@@ -420,6 +440,46 @@ element_force_kernel(const ElemArgs p)
     g_next             = g_nn;
     stage ^= 1;
   }
+}
+
+// Boundary-first schedule: flag the groups that touch a node shared with another rank and list them.
+__global__ void __launch_bounds__(256)
+mark_shared_nodes_kernel(int64_t n_shared, const int* __restrict__ shared_node, unsigned char* node_flag)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_shared) node_flag[shared_node[i]] = 1;
+}
+
+__global__ void __launch_bounds__(256)
+flag_groups_kernel(int64_t n_elem, const int* __restrict__ conn, const unsigned char* __restrict__ node_flag,
+                   unsigned char* group_flag, int* group_list, unsigned long long* n_list)
+{
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (n_elem + kElemsPerWarp - 1) / kElemsPerWarp) return;
+  bool touched = false;
+  for (int k = 0; k < kElemsPerWarp * 8; ++k) {
+    const int64_t s = g * kElemsPerWarp * 8 + k;
+    if (s < n_elem * 8 && node_flag[conn[s]]) touched = true;
+  }
+  group_flag[g] = touched ? 1 : 0;
+  if (touched) group_list[atomicAdd(n_list, 1ULL)] = (int)g;
+}
+
+// ORDERED assembly with a peer exchange: nodal sums of the shared nodes only (the boundary groups are done)
+__global__ void __launch_bounds__(256)
+gather_shared_nodes_kernel(int64_t n_shared, const int* __restrict__ shared_node, const double* __restrict__ ef,
+                           const int64_t* __restrict__ adj_off, const uint32_t* __restrict__ adj_slot, double* f0, double* f1,
+                           double* f2)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_shared) return;
+  const int nd = shared_node[i];
+  double    a = 0.0, b = 0.0, c = 0.0;
+  for (int64_t k = adj_off[nd]; k < adj_off[nd + 1]; ++k) {
+    const double* s = ef + (int64_t)adj_slot[k] * 3;
+    a += s[0], b += s[1], c += s[2];
+  }
+  f0[nd] = a, f1[nd] = b, f2[nd] = c;
 }
 
 // Inverse reference Jacobians b^-1 of every Gauss point, computed once (NSM_FLAG_CACHE_REF_JACOBIAN):

@@ -34,6 +34,10 @@ struct Block
   int*             conn      = nullptr;
   int64_t          elem_base = 0;  // first global element (ascending block id order)
   int64_t          group_base = 0; // first 4-element group of the block in the b^-1 cache
+  // boundary-first schedule (peer exchange attached): groups touching a node shared with another rank
+  unsigned char*   group_flag = nullptr;
+  int*             group_list = nullptr;
+  int64_t          n_list     = 0;
 };
 
 thread_local std::string g_create_error;
@@ -96,6 +100,10 @@ struct nsm_b200_ctx
   int64_t                  prof_steps   = 0;
 
   PeerExchange comm;
+  // overlap of the shared-node exchange with the interior elements (nsm_b200_step)
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t  ev_boundary = nullptr, ev_packed = nullptr;
+  bool         overlap     = false;
 };
 
 namespace {
@@ -184,9 +192,13 @@ node_args(nsm_b200_ctx* c, int64_t bc_row = 0)
 }
 
 ElemArgs
-elem_args(nsm_b200_ctx* c, const Block& b)
+elem_args(nsm_b200_ctx* c, const Block& b, int sched = kSchedAll)
 {
   ElemArgs p{};
+  p.sched      = sched;
+  p.group_flag = b.group_flag;
+  p.group_list = b.group_list;
+  p.n_list     = b.n_list;
   p.n_elem = b.n_elem;
   p.conn   = b.conn;
   for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.f[i] = c->f[i];
@@ -213,19 +225,25 @@ template <int MAT, bool ORDERED, int MODE>
 cudaError_t
 launch_element(const ElemArgs& p, cudaStream_t s)
 {
-  static int  wave = 0;
-  auto        k    = element_force_kernel<MAT, ORDERED, MODE>;
+  // function attributes and occupancy are per device: a process may drive several GPUs (one thread each)
+  static int wave_of_device[64] = {0};
+  auto       k                  = element_force_kernel<MAT, ORDERED, MODE>;
+  int        dev                = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  int wave = wave_of_device[dev];
   if (wave == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kElemSmemBytes);
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kElemSmemBytes);
     if (e != cudaSuccess) return e;
-    int dev = 0, sms = 0, per_sm = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    int sms = 0, per_sm = 0;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kElemThreads, kElemSmemBytes)) != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    wave = sms * per_sm;
+    wave = wave_of_device[dev] = sms * per_sm;
   }
-  const int64_t need = (groups_of(p.n_elem) + kElemWarps - 1) / kElemWarps;
+  const int64_t positions = p.sched == kSchedList ? p.n_list : groups_of(p.n_elem);
+  const int64_t need      = std::max<int64_t>((positions + kElemWarps * kTicketChunk - 1) / (kElemWarps * kTicketChunk), 1);
   k<<<(unsigned)std::min<int64_t>(need, wave), kElemThreads, kElemSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
@@ -267,7 +285,7 @@ ensure_ipt(nsm_b200_ctx* c)
 
 // element kernels of all blocks, ascending block id (src/nimble_model_data.cc:636-659)
 int
-enqueue_element_kernels(nsm_b200_ctx* c, bool store_ipt)
+enqueue_element_kernels(nsm_b200_ctx* c, bool store_ipt, int sched = kSchedAll)
 {
   const bool ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
   int        mode    = 0;
@@ -279,9 +297,9 @@ enqueue_element_kernels(nsm_b200_ctx* c, bool store_ipt)
   if (c->binv) mode |= kModeReadBinv;
   for (auto& kv : c->blocks) {
     const Block& b = kv.second;
-    if (b.n_elem == 0) continue;
+    if (b.n_elem == 0 || (sched == kSchedList && b.n_list == 0)) continue;
     NSM_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned long long), c->stream));
-    NSM_CUDA(c, launch_element_any(elem_args(c, b), b.material, ordered, mode, c->stream));
+    NSM_CUDA(c, launch_element_any(elem_args(c, b, sched), b.material, ordered, mode, c->stream));
     c->launches++;
   }
   return NSM_OK;
@@ -486,7 +504,10 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   }
   fr(c->mass), fr(c->staging), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
   fr(c->bc_kind), fr(c->bc_value), fr(c->d_flags), fr(c->d_min_dt), fr(c->d_ticket);
-  for (auto& kv : c->blocks) fr(kv.second.conn);
+  for (auto& kv : c->blocks) fr(kv.second.conn), fr(kv.second.group_flag), fr(kv.second.group_list);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
+  if (c->ev_packed) cudaEventDestroy(c->ev_packed);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_start);
   cudaEventDestroy(c->ev_stop);
@@ -926,17 +947,39 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
       c->launches++;
     }
     if (c->profiling) prof_event(c);
-    int rc = enqueue_element_kernels(c, store);
-    if (rc) return rc;
+    int rc;
+    if (c->overlap) {
+      // boundary-first: the groups that touch shared nodes run first, their nodal forces travel to the peers on
+      // the exchange stream while the interior groups compute on this one
+      if ((rc = enqueue_element_kernels(c, store, kSchedList))) return rc;
+      if (ordered && c->comm.num_shared_nodes() > 0) {
+        const int64_t ns = c->comm.num_shared_nodes();
+        gather_shared_nodes_kernel<<<grid_for(ns, 256), 256, 0, c->stream>>>(ns, c->comm.shared_nodes_device(), c->ef, c->adj_off,
+                                                                             c->adj_slot, c->f[0], c->f[1], c->f[2]);
+        c->launches++;
+      }
+      NSM_CUDA(c, cudaEventRecord(c->ev_boundary, c->stream));
+      NSM_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_boundary, 0));
+      if (c->comm.pack(c->comm_stream, c->f, 3, &c->launches)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+      NSM_CUDA(c, cudaEventRecord(c->ev_packed, c->comm_stream));
+      if ((rc = enqueue_element_kernels(c, store, kSchedSkipFlagged))) return rc;
+    } else {
+      if ((rc = enqueue_element_kernels(c, store))) return rc;
+    }
     if (c->profiling) prof_event(c);
     if (n > 0) {
       const NodeArgs na = node_args(c, s + 1);  // boundary-condition magnitudes of the step the fused pass opens
       if (c->comm.active()) {
+        if (c->overlap) NSM_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_packed, 0));  // the pack has read f before it changes
         if (ordered) {
           node_correct_kernel<true, false><<<ngrid, 256, 0, c->stream>>>(na, 0.0, 0);
           c->launches++;
         }
-        if (c->comm.reduce(c->stream, c->f, 3, &c->launches)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+        if (c->overlap) {
+          if (c->comm.finish(c->stream, c->f, 3, &c->launches)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+        } else if (c->comm.reduce(c->stream, c->f, 3, &c->launches)) {
+          return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+        }
       }
       if (s + 1 < n_steps) {
         const double dt_next  = (t + dt_user) - t;
@@ -1071,7 +1114,43 @@ nsm_b200_comm_ready(nsm_b200_ctx* c)
   NSM_REQUIRE(c, c && c->finalized, "comm_ready: context not finalized");
   NSM_CUDA(c, cudaSetDevice(c->device));
   if (c->comm.ready(c->stream)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  // boundary-first element schedule: flag and list the groups that touch a shared node
+  const int64_t ns = c->comm.num_shared_nodes();
+  if (ns > 0 && c->n_nodes > 0) {
+    unsigned char*      node_flag = nullptr;
+    unsigned long long* d_count   = nullptr;
+    NSM_CUDA(c, cudaMalloc((void**)&node_flag, (size_t)c->n_nodes));
+    NSM_CUDA(c, cudaMalloc((void**)&d_count, sizeof(unsigned long long)));
+    NSM_CUDA(c, cudaMemsetAsync(node_flag, 0, (size_t)c->n_nodes, c->stream));
+    mark_shared_nodes_kernel<<<grid_for(ns, 256), 256, 0, c->stream>>>(ns, c->comm.shared_nodes_device(), node_flag);
+    c->launches++;
+    for (auto& kv : c->blocks) {
+      Block& b = kv.second;
+      if (b.n_elem == 0) continue;
+      const int64_t ng     = groups_of(b.n_elem);
+      const int64_t padded = (ng + kTicketChunk - 1) / kTicketChunk * kTicketChunk;
+      int           rc;
+      if ((rc = dev_alloc(c, &b.group_flag, padded))) return rc;
+      if ((rc = dev_alloc(c, &b.group_list, ng))) return rc;
+      NSM_CUDA(c, cudaMemsetAsync(b.group_flag, 0, (size_t)padded, c->stream));
+      NSM_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), c->stream));
+      flag_groups_kernel<<<grid_for(ng, 256), 256, 0, c->stream>>>(b.n_elem, b.conn, node_flag, b.group_flag, b.group_list, d_count);
+      c->launches++;
+      unsigned long long h = 0;
+      NSM_CUDA(c, cudaMemcpyAsync(&h, d_count, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+      b.n_list = (int64_t)h;
+    }
+    NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(node_flag);
+    cudaFree(d_count);
+    NSM_CUDA(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    NSM_CUDA(c, cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
+    NSM_CUDA(c, cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    c->overlap = true;
+  }
   return NSM_OK;
+
 }
 
 // ---- measurement ------------------------------------------------------------------------------------

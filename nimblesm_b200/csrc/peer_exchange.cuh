@@ -273,8 +273,11 @@ class PeerExchange
   }
 
   // f[c][node] <- sum over holders, for every shared node.  All ranks must call in the same order.
+  // Two halves so that the caller can put independent work between them (interior elements):
+  //   pack    reads this rank's partial values of the shared nodes and stores them into the peers' buffers
+  //   finish  waits for every peer's values of the same call and forms the rank-ordered sums in place
   int
-  reduce(cudaStream_t stream, double* const* f, int ncomp, int64_t* launches)
+  pack(cudaStream_t stream, double* const* f, int ncomp, int64_t* launches)
   {
     if (!ready_) return set_err("reduce before comm_ready");
     if (peers_.empty()) return 0;
@@ -295,6 +298,17 @@ class PeerExchange
     p.done_counter = d_counter_;
     const unsigned grid = (unsigned)std::max<int64_t>((total_ + 255) / 256, 1);
     comm_pack_kernel<<<grid, 256, 0, stream>>>(p);
+    if (launches) *launches += 1;
+    if (cudaGetLastError() != cudaSuccess) return set_err("peer exchange kernel launch failed");
+    return 0;
+  }
+
+  int
+  finish(cudaStream_t stream, double* const* f, int ncomp, int64_t* launches)
+  {
+    if (!ready_) return set_err("reduce before comm_ready");
+    if (peers_.empty()) return 0;
+    const int parity = (int)(seq_ & 1);
     comm_wait_kernel<<<1, 32, 0, stream>>>((const volatile unsigned long long*)buf_, d_peer_ranks_, (int)peers_.size(),
                                            seq_, timeout_ns_, d_err_);
     UnpackArgs u{};
@@ -303,9 +317,28 @@ class PeerExchange
              (int64_t)parity * std::max<int64_t>(total_, 1) * kCommComps;
     for (int c = 0; c < 3; ++c) u.f[c] = c < ncomp ? f[c] : nullptr;
     if (n_shared_ > 0) comm_unpack_kernel<<<(unsigned)((n_shared_ + 255) / 256), 256, 0, stream>>>(u);
-    if (launches) *launches += 3;
+    if (launches) *launches += 2;
     if (cudaGetLastError() != cudaSuccess) return set_err("peer exchange kernel launch failed");
     return 0;
+  }
+
+  int
+  reduce(cudaStream_t stream, double* const* f, int ncomp, int64_t* launches)
+  {
+    if (pack(stream, f, ncomp, launches)) return 1;
+    return finish(stream, f, ncomp, launches);
+  }
+
+  // shared nodes of this rank (unique local ids, device / host) for the boundary-first element schedule
+  const int*
+  shared_nodes_device() const
+  {
+    return d_node_;
+  }
+  int64_t
+  num_shared_nodes() const
+  {
+    return n_shared_;
   }
 
   // non-zero when a wait timed out (checked by the caller together with the Jacobian flag)
