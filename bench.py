@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RHO, BULK, SHEAR = 7.8, 1.6e12, 0.8e12  # test/dynamics/notched_plate_native_neohookean deck constants
+MATERIAL_2 = (1.333e12, 0.1379e12, 5.0)  # bulk, shear, density of test/dynamics/brick_with_fibers material_2
 # executed DADD+DMUL+DFMA+DSETP lane-instructions per element, from the ncu source page of the profiled kernel
 # (scripts/ncu_sass_mix.py on profiles/r01g_*): [flags & 2 == 0 (b^-1 recomputed), flags & 2 (b^-1 cached)]
 DP_INSTR_PER_ELEMENT = {"neohookean": (10730, 9072), "elastic": (6080, 4424)}
@@ -157,9 +158,12 @@ def run_reference(args):
 
 
 def workload_config(args, n_edge):
+    two = getattr(args, "workload", "cube") == "twoblock"
+    mat = "elastic block 1 (x < mid) + neohookean block 2, prescribed velocity on both x faces" if two else args.material
     return {"workload": "synthetic structured hex8 cube %d^3 = %d elements per GPU, %s, explicit central difference"
-                        % (n_edge, n_edge ** 3, args.material),
-            "elements_per_gpu": n_edge ** 3, "material": args.material, "assembly": args.assembly,
+                        % (n_edge, n_edge ** 3, mat),
+            "elements_per_gpu": n_edge ** 3, "material": "elastic+neohookean" if two else args.material,
+            "assembly": args.assembly,
             "l2_policy": "inputs larger than L2 (per-step traffic >> 126 MB)" if n_edge ** 3 * 234 > 4e8
                          else "small workload: L2-resident"}
 
@@ -172,6 +176,10 @@ def main():
     ap.add_argument("--n", "--edge", dest="n", type=int, default=400,
                     help="cube edge in elements per GPU (400 -> 64 M elements); spell it --edge under torchrun")
     ap.add_argument("--material", default="neohookean", choices=["neohookean", "elastic"])
+    ap.add_argument("--workload", default="cube", choices=["cube", "twoblock"],
+                    help="twoblock: BASELINE.json configs[4], every brick split at its mid-x plane into an elastic "
+                         "block 1 and a neohookean block 2 (brick_with_fibers material_2 constants), prescribed "
+                         "velocity on both global x faces")
     ap.add_argument("--assembly", default="atomic", choices=["atomic", "ordered"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--flags", type=int, default=2, help="nsm_b200_finalize flags (2 = cache the reference Jacobians)")
@@ -204,13 +212,16 @@ def main():
 
     n = args.n
     rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
-    mesh = weak_brick(n, (px, py, pz), (rx, ry, rz))
-    conn = mesh["conn"][1]
-    n_elem, n_nodes = len(conn), len(mesh["x"])
+    mesh = weak_brick(n, (px, py, pz), (rx, ry, rz), args.workload == "twoblock")
+    n_elem, n_nodes = sum(len(cn) for cn in mesh["conn"].values()), len(mesh["x"])
 
     c = capi.Context(local_rank)
     c.set_nodes(mesh["x"], mesh["y"], mesh["z"])
-    c.add_block(1, conn, args.material, BULK, SHEAR, RHO)
+    if args.workload == "twoblock":
+        c.add_block(1, mesh["conn"][1], "elastic", BULK, SHEAR, RHO)
+        c.add_block(2, mesh["conn"][2], "neohookean", *MATERIAL_2)
+    else:
+        c.add_block(1, mesh["conn"][1], args.material, BULK, SHEAR, RHO)
     c.finalize(capi.ASSEMBLY_ORDERED if args.assembly == "ordered" else capi.ASSEMBLY_ATOMIC, args.flags)
     if world > 1:
         import torch
@@ -239,10 +250,12 @@ def main():
     c.upload("velocity", v0)
     # prescribed_velocity 0 on the x = 0 face
     face = mesh["node_sets"][2]
-    if len(face):
-        c.set_bc_table(np.repeat(face, 3), np.tile(np.arange(3, dtype=np.int32), len(face)),
-                       np.zeros(3 * len(face), np.int32))
-        c.set_bc_values(np.zeros(3 * len(face)))
+    far = mesh["node_sets"][3] if args.workload == "twoblock" else face[:0]  # prescribed_velocity x 1000 on x = L
+    if len(face) + len(far):
+        nodes = np.concatenate([np.repeat(face, 3), far]).astype(np.int32)
+        comps = np.concatenate([np.tile(np.arange(3, dtype=np.int32), len(face)), np.zeros(len(far), np.int32)])
+        c.set_bc_table(nodes, comps, np.zeros(len(nodes), np.int32))
+        c.set_bc_values(np.concatenate([np.zeros(3 * len(face)), np.full(len(far), 1000.0)]))
 
     def barrier():
         c.sync()
@@ -329,10 +342,14 @@ def main():
     step_bytes = 32.0 + 200.0 * r  # + node kernel: f 24, m 8, v 24, u 24 read, v 24, u 24 write (SURVEY §8d B_min)
     ach = elem_bytes * n_elem / (elem_ms * 1e-3) / 1e9 if elem_ms > 0 else None
     dadd, dfma = c.fp64_peak()
-    dp = DP_INSTR_PER_ELEMENT[args.material][1 if args.flags & 2 else 0]
+    fi = 1 if args.flags & 2 else 0
+    if args.workload == "twoblock":  # the two blocks' element kernels run back to back; figures are per-element means
+        dp = 0.5 * (DP_INSTR_PER_ELEMENT["elastic"][fi] + DP_INSTR_PER_ELEMENT["neohookean"][fi])
+    else:
+        dp = DP_INSTR_PER_ELEMENT[args.material][fi]
     roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": (ach / peaks["hbm_gbs"]) if ach else None,
-            "traffic": DRAM_TRAFFIC_PER_ELEMENT[args.material][1 if args.flags & 2 else 0] * n_elem,
+            "traffic": DRAM_TRAFFIC_PER_ELEMENT[args.material][fi] * n_elem,
             "traffic_source": "ncu --set full capture of the same kernel on a 200^3 cube (profiles/), scaled per element; "
                               "flags & 2 adds the cached inverse reference Jacobians (576 B/element) to the 105 B/element "
                               "of algorithmic traffic",
@@ -368,8 +385,9 @@ def main():
         dist.destroy_process_group()
 
 
-def weak_brick(n, grid, pos):
-    """EDGE^3-element brick at grid position `pos` of a (n*px, n*py, n*pz) block with spacing 1/(n*px)."""
+def weak_brick(n, grid, pos, twoblock=False):
+    """EDGE^3-element brick at grid position `pos` of a (n*px, n*py, n*pz) block with spacing 1/(n*px).
+    twoblock: elements with local i < n/2 form block 1, the rest block 2 (every rank holds both materials)."""
     px, py, pz = grid
     rx, ry, rz = pos
     N = (n * px, n * py, n * pz)
@@ -388,9 +406,15 @@ def weak_brick(n, grid, pos):
 
     for c_, (di, dj, dk) in enumerate(HEX_CORNERS):
         conn[:, c_] = (ei + di) + nn * ((ej + dj) + nn * (ek + dk))
-    mesh["conn"][1] = conn
+    if twoblock:
+        mesh["block_ids"] = [1, 2]
+        mesh["conn"][1] = np.ascontiguousarray(conn[ei < n // 2])
+        mesh["conn"][2] = np.ascontiguousarray(conn[ei >= n // 2])
+    else:
+        mesh["conn"][1] = conn
     allnodes = np.arange(nn ** 3, dtype=np.int32)
     mesh["node_sets"][2] = allnodes[gi == 0]
+    mesh["node_sets"][3] = allnodes[gi == N[0]]
     surf = np.zeros(nn ** 3, dtype=bool)
     for loc, r_, p_ in ((i, rx, px), (j, ry, py), (k, rz, pz)):
         if r_ > 0:
