@@ -37,7 +37,10 @@ constexpr int kStageDoubles  = 2 * kCoordDoubles;    // X and u of one group, fi
 constexpr int kShareStride   = 33;                   // odd: the 8x8 transpose is bank-conflict free
 constexpr int kShareDoubles  = 24 * kShareStride;
 constexpr int kBinvGroupDoubles = 9 * 32;            // cached b^-1 of one group: [9][32 lanes]
-constexpr int kWarpSmemDoubles = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDoubles + kBinvGroupDoubles;  // stages, K, C, shares, b^-1
+constexpr int kWarpSmemBase   = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDoubles;  // stages, K, C, shares (+ staged b^-1)
+#ifndef NSM_BINV_STAGE
+#define NSM_BINV_STAGE 1
+#endif
 
 struct ElemArgs
 {
@@ -50,16 +53,18 @@ struct ElemArgs
   double*       ipt;         // [n_elem][8][15] or nullptr
   double*       binv_cache;  // [n_groups][9][32] or nullptr, already offset to the block
   double        bulk, shear;
-  unsigned long long* ticket;  // next unclaimed 4-element group of this launch (zeroed by the host)
+  unsigned*     ticket;      // next unclaimed chunk of 4-element groups of this launch (zeroed by the host)
   int           zero;        // always 0: keeps ptxas from proving the ticket address warp-uniform (see draw_ticket)
   // Element schedule of this launch (multi-GPU overlap, nsm_b200_step): kSchedAll walks every group;
   // kSchedList walks group_list[0 .. n_list) (the groups that touch a node shared with another rank, run first so
-  // that their forces can travel while the rest computes); kSchedSkipFlagged walks every group whose
-  // group_flag byte is 0 (the rest).
+  // that their forces can travel while the rest computes); kSchedSkipFlagged walks every group whose bit in
+  // chunk_mask is 0 (the rest).  Group indices are 32-bit (a block holds < 2^33 elements): the loop-carried state
+  // of the persistent warp must stay in registers (profiles/r01m: a 20-byte spill of it cost a local-memory
+  // round trip through L2 per pass, 6 % of the warp's time).
   int                  sched;
-  const unsigned char* group_flag;  // [n_groups rounded up to kTicketChunk], 1 = touches a shared node
+  const unsigned char* chunk_mask;  // [chunks of kTicketChunk groups] bit i: group chunk*8+i touches a shared node
   const int*           group_list;
-  int64_t              n_list;
+  int                  n_list;
   int*          flags;       // [0] bit 0: non-positive Jacobian seen; [1]: integration points redone in IEEE mode
 };
 
@@ -125,7 +130,7 @@ accumulate_one(const ShapeAtPoint& sh, const double* sC, int ew, double (&a)[3][
 }
 
 enum { kSchedAll = 0, kSchedList = 1, kSchedSkipFlagged = 2 };
-static_assert(kTicketChunk == 8, "the skip-flag mask packs one chunk of 8 group flags into 64 bits");
+static_assert(kTicketChunk == 8, "the skip mask holds the flag bits of one chunk of 8 groups in a byte");
 
 // MAT: nsm_material_kind; ORDERED: store element forces instead of atomics; MODE bit0: store F/sigma,
 // bit1: read cached b^-1 (filled once by binv_cache_kernel).
@@ -138,8 +143,15 @@ enum { kModeStoreIpt = 1, kModeReadBinv = 2 };
 template <int MAT, int MODE>
 struct BinvStaged
 {
-  static constexpr bool value = (MODE & kModeReadBinv) && MAT == 1;
+  static constexpr bool value = NSM_BINV_STAGE && (MODE & kModeReadBinv) && MAT == 1;
 };
+
+template <int MAT, int MODE>
+__host__ __device__ constexpr int
+warp_smem_doubles()
+{
+  return kWarpSmemBase + (BinvStaged<MAT, MODE>::value ? kBinvGroupDoubles : 0);
+}
 
 template <int N>
 __device__ __forceinline__ void
@@ -245,27 +257,27 @@ integration_point(const ShapeAtPoint& sh, const double* sX, const double* sK, co
 // warp-uniform address into its warp-aggregated form, whose shuffle waits for the L2 round trip on the spot
 // (profiles/r01f: 0.66 long-scoreboard stalls per issue); `lane * zero` (a kernel argument that is always 0)
 // hides the uniformity, so a plain ATOMG is issued and its result is not touched until the caller needs it.
-__device__ __forceinline__ unsigned long long*
-ticket_address(unsigned long long* ticket, int lane, int zero)
+__device__ __forceinline__ unsigned*
+ticket_address(unsigned* ticket, int lane, int zero)
 {
   int opaque = lane;
   asm volatile("" : "+r"(opaque));  // the compiler must not fold `lane` to 0 under `if (lane == 0)`
   return ticket + opaque * zero;
 }
 
-__device__ __forceinline__ int64_t
-claim_group(unsigned long long* address, int lane)
+__device__ __forceinline__ int
+claim_group(unsigned* address, int lane)
 {
-  unsigned long long t = 0;
-  if (lane == 0) t = atomicAdd(address, 1ULL);
-  return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+  unsigned t = 0;
+  if (lane == 0) t = atomicAdd(address, 1u);
+  return (int)__shfl_sync(0xffffffffu, t, 0);
 }
 
 // Node id of this lane's (element, local node) in group g, or -1 beyond the block's last element.
 __device__ __forceinline__ int
-group_node(const ElemArgs& p, int64_t g, int ew, int q)
+group_node(const ElemArgs& p, int g, int ew, int q)
 {
-  const int64_t e = g * kElemsPerWarp + ew;
+  const int64_t e = (int64_t)g * kElemsPerWarp + ew;
   return e < p.n_elem ? __ldg(p.conn + e * 8 + q) : -1;
 }
 
@@ -295,8 +307,13 @@ stage_gather(const ElemArgs& p, double* st, int node, int q, int ew)
 // Persistent: every warp walks the block's groups with the grid-wide warp stride.  While group g is computed
 // (FP64-pipe bound, ~10 k DP lane-ops per element) the gather of group g+W is in flight (cp.async, double
 // buffered), the connectivity of group g+2W is being loaded and the cached b^-1 of group g+W is pulled into L2.
+#ifdef NSM_ELEM_MAXREG  // A/B builds: an explicit register cap instead of the one __launch_bounds__ derives
+#define NSM_ELEM_BOUNDS __maxnreg__(NSM_ELEM_MAXREG)
+#else
+#define NSM_ELEM_BOUNDS __launch_bounds__(kElemThreads, NSM_ELEM_MIN_BLOCKS)
+#endif
 template <int MAT, bool ORDERED, int MODE>
-__global__ void __launch_bounds__(kElemThreads, NSM_ELEM_MIN_BLOCKS)
+__global__ void NSM_ELEM_BOUNDS
 element_force_kernel(const ElemArgs p)
 {
   extern __shared__ double smem[];
@@ -304,12 +321,12 @@ element_force_kernel(const ElemArgs p)
   const int     warp = threadIdx.x >> 5;
   const int     q    = lane & 7;   // Gauss point (compute) == local node (gather / assemble)
   const int     ew   = lane >> 3;  // element within the group
-  double*       wsm  = smem + warp * kWarpSmemDoubles;
+  double*       wsm  = smem + warp * warp_smem_doubles<MAT, MODE>();
   double*       sK    = wsm + 2 * kStageDoubles;  // ref + ((ref + disp) - ref): F-path coordinates
   double*       sC    = sK + kCoordDoubles;         // ref + disp: force-path coordinates
   double*       share = sC + kCoordDoubles;         // [24][kShareStride] nodal-force shares of the 32 points
   double*       sB    = share + kShareDoubles + lane;  // [9][32] staged b^-1: this lane's column
-  const int64_t n_groups = (p.n_elem + kElemsPerWarp - 1) / kElemsPerWarp;
+  const int     n_groups = (int)((p.n_elem + kElemsPerWarp - 1) / kElemsPerWarp);
 
   ShapeAtPoint sh;
   sh.init(q);
@@ -319,30 +336,29 @@ element_force_kernel(const ElemArgs p)
   // (profiles/r01e: 14 of 16 warps active on average).  The next chunk's ticket is drawn when the current chunk
   // is entered and first read kTicketChunk passes later, so the atomic's round trip (which queues behind every
   // other warp's on the one counter) never shows; groups are looked up two passes ahead (connectivity load).
-  unsigned long long* const ticket_at = ticket_address(p.ticket, lane, p.zero);
-  const int64_t n_tickets  = p.sched == kSchedList ? p.n_list : n_groups;  // positions the counter hands out
-  int64_t       chunk_base = claim_group(ticket_at, lane) * kTicketChunk;  // chunk that holds the position two passes ahead
-  int           chunk_off  = -1;
-  unsigned long long ticket = 0;                                           // lane 0: the chunk after that one
-  if (lane == 0) ticket = atomicAdd(ticket_at, 1ULL);
-  unsigned long long skip_mask = 0;  // kSchedSkipFlagged: the 8 flag bytes of the current chunk
-  if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets) skip_mask = *(const unsigned long long*)(p.group_flag + chunk_base);
-  auto next_group = [&]() -> int64_t {
+  unsigned* const ticket_at = ticket_address(p.ticket, lane, p.zero);
+  const int n_tickets  = p.sched == kSchedList ? p.n_list : n_groups;  // positions the counter hands out
+  int       chunk_base = claim_group(ticket_at, lane) * kTicketChunk;  // chunk that holds the position two passes ahead
+  int       chunk_off  = -1;
+  unsigned  ticket     = 0;                                            // lane 0: the chunk after that one
+  if (lane == 0) ticket = atomicAdd(ticket_at, 1u);
+  unsigned skip_mask = 0;  // kSchedSkipFlagged: the 8 flag bits of the current chunk
+  if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets) skip_mask = __ldg(p.chunk_mask + chunk_base / kTicketChunk);
+  auto next_group = [&]() -> int {
     for (;;) {
       if (++chunk_off == kTicketChunk) {
-        chunk_base = (int64_t)__shfl_sync(0xffffffffu, ticket, 0) * kTicketChunk;
+        chunk_base = (int)__shfl_sync(0xffffffffu, ticket, 0) * kTicketChunk;
         chunk_off  = 0;
-        if (lane == 0 && chunk_base < n_tickets) ticket = atomicAdd(ticket_at, 1ULL);
-        if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets)
-          skip_mask = *(const unsigned long long*)(p.group_flag + chunk_base);
+        if (lane == 0 && chunk_base < n_tickets) ticket = atomicAdd(ticket_at, 1u);
+        if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets) skip_mask = __ldg(p.chunk_mask + chunk_base / kTicketChunk);
       }
-      const int64_t pos = chunk_base + chunk_off;
+      const int pos = chunk_base + chunk_off;
       if (pos >= n_tickets) return n_groups;
-      if (p.sched == kSchedSkipFlagged && ((skip_mask >> (8 * chunk_off)) & 0xffULL)) continue;
-      return p.sched == kSchedList ? (int64_t)__ldg(p.group_list + pos) : pos;
+      if (p.sched == kSchedSkipFlagged && ((skip_mask >> chunk_off) & 1u)) continue;
+      return p.sched == kSchedList ? __ldg(p.group_list + pos) : pos;
     }
   };
-  int64_t g = next_group(), g_next = g < n_groups ? next_group() : n_groups;
+  int g = next_group(), g_next = g < n_groups ? next_group() : n_groups;
   if (g >= n_groups) return;
   int node      = group_node(p, g, ew, q);
   int node_next = (g_next < n_groups) ? group_node(p, g_next, ew, q) : -1;
@@ -350,7 +366,7 @@ element_force_kernel(const ElemArgs p)
   cp_async_commit();
   if (BinvStaged<MAT, MODE>::value) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) cp_async8(sB + i * 32, p.binv_cache + g * kBinvGroupDoubles + lane + i * 32);
+    for (int i = 0; i < 9; ++i) cp_async8(sB + i * 32, p.binv_cache + (int64_t)g * kBinvGroupDoubles + lane + i * 32);
     cp_async_commit();
   }
   int stage = 0;
@@ -362,12 +378,12 @@ element_force_kernel(const ElemArgs p)
     cp_async_wait<1>();
     __syncwarp();
 
-    const int64_t e    = g * kElemsPerWarp + ew;
+    const int64_t e    = (int64_t)g * kElemsPerWarp + ew;
     const bool    live = node >= 0;
     const double* sX   = wsm + stage * kStageDoubles;
     const double* sU   = sX + kCoordDoubles;
-    const double* binv_row  = (MODE & kModeReadBinv) ? p.binv_cache + g * kBinvGroupDoubles + lane : nullptr;
-    const double* binv_next = ((MODE & kModeReadBinv) && has_next) ? p.binv_cache + g_next * kBinvGroupDoubles + lane : nullptr;
+    const double* binv_row  = (MODE & kModeReadBinv) ? p.binv_cache + (int64_t)g * kBinvGroupDoubles + lane : nullptr;
+    const double* binv_next = ((MODE & kModeReadBinv) && has_next) ? p.binv_cache + (int64_t)g_next * kBinvGroupDoubles + lane : nullptr;
 
     // current coordinates: the block functor forms cur = ref + disp (src/nimble_block.cc:309-316); the
     // serial F wrapper then passes disp' = cur - ref and the kernel re-adds it (src/nimble_element.cc:341-344,
@@ -431,11 +447,11 @@ element_force_kernel(const ElemArgs p)
       }
     }
     // roll the pipeline
-    const int64_t g_nn = has_next ? next_group() : n_groups;
+    const int g_nn     = has_next ? next_group() : n_groups;
     node               = node_next;
     node_next          = (g_nn < n_groups) ? group_node(p, g_nn, ew, q) : -1;
     if ((MODE & kModeReadBinv) && g_nn < n_groups && lane < (kBinvGroupDoubles * 8) / 128)
-      prefetch_l2(p.binv_cache + g_nn * kBinvGroupDoubles + lane * 16);  // DRAM -> L2 a full pass before the cp.async
+      prefetch_l2(p.binv_cache + (int64_t)g_nn * kBinvGroupDoubles + lane * 16);  // DRAM -> L2 a full pass before the cp.async
     g                  = g_next;
     g_next             = g_nn;
     stage ^= 1;
@@ -452,7 +468,7 @@ mark_shared_nodes_kernel(int64_t n_shared, const int* __restrict__ shared_node, 
 
 __global__ void __launch_bounds__(256)
 flag_groups_kernel(int64_t n_elem, const int* __restrict__ conn, const unsigned char* __restrict__ node_flag,
-                   unsigned char* group_flag, int* group_list, unsigned long long* n_list)
+                   unsigned* group_bits, int* group_list, unsigned* n_list)
 {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (n_elem + kElemsPerWarp - 1) / kElemsPerWarp) return;
@@ -461,8 +477,10 @@ flag_groups_kernel(int64_t n_elem, const int* __restrict__ conn, const unsigned 
     const int64_t s = g * kElemsPerWarp * 8 + k;
     if (s < n_elem * 8 && node_flag[conn[s]]) touched = true;
   }
-  group_flag[g] = touched ? 1 : 0;
-  if (touched) group_list[atomicAdd(n_list, 1ULL)] = (int)g;
+  if (touched) {  // bit g of a little-endian bit set: byte c holds the flags of chunk c (kTicketChunk == 8)
+    atomicOr(group_bits + (g >> 5), 1u << (g & 31));
+    group_list[atomicAdd(n_list, 1u)] = (int)g;
+  }
 }
 
 // ORDERED assembly with a peer exchange: nodal sums of the shared nodes only (the boundary groups are done)

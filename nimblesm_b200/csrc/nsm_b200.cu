@@ -35,9 +35,9 @@ struct Block
   int64_t          elem_base = 0;  // first global element (ascending block id order)
   int64_t          group_base = 0; // first 4-element group of the block in the b^-1 cache
   // boundary-first schedule (peer exchange attached): groups touching a node shared with another rank
-  unsigned char*   group_flag = nullptr;
+  unsigned*        group_bits = nullptr;  // bit g: group g touches a node shared with another rank
   int*             group_list = nullptr;
-  int64_t          n_list     = 0;
+  int              n_list     = 0;
 };
 
 thread_local std::string g_create_error;
@@ -86,7 +86,7 @@ struct nsm_b200_ctx
   double* bc_value = nullptr;
 
   int*                d_flags  = nullptr;
-  unsigned long long* d_ticket = nullptr;  // element-kernel work counter
+  unsigned*        d_ticket = nullptr;  // element-kernel work counter
   unsigned long long* d_min_dt = nullptr;
 
   int64_t launches     = 0;
@@ -196,7 +196,7 @@ elem_args(nsm_b200_ctx* c, const Block& b, int sched = kSchedAll)
 {
   ElemArgs p{};
   p.sched      = sched;
-  p.group_flag = b.group_flag;
+  p.chunk_mask = (const unsigned char*)b.group_bits;
   p.group_list = b.group_list;
   p.n_list     = b.n_list;
   p.n_elem = b.n_elem;
@@ -212,8 +212,6 @@ elem_args(nsm_b200_ctx* c, const Block& b, int sched = kSchedAll)
   return p;
 }
 
-constexpr size_t kElemSmemBytes = (size_t)kElemWarps * kWarpSmemDoubles * sizeof(double);
-
 inline int64_t
 groups_of(int64_t n_elem)
 {
@@ -228,6 +226,7 @@ launch_element(const ElemArgs& p, cudaStream_t s)
   // function attributes and occupancy are per device: a process may drive several GPUs (one thread each)
   static int wave_of_device[64] = {0};
   auto       k                  = element_force_kernel<MAT, ORDERED, MODE>;
+  constexpr size_t kElemSmemBytes = (size_t)kElemWarps * warp_smem_doubles<MAT, MODE>() * sizeof(double);
   int        dev                = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -298,7 +297,7 @@ enqueue_element_kernels(nsm_b200_ctx* c, bool store_ipt, int sched = kSchedAll)
   for (auto& kv : c->blocks) {
     const Block& b = kv.second;
     if (b.n_elem == 0 || (sched == kSchedList && b.n_list == 0)) continue;
-    NSM_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned long long), c->stream));
+    NSM_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned), c->stream));
     NSM_CUDA(c, launch_element_any(elem_args(c, b, sched), b.material, ordered, mode, c->stream));
     c->launches++;
   }
@@ -504,7 +503,7 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   }
   fr(c->mass), fr(c->staging), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
   fr(c->bc_kind), fr(c->bc_value), fr(c->d_flags), fr(c->d_min_dt), fr(c->d_ticket);
-  for (auto& kv : c->blocks) fr(kv.second.conn), fr(kv.second.group_flag), fr(kv.second.group_list);
+  for (auto& kv : c->blocks) fr(kv.second.conn), fr(kv.second.group_bits), fr(kv.second.group_list);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
   if (c->ev_packed) cudaEventDestroy(c->ev_packed);
@@ -536,6 +535,7 @@ nsm_b200_add_block(nsm_b200_ctx* c, int block_id, int64_t n_elem, const int32_t*
   NSM_REQUIRE(c, c != nullptr, "null context");
   NSM_REQUIRE(c, !c->finalized, "add_block after finalize");
   NSM_REQUIRE(c, n_elem >= 0 && (n_elem == 0 || conn), "bad element count / null connectivity");
+  NSM_REQUIRE(c, n_elem <= ((int64_t)1 << 32), "a block holds at most 2^32 elements (32-bit group indices)");
   NSM_REQUIRE(c, c->blocks.find(block_id) == c->blocks.end(), "duplicate block id");
   if (material_kind != NSM_MAT_ELASTIC && material_kind != NSM_MAT_NEOHOOKEAN)
     return fail(c, NSM_ERR_MATERIAL, "unknown material kind %d (0 = elastic, 1 = neohookean)", material_kind);
@@ -1118,9 +1118,9 @@ nsm_b200_comm_ready(nsm_b200_ctx* c)
   const int64_t ns = c->comm.num_shared_nodes();
   if (ns > 0 && c->n_nodes > 0) {
     unsigned char*      node_flag = nullptr;
-    unsigned long long* d_count   = nullptr;
+    unsigned*           d_count   = nullptr;
     NSM_CUDA(c, cudaMalloc((void**)&node_flag, (size_t)c->n_nodes));
-    NSM_CUDA(c, cudaMalloc((void**)&d_count, sizeof(unsigned long long)));
+    NSM_CUDA(c, cudaMalloc((void**)&d_count, sizeof(unsigned)));
     NSM_CUDA(c, cudaMemsetAsync(node_flag, 0, (size_t)c->n_nodes, c->stream));
     mark_shared_nodes_kernel<<<grid_for(ns, 256), 256, 0, c->stream>>>(ns, c->comm.shared_nodes_device(), node_flag);
     c->launches++;
@@ -1128,18 +1128,18 @@ nsm_b200_comm_ready(nsm_b200_ctx* c)
       Block& b = kv.second;
       if (b.n_elem == 0) continue;
       const int64_t ng     = groups_of(b.n_elem);
-      const int64_t padded = (ng + kTicketChunk - 1) / kTicketChunk * kTicketChunk;
+      const int64_t words = (ng + 31) / 32;
       int           rc;
-      if ((rc = dev_alloc(c, &b.group_flag, padded))) return rc;
+      if ((rc = dev_alloc(c, &b.group_bits, words))) return rc;
       if ((rc = dev_alloc(c, &b.group_list, ng))) return rc;
-      NSM_CUDA(c, cudaMemsetAsync(b.group_flag, 0, (size_t)padded, c->stream));
-      NSM_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), c->stream));
-      flag_groups_kernel<<<grid_for(ng, 256), 256, 0, c->stream>>>(b.n_elem, b.conn, node_flag, b.group_flag, b.group_list, d_count);
+      NSM_CUDA(c, cudaMemsetAsync(b.group_bits, 0, (size_t)words * sizeof(unsigned), c->stream));
+      NSM_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(unsigned), c->stream));
+      flag_groups_kernel<<<grid_for(ng, 256), 256, 0, c->stream>>>(b.n_elem, b.conn, node_flag, b.group_bits, b.group_list, d_count);
       c->launches++;
-      unsigned long long h = 0;
+      unsigned h = 0;
       NSM_CUDA(c, cudaMemcpyAsync(&h, d_count, sizeof h, cudaMemcpyDeviceToHost, c->stream));
       NSM_CUDA(c, cudaStreamSynchronize(c->stream));
-      b.n_list = (int64_t)h;
+      b.n_list = (int)h;
     }
     NSM_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFree(node_flag);

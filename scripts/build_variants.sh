@@ -1,17 +1,18 @@
 #!/bin/bash
-# scripts/build_variants.sh — A/B builds of libnsm_b200.so (CTA size / resident CTAs / ticket chunk) into
+# scripts/build_variants.sh — A/B builds of libnsm_b200.so (CTA size / resident CTAs / b^-1 staging) into
 # nimblesm_b200/lib/variants/; select one at run time with NSM_B200_LIB=<path>.
 set -e
 cd "$(dirname "$0")/../nimblesm_b200/csrc"
 mkdir -p ../lib/variants
+rm -f ../lib/variants/*
 build() { # name, extra flags
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
      -Xcompiler -fPIC -ccbin /usr/bin/g++ $2 -shared -o ../lib/variants/libnsm_b200_$1.so nsm_b200.cu \
      -Xptxas -v 2> ../lib/variants/ptxas_$1.log &
 }
-build chunk1 "-DNSM_TICKET_CHUNK=1"
-build chunk4 "-DNSM_TICKET_CHUNK=4"
-build chunk32 "-DNSM_TICKET_CHUNK=32"
-build t128b4 "-DNSM_ELEM_THREADS=128 -DNSM_ELEM_MIN_BLOCKS=4"
+build t256b2_nostage "-DNSM_BINV_STAGE=0"
+build t192b3_nostage "-DNSM_ELEM_THREADS=192 -DNSM_ELEM_MIN_BLOCKS=3 -DNSM_BINV_STAGE=0"
+build t192b3_r112_nostage "-DNSM_ELEM_THREADS=192 -DNSM_ELEM_MIN_BLOCKS=3 -DNSM_BINV_STAGE=0 -DNSM_ELEM_MAXREG=112"
+build t160b4_nostage "-DNSM_ELEM_THREADS=160 -DNSM_ELEM_MIN_BLOCKS=4 -DNSM_BINV_STAGE=0"
 wait
-for f in ../lib/variants/ptxas_*.log; do echo $f; grep -A2 "element_force_kernelILi1ELb0ELi2E" $f | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores"; done
+for f in ../lib/variants/ptxas_*.log; do echo $f; grep -A2 "element_force_kernelILi1ELb0ELi2E\|element_force_kernelILi0ELb0ELi2E" $f | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores"; done
