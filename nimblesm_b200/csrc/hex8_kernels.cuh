@@ -37,7 +37,8 @@ constexpr int kStageDoubles  = 2 * kCoordDoubles;    // X and u of one group, fi
 constexpr int kShareStride   = 33;                   // odd: the 8x8 transpose is bank-conflict free
 constexpr int kShareDoubles  = 24 * kShareStride;
 constexpr int kBinvGroupDoubles = 9 * 32;            // cached b^-1 of one group: [9][32 lanes]
-constexpr int kWarpSmemBase   = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDoubles;  // stages, K, C, shares (+ staged b^-1)
+constexpr int kConnSlotDoubles = 3 * 32 / 2;                   // connectivity of three groups in flight: [3][32 lanes] int
+constexpr int kWarpSmemBase   = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDoubles + kConnSlotDoubles;  // stages, K, C, shares, conn (+ staged b^-1)
 #ifndef NSM_BINV_STAGE
 #define NSM_BINV_STAGE 1
 #endif
@@ -81,6 +82,12 @@ cp_async8_after(double* smem_dst, const double* gsrc, double dep)
 {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("{ .reg .b64 t; mov.b64 t, %2; cp.async.ca.shared.global [%0], [%1], 8; }" ::"r"(d), "l"(gsrc), "d"(dep) : "memory");
+}
+__device__ __forceinline__ void
+cp_async4(int* smem_dst, const int* gsrc)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void
 cp_async_commit()
@@ -281,6 +288,18 @@ group_node(const ElemArgs& p, int g, int ew, int q)
   return e < p.n_elem ? __ldg(p.conn + e * 8 + q) : -1;
 }
 
+// The same lookup, asynchronous: global -> this lane's connectivity slot (cp.async, lands with the copy group it
+// is committed in); -1 for a group beyond the schedule or a lane beyond the block's last element.
+__device__ __forceinline__ void
+stage_group_node(const ElemArgs& p, int* slot, int g, int n_groups, int ew, int q)
+{
+  const int64_t e = (int64_t)g * kElemsPerWarp + ew;
+  if (g < n_groups && e < p.n_elem)
+    cp_async4(slot, p.conn + e * 8 + q);
+  else
+    *slot = -1;
+}
+
 // Asynchronous gather of one group's X and u into a stage buffer: lane j <- node j of its element, global ->
 // shared without passing through registers.  Lanes beyond the last element stage a unit cube at rest, so
 // the tail of the last group computes finite values (and raises no Jacobian flag).
@@ -325,7 +344,6 @@ element_force_kernel(const ElemArgs p)
   double*       sK    = wsm + 2 * kStageDoubles;  // ref + ((ref + disp) - ref): F-path coordinates
   double*       sC    = sK + kCoordDoubles;         // ref + disp: force-path coordinates
   double*       share = sC + kCoordDoubles;         // [24][kShareStride] nodal-force shares of the 32 points
-  double*       sB    = share + kShareDoubles + lane;  // [9][32] staged b^-1: this lane's column
   const int     n_groups = (int)((p.n_elem + kElemsPerWarp - 1) / kElemsPerWarp);
 
   ShapeAtPoint sh;
@@ -358,28 +376,45 @@ element_force_kernel(const ElemArgs p)
       return p.sched == kSchedList ? __ldg(p.group_list + pos) : pos;
     }
   };
-  int g = next_group(), g_next = g < n_groups ? next_group() : n_groups;
+  int g = next_group();
   if (g >= n_groups) return;
-  int node      = group_node(p, g, ew, q);
-  int node_next = (g_next < n_groups) ? group_node(p, g_next, ew, q) : -1;
-  stage_gather(p, wsm, node, q, ew);
-  cp_async_commit();
+  int g_next = next_group();
+  int g_nn   = g_next < n_groups ? next_group() : n_groups;
+  // Connectivity travels three groups deep: slot k % 3 holds the node ids of the k-th group this warp works on.
+  // The copy for group k+2 is issued at the top of pass k and read at the top of pass k+1 (to address the gather
+  // of X and u) -- a whole pass later, so the DRAM latency of the streamed connectivity never shows
+  // (profiles/r01o: a load issued at the end of a pass and consumed at the top of the next one stalled the warp
+  // for 5 % of its time).  No node id is carried in a register across the pass.
+  int* const    sN = reinterpret_cast<int*>(share + kShareDoubles) + lane;   // [3][32]: this lane's column
+  double* const sB = share + kShareDoubles + kConnSlotDoubles + lane;        // [9][32] staged b^-1: this lane's column
+  {
+    const int n0 = group_node(p, g, ew, q);
+    sN[0]        = n0;
+    sN[32]       = g_next < n_groups ? group_node(p, g_next, ew, q) : -1;
+    stage_gather(p, wsm, n0, q, ew);
+    cp_async_commit();
+  }
   if (BinvStaged<MAT, MODE>::value) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) cp_async8(sB + i * 32, p.binv_cache + (int64_t)g * kBinvGroupDoubles + lane + i * 32);
     cp_async_commit();
   }
-  int stage = 0;
+  int stage = 0, slot = 0;
 
   while (g < n_groups) {
-    const bool has_next = g_next < n_groups;
-    if (has_next) stage_gather(p, wsm + (stage ^ 1) * kStageDoubles, node_next, q, ew);
-    cp_async_commit();
-    cp_async_wait<1>();
+    // everything issued during the previous pass has had a pass to land: this group's X / u / b^-1 and the next
+    // group's connectivity
+    cp_async_wait<0>();
     __syncwarp();
+    const bool has_next  = g_next < n_groups;
+    const int  slot_next = slot == 2 ? 0 : slot + 1, slot_nn = slot == 0 ? 2 : slot - 1;
+    if (has_next) stage_gather(p, wsm + (stage ^ 1) * kStageDoubles, sN[slot_next * 32], q, ew);
+    stage_group_node(p, sN + slot_nn * 32, g_nn, n_groups, ew, q);
+    cp_async_commit();
+    if ((MODE & kModeReadBinv) && g_nn < n_groups && lane < (kBinvGroupDoubles * 8) / 128)
+      prefetch_l2(p.binv_cache + (int64_t)g_nn * kBinvGroupDoubles + lane * 16);  // DRAM -> L2 a full pass before the cp.async
 
     const int64_t e    = (int64_t)g * kElemsPerWarp + ew;
-    const bool    live = node >= 0;
     const double* sX   = wsm + stage * kStageDoubles;
     const double* sU   = sX + kCoordDoubles;
     const double* binv_row  = (MODE & kModeReadBinv) ? p.binv_cache + (int64_t)g * kBinvGroupDoubles + lane : nullptr;
@@ -416,6 +451,8 @@ element_force_kernel(const ElemArgs p)
       st = integration_point<MAT, MODE, false>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear, share,
                                                F, sig);
     }
+    const int  node = sN[slot * 32];
+    const bool live = node >= 0;
     if (live && (st & 2u)) atomicOr(p.flags, 1);
 
     if ((MODE & kModeStoreIpt) && live) {
@@ -447,13 +484,10 @@ element_force_kernel(const ElemArgs p)
       }
     }
     // roll the pipeline
-    const int g_nn     = has_next ? next_group() : n_groups;
-    node               = node_next;
-    node_next          = (g_nn < n_groups) ? group_node(p, g_nn, ew, q) : -1;
-    if ((MODE & kModeReadBinv) && g_nn < n_groups && lane < (kBinvGroupDoubles * 8) / 128)
-      prefetch_l2(p.binv_cache + (int64_t)g_nn * kBinvGroupDoubles + lane * 16);  // DRAM -> L2 a full pass before the cp.async
-    g                  = g_next;
-    g_next             = g_nn;
+    g      = g_next;
+    g_next = g_nn;
+    g_nn   = g_nn < n_groups ? next_group() : n_groups;
+    slot   = slot_next;
     stage ^= 1;
   }
 }
