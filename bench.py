@@ -29,10 +29,11 @@ sys.path.insert(0, ROOT)
 RHO, BULK, SHEAR = 7.8, 1.6e12, 0.8e12  # test/dynamics/notched_plate_native_neohookean deck constants
 MATERIAL_2 = (1.333e12, 0.1379e12, 5.0)  # bulk, shear, density of test/dynamics/brick_with_fibers material_2
 # executed DADD+DMUL+DFMA+DSETP lane-instructions per element, from the ncu source page of the profiled kernel
-# (scripts/ncu_sass_mix.py on profiles/r01g_*): [flags & 2 == 0 (b^-1 recomputed), flags & 2 (b^-1 cached)]
-DP_INSTR_PER_ELEMENT = {"neohookean": (10730, 9072), "elastic": (6080, 4424)}
+# (sm__inst_executed_pipe_fp64.sum x 32 / elements, profiles/r01q_dp_counts.txt): [flags & 2 == 0 (b^-1 recomputed),
+# flags & 2 (b^-1 cached)]
+DP_INSTR_PER_ELEMENT = {"neohookean": (10640, 8968), "elastic": (5984, 4312)}
 # dram__bytes_read.sum + dram__bytes_write.sum of one element-kernel launch / elements, same captures (200^3 cube)
-DRAM_TRAFFIC_PER_ELEMENT = {"neohookean": (128.2, 705.6), "elastic": (128.2, 705.6)}
+DRAM_TRAFFIC_PER_ELEMENT = {"neohookean": (127.4, 721.4), "elastic": (128.2, 706.2)}
 
 
 def env_int(k, d):

@@ -31,13 +31,14 @@ constexpr int kElemsPerWarp  = 4;
 #define NSM_TICKET_CHUNK 8
 #endif
 constexpr int kTicketChunk   = NSM_TICKET_CHUNK;   // groups per work ticket
-constexpr int kCoordStride   = 4;                    // [c*8+j][e_w]
-constexpr int kCoordDoubles  = 24 * kCoordStride;    // one [3][8] coordinate set of the warp's 4 elements
+constexpr int kCoordStride   = 4;                    // [c][j][e_w], rows 4..7 of a component shifted by 2 doubles (coord_row)
+constexpr int kCoordComp     = 8 * kCoordStride + 2; // doubles per component
+constexpr int kCoordDoubles  = 3 * kCoordComp;       // one [3][8] coordinate set of the warp's 4 elements
 constexpr int kStageDoubles  = 2 * kCoordDoubles;    // X and u of one group, filled by cp.async
-constexpr int kShareStride   = 33;                   // odd: the 8x8 transpose is bank-conflict free
+constexpr int kShareStride   = 34;                   // even: the transposed read takes Gauss-point pairs as 16-byte loads; rows 3 apart land 12 banks apart, conflict free
 constexpr int kShareDoubles  = 24 * kShareStride;
 constexpr int kBinvGroupDoubles = 9 * 32;            // cached b^-1 of one group: [9][32 lanes]
-constexpr int kConnSlotDoubles = 3 * 32 / 2;                   // connectivity of three groups in flight: [3][32 lanes] int
+constexpr int kConnSlotDoubles = 3 * 32 / 2 + 2;               // connectivity of three groups in flight: [3][32 lanes] int; + the next chunk's skip-mask word
 constexpr int kWarpSmemBase   = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDoubles + kConnSlotDoubles;  // stages, K, C, shares, conn (+ staged b^-1)
 #ifndef NSM_BINV_STAGE
 #define NSM_BINV_STAGE 1
@@ -106,13 +107,23 @@ prefetch_l2(const void* g)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
 }
 
+// Offset of node row j within a component of a coordinate set.  Rows 4..7 sit two doubles further: when lane
+// (q, ew) touches row q (gather copies, X / u reads, K / C stores) the 16 lanes of a half-warp then fall into 16
+// distinct bank pairs (un-shifted, rows q and q + 4 collide: profiles/r01q, 4x / 2x excess wavefronts), while
+// the broadcast read of one node by all lanes still touches four consecutive doubles.
+__host__ __device__ constexpr int
+coord_row(int j)
+{
+  return j * kCoordStride + 2 * (j >> 2);
+}
+
 template <int J>
 __device__ __forceinline__ void
 load_node(const double* sm, int ew, double& x0, double& x1, double& x2)
 {
-  x0 = sm[(0 * 8 + J) * kCoordStride + ew];
-  x1 = sm[(1 * 8 + J) * kCoordStride + ew];
-  x2 = sm[(2 * 8 + J) * kCoordStride + ew];
+  x0 = sm[0 * kCoordComp + coord_row(J) + ew];
+  x1 = sm[1 * kCoordComp + coord_row(J) + ew];
+  x2 = sm[2 * kCoordComp + coord_row(J) + ew];
 }
 
 template <int J>
@@ -306,20 +317,20 @@ stage_group_node(const ElemArgs& p, int* slot, int g, int n_groups, int ew, int 
 __device__ __forceinline__ void
 stage_gather(const ElemArgs& p, double* st, int node, int q, int ew)
 {
-  double* sx = st + q * kCoordStride + ew;
+  double* sx = st + coord_row(q) + ew;
   double* su = sx + kCoordDoubles;
   if (node >= 0) {
-    cp_async8(sx + 0 * 8 * kCoordStride, p.X[0] + node);
-    cp_async8(sx + 1 * 8 * kCoordStride, p.X[1] + node);
-    cp_async8(sx + 2 * 8 * kCoordStride, p.X[2] + node);
-    cp_async8(su + 0 * 8 * kCoordStride, p.u[0] + node);
-    cp_async8(su + 1 * 8 * kCoordStride, p.u[1] + node);
-    cp_async8(su + 2 * 8 * kCoordStride, p.u[2] + node);
+    cp_async8(sx + 0 * kCoordComp, p.X[0] + node);
+    cp_async8(sx + 1 * kCoordComp, p.X[1] + node);
+    cp_async8(sx + 2 * kCoordComp, p.X[2] + node);
+    cp_async8(su + 0 * kCoordComp, p.u[0] + node);
+    cp_async8(su + 1 * kCoordComp, p.u[1] + node);
+    cp_async8(su + 2 * kCoordComp, p.u[2] + node);
   } else {
-    sx[0 * 8 * kCoordStride] = ((q & 3) == 1 || (q & 3) == 2) ? 1.0 : 0.0;
-    sx[1 * 8 * kCoordStride] = (q & 2) ? 1.0 : 0.0;
-    sx[2 * 8 * kCoordStride] = (q & 4) ? 1.0 : 0.0;
-    su[0 * 8 * kCoordStride] = 0.0, su[1 * 8 * kCoordStride] = 0.0, su[2 * 8 * kCoordStride] = 0.0;
+    sx[0 * kCoordComp] = ((q & 3) == 1 || (q & 3) == 2) ? 1.0 : 0.0;
+    sx[1 * kCoordComp] = (q & 2) ? 1.0 : 0.0;
+    sx[2 * kCoordComp] = (q & 4) ? 1.0 : 0.0;
+    su[0 * kCoordComp] = 0.0, su[1 * kCoordComp] = 0.0, su[2 * kCoordComp] = 0.0;
   }
 }
 
@@ -362,13 +373,26 @@ element_force_kernel(const ElemArgs p)
   if (lane == 0) ticket = atomicAdd(ticket_at, 1u);
   unsigned skip_mask = 0;  // kSchedSkipFlagged: the 8 flag bits of the current chunk
   if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets) skip_mask = __ldg(p.chunk_mask + chunk_base / kTicketChunk);
+  // ... and the mask word of the next chunk, copied to shared memory half a chunk ahead (its ticket has arrived by
+  // then), so that the L2 round trip does not show at the rollover either
+  int* const sMask = reinterpret_cast<int*>(wsm + kWarpSmemBase - 2);
   auto next_group = [&]() -> int {
     for (;;) {
       if (++chunk_off == kTicketChunk) {
         chunk_base = (int)__shfl_sync(0xffffffffu, ticket, 0) * kTicketChunk;
         chunk_off  = 0;
         if (lane == 0 && chunk_base < n_tickets) ticket = atomicAdd(ticket_at, 1u);
-        if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets) skip_mask = __ldg(p.chunk_mask + chunk_base / kTicketChunk);
+        if (p.sched == kSchedSkipFlagged && chunk_base < n_tickets) {
+          cp_async_commit();  // (a rollover inside a run of skipped positions follows the copy at once)
+          cp_async_wait<0>();
+          __syncwarp();
+          skip_mask = ((unsigned)*sMask >> (8 * ((chunk_base / kTicketChunk) & 3))) & 0xffu;
+        }
+      } else if (p.sched == kSchedSkipFlagged && chunk_off == kTicketChunk / 2) {
+        const int next_chunk = (int)__shfl_sync(0xffffffffu, ticket, 0);
+        __syncwarp();
+        if (lane == 0 && next_chunk * kTicketChunk < n_tickets)
+          cp_async4(sMask, reinterpret_cast<const int*>(p.chunk_mask) + next_chunk / 4);
       }
       const int pos = chunk_base + chunk_off;
       if (pos >= n_tickets) return n_groups;
@@ -423,19 +447,18 @@ element_force_kernel(const ElemArgs p)
     // current coordinates: the block functor forms cur = ref + disp (src/nimble_block.cc:309-316); the
     // serial F wrapper then passes disp' = cur - ref and the kernel re-adds it (src/nimble_element.cc:341-344,
     // src/nimble_element.h:455-457); the force wrapper uses cur itself (src/nimble_element.cc:462-463).
-    const double X0 = sX[(0 * 8 + q) * kCoordStride + ew], X1 = sX[(1 * 8 + q) * kCoordStride + ew],
-                 X2 = sX[(2 * 8 + q) * kCoordStride + ew];
-    const double u0 = sU[(0 * 8 + q) * kCoordStride + ew], u1 = sU[(1 * 8 + q) * kCoordStride + ew],
-                 u2 = sU[(2 * 8 + q) * kCoordStride + ew];
+    const int    own = coord_row(q) + ew;  // this lane's node in a coordinate set
+    const double X0 = sX[0 * kCoordComp + own], X1 = sX[1 * kCoordComp + own], X2 = sX[2 * kCoordComp + own];
+    const double u0 = sU[0 * kCoordComp + own], u1 = sU[1 * kCoordComp + own], u2 = sU[2 * kCoordComp + own];
     const double c0 = X0 + u0, c1 = X1 + u1, c2 = X2 + u2;
     const double k0 = X0 + (c0 - X0), k1 = X1 + (c1 - X1), k2 = X2 + (c2 - X2);
     const bool   differs = (k0 != c0) || (k1 != c1) || (k2 != c2);
-    sK[(0 * 8 + q) * kCoordStride + ew] = k0;
-    sK[(1 * 8 + q) * kCoordStride + ew] = k1;
-    sK[(2 * 8 + q) * kCoordStride + ew] = k2;
-    sC[(0 * 8 + q) * kCoordStride + ew] = c0;
-    sC[(1 * 8 + q) * kCoordStride + ew] = c1;
-    sC[(2 * 8 + q) * kCoordStride + ew] = c2;
+    sK[0 * kCoordComp + own] = k0;
+    sK[1 * kCoordComp + own] = k1;
+    sK[2 * kCoordComp + own] = k2;
+    sC[0 * kCoordComp + own] = c0;
+    sC[1 * kCoordComp + own] = c1;
+    sC[2 * kCoordComp + own] = c2;
     // The F-path and force-path Jacobians coincide unless ref + ((ref+d) - ref) != ref + d for some node of
     // the warp's elements (possible only when |d| is comparable to |ref|); decided warp-uniformly.
     const bool jacobians_differ = __any_sync(0xffffffffu, differs);
@@ -465,13 +488,13 @@ element_force_kernel(const ElemArgs p)
     __syncwarp();
 
     // ---- lane n: node n, Gauss points in ascending order: force -= share (src/nimble_element.h:609-611)
-    double        fx = 0.0, fy = 0.0, fz = 0.0;
-    const double* col = share + (q * 3) * kShareStride + ew * 8;
+    double         fx = 0.0, fy = 0.0, fz = 0.0;
+    const double2* col = reinterpret_cast<const double2*>(share + (q * 3) * kShareStride + ew * 8);
 #pragma unroll
-    for (int gq = 0; gq < 8; ++gq) {
-      fx -= col[0 * kShareStride + gq];
-      fy -= col[1 * kShareStride + gq];
-      fz -= col[2 * kShareStride + gq];
+    for (int gq = 0; gq < 4; ++gq) {
+      const double2 sx = col[0 * (kShareStride / 2) + gq], sy = col[1 * (kShareStride / 2) + gq], sz = col[2 * (kShareStride / 2) + gq];
+      fx -= sx.x, fy -= sy.x, fz -= sz.x;
+      fx -= sx.y, fy -= sy.y, fz -= sz.y;
     }
     if (live) {
       if (ORDERED) {
