@@ -149,6 +149,35 @@ int nsm_b200_set_bc_values(nsm_b200_ctx* ctx, int64_t n, const double* value);
  * evaluates expression(x,y,z,t) exactly where the reference does (src/nimble_boundary_condition_manager.h:166-201)
  * and uploads the table, so that runs of steps stay on the device.  nsm_b200_set_bc_values returns to one row. */
 int nsm_b200_set_bc_values_steps(nsm_b200_ctx* ctx, int n_rows, int64_t n, const double* value);
+/* Device-evaluated magnitudes (replaces the per-node ExpressionParsing::BoundaryConditionFunctor call of
+ * src/nimble_boundary_condition_manager.h:166-201, src/nimble_expression_parser.h:694-760, for expressions
+ * whose position-dependent part is IEEE-exact arithmetic).  A program is postfix code over a value stack,
+ * code word = op | (arg << 8):
+ *   NSM_BCOP_CONST arg -> consts[arg]     NSM_BCOP_X / _Y / _Z -> reference coordinate of the entry's node
+ *   NSM_BCOP_SLOT arg  -> slots[step][arg], a scalar the HOST evaluated for that step (the time, and every
+ *                         sub-expression of t alone -- cos(t*pi/T) keeps glibc's bits that way)
+ *   ADD SUB MUL DIV FMOD NEG SQRT ABS FLOOR CEIL ROUND, LT LE GT GE EQ AND OR XOR NOT (1.0 / 0.0 results),
+ *   SELECT (a b c -> a != 0 ? b : c): all correctly rounded / exact on both sides, hence bit-identical to the
+ *   host evaluation.
+ * program_of_entry[k] >= 0 makes entry k of the BC table take program's value instead of value[k]; -1 keeps
+ * the host-evaluated magnitude.  Per step only n_slots scalars cross the bus, not one value per BC node. */
+typedef enum {
+  NSM_BCOP_CONST = 0, NSM_BCOP_X = 1, NSM_BCOP_Y = 2, NSM_BCOP_Z = 3, NSM_BCOP_SLOT = 4,
+  NSM_BCOP_ADD = 5, NSM_BCOP_SUB = 6, NSM_BCOP_MUL = 7, NSM_BCOP_DIV = 8, NSM_BCOP_FMOD = 9, NSM_BCOP_NEG = 10,
+  NSM_BCOP_SQRT = 11, NSM_BCOP_ABS = 12, NSM_BCOP_FLOOR = 13, NSM_BCOP_CEIL = 14, NSM_BCOP_ROUND = 15,
+  NSM_BCOP_LT = 16, NSM_BCOP_LE = 17, NSM_BCOP_GT = 18, NSM_BCOP_GE = 19, NSM_BCOP_EQ = 20,
+  NSM_BCOP_AND = 21, NSM_BCOP_OR = 22, NSM_BCOP_XOR = 23, NSM_BCOP_NOT = 24, NSM_BCOP_SELECT = 25,
+  NSM_BCOP_COUNT = 26
+} nsm_bc_op;
+#define NSM_BC_STACK_DEPTH 16
+/* Call after nsm_b200_set_bc_table.  program_offsets has n_programs + 1 entries into code; n_entries must equal
+ * the BC table length.  Programs are validated here (stack depth, operand indices); n_programs = 0 removes them. */
+int nsm_b200_set_bc_programs(nsm_b200_ctx* ctx, int n_programs, const int32_t* program_offsets, const int32_t* code,
+                             int n_consts, const double* consts, int n_slots, int64_t n_entries,
+                             const int32_t* program_of_entry);
+/* slots[r][s] for step r of the next nsm_b200_step call (r = 0 .. n_rows-1; that call must not ask for more steps
+ * than rows); row 0 also serves nsm_b200_apply_kinematic_bc. */
+int nsm_b200_set_bc_slots_steps(nsm_b200_ctx* ctx, int n_rows, int n_slots, const double* slots);
 /* Applies the table once at (time_current, time_previous) to the device velocity (row 0 of the magnitudes). */
 int nsm_b200_apply_kinematic_bc(nsm_b200_ctx* ctx, double time_current, double time_previous);
 

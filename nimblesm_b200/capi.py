@@ -39,7 +39,8 @@ SYMBOLS = [
     "nsm_b200_step", "nsm_b200_get_element_data", "nsm_b200_derived_element_data", "nsm_b200_comm_init",
     "nsm_b200_comm_export", "nsm_b200_comm_attach", "nsm_b200_comm_ready", "nsm_b200_timer_start",
     "nsm_b200_timer_stop", "nsm_b200_launch_count", "nsm_b200_profile", "nsm_b200_profile_read",
-    "nsm_b200_fp64_peak", "nsm_b200_cold_points", "nsm_b200_set_bc_values_steps",
+    "nsm_b200_fp64_peak", "nsm_b200_cold_points", "nsm_b200_set_bc_values_steps", "nsm_b200_set_bc_programs",
+    "nsm_b200_set_bc_slots_steps",
 ]
 
 
@@ -94,6 +95,8 @@ def lib():
         "nsm_b200_set_bc_table": (i32, [vp, i64, ip, ip, ip]),
         "nsm_b200_set_bc_values": (i32, [vp, i64, dp]),
         "nsm_b200_set_bc_values_steps": (i32, [vp, i32, i64, dp]),
+        "nsm_b200_set_bc_programs": (i32, [vp, i32, ip, ip, i32, dp, i32, i64, ip]),
+        "nsm_b200_set_bc_slots_steps": (i32, [vp, i32, i32, dp]),
         "nsm_b200_apply_kinematic_bc": (i32, [vp, dbl, dbl]),
         "nsm_b200_step": (i32, [vp, i32, dp, dbl, i32]),
         "nsm_b200_get_element_data": (i32, [vp, i32, dp]),
@@ -280,6 +283,19 @@ class Context:
         values = np.ascontiguousarray(values, dtype=np.float64)
         assert values.ndim == 2
         self._ck(self._L.nsm_b200_set_bc_values_steps(self._h, values.shape[0], values.shape[1], _dptr(values)))
+
+    def set_bc_programs(self, offsets, code, consts, n_slots, program_of_entry):
+        """Device-evaluated magnitudes (include/nsm_b200.h, nsm_bc_op): postfix programs, one id (or -1) per entry."""
+        offsets, code, poe = (np.ascontiguousarray(a, dtype=np.int32) for a in (offsets, code, program_of_entry))
+        consts = np.ascontiguousarray(consts, dtype=np.float64)
+        self._ck(self._L.nsm_b200_set_bc_programs(self._h, len(offsets) - 1, _iptr(offsets), _iptr(code), len(consts),
+                                                   _dptr(consts), int(n_slots), len(poe), _iptr(poe)))
+
+    def set_bc_slots_steps(self, slots):
+        """slots[r][s]: host-evaluated scalar s (a function of t alone) at the time of step r of the next step() call."""
+        slots = np.ascontiguousarray(slots, dtype=np.float64)
+        assert slots.ndim == 2
+        self._ck(self._L.nsm_b200_set_bc_slots_steps(self._h, slots.shape[0], slots.shape[1], _dptr(slots)))
 
     def apply_kinematic_bc(self, time_current, time_previous):
         self._ck(self._L.nsm_b200_apply_kinematic_bc(self._h, time_current, time_previous))

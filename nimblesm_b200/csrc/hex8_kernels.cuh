@@ -761,6 +761,87 @@ node_fused_kernel(const NodeArgs p, double hdt, double hdt_next, double dt_next)
   }
 }
 
+// Boundary-condition programs (include/nsm_b200.h, nsm_bc_op): one thread per BC table entry evaluates its
+// program at the entry's node for one step and writes the magnitude the node kernels read.  Every operation is
+// IEEE-exact (no FMA contraction in this translation unit), so the value equals the host evaluation of the same
+// expression tree bit for bit; sub-expressions of t alone arrive as host-evaluated slots.
+struct BcProgramArgs
+{
+  int64_t       n_entries;
+  const int*    program_of_entry;  // -1: keep the host magnitude
+  const int*    node_of_entry;
+  const int*    offsets;           // [n_programs + 1]
+  const int*    code;
+  const double* consts;
+  const double* slots;             // this step's row
+  const double* X[3];
+  double*       value;             // [n_entries]
+};
+
+__global__ void __launch_bounds__(128)
+bc_program_kernel(const BcProgramArgs p)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.n_entries) return;
+  const int prog = p.program_of_entry[k];
+  if (prog < 0) return;
+  const int nd = p.node_of_entry[k];
+  double    st[16];
+  int       sp = 0;
+  for (int pc = p.offsets[prog]; pc < p.offsets[prog + 1]; ++pc) {
+    const int word = p.code[pc], op = word & 0xff, arg = word >> 8;
+    if (op <= 4) {  // pushes
+      double v;
+      switch (op) {
+        case 0: v = p.consts[arg]; break;
+        case 1: v = p.X[0][nd]; break;
+        case 2: v = p.X[1][nd]; break;
+        case 3: v = p.X[2][nd]; break;
+        default: v = p.slots[arg]; break;
+      }
+      st[sp++] = v;
+    } else if (op == 10 || (op >= 11 && op <= 15) || op == 24) {  // unary
+      const double a = st[sp - 1];
+      double       r;
+      switch (op) {
+        case 10: r = -a; break;
+        case 11: r = sqrt(a); break;
+        case 12: r = fabs(a); break;
+        case 13: r = floor(a); break;
+        case 14: r = ceil(a); break;
+        case 15: r = round(a); break;
+        default: r = a != 0.0 ? 0.0 : 1.0; break;
+      }
+      st[sp - 1] = r;
+    } else if (op == 25) {  // select
+      const double c = st[sp - 1], b = st[sp - 2], a = st[sp - 3];
+      sp -= 2;
+      st[sp - 1] = a != 0.0 ? b : c;
+    } else {  // binary
+      const double b = st[sp - 1], a = st[sp - 2];
+      double       r;
+      --sp;
+      switch (op) {
+        case 5: r = a + b; break;
+        case 6: r = a - b; break;
+        case 7: r = a * b; break;
+        case 8: r = a / b; break;
+        case 9: r = fmod(a, b); break;
+        case 16: r = a < b ? 1.0 : 0.0; break;
+        case 17: r = a <= b ? 1.0 : 0.0; break;
+        case 18: r = a > b ? 1.0 : 0.0; break;
+        case 19: r = a >= b ? 1.0 : 0.0; break;
+        case 20: r = a == b ? 1.0 : 0.0; break;
+        case 21: r = ((a != 0.0) & (b != 0.0)) ? 1.0 : 0.0; break;
+        case 22: r = ((a != 0.0) | (b != 0.0)) ? 1.0 : 0.0; break;
+        default: r = ((a != 0.0) ^ (b != 0.0)) ? 1.0 : 0.0; break;
+      }
+      st[sp - 1] = r;
+    }
+  }
+  p.value[k] = st[0];
+}
+
 // BoundaryConditionManager::ApplyKinematicBC alone (output steps, t = 0): table entries in deck order;
 // duplicates of a dof were resolved to the last entry when the dof map was built.
 __global__ void __launch_bounds__(256)

@@ -84,6 +84,14 @@ struct nsm_b200_ctx
   int*    bc_of_dof[3] = {nullptr, nullptr, nullptr};
   int*    bc_kind  = nullptr;
   double* bc_value = nullptr;
+  int*    bc_node  = nullptr;  // node of every table entry (boundary-condition programs read its coordinates)
+  // boundary-condition programs (nsm_b200_set_bc_programs): magnitudes evaluated on the device each step
+  int     bcp_programs = 0, bcp_slots = 0, bcp_rows = 0, bcp_rows_cap = 0;
+  int*    bcp_offsets = nullptr;
+  int*    bcp_code    = nullptr;
+  double* bcp_consts  = nullptr;
+  int*    bcp_of_entry = nullptr;
+  double* bcp_slot_values = nullptr;  // [bcp_rows][bcp_slots]
 
   int*                d_flags  = nullptr;
   unsigned*        d_ticket = nullptr;  // element-kernel work counter
@@ -184,11 +192,44 @@ node_args(nsm_b200_ctx* c, int64_t bc_row = 0)
   }
   p.mass     = c->mass;
   p.bc_kind  = c->bc_kind;
-  p.bc_value = c->bc_value ? c->bc_value + (c->bc_rows > 1 ? bc_row : 0) * c->n_bc : nullptr;
+  // with boundary-condition programs the single row is rewritten on the device before each use
+  p.bc_value = c->bc_value ? c->bc_value + ((c->bc_rows > 1 && c->bcp_programs == 0) ? bc_row : 0) * c->n_bc : nullptr;
   p.ef       = c->ef;
   p.adj_off  = c->adj_off;
   p.adj_slot = c->adj_slot;
   return p;
+}
+
+// Evaluates the boundary-condition programs for one step (slot row `row`) into row 0 of the magnitudes.
+int
+enqueue_bc_programs(nsm_b200_ctx* c, int64_t row)
+{
+  if (c->bcp_programs == 0 || c->n_bc == 0) return NSM_OK;
+  BcProgramArgs p{};
+  p.n_entries        = c->n_bc;
+  p.program_of_entry = c->bcp_of_entry;
+  p.node_of_entry    = c->bc_node;
+  p.offsets          = c->bcp_offsets;
+  p.code             = c->bcp_code;
+  p.consts           = c->bcp_consts;
+  p.slots            = c->bcp_slot_values + (c->bcp_rows > 1 ? row : 0) * c->bcp_slots;
+  for (int i = 0; i < 3; ++i) p.X[i] = c->X[i];
+  p.value = c->bc_value;
+  bc_program_kernel<<<grid_for(c->n_bc, 128), 128, 0, c->stream>>>(p);
+  c->launches++;
+  NSM_CUDA(c, cudaGetLastError());
+  return NSM_OK;
+}
+
+void
+free_bc_programs(nsm_b200_ctx* c)
+{
+  auto fr = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  fr(c->bcp_offsets), fr(c->bcp_code), fr(c->bcp_consts), fr(c->bcp_of_entry), fr(c->bcp_slot_values);
+  c->bcp_programs = c->bcp_slots = c->bcp_rows = c->bcp_rows_cap = 0;
 }
 
 ElemArgs
@@ -502,7 +543,8 @@ nsm_b200_destroy(nsm_b200_ctx* c)
     fr(c->X[i]), fr(c->u[i]), fr(c->v[i]), fr(c->a[i]), fr(c->f[i]), fr(c->fext[i]), fr(c->bc_of_dof[i]);
   }
   fr(c->mass), fr(c->staging), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
-  fr(c->bc_kind), fr(c->bc_value), fr(c->d_flags), fr(c->d_min_dt), fr(c->d_ticket);
+  fr(c->bc_kind), fr(c->bc_value), fr(c->bc_node), fr(c->d_flags), fr(c->d_min_dt), fr(c->d_ticket);
+  free_bc_programs(c);
   for (auto& kv : c->blocks) fr(kv.second.conn), fr(kv.second.group_bits), fr(kv.second.group_list);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
@@ -837,7 +879,9 @@ nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int
   }
   if (c->bc_kind) cudaFree(c->bc_kind);
   if (c->bc_value) cudaFree(c->bc_value);
-  c->bc_kind = nullptr, c->bc_value = nullptr;
+  if (c->bc_node) cudaFree(c->bc_node);
+  c->bc_kind = nullptr, c->bc_value = nullptr, c->bc_node = nullptr;
+  free_bc_programs(c);
   c->n_bc = n;
   if (n == 0) return NSM_OK;
   // dof -> last table entry constraining it (later entries win, like the reference's sequential loop)
@@ -858,6 +902,8 @@ nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int
   }
   if ((rc = dev_alloc(c, &c->bc_kind, n))) return rc;
   if ((rc = dev_alloc(c, &c->bc_value, n))) return rc;
+  if ((rc = dev_alloc(c, &c->bc_node, n))) return rc;
+  NSM_CUDA(c, cudaMemcpyAsync(c->bc_node, node, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   c->bc_rows = 1, c->bc_rows_cap = 1;
   NSM_CUDA(c, cudaMemcpyAsync(c->bc_kind, kind, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemsetAsync(c->bc_value, 0, (size_t)n * sizeof(double), c->stream));
@@ -898,10 +944,92 @@ nsm_b200_set_bc_values_steps(nsm_b200_ctx* c, int n_rows, int64_t n, const doubl
 }
 
 int
+nsm_b200_set_bc_programs(nsm_b200_ctx* c, int n_programs, const int32_t* program_offsets, const int32_t* code, int n_consts,
+                         const double* consts, int n_slots, int64_t n_entries, const int32_t* program_of_entry)
+{
+  NSM_REQUIRE(c, c && c->finalized, "set_bc_programs: context not finalized");
+  NSM_REQUIRE(c, n_programs >= 0 && n_consts >= 0 && n_slots >= 0, "set_bc_programs: negative count");
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_bc_programs(c);
+  if (n_programs == 0) return NSM_OK;
+  NSM_REQUIRE(c, program_offsets && code && program_of_entry && (n_consts == 0 || consts), "set_bc_programs: null argument");
+  NSM_REQUIRE(c, n_entries == c->n_bc && c->n_bc > 0, "set_bc_programs: length differs from the BC table");
+  NSM_REQUIRE(c, program_offsets[0] == 0, "set_bc_programs: offsets must start at 0");
+  // validate: every program leaves exactly one value, never underflows or exceeds the device stack, and only
+  // names constants / slots that exist
+  for (int p = 0; p < n_programs; ++p) {
+    NSM_REQUIRE(c, program_offsets[p + 1] > program_offsets[p], "set_bc_programs: empty program");
+    int depth = 0;
+    for (int pc = program_offsets[p]; pc < program_offsets[p + 1]; ++pc) {
+      const int op = code[pc] & 0xff, arg = code[pc] >> 8;
+      int       pops = 2;
+      if (op <= NSM_BCOP_SLOT) {
+        pops = 0;
+        if (op == NSM_BCOP_CONST && (arg < 0 || arg >= n_consts)) return fail(c, NSM_ERR_ARG, "set_bc_programs: constant %d out of range", arg);
+        if (op == NSM_BCOP_SLOT && (arg < 0 || arg >= n_slots)) return fail(c, NSM_ERR_ARG, "set_bc_programs: slot %d out of range", arg);
+      } else if (op == NSM_BCOP_NEG || (op >= NSM_BCOP_SQRT && op <= NSM_BCOP_ROUND) || op == NSM_BCOP_NOT)
+        pops = 1;
+      else if (op == NSM_BCOP_SELECT)
+        pops = 3;
+      else if (op >= NSM_BCOP_COUNT)
+        return fail(c, NSM_ERR_ARG, "set_bc_programs: unknown operation %d", op);
+      if (depth < pops) return fail(c, NSM_ERR_ARG, "set_bc_programs: program %d underflows its stack", p);
+      depth += 1 - pops;
+      if (depth > NSM_BC_STACK_DEPTH) return fail(c, NSM_ERR_ARG, "set_bc_programs: program %d needs more than %d stack entries", p, NSM_BC_STACK_DEPTH);
+    }
+    if (depth != 1) return fail(c, NSM_ERR_ARG, "set_bc_programs: program %d leaves %d values", p, depth);
+  }
+  for (int64_t k = 0; k < n_entries; ++k)
+    if (program_of_entry[k] < -1 || program_of_entry[k] >= n_programs)
+      return fail(c, NSM_ERR_ARG, "set_bc_programs: entry %lld names program %d", (long long)k, program_of_entry[k]);
+  const int n_code = program_offsets[n_programs];
+  int       rc;
+  if ((rc = dev_alloc(c, &c->bcp_offsets, n_programs + 1))) return rc;
+  if ((rc = dev_alloc(c, &c->bcp_code, n_code))) return rc;
+  if ((rc = dev_alloc(c, &c->bcp_consts, std::max(n_consts, 1)))) return rc;
+  if ((rc = dev_alloc(c, &c->bcp_of_entry, n_entries))) return rc;
+  if ((rc = dev_alloc(c, &c->bcp_slot_values, std::max(n_slots, 1)))) return rc;
+  NSM_CUDA(c, cudaMemcpyAsync(c->bcp_offsets, program_offsets, (size_t)(n_programs + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemcpyAsync(c->bcp_code, code, (size_t)n_code * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (n_consts) NSM_CUDA(c, cudaMemcpyAsync(c->bcp_consts, consts, (size_t)n_consts * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemcpyAsync(c->bcp_of_entry, program_of_entry, (size_t)n_entries * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemsetAsync(c->bcp_slot_values, 0, (size_t)std::max(n_slots, 1) * sizeof(double), c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->bcp_programs = n_programs, c->bcp_slots = n_slots, c->bcp_rows = 1, c->bcp_rows_cap = 1;
+  return NSM_OK;
+}
+
+int
+nsm_b200_set_bc_slots_steps(nsm_b200_ctx* c, int n_rows, int n_slots, const double* slots)
+{
+  NSM_REQUIRE(c, c && c->finalized, "set_bc_slots_steps: context not finalized");
+  NSM_REQUIRE(c, c->bcp_programs > 0, "set_bc_slots_steps: no boundary-condition programs set");
+  NSM_REQUIRE(c, n_rows >= 1 && n_slots == c->bcp_slots && (n_slots == 0 || slots), "set_bc_slots_steps: bad arguments");
+  if (n_slots == 0) {
+    c->bcp_rows = n_rows;
+    return NSM_OK;
+  }
+  if (n_rows > c->bcp_rows_cap) {
+    NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->bcp_slot_values) cudaFree(c->bcp_slot_values);
+    c->bcp_slot_values = nullptr;
+    int rc             = dev_alloc(c, &c->bcp_slot_values, (int64_t)n_rows * n_slots);
+    if (rc) return rc;
+    c->bcp_rows_cap = n_rows;
+  }
+  c->bcp_rows = n_rows;
+  NSM_CUDA(c, cudaMemcpyAsync(c->bcp_slot_values, slots, (size_t)n_rows * n_slots * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
 nsm_b200_apply_kinematic_bc(nsm_b200_ctx* c, double time_current, double time_previous)
 {
   NSM_REQUIRE(c, c && c->finalized, "apply_kinematic_bc: context not finalized");
   if (c->n_bc == 0 || c->n_nodes == 0) return NSM_OK;
+  int rc_p = enqueue_bc_programs(c, 0);
+  if (rc_p) return rc_p;
   const double dt = time_current - time_previous;
   apply_bc_kernel<<<grid_for(c->n_nodes, 256), 256, 0, c->stream>>>(node_args(c), dt);
   c->launches++;
@@ -916,6 +1044,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
   NSM_REQUIRE(c, c && c->finalized, "step: context not finalized");
   NSM_REQUIRE(c, time != nullptr && n_steps >= 0, "step: bad arguments");
   NSM_REQUIRE(c, c->bc_rows <= 1 || n_steps <= c->bc_rows, "step: more steps than per-step boundary-condition rows");
+  NSM_REQUIRE(c, c->bcp_programs == 0 || c->bcp_rows <= 1 || n_steps <= c->bcp_rows, "step: more steps than per-step boundary-condition slot rows");
   const bool     ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
   const bool     has_bc  = c->n_bc > 0;
   const int64_t  n       = c->n_nodes;
@@ -932,6 +1061,8 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     const bool   store =
         (store_ipt_last && s == n_steps - 1) || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP);
     if (n > 0 && s == 0) {  // later first halves ride in the previous step's fused node pass
+      int rc_p = enqueue_bc_programs(c, 0);
+      if (rc_p) return rc_p;
       const NodeArgs na = node_args(c, 0);
       if (has_bc) {
         if (ordered)
@@ -982,6 +1113,8 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
         }
       }
       if (s + 1 < n_steps) {
+        int rc_p = enqueue_bc_programs(c, s + 1);  // magnitudes of the step the fused pass opens
+        if (rc_p) return rc_p;
         const double dt_next  = (t + dt_user) - t;
         const double hdt_next = 0.5 * dt_next;
         const int    variant  = (gather_in_node_kernel ? 4 : 0) | (c->has_fext ? 2 : 0) | (has_bc ? 1 : 0);

@@ -1,6 +1,8 @@
 // nimblesm_b200/host/boundary_condition.cc — see boundary_condition.h.
 #include "boundary_condition.h"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <sstream>
 #include <stdexcept>
@@ -108,6 +110,30 @@ BoundaryConditionManager::Initialize(std::map<int, std::string> const& node_set_
     }
     if (bc.has_expression_ && bc.expression_.depends_on_time()) time_dependent_ = true;
   }
+  // device programs for the time-dependent magnitudes: all of them or none (one code path per run)
+  programs_ = DevicePrograms();
+  const char* force_host = std::getenv("NSM_B200_HOST_BC");
+  if (time_dependent_ && dim_ == 3 && !(force_host && force_host[0] == '1')) {
+    DevicePrograms   p;
+    std::vector<int> program_of_bc(boundary_conditions_.size(), -1);
+    bool             ok = true;
+    for (size_t b = 0; b < boundary_conditions_.size() && ok; ++b) {
+      const BoundaryCondition& bc = boundary_conditions_[b];
+      if (bc.bc_type_ != BoundaryCondition::PRESCRIBED_VELOCITY && bc.bc_type_ != BoundaryCondition::PRESCRIBED_DISPLACEMENT)
+        continue;
+      if (!bc.has_expression_ || !bc.expression_.depends_on_time()) continue;
+      ok = bc.expression_.compile(p.code, p.consts, p.slots, 16);
+      if (ok) {
+        program_of_bc[b] = (int)p.offsets.size() - 1;
+        p.offsets.push_back((int)p.code.size());
+      }
+    }
+    if (ok) {
+      for (int b : table_.bc_index) p.program_of_entry.push_back(program_of_bc[b]);
+      p.active  = true;
+      programs_ = std::move(p);
+    }
+  }
 }
 
 void
@@ -151,12 +177,16 @@ BoundaryConditionManager::ApplyKinematicBC(double time_current, double time_prev
 }
 
 void
-BoundaryConditionManager::EvaluateMagnitudes(double t, const Viewify<2>& X, double* values) const
+BoundaryConditionManager::EvaluateMagnitudes(double t, const Viewify<2>& X, double* values, bool skip_program_entries) const
 {
   const size_t n = table_.node.size();
   for (size_t k = 0; k < n; ++k) {
     const BoundaryCondition& bc = boundary_conditions_[table_.bc_index[k]];
     const int                nd = table_.node[k];
+    if (skip_program_entries && programs_.active && programs_.program_of_entry[k] >= 0) {
+      values[k] = 0.0;  // rewritten on the device every step
+      continue;
+    }
     values[k] = bc.has_expression_ ? bc.expression_.eval(X(nd, 0), X(nd, 1), dim_ == 3 ? X(nd, 2) : 0.0, t) : bc.magnitude_;
   }
 }

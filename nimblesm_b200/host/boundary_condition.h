@@ -96,9 +96,35 @@ class BoundaryConditionManager
   {
     return time_dependent_;
   }
-  // magnitudes of all table entries at time t (x, y, z = reference coordinates of the entry's node)
+  // magnitudes of all table entries at time t (x, y, z = reference coordinates of the entry's node); with
+  // skip_program_entries the entries served by a device program (below) are left at 0
   void
-  EvaluateMagnitudes(double t, const Viewify<2>& reference_coordinates, double* values) const;
+  EvaluateMagnitudes(double t, const Viewify<2>& reference_coordinates, double* values, bool skip_program_entries = false) const;
+
+  // ---- device programs (include/nsm_b200.h, nsm_b200_set_bc_programs) ----------------------------------
+  // When every time-dependent expression compiles (Expression::compile), the step loop evaluates the magnitudes on
+  // the device: per step the host supplies only the values of `slots` (sub-expressions of t alone).  Otherwise
+  // (or with NSM_B200_HOST_BC=1 in the environment) active == false and the host evaluates one row of magnitudes
+  // per step, as the reference does.
+  struct DevicePrograms
+  {
+    bool                 active = false;
+    std::vector<int>     offsets{0};        // [n_programs + 1]
+    std::vector<int32_t> code;
+    std::vector<double>  consts;
+    std::vector<Expression> slots;
+    std::vector<int>     program_of_entry;  // [table entries], -1 = host magnitude
+  };
+  const DevicePrograms&
+  GetDevicePrograms() const
+  {
+    return programs_;
+  }
+  void
+  EvaluateSlots(double t, double* values) const
+  {
+    for (size_t k = 0; k < programs_.slots.size(); ++k) values[k] = programs_.slots[k].eval(0.0, 0.0, 0.0, t);
+  }
 
  private:
   std::map<int, std::string>      node_set_names_, side_set_names_;
@@ -108,6 +134,7 @@ class BoundaryConditionManager
   Time_Integration_Scheme         scheme_{EXPLICIT};
   DeviceTable                     table_;
   bool                            time_dependent_{false};
+  DevicePrograms                  programs_;
 };
 
 }  // namespace nimble_b200

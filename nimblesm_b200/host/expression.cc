@@ -2,6 +2,7 @@
 #include "expression.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
 #include <vector>
@@ -349,7 +350,132 @@ uses(const Expression::Node* n, int lo, int hi)
   return uses(n->a.get(), lo, hi) || uses(n->b.get(), lo, hi) || uses(n->c.get(), lo, hi);
 }
 
+// canonical text of a sub-tree (slot de-duplication only)
+std::string
+show(const Expression::Node* n)
+{
+  if (!n) return "";
+  char buf[64];
+  switch (n->kind) {
+    case Kind::CONST:
+    case Kind::BCONST: std::snprintf(buf, sizeof buf, "%a", n->value); return buf;
+    case Kind::VAR: return std::string(1, "xyzt"[n->index]);
+    default: break;
+  }
+  std::snprintf(buf, sizeof buf, "(%d:%d ", (int)n->kind, n->index);
+  return std::string(buf) + show(n->a.get()) + "," + show(n->b.get()) + "," + show(n->c.get()) + ")";
+}
+
+struct Emitter
+{
+  std::vector<int32_t>                 code;
+  std::vector<double>                  consts;
+  std::vector<NodeP>                   slot_nodes;
+  std::vector<std::string>             slot_keys;
+  int                                  depth = 0, max_seen = 0;
+  void
+  push(int op, int arg)
+  {
+    code.push_back(op | (arg << 8));
+    if (++depth > max_seen) max_seen = depth;
+  }
+  void
+  apply(int op, int pops)
+  {
+    code.push_back(op);
+    depth += 1 - pops;
+  }
+};
+
+// op codes of include/nsm_b200.h (nsm_bc_op); kept numeric here: the host layer does not include the CUDA ABI
+enum { OP_CONST = 0, OP_X = 1, OP_SLOT = 4, OP_ADD = 5, OP_SUB = 6, OP_MUL = 7, OP_DIV = 8, OP_FMOD = 9, OP_NEG = 10, OP_SQRT = 11,
+       OP_ABS = 12, OP_FLOOR = 13, OP_CEIL = 14, OP_ROUND = 15, OP_LT = 16, OP_LE = 17, OP_GT = 18, OP_GE = 19, OP_EQ = 20,
+       OP_AND = 21, OP_OR = 22, OP_XOR = 23, OP_NOT = 24, OP_SELECT = 25 };
+
+bool
+emit(const NodeP& n, Emitter& e)
+{
+  if (n->kind == Kind::CONST || n->kind == Kind::BCONST) {
+    e.consts.push_back(n->value);
+    e.push(OP_CONST, (int)e.consts.size() - 1);
+    return true;
+  }
+  if (!uses(n.get(), 0, 2)) {  // a function of t alone (or of constants): evaluated by the host, once per step
+    const std::string key = show(n.get());
+    size_t            k   = 0;
+    while (k < e.slot_keys.size() && e.slot_keys[k] != key) ++k;
+    if (k == e.slot_keys.size()) {
+      e.slot_keys.push_back(key);
+      e.slot_nodes.push_back(n);
+    }
+    e.push(OP_SLOT, (int)k);
+    return true;
+  }
+  auto binary = [&](int op) {
+    if (!emit(n->a, e) || !emit(n->b, e)) return false;
+    e.apply(op, 2);
+    return true;
+  };
+  auto unary = [&](int op) {
+    if (!emit(n->a, e)) return false;
+    e.apply(op, 1);
+    return true;
+  };
+  switch (n->kind) {
+    case Kind::VAR: e.push(OP_X + n->index, 0); return true;  // x, y, z (t never reaches here)
+    case Kind::ADD: return binary(OP_ADD);
+    case Kind::SUB: return binary(OP_SUB);
+    case Kind::MUL: return binary(OP_MUL);
+    case Kind::DIV: return binary(OP_DIV);
+    case Kind::MOD: return binary(OP_FMOD);
+    case Kind::NEG: return unary(OP_NEG);
+    case Kind::LT: return binary(OP_LT);
+    case Kind::LE: return binary(OP_LE);
+    case Kind::GT: return binary(OP_GT);
+    case Kind::GE: return binary(OP_GE);
+    case Kind::EQ: return binary(OP_EQ);
+    case Kind::AND: return binary(OP_AND);
+    case Kind::OR: return binary(OP_OR);
+    case Kind::XOR: return binary(OP_XOR);
+    case Kind::NOT: return unary(OP_NOT);
+    case Kind::COND:
+      if (!emit(n->a, e) || !emit(n->b, e) || !emit(n->c, e)) return false;
+      e.apply(OP_SELECT, 3);
+      return true;
+    case Kind::FUNC:
+      switch (n->index) {  // kFuncs: only the correctly rounded / exact ones have a device counterpart
+        case 6: return unary(OP_ABS);
+        case 10: return unary(OP_SQRT);
+        case 13: return unary(OP_CEIL);
+        case 14: return unary(OP_ROUND);
+        case 15: return unary(OP_FLOOR);
+        default: return false;
+      }
+    default: return false;  // POW / IPOW of a position: glibc's pow is not reproducible on the device
+  }
+}
+
 }  // namespace
+
+bool
+Expression::compile(std::vector<int32_t>& code, std::vector<double>& consts, std::vector<Expression>& slots, int max_depth) const
+{
+  if (!root_) return false;
+  Emitter e;
+  for (const Expression& s : slots) {
+    e.slot_keys.push_back(show(s.root_.get()));
+    e.slot_nodes.push_back(s.root_);
+  }
+  const size_t const_base = consts.size();
+  if (!emit(root_, e) || e.max_seen > max_depth) return false;
+  for (int32_t w : e.code) {
+    const int op = w & 0xff, arg = w >> 8;
+    code.push_back(op == OP_CONST ? (op | ((arg + (int)const_base) << 8)) : w);
+  }
+  consts.insert(consts.end(), e.consts.begin(), e.consts.end());
+  for (size_t k = slots.size(); k < e.slot_nodes.size(); ++k) slots.push_back(Expression(e.slot_nodes[k], e.slot_keys[k]));
+  return true;
+}
 
 Expression::Expression(const std::string& text) : text_(text)
 {

@@ -45,6 +45,29 @@ nsmh_expression_eval(const char* text, double x, double y, double z, double t, d
   }
 }
 
+// Expression::compile for one expression: the device program, its constants, and its slots evaluated at time t.
+// Returns 0 = compiled, 2 = no bit-exact device form (the host evaluates it), 1 = parse error.
+int
+nsmh_expression_compile(const char* text, double t, int max_words, int* n_words, int* code, int max_consts, int* n_consts,
+                        double* consts, int max_slots, int* n_slots, double* slot_values, char* err, int errlen)
+{
+  try {
+    Expression              e(text);
+    std::vector<int32_t>    c;
+    std::vector<double>     k;
+    std::vector<Expression> s;
+    if (!e.compile(c, k, s, 16)) return 2;
+    if ((int)c.size() > max_words || (int)k.size() > max_consts || (int)s.size() > max_slots) return fail(err, errlen, "buffers too small");
+    *n_words = (int)c.size(), *n_consts = (int)k.size(), *n_slots = (int)s.size();
+    for (size_t i = 0; i < c.size(); ++i) code[i] = c[i];
+    for (size_t i = 0; i < k.size(); ++i) consts[i] = k[i];
+    for (size_t i = 0; i < s.size(); ++i) slot_values[i] = s[i].eval(0.0, 0.0, 0.0, t);
+    return 0;
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
 int
 nsmh_io_file_name(const char* serial, const char* ext, const char* label, int rank, int nranks, char* out, int outlen)
 {

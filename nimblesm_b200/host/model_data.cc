@@ -334,7 +334,29 @@ ModelData::AdvanceOnDevice(DataManager& data_manager, int n_steps, double& time_
   }
   if (n_bc > 0) {
     Viewify<2> X = GetVectorNodeData("reference_coordinate");
-    if (bc->HasTimeDependentMagnitudes()) {
+    const auto& programs = bc->GetDevicePrograms();
+    if (programs.active) {
+      // time-dependent magnitudes are evaluated on the device: one row of host magnitudes for the other entries
+      // and, per step, the sub-expressions of t (accumulated like the loop does, :192-195)
+      if (!bc_programs_sent_) {
+        d.check(nsm_b200_set_bc_programs(d.get(), (int)programs.offsets.size() - 1, programs.offsets.data(), programs.code.data(),
+                                         (int)programs.consts.size(), programs.consts.data(), (int)programs.slots.size(), n_bc,
+                                         programs.program_of_entry.data()),
+                "ModelData::AdvanceOnDevice (boundary-condition programs)");
+        bc_programs_sent_ = true;
+      }
+      bc_values_.resize((size_t)n_bc);
+      bc->EvaluateMagnitudes(time_current, X, bc_values_.data(), true);
+      d.check(nsm_b200_set_bc_values(d.get(), n_bc, bc_values_.data()), "ModelData::AdvanceOnDevice (magnitudes)");
+      const size_t n_slots = programs.slots.size();
+      bc_slots_.resize((size_t)n_steps * std::max<size_t>(n_slots, 1));
+      double t = time_current;
+      for (int s = 0; s < n_steps; ++s) {
+        t += user_time_step;
+        bc->EvaluateSlots(t, bc_slots_.data() + (size_t)s * n_slots);
+      }
+      d.check(nsm_b200_set_bc_slots_steps(d.get(), n_steps, (int)n_slots, bc_slots_.data()), "ModelData::AdvanceOnDevice (slots)");
+    } else if (bc->HasTimeDependentMagnitudes()) {
       // one row per step, evaluated at the time_current of that step, accumulated like the loop does (:192-195)
       bc_values_.resize((size_t)n_steps * n_bc);
       double t = time_current;

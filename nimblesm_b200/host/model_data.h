@@ -230,7 +230,8 @@ class ModelData : public ModelDataBase
   std::vector<int>                      block_ids_;
   std::map<int, std::vector<double>>    element_data_np1_;
   std::vector<double>                   bc_values_;
-  bool                                  bc_table_sent_ = false;
+  std::vector<double>                   bc_slots_;
+  bool                                  bc_table_sent_ = false, bc_programs_sent_ = false;
   int                                   num_nodes_     = 0;
 };
 

@@ -344,3 +344,128 @@ def test_full_size_properties():
     with _ctx(mesh, "elastic", capi.ASSEMBLY_ORDERED) as c:
         f1o = c.internal_force_host(u1)
     assert np.abs(f1o - f1).max() <= 1e-12 * scale
+
+
+def _host_lib():
+    import ctypes as C
+    import os
+
+    from tests.conftest import ROOT
+
+    return C.CDLL(os.path.join(ROOT, "nimblesm_b200", "lib", "libnsm_host_c.so"))
+
+
+def _bc_program_setup(c, mesh, ref, exprs, times, last_is_displacement=True):
+    """BC table: expression k on component k % 3 of the nodes of face x = 0 (prescribed velocity; the last
+    expression as a prescribed displacement).  Returns (nodes, comps, kinds, host rows [len(times)][n], slots rows)."""
+    from nimblesm_b200 import capi
+    from tests import bc_program as bp
+
+    host = _host_lib()
+    face = mesh["node_sets"][2]
+    nodes, comps, kinds, prog_of = [], [], [], []
+    offsets, code, consts = [0], [], []
+    slot_rows = [[] for _ in times]
+    for k, ex in enumerate(exprs):
+        nodes += list(face)
+        comps += [k % 3] * len(face)
+        kinds += [capi.BC_PRESCRIBED_DISPLACEMENT if (last_is_displacement and k == len(exprs) - 1) else capi.BC_PRESCRIBED_VELOCITY] * len(face)
+        prog = bp.compile_expression(host, ex, times[0])
+        assert prog is not None, ex
+        pc, pk, _ = prog
+        base_c, base_s = len(consts), len(slot_rows[0])
+        for w in pc:  # relocate constant / slot indices into the shared pools
+            op, arg = int(w) & 0xff, int(w) >> 8
+            code.append(op | ((arg + (base_c if op == bp.CONST else base_s if op == bp.SLOT else 0)) << 8))
+        consts += list(pk)
+        for r, t in enumerate(times):
+            slot_rows[r] += list(bp.compile_expression(host, ex, t)[2])
+        offsets.append(len(code))
+        prog_of += [k] * len(face)
+    rows = np.array([[bp.host_eval(host, exprs[p], *ref[n], t) for n, p in zip(nodes, prog_of)] for t in times])
+    c.set_bc_table(nodes, comps, kinds)
+    return nodes, comps, kinds, rows, (offsets, code, consts, np.array(slot_rows).reshape(len(times), -1), prog_of)
+
+
+BC_EXPRESSIONS = ["cos(t*3.141592653589793/2.0e-6)*x + y/3", "sqrt(x*x+y*y)*exp(-0.2*t) - abs(z)*t", "t>1.0e-8 ? 10*y : -z",
+                  "1.0e-3*(y+1)*(z+2)/(x+3)*log(t+2)", "floor(10*y)+ceil(z)+round(y*4)+1.0e6*t", "(y % 0.3)*t*1.0e5"]
+
+
+def test_bc_programs_bitwise():
+    """nsm_b200_set_bc_programs: the device evaluates expression(x, y, z, t) per boundary node with host-supplied
+    slots for the sub-expressions of t; the magnitudes equal the host evaluation of the same tree bit for bit
+    (read back through apply_kinematic_bc, which writes v = magnitude for a prescribed velocity)."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, _ = perturbed_cube(5, 0.0)
+    exprs = BC_EXPRESSIONS[:3]  # one per component, all prescribed velocities
+    for t in (0.0, 3.0e-7, 2.5e-6):
+        c = _ctx(mesh, "elastic", capi.ASSEMBLY_ATOMIC)
+        nodes, comps, kinds, rows, (off, code, consts, slots, prog_of) = _bc_program_setup(c, mesh, ref, exprs, [t], False)
+        c.set_bc_programs(off, code, consts, slots.shape[1], prog_of)
+        c.set_bc_values(np.full(len(nodes), 123.0))  # must be overwritten for every entry that has a program
+        c.set_bc_slots_steps(slots)
+        c.apply_kinematic_bc(t, t)
+        v = c.download("velocity")
+        n_face = len(mesh["node_sets"][2])
+        for k in range(3):
+            sl = slice(k * n_face, (k + 1) * n_face)
+            got = v[np.array(nodes[sl]), k]
+            assert np.array_equal(got.view(np.int64), rows[0, sl].view(np.int64)), (exprs[k], t)
+        c.close()
+    # argument errors are reported, not executed
+    c = _ctx(mesh, "elastic", capi.ASSEMBLY_ATOMIC)
+    c.set_bc_table([0], [0], [0])
+    for bad_code in ([5], [0 | (7 << 8)], [1, 1]):  # underflow, constant out of range, two values left
+        with pytest.raises(capi.NsmError):
+            c.set_bc_programs([0, len(bad_code)], bad_code, [1.0], 0, [0])
+    c.close()
+
+
+@pytest.mark.parametrize("assembly", ["ordered", "atomic"])
+def test_bc_programs_steps_equal_host_rows(assembly):
+    """A run of steps with device-evaluated time-dependent magnitudes == the same run with one host-evaluated row
+    per step (nsm_b200_set_bc_values_steps), bit for bit in ORDERED mode, in one call and in chunks."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, _ = perturbed_cube(6, 0.0)
+    dt = 0.2 * (1.0 / 6) / np.sqrt(K / RHO)
+    n_steps = 9
+    times, t = [], 0.0
+    for _ in range(n_steps):
+        t += dt
+        times.append(t)
+    v0 = np.zeros_like(ref)
+    v0[:, 0] = 1000.0 * ref[:, 0]
+    asm = capi.ASSEMBLY_ORDERED if assembly == "ordered" else capi.ASSEMBLY_ATOMIC
+    out = []
+    for mode in ("host", "device", "device-chunks"):
+        c = _ctx(mesh, "neohookean", asm, 2)
+        c.compute_lumped_mass()
+        c.upload("velocity", v0)
+        nodes, comps, kinds, rows, (off, code, consts, slots, prog_of) = _bc_program_setup(c, mesh, ref, BC_EXPRESSIONS, times)
+        if mode == "host":
+            c.set_bc_values_steps(rows)
+            tt = c.step(n_steps, 0.0, dt, store_ipt_last=True)
+        else:
+            c.set_bc_programs(off, code, consts, slots.shape[1], prog_of)
+            c.set_bc_values(np.zeros(len(nodes)))
+            if mode == "device":
+                c.set_bc_slots_steps(slots)
+                tt = c.step(n_steps, 0.0, dt, store_ipt_last=True)
+            else:
+                tt, s0 = 0.0, 0
+                for k in (4, 1, 4):
+                    c.set_bc_slots_steps(slots[s0:s0 + k])
+                    tt = c.step(k, tt, dt, store_ipt_last=(s0 + k == n_steps))
+                    s0 += k
+        out.append((tt, [c.download(l) for l in ("displacement", "velocity", "acceleration", "internal_force")]))
+        c.close()
+    assert np.abs(out[0][1][1]).max() > 0
+    for tt, fields in out[1:]:
+        assert tt == out[0][0]
+        for a, b in zip(fields, out[0][1]):
+            if assembly == "ordered":
+                assert np.array_equal(a.view(np.int64), b.view(np.int64))
+            else:
+                assert _rel(a, b) <= 1e-9

@@ -70,6 +70,32 @@ def test_expression_known_answers(host):
         assert int(np.float64(a.value).view(np.int64)) == bits, (ex, p)
 
 
+def test_expression_programs_reproduce_host_evaluation(host):
+    """Expression::compile -> device program (nsm_bc_op): interpreted with IEEE doubles it returns the bits of the
+    host evaluation, with every sub-expression of t alone supplied as a host-evaluated slot; expressions whose
+    position-dependent part needs libm are refused (the host keeps evaluating them)."""
+    from tests import bc_program as bp
+
+    compiled = 0
+    for ex in EXPRESSIONS + bp.EXTRA_EXPRESSIONS:
+        for (x, y, z, t) in POINTS:
+            prog = bp.compile_expression(host, ex, t)
+            if prog is None:
+                continue
+            compiled += 1
+            got, want = bp.interpret(*prog, x, y, z), bp.host_eval(host, ex, x, y, z, t)
+            assert np.float64(got).view(np.int64) == np.float64(want).view(np.int64) or (got != got and want != want), (ex, x, y, z, t)
+    assert compiled >= 4 * (len(bp.EXTRA_EXPRESSIONS) + 10)
+    for ex in bp.NOT_COMPILABLE:
+        assert bp.compile_expression(host, ex, 0.5) is None, ex
+    # a function of t alone is ONE slot and nothing else crosses per step
+    code, consts, slots = bp.compile_expression(host, " 0.0635 * (-0.5*cos(t*3.141592653589793/2.0e-4) + 0.5)", 1.0e-4)
+    assert len(code) == 1 and (code[0] & 0xff) == bp.SLOT and len(slots) == 1
+    # ... and repeated sub-expressions share their slot
+    code, consts, slots = bp.compile_expression(host, "x*cos(t) + y*cos(t)", 0.3)
+    assert len(slots) == 1
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_parser_and_material_factory_on_reference_decks(host, case):
     from nimblesm_b200.deck import parse_deck
