@@ -195,6 +195,11 @@ int nsm_b200_step(nsm_b200_ctx* ctx, int n_steps, double* time, double dt_user, 
 int nsm_b200_get_element_data(nsm_b200_ctx* ctx, int block_id, double* out /*[n_elem][8][15]*/);
 /* out [16][n_elem]: volume, then volume averages of F (9) and sigma (6) in storage order. */
 int nsm_b200_derived_element_data(nsm_b200_ctx* ctx, int block_id, double* out);
+/* Selected integration-point components of one block, split on the device: out[k][e] = ipt[e][offsets[k]],
+ * offsets in 0..119 = 15 * point + field (the reference's per-element label order, src/nimble_block.cc:84-108).
+ * Replaces the host loop of ModelData::WriteExodusOutput over GetElementDataNew (src/nimble_model_data.cc:557-596):
+ * only the requested columns cross the bus (8 B per element and component instead of 960 B per element). */
+int nsm_b200_get_element_components(nsm_b200_ctx* ctx, int block_id, int n_components, const int32_t* offsets, double* out);
 
 /* ---- shared-node exchange over NVLink peer memory (replaces VectorCommunicator::VectorReduction /
  *      ReductionClique_t MPI_Iallreduce, src/nimble_vector_communicator.h:104-157,

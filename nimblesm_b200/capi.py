@@ -40,7 +40,7 @@ SYMBOLS = [
     "nsm_b200_comm_export", "nsm_b200_comm_attach", "nsm_b200_comm_ready", "nsm_b200_timer_start",
     "nsm_b200_timer_stop", "nsm_b200_launch_count", "nsm_b200_profile", "nsm_b200_profile_read",
     "nsm_b200_fp64_peak", "nsm_b200_cold_points", "nsm_b200_set_bc_values_steps", "nsm_b200_set_bc_programs",
-    "nsm_b200_set_bc_slots_steps",
+    "nsm_b200_set_bc_slots_steps", "nsm_b200_get_element_components",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
         "nsm_b200_step": (i32, [vp, i32, dp, dbl, i32]),
         "nsm_b200_get_element_data": (i32, [vp, i32, dp]),
         "nsm_b200_derived_element_data": (i32, [vp, i32, dp]),
+        "nsm_b200_get_element_components": (i32, [vp, i32, i32, ip, dp]),
         "nsm_b200_comm_init": (i32, [vp, i32, i32, i32, ip, lp, ip]),
         "nsm_b200_comm_export": (i32, [vp, C.c_char_p]),
         "nsm_b200_comm_attach": (i32, [vp, i32, C.c_char_p]),
@@ -308,6 +309,13 @@ class Context:
     def element_data(self, block_id):
         out = np.empty((self.block_nelem[block_id], 8, 15))
         self._ck(self._L.nsm_b200_get_element_data(self._h, block_id, _dptr(out)))
+        return out
+
+    def element_components(self, block_id, offsets):
+        """out[k][e] = integration-point value offsets[k] (0..119 = 15*point + field) of element e, split on the device."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        out = np.empty((len(offsets), self.block_nelem[block_id]))
+        self._ck(self._L.nsm_b200_get_element_components(self._h, block_id, len(offsets), _iptr(offsets), _dptr(out)))
         return out
 
     def derived_element_data(self, block_id):

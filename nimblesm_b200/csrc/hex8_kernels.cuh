@@ -1020,6 +1020,17 @@ derived_kernel(int64_t n_elem, const int* __restrict__ conn, const double* X0, c
   for (int i = 0; i < 15; ++i) out[(int64_t)(i + 1) * n_elem + e] = avg[i] / vol;
 }
 
+// Output: component split of the integration-point data, out[k][e - e0] = ipt[e][off[k]] for a range of elements
+__global__ void __launch_bounds__(256)
+select_ipt_components_kernel(int64_t e0, int64_t n, int n_comp, const int* __restrict__ off, const double* __restrict__ ipt,
+                             double* __restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * n_comp) return;
+  const int64_t k = i / n, e = i - k * n;
+  out[i]          = ipt[(e0 + e) * 120 + off[k]];
+}
+
 // F = identity, sigma = 0 (Block::InitializeElementData, src/nimble_block.cc:148-207)
 __global__ void __launch_bounds__(256)
 init_ipt_kernel(int64_t n_points, double* ipt)

@@ -1205,6 +1205,45 @@ nsm_b200_derived_element_data(nsm_b200_ctx* c, int block_id, double* out)
   return NSM_OK;
 }
 
+int
+nsm_b200_get_element_components(nsm_b200_ctx* c, int block_id, int n_components, const int32_t* offsets, double* out)
+{
+  NSM_REQUIRE(c, c && c->finalized, "get_element_components: context not finalized");
+  auto it = c->blocks.find(block_id);
+  NSM_REQUIRE(c, it != c->blocks.end(), "get_element_components: unknown block id");
+  NSM_REQUIRE(c, n_components >= 0 && (n_components == 0 || (offsets && out)), "get_element_components: bad arguments");
+  for (int k = 0; k < n_components; ++k)
+    if (offsets[k] < 0 || offsets[k] >= 120) return fail(c, NSM_ERR_ARG, "get_element_components: offset %d out of 0..119", offsets[k]);
+  int rc = ensure_ipt(c);
+  if (rc) return rc;
+  const Block& b = it->second;
+  if (b.n_elem == 0 || n_components == 0) return NSM_OK;
+  // bounded staging: ranges of elements, [n_components][range] on the device, one strided copy per range
+  const int64_t range = std::min<int64_t>(b.n_elem, std::max<int64_t>(((int64_t)32 << 20) / n_components, 1024));
+  int*          d_off = nullptr;
+  double*       d_out = nullptr;
+  NSM_CUDA(c, cudaMalloc((void**)&d_off, (size_t)n_components * sizeof(int)));
+  cudaError_t e = cudaMalloc((void**)&d_out, (size_t)range * n_components * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaFree(d_off);
+    return fail(c, NSM_ERR_CUDA, "get_element_components: %s", cudaGetErrorString(e));
+  }
+  cudaMemcpyAsync(d_off, offsets, (size_t)n_components * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+  for (int64_t e0 = 0; e0 < b.n_elem && e == cudaSuccess; e0 += range) {
+    const int64_t n = std::min(range, b.n_elem - e0);
+    select_ipt_components_kernel<<<grid_for(n * n_components, 256), 256, 0, c->stream>>>(e0, n, n_components, d_off,
+                                                                                         c->ipt + b.elem_base * 120, d_out);
+    c->launches++;
+    e = cudaMemcpy2DAsync(out + e0, (size_t)b.n_elem * sizeof(double), d_out, (size_t)n * sizeof(double), (size_t)n * sizeof(double),
+                          (size_t)n_components, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // d_out is reused by the next range
+  }
+  cudaFree(d_off);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(c, NSM_ERR_CUDA, "get_element_components: %s", cudaGetErrorString(e));
+  return NSM_OK;
+}
+
 // ---- peer exchange ---------------------------------------------------------------------------------
 int
 nsm_b200_comm_init(nsm_b200_ctx* c, int rank, int world_size, int n_peers, const int32_t* peer_ranks,

@@ -420,14 +420,15 @@ ModelData::WriteExodusOutput(DataManager& data_manager, double time_current)
     const auto&   want_e = output_element_component_labels_.at(id);
     const auto&   want_d = derived_output_element_data_labels_.at(id);
     if (!want_e.empty()) {
-      const std::vector<double>& ed    = GetElementDataNew(id);
-      const auto&                comps = element_component_labels_.at(id);
+      // the requested columns are split out on the device; only they cross the bus
+      const auto&          comps = element_component_labels_.at(id);
+      std::vector<int32_t> offs(want_e.size());
+      for (size_t k = 0; k < want_e.size(); ++k) offs[k] = (int32_t)(std::find(comps.begin(), comps.end(), want_e[k]) - comps.begin());
+      std::vector<double> flat(want_e.size() * (size_t)ne);
+      d.check(nsm_b200_get_element_components(d.get(), id, (int)offs.size(), offs.data(), flat.data()),
+              "ModelData::WriteExodusOutput (integration-point components)");
       eo.resize(want_e.size());
-      for (size_t k = 0; k < want_e.size(); ++k) {
-        const size_t off = std::find(comps.begin(), comps.end(), want_e[k]) - comps.begin();
-        eo[k].resize(ne);
-        for (int64_t e = 0; e < ne; ++e) eo[k][e] = ed[(size_t)e * 120 + off];
-      }
+      for (size_t k = 0; k < want_e.size(); ++k) eo[k].assign(flat.begin() + k * (size_t)ne, flat.begin() + (k + 1) * (size_t)ne);
     }
     if (!want_d.empty()) {
       std::vector<double> flat((size_t)16 * ne);

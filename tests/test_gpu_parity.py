@@ -469,3 +469,28 @@ def test_bc_programs_steps_equal_host_rows(assembly):
                 assert np.array_equal(a.view(np.int64), b.view(np.int64))
             else:
                 assert _rel(a, b) <= 1e-9
+
+
+def test_element_components_equal_full_download():
+    """nsm_b200_get_element_components (device-side column split for the output step) == the same columns of the
+    full [n_elem][8][15] download, on two ragged blocks."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, disp = perturbed_cube(6, 1e-2)
+    conn = mesh["conn"][1]
+    mesh["block_ids"] = [2, 5]
+    mesh["conn"] = {2: np.ascontiguousarray(conn[:77]), 5: np.ascontiguousarray(conn[77:])}
+    c = _ctx(mesh, None, capi.ASSEMBLY_ATOMIC, 0, {2: ("neohookean", K, G, RHO), 5: ("elastic", K, G, RHO)})
+    c.upload("displacement", disp)
+    c.internal_force(store_ipt=True)
+    offs = [0, 14, 15 * 3 + 9, 119, 15 * 7 + 4, 0]
+    for b in (2, 5):
+        full = c.element_data(b).reshape(-1, 120)
+        got = c.element_components(b, offs)
+        assert got.shape == (len(offs), len(full))
+        for k, o in enumerate(offs):
+            assert np.array_equal(got[k].view(np.int64), full[:, o].view(np.int64))
+        assert np.abs(full[:, 9:15]).max() > 0
+    with pytest.raises(capi.NsmError):
+        c.element_components(2, [120])
+    c.close()
