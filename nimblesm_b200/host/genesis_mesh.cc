@@ -2,6 +2,10 @@
 // schema found in the reference's test meshes.
 #include "genesis_mesh.h"
 
+#include <algorithm>
+
+#include <array>
+
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
@@ -266,6 +270,123 @@ GenesisMesh::Print(bool verbose, int my_rank) const
       std::cout << "  block " << id << " \"" << block_names_.at(id) << "\": " << GetNumElementsInBlock(id) << " "
                 << GetElementType(id) << "\n";
     for (int id : node_set_ids_) std::cout << "  node set " << id << " \"" << node_set_names_.at(id) << "\": " << node_sets_.at(id).size() << " nodes\n";
+  }
+}
+
+std::vector<int>
+GenesisMesh::RcbElementPartition(int n_parts) const
+{
+  std::vector<std::array<double, 3>> cent;
+  for (int id : block_ids_) {
+    const int               npe  = block_num_nodes_per_elem_.at(id);
+    const std::vector<int>& conn = block_elem_connectivity_.at(id);
+    const size_t            nel  = npe ? conn.size() / npe : 0;
+    for (size_t e = 0; e < nel; ++e) {
+      std::array<double, 3> s{0.0, 0.0, 0.0};
+      const double*         xyz[3] = {node_x_.data(), node_y_.data(), dim_ == 3 ? node_z_.data() : nullptr};
+      for (int d = 0; d < 3; ++d) {
+        if (!xyz[d]) continue;
+        const int* n = &conn[e * npe];
+        if (npe == 8)  // balanced tree: the summation order of the Python mirror (nimblesm_b200/mesh.py, numpy's 8-way reduction)
+          s[d] = ((xyz[d][n[0]] + xyz[d][n[1]]) + (xyz[d][n[2]] + xyz[d][n[3]])) + ((xyz[d][n[4]] + xyz[d][n[5]]) + (xyz[d][n[6]] + xyz[d][n[7]]));
+        else
+          for (int j = 0; j < npe; ++j) s[d] += xyz[d][n[j]];
+        s[d] /= npe;
+      }
+      cent.push_back(s);
+    }
+  }
+  std::vector<int> part(cent.size(), 0), ids(cent.size());
+  for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;
+  // explicit stack of (begin, end, first part, number of parts) over `ids`; ties keep the order of the level above
+  // (ascending element order at the root)
+  struct Job { size_t b, e; int p0, np; };
+  std::vector<Job> jobs{{0, ids.size(), 0, n_parts < 1 ? 1 : n_parts}};
+  while (!jobs.empty()) {
+    const Job j = jobs.back();
+    jobs.pop_back();
+    if (j.np == 1) {
+      for (size_t i = j.b; i < j.e; ++i) part[ids[i]] = j.p0;
+      continue;
+    }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (size_t i = j.b; i < j.e; ++i)
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = std::min(lo[d], cent[ids[i]][d]);
+        hi[d] = std::max(hi[d], cent[ids[i]][d]);
+      }
+    int d = 0;
+    for (int k = 1; k < 3; ++k)
+      if (hi[k] - lo[k] > hi[d] - lo[d]) d = k;
+    std::stable_sort(ids.begin() + j.b, ids.begin() + j.e, [&](int a, int b) { return cent[a][d] < cent[b][d]; });
+    const int    left = j.np / 2;
+    const size_t cut  = j.b + ((j.e - j.b) * (size_t)left) / (size_t)j.np;
+    jobs.push_back({j.b, cut, j.p0, left});
+    jobs.push_back({cut, j.e, j.p0 + left, j.np - left});
+  }
+  return part;
+}
+
+void
+GenesisMesh::KeepPart(std::vector<int> const& part_of_element, int part)
+{
+  std::vector<char> used(node_x_.size(), 0);
+  size_t            flat = 0;
+  std::vector<int>  kept_blocks, new_elem_gid;
+  for (int id : block_ids_) {
+    const int         npe  = block_num_nodes_per_elem_.at(id);
+    std::vector<int>& conn = block_elem_connectivity_.at(id);
+    std::vector<int>& gids = block_elem_global_ids_.at(id);
+    const size_t      nel  = npe ? conn.size() / npe : 0;
+    std::vector<int>  c2, g2;
+    for (size_t e = 0; e < nel; ++e, ++flat) {
+      if (flat >= part_of_element.size()) throw std::invalid_argument("GenesisMesh::KeepPart: partition vector too short");
+      if (part_of_element[flat] != part) continue;
+      for (int j = 0; j < npe; ++j) {
+        c2.push_back(conn[e * npe + j]);
+        used[conn[e * npe + j]] = 1;
+      }
+      g2.push_back(gids[e]);
+    }
+    conn.swap(c2);
+    gids.swap(g2);
+    if (!gids.empty()) {
+      kept_blocks.push_back(id);
+      new_elem_gid.insert(new_elem_gid.end(), gids.begin(), gids.end());
+    }
+  }
+  // blocks without an element in this part disappear from the local list (as in a Nemesis piece); names stay global
+  for (int id : block_ids_)
+    if (std::find(kept_blocks.begin(), kept_blocks.end(), id) == kept_blocks.end()) {
+      block_elem_connectivity_.erase(id), block_elem_global_ids_.erase(id), block_num_nodes_per_elem_.erase(id);
+      block_names_.erase(id);
+    }
+  block_ids_      = kept_blocks;
+  elem_global_id_ = new_elem_gid;
+  std::vector<int> remap(node_x_.size(), -1);
+  std::vector<int>    gid2;
+  std::vector<double> x2, y2, z2;
+  for (size_t n = 0; n < used.size(); ++n)
+    if (used[n]) {
+      remap[n] = (int)gid2.size();
+      gid2.push_back(node_global_id_[n]);
+      x2.push_back(node_x_[n]), y2.push_back(node_y_[n]);
+      if (n < node_z_.size()) z2.push_back(node_z_[n]);
+    }
+  node_global_id_.swap(gid2), node_x_.swap(x2), node_y_.swap(y2), node_z_.swap(z2);
+  for (int id : block_ids_)
+    for (int& n : block_elem_connectivity_.at(id)) n = remap[n];
+  for (auto& kv : node_sets_) {
+    std::vector<int>     keep;
+    std::vector<double>  df;
+    std::vector<double>& old_df = ns_distribution_factors_[kv.first];
+    for (size_t k = 0; k < kv.second.size(); ++k)
+      if (remap[kv.second[k]] >= 0) {
+        keep.push_back(remap[kv.second[k]]);
+        if (k < old_df.size()) df.push_back(old_df[k]);
+      }
+    kv.second.swap(keep);
+    old_df.swap(df);
   }
 }
 

@@ -175,6 +175,19 @@ class GenesisMesh
   void
   Print(bool verbose = false, int my_rank = 0) const;
 
+  // ---- in-driver domain decomposition (the B200 build's replacement for the offline SEACAS `decomp` step the
+  //      reference needs before an MPI run, test/_wip/scaling_study/decomp.sh) ---------------------------------
+  // Recursive coordinate bisection of the ELEMENTS by centroid: part of every element, blocks in GetBlockIds()
+  // order, elements in block order.  Cuts fall on the longest extent; ties keep ascending element order, so every
+  // rank computes the same partition from the same file.
+  std::vector<int>
+  RcbElementPartition(int n_parts) const;
+  // Reduces this mesh to one part, exactly as a Nemesis piece presents it: the part's elements (block order kept),
+  // every node they touch (ascending, shared nodes duplicated between parts and matched by global id,
+  // src/nimble.mpi.reduction.cc:50-123), node sets restricted to those nodes, all block ids / names kept.
+  void
+  KeepPart(std::vector<int> const& part_of_element, int part);
+
  protected:
   std::string                        file_name_;
   int                                dim_;

@@ -156,6 +156,55 @@ nsmh_mesh_summary(const char* path, char* out, int outlen, char* err, int errlen
 // reads a Genesis file and writes an Exodus file with `n_steps` planes of synthetic data through ExodusOutput:
 // nodal displacement_{x,y,z} = (step+1) * coordinate, element "volume" = element index + step, per-point
 // "ipt01_stress_xx" = 10 * element index + step.  The test reads the file back with scipy.
+// GenesisMesh::RcbElementPartition + KeepPart: JSON summary of one part of a serial mesh
+int
+nsmh_mesh_part(const char* path, int n_parts, int part, char* out, int outlen, char* err, int errlen)
+{
+  try {
+    GenesisMesh m;
+    m.ReadFile(path);
+    m.KeepPart(m.RcbElementPartition(n_parts), part);
+    std::ostringstream j;
+    j.precision(17);
+    auto list = [&](const int* p, size_t n) {
+      j << "[";
+      for (size_t i = 0; i < n; ++i) j << (i ? "," : "") << p[i];
+      j << "]";
+    };
+    j << "{\"node_gid\":";
+    list(m.GetNodeGlobalIds(), m.GetNumNodes());
+    j << ",\"x\":[";
+    for (unsigned i = 0; i < m.GetNumNodes(); ++i) j << (i ? "," : "") << m.GetCoordinatesX()[i];
+    j << "],\"block_ids\":";
+    auto ids = m.GetBlockIds();
+    list(ids.data(), ids.size());
+    j << ",\"all_block_ids\":";
+    auto all = m.GetAllBlockIds();
+    list(all.data(), all.size());
+    j << ",\"elem_gid\":{";
+    for (size_t b = 0; b < ids.size(); ++b) {
+      j << (b ? "," : "") << "\"" << ids[b] << "\":";
+      list(m.GetElementGlobalIdsInBlock(ids[b]).data(), m.GetElementGlobalIdsInBlock(ids[b]).size());
+    }
+    j << "},\"conn\":{";
+    for (size_t b = 0; b < ids.size(); ++b) {
+      j << (b ? "," : "") << "\"" << ids[b] << "\":";
+      list(m.GetConnectivity(ids[b]), (size_t)m.GetNumElementsInBlock(ids[b]) * m.GetNumNodesPerElement(ids[b]));
+    }
+    j << "},\"node_sets\":{";
+    bool first = true;
+    for (auto const& kv : m.GetNodeSets()) {
+      j << (first ? "" : ",") << "\"" << kv.first << "\":";
+      list(kv.second.data(), kv.second.size());
+      first = false;
+    }
+    j << "}}";
+    return put(out, outlen, j.str(), err, errlen);
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
 int
 nsmh_exodus_roundtrip(const char* genesis_path, const char* out_path, int n_steps, char* err, int errlen)
 {

@@ -3,6 +3,7 @@
 
 #include <chrono>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <thread>
 
@@ -234,7 +235,17 @@ NimbleApplication::ExecRank(int rank, std::shared_ptr<RankGroup> group)
       std::cout << "\n-- NimbleSM_b200 (" << nsm_b200_version() << ")\n-- input deck " << options_.input_file << ", " << options_.num_ranks
                 << " rank(s), one B200 each\n";
     GenesisMesh mesh;
-    mesh.ReadFile(IOFileName(parser->GenesisFileName(), "g", "", rank, options_.num_ranks));
+    const std::string piece = IOFileName(parser->GenesisFileName(), "g", "", rank, options_.num_ranks);
+    if (options_.num_ranks > 1 && !std::ifstream(piece).good() && std::ifstream(parser->GenesisFileName()).good()) {
+      // no Nemesis pieces on disk: decompose the serial mesh here (the reference needs an offline SEACAS decomp run)
+      mesh.ReadFile(parser->GenesisFileName());
+      mesh.KeepPart(mesh.RcbElementPartition(options_.num_ranks), rank);
+      if (rank == 0 && !options_.quiet)
+        std::cout << "-- " << parser->GenesisFileName() << " decomposed in the driver: recursive coordinate bisection of elements into "
+                  << options_.num_ranks << " parts\n";
+    } else {
+      mesh.ReadFile(piece);
+    }
     DataManager data_manager(*parser, mesh, rank, options_.assembly, options_.flags, group);
     data_manager.SetBlockMaterialInterfaceFactory(CreateBlockMaterialInterfaceFactory());
     data_manager.GetModelData()->InitializeBlocks(data_manager, CreateMaterialFactory());

@@ -156,6 +156,34 @@ def test_driver_on_decomposed_meshes(case, P, tmp_path):
     _check_against_reference(mesh, gold, ref, res)
 
 
+@pytest.mark.parametrize("case,P", [("brick_with_fibers", 2), ("wave_in_bar", 2), ("notched_plate_native_neohookean", 4)])
+def test_driver_decomposes_a_serial_mesh(case, P, tmp_path):
+    """`NimbleSM_b200 --gpus P` on a SERIAL Genesis file with no Nemesis pieces on disk: the driver bisects the
+    elements itself (GenesisMesh::RcbElementPartition), runs one rank per part and writes per-rank outputs whose
+    id maps join into the serial result (gold file + reference snapshots).  Needs P GPUs."""
+    if _num_gpus() < P:
+        pytest.skip("needs %d GPUs" % P)
+    import re
+
+    from nimblesm_b200.exodus_py import read_results
+
+    deck, mesh, gold, ref, _pieces, _out = _run(tmp_path, case, extra=("--gpus", str(P)))
+    out = re.search(r"exodus output file:\s*(\S+)", deck).group(1)
+    stem = out[:-2] if out.endswith(".e") else out
+    pieces = {}
+    for r in range(P):
+        pr = read_results(str(tmp_path / ("%s.out.e.%d.%d" % (stem, P, r))))
+        eg, k = {}, 0
+        for b, n in zip(pr["block_ids"], pr["num_el_in_blk"]):
+            if n:
+                eg[b] = pr["elem_gid"][k:k + n]
+            k += n
+        pieces[(P, r)] = {"node_gid": pr["node_gid"], "elem_gid": eg}
+    assert sum(len(p["node_gid"]) for p in pieces.values()) > len(mesh["x"])  # shared nodes are duplicated
+    res = _join_pieces(tmp_path, stem, P, pieces, mesh)
+    _check_against_reference(mesh, gold, ref, res)
+
+
 def test_driver_time_dependent_bc_on_device_equals_host_evaluation(tmp_path):
     """A deck with time-dependent expression BCs: the driver compiles them into device programs (only the
     sub-expressions of t are evaluated on the host, one scalar per step); with NSM_B200_HOST_BC=1 it evaluates one

@@ -191,6 +191,36 @@ def test_genesis_reader_on_the_reference_files(host):
     assert n >= 20
 
 
+@pytest.mark.parametrize("case,P", [("brick_with_fibers", 2), ("notched_plate_native_neohookean", 4), ("wave_in_bar", 3),
+                                    ("simple_deformation_modes", 8)])
+def test_driver_side_rcb_decomposition(host, tmp_path, case, P):
+    """GenesisMesh::RcbElementPartition + KeepPart (what `NimbleSM_b200 --gpus P` does to a serial mesh when no
+    Nemesis pieces exist) against the Python mirror nimblesm_b200.mesh.rcb_partition: same parts, same local
+    numbering, node sets restricted alike; every element lands in exactly one part."""
+    from nimblesm_b200.exodus_py import write_genesis
+    from nimblesm_b200.mesh import rcb_partition
+
+    _deck, mesh, _gold, _ref, _pieces = load_golden(case)
+    p = str(tmp_path / "m.g")
+    write_genesis(p, mesh)
+    want = rcb_partition(mesh, P)
+    seen = {b: [] for b in mesh["block_ids"]}
+    for r in range(P):
+        got = _call_json(host.nsmh_mesh_part, p.encode(), P, r)
+        w = want[r]
+        assert got["block_ids"] == list(w["block_ids"]) and got["all_block_ids"] == list(mesh["all_block_ids"])
+        assert got["node_gid"] == [int(g) for g in w["node_gid"]]
+        assert np.array_equal(np.array(got["x"]), w["x"])
+        for b in w["block_ids"]:
+            assert got["elem_gid"][str(b)] == [int(g) for g in w["elem_gid"][b]]
+            assert got["conn"][str(b)] == [int(n) for n in w["conn"][b].ravel()]
+            seen[b] += got["elem_gid"][str(b)]
+        for sid, ns in w["node_sets"].items():
+            assert got["node_sets"][str(sid)] == [int(n) for n in ns]
+    for b in mesh["block_ids"]:
+        assert sorted(seen[b]) == sorted(int(g) for g in mesh["elem_gid"][b])
+
+
 def test_exodus_writer_round_trip(host, tmp_path):
     from nimblesm_b200.exodus_py import read_results, write_genesis
 
