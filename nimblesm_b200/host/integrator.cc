@@ -2,6 +2,7 @@
 #include "integrator.h"
 
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -246,6 +247,8 @@ NimbleApplication::ExecRank(int rank, std::shared_ptr<RankGroup> group)
     } else {
       mesh.ReadFile(piece);
     }
+    // one GPU per rank.  (Ranks cannot share a device: a rank's in-kernel wait for its peer would sit in front of
+    // every device-synchronising call of that peer's host thread.)
     DataManager data_manager(*parser, mesh, rank, options_.assembly, options_.flags, group);
     data_manager.SetBlockMaterialInterfaceFactory(CreateBlockMaterialInterfaceFactory());
     data_manager.GetModelData()->InitializeBlocks(data_manager, CreateMaterialFactory());

@@ -109,6 +109,13 @@ def _num_gpus():
         return 0
 
 
+def _rank_flags(P):
+    """One GPU per rank (ranks cannot share a device, see NimbleApplication::ExecRank)."""
+    if _num_gpus() < P:
+        pytest.skip("needs %d GPUs" % P)
+    return ("--gpus", str(P))
+
+
 def _join_pieces(tmp_path, stem, P, pieces, mesh):
     """epu: per-rank results -> global arrays by global node / element id (shared nodes must agree bit for bit)."""
     from nimblesm_b200.exodus_py import read_results
@@ -145,11 +152,9 @@ def test_driver_on_decomposed_meshes(case, P, tmp_path):
     """The reference's -np2 / -np4 regression runs: one rank (thread + GPU) per Nemesis piece, shared-node forces
     summed over NVLink peer memory, per-rank outputs joined by global id and compared with the SERIAL gold file and
     the serial reference snapshots.  Needs P GPUs (gpurun --gpus P)."""
-    if _num_gpus() < P:
-        pytest.skip("needs %d GPUs" % P)
     import re
 
-    deck, mesh, gold, ref, pieces, _out = _run(tmp_path, case, extra=("--gpus", str(P)), pieces=P)
+    deck, mesh, gold, ref, pieces, _out = _run(tmp_path, case, extra=_rank_flags(P), pieces=P)
     out = re.search(r"exodus output file:\s*(\S+)", deck).group(1)
     stem = out[:-2] if out.endswith(".e") else out
     res = _join_pieces(tmp_path, stem, P, pieces, mesh)
@@ -160,14 +165,12 @@ def test_driver_on_decomposed_meshes(case, P, tmp_path):
 def test_driver_decomposes_a_serial_mesh(case, P, tmp_path):
     """`NimbleSM_b200 --gpus P` on a SERIAL Genesis file with no Nemesis pieces on disk: the driver bisects the
     elements itself (GenesisMesh::RcbElementPartition), runs one rank per part and writes per-rank outputs whose
-    id maps join into the serial result (gold file + reference snapshots).  Needs P GPUs."""
-    if _num_gpus() < P:
-        pytest.skip("needs %d GPUs" % P)
+    id maps join into the serial result (gold file + reference snapshots)."""
     import re
 
     from nimblesm_b200.exodus_py import read_results
 
-    deck, mesh, gold, ref, _pieces, _out = _run(tmp_path, case, extra=("--gpus", str(P)))
+    deck, mesh, gold, ref, _pieces, _out = _run(tmp_path, case, extra=_rank_flags(P))
     out = re.search(r"exodus output file:\s*(\S+)", deck).group(1)
     stem = out[:-2] if out.endswith(".e") else out
     pieces = {}
