@@ -43,6 +43,9 @@ constexpr int kWarpSmemBase   = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDo
 #ifndef NSM_BINV_STAGE
 #define NSM_BINV_STAGE 1
 #endif
+#ifndef NSM_BINV_STAGE_ELASTIC
+#define NSM_BINV_STAGE_ELASTIC 0
+#endif
 
 struct ElemArgs
 {
@@ -161,7 +164,7 @@ enum { kModeStoreIpt = 1, kModeReadBinv = 2 };
 template <int MAT, int MODE>
 struct BinvStaged
 {
-  static constexpr bool value = NSM_BINV_STAGE && (MODE & kModeReadBinv) && MAT == 1;
+  static constexpr bool value = NSM_BINV_STAGE && (MODE & kModeReadBinv) && (MAT == 1 || NSM_BINV_STAGE_ELASTIC);
 };
 
 template <int MAT, int MODE>
@@ -435,8 +438,10 @@ element_force_kernel(const ElemArgs p)
     if (has_next) stage_gather(p, wsm + (stage ^ 1) * kStageDoubles, sN[slot_next * 32], q, ew);
     stage_group_node(p, sN + slot_nn * 32, g_nn, n_groups, ew, q);
     cp_async_commit();
+#ifdef NSM_BINV_PREFETCH  // measured (r01y): the L2 prefetch a pass ahead of the copy costs 0.5 % instead of helping
     if ((MODE & kModeReadBinv) && g_nn < n_groups && lane < (kBinvGroupDoubles * 8) / 128)
       prefetch_l2(p.binv_cache + (int64_t)g_nn * kBinvGroupDoubles + lane * 16);  // DRAM -> L2 a full pass before the cp.async
+#endif
 
     const int64_t e    = (int64_t)g * kElemsPerWarp + ew;
     const double* sX   = wsm + stage * kStageDoubles;

@@ -10,9 +10,8 @@ build() { # name, extra flags
      -Xcompiler -fPIC -ccbin /usr/bin/g++ $2 -shared -o ../lib/variants/libnsm_b200_$1.so nsm_b200.cu \
      -Xptxas -v 2> ../lib/variants/ptxas_$1.log &
 }
-build t256b2_nostage "-DNSM_BINV_STAGE=0"
-build t192b3_nostage "-DNSM_ELEM_THREADS=192 -DNSM_ELEM_MIN_BLOCKS=3 -DNSM_BINV_STAGE=0"
-build t192b3_r112_nostage "-DNSM_ELEM_THREADS=192 -DNSM_ELEM_MIN_BLOCKS=3 -DNSM_BINV_STAGE=0 -DNSM_ELEM_MAXREG=112"
-build t160b4_nostage "-DNSM_ELEM_THREADS=160 -DNSM_ELEM_MIN_BLOCKS=4 -DNSM_BINV_STAGE=0"
+build stage_elastic "-DNSM_BINV_STAGE_ELASTIC=1"
+build prefetch "-DNSM_BINV_PREFETCH"
+build expensive "-Xptxas --allow-expensive-optimizations=true"
 wait
 for f in ../lib/variants/ptxas_*.log; do echo $f; grep -A2 "element_force_kernelILi1ELb0ELi2E\|element_force_kernelILi0ELb0ELi2E" $f | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores"; done
