@@ -22,7 +22,10 @@ constexpr int kLenName = 256;  // the reference writes MAX_NAME_LENGTH = 255 + 1
 }  // namespace
 
 ExodusOutput::ExodusOutput()  = default;
-ExodusOutput::~ExodusOutput() = default;
+ExodusOutput::~ExodusOutput()
+{
+  if (writer_.joinable()) writer_.join();
+}
 
 void
 ExodusOutput::Initialize(std::string const& filename, GenesisMesh const& mesh)
@@ -209,6 +212,17 @@ ExodusOutput::WriteStep(double time, std::vector<double> const& global_data, std
                         std::map<int, std::vector<std::vector<double>>> const& derived_elem_data)
 {
   if (!file_) throw std::runtime_error("ExodusOutput::WriteStep before InitializeDatabase");
+  Wait();
+  WritePlane(time, global_data, node_data, elem_data_names, elem_data, derived_elem_data_names, derived_elem_data);
+}
+
+void
+ExodusOutput::WritePlane(double time, std::vector<double> const& global_data, std::vector<std::vector<double>> const& node_data,
+                         std::map<int, std::vector<std::string>> const& elem_data_names,
+                         std::map<int, std::vector<std::vector<double>>> const& elem_data,
+                         std::map<int, std::vector<std::string>> const& derived_elem_data_names,
+                         std::map<int, std::vector<std::vector<double>>> const& derived_elem_data)
+{
   nc3::Writer&  f   = *file_;
   const int64_t rec = exodus_write_count_;
   exodus_write_count_ += 1;
@@ -229,8 +243,39 @@ ExodusOutput::WriteStep(double time, std::vector<double> const& global_data, std
 }
 
 void
+ExodusOutput::WriteStepAsync(double time, std::vector<double> global_data, std::vector<std::vector<double>> node_data,
+                             std::map<int, std::vector<std::string>> elem_data_names,
+                             std::map<int, std::vector<std::vector<double>>> elem_data,
+                             std::map<int, std::vector<std::string>> derived_elem_data_names,
+                             std::map<int, std::vector<std::vector<double>>> derived_elem_data)
+{
+  if (!file_) throw std::runtime_error("ExodusOutput::WriteStepAsync before InitializeDatabase");
+  Wait();
+  writer_ = std::thread([this, time, g = std::move(global_data), n = std::move(node_data), en = std::move(elem_data_names),
+                         e = std::move(elem_data), dn = std::move(derived_elem_data_names), d = std::move(derived_elem_data)] {
+    try {
+      WritePlane(time, g, n, en, e, dn, d);
+    } catch (...) {
+      writer_error_ = std::current_exception();
+    }
+  });
+}
+
+void
+ExodusOutput::Wait()
+{
+  if (writer_.joinable()) writer_.join();
+  if (writer_error_) {
+    std::exception_ptr e = writer_error_;
+    writer_error_        = nullptr;
+    std::rethrow_exception(e);
+  }
+}
+
+void
 ExodusOutput::Close()
 {
+  Wait();
   if (file_) file_->close();
 }
 

@@ -3,9 +3,11 @@
 // direct NetCDF-3 (64-bit offset) writer producing the same dimensions / variables / names the reference's
 // outputs contain, so that exodiff / epu / ParaView read the file like a reference one.
 #pragma once
+#include <exception>
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace nimble_b200 {
@@ -41,6 +43,17 @@ class ExodusOutput
             std::map<int, std::vector<std::vector<double>>> const& elem_data,
             std::map<int, std::vector<std::string>> const& derived_elem_data_names,
             std::map<int, std::vector<std::vector<double>>> const& derived_elem_data);
+  // The same time plane, written by a background thread while the caller goes on stepping (the data is moved
+  // into the job; at most one plane is in flight: the call first waits for the previous one).  At 8 M elements a
+  // plane of 12 variables is 0.8 GB of file I/O, about as long as the 500 steps between two outputs.  Errors of
+  // the writer thread surface at the next WriteStep / WriteStepAsync / Wait / Close.
+  void
+  WriteStepAsync(double time, std::vector<double> global_data, std::vector<std::vector<double>> node_data,
+                 std::map<int, std::vector<std::string>> elem_data_names, std::map<int, std::vector<std::vector<double>>> elem_data,
+                 std::map<int, std::vector<std::string>> derived_elem_data_names,
+                 std::map<int, std::vector<std::vector<double>>> derived_elem_data);
+  void
+  Wait();
   int
   GetNumWrites() const
   {
@@ -50,6 +63,12 @@ class ExodusOutput
   Close();
 
  private:
+  void
+  WritePlane(double time, std::vector<double> const& global_data, std::vector<std::vector<double>> const& node_data,
+             std::map<int, std::vector<std::string>> const& elem_data_names,
+             std::map<int, std::vector<std::vector<double>>> const& elem_data,
+             std::map<int, std::vector<std::string>> const& derived_elem_data_names,
+             std::map<int, std::vector<std::vector<double>>> const& derived_elem_data);
   std::string                  filename_;
   int                          dim_ = 3, num_nodes_ = 0, num_elements_ = 0, num_blocks_ = 0, num_global_blocks_ = 0;
   int                          num_node_sets_ = 0;
@@ -59,6 +78,8 @@ class ExodusOutput
   int                          num_node_vars_ = 0, num_global_vars_ = 0;
   int                          exodus_write_count_ = 0;
   std::unique_ptr<nc3::Writer> file_;
+  std::thread                  writer_;
+  std::exception_ptr           writer_error_;
 };
 
 }  // namespace nimble_b200

@@ -153,9 +153,6 @@ nsmh_mesh_summary(const char* path, char* out, int outlen, char* err, int errlen
   }
 }
 
-// reads a Genesis file and writes an Exodus file with `n_steps` planes of synthetic data through ExodusOutput:
-// nodal displacement_{x,y,z} = (step+1) * coordinate, element "volume" = element index + step, per-point
-// "ipt01_stress_xx" = 10 * element index + step.  The test reads the file back with scipy.
 // GenesisMesh::RcbElementPartition + KeepPart: JSON summary of one part of a serial mesh
 int
 nsmh_mesh_part(const char* path, int n_parts, int part, char* out, int outlen, char* err, int errlen)
@@ -205,6 +202,9 @@ nsmh_mesh_part(const char* path, int n_parts, int part, char* out, int outlen, c
   }
 }
 
+// reads a Genesis file and writes an Exodus file with `n_steps` planes of synthetic data through ExodusOutput:
+// nodal displacement_{x,y,z} = (step+1) * coordinate, element "volume" = element index + step, per-point
+// "ipt01_stress_xx" = 10 * element index + step.  The test reads the file back with scipy.
 int
 nsmh_exodus_roundtrip(const char* genesis_path, const char* out_path, int n_steps, char* err, int errlen)
 {
@@ -234,7 +234,10 @@ nsmh_exodus_roundtrip(const char* genesis_path, const char* out_path, int n_step
         derived[id].assign(1, std::vector<double>(ne));
         for (int e = 0; e < ne; ++e) elem[id][0][e] = 10.0 * e + s, derived[id][0][e] = e + s;
       }
-      ex.WriteStep(0.25 * s, {}, node, elem_names, elem, derived_names, derived);
+      if (s % 2)  // both entries: the synchronous one and the background writer (copies are moved into the job)
+        ex.WriteStepAsync(0.25 * s, {}, node, elem_names, elem, derived_names, derived);
+      else
+        ex.WriteStep(0.25 * s, {}, node, elem_names, elem, derived_names, derived);
     }
     ex.Close();
     return 0;

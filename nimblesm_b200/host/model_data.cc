@@ -446,8 +446,10 @@ ModelData::WriteExodusOutput(DataManager& data_manager, double time_current)
       }
     }
   }
-  data_manager.GetExodusOutput()->WriteStep(time_current, global_data, node_out, output_element_component_labels_, elem_out,
-                                            derived_output_element_data_labels_, derived_out);
+  // the file I/O of this plane runs on the writer thread while the integrator goes on stepping
+  data_manager.GetExodusOutput()->WriteStepAsync(time_current, std::move(global_data), std::move(node_out),
+                                                 output_element_component_labels_, std::move(elem_out),
+                                                 derived_output_element_data_labels_, std::move(derived_out));
 }
 
 }  // namespace nimble_b200
