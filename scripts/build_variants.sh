@@ -10,8 +10,7 @@ build() { # name, extra flags
      -Xcompiler -fPIC -ccbin /usr/bin/g++ $2 -shared -o ../lib/variants/libnsm_b200_$1.so nsm_b200.cu \
      -Xptxas -v 2> ../lib/variants/ptxas_$1.log &
 }
-build stage_elastic "-DNSM_BINV_STAGE_ELASTIC=1"
 build prefetch "-DNSM_BINV_PREFETCH"
-build expensive "-Xptxas --allow-expensive-optimizations=true"
+build stage_elastic "-DNSM_BINV_STAGE_ELASTIC=1"
 wait
 for f in ../lib/variants/ptxas_*.log; do echo $f; grep -A2 "element_force_kernelILi1ELb0ELi2E\|element_force_kernelILi0ELb0ELi2E" $f | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores"; done
