@@ -99,7 +99,7 @@ def initial_velocity(mesh):
     return v
 
 
-def cpu_baseline(material, cores, budget_s=15.0):
+def cpu_baseline(material, cores, budget_s=15.0, single_core=False):
     """The reference's own serial per-element code (oracle/_ref, compiled from /root/reference/src) on `cores`
     host threads, bounded sample; falls back to the plain-C port when the reference objects are absent."""
     from nimblesm_b200.mesh import structured_cube
@@ -127,9 +127,16 @@ def cpu_baseline(material, cores, budget_s=15.0):
     t1 = run(1)
     steps = int(max(2, min(400, budget_s / max(t1, 1e-3))))
     t = run(steps)
-    return {"value": len(conn) * steps / t, "unit": "element-updates/s", "cores": cores, "kind": kind,
-            "sample": "%d^3 hex8 cube (%d elements), %s, %d explicit steps, %d threads over element chunks, %.1f s"
-                      % (n, len(conn), material, steps, cores, t)}, t / steps
+    out = {"value": len(conn) * steps / t, "unit": "element-updates/s", "cores": cores, "kind": kind,
+           "sample": "%d^3 hex8 cube (%d elements), %s, %d explicit steps, %d threads over element chunks, %.1f s"
+                     % (n, len(conn), material, steps, cores, t)}
+    if single_core:
+        # the reference's own build is serial (its only multi-core path is Kokkos-OpenMP): one thread
+        cores_all, cores = cores, 1
+        ts = run(2)
+        out["single_core_value"] = len(conn) * 2 / ts
+        cores = cores_all
+    return out, t / steps
 
 
 def run_reference(args):
@@ -377,7 +384,7 @@ def main():
         out["e2e"] = e2e
     if not args.no_cpu and world == 1:
         try:
-            out["cpu_baseline"], _ = cpu_baseline(args.material, os.cpu_count() or 1)
+            out["cpu_baseline"], _ = cpu_baseline(args.material, os.cpu_count() or 1, single_core=True)
         except Exception as ex:  # the checker libraries are test infrastructure; report, do not hide
             out["cpu_baseline"] = {"error": str(ex)}
     print(json.dumps(out))
