@@ -37,6 +37,7 @@ constexpr int kCoordDoubles  = 3 * kCoordComp;       // one [3][8] coordinate se
 constexpr int kStageDoubles  = 2 * kCoordDoubles;    // X and u of one group, filled by cp.async
 constexpr int kShareStride   = 34;                   // even: the transposed read takes Gauss-point pairs as 16-byte loads; rows 3 apart land 12 banks apart, conflict free
 constexpr int kShareDoubles  = 24 * kShareStride;
+constexpr int kEfStride      = 3;                    // ORDERED: (element, node) slots of fx, fy, fz, contiguous: neighbouring nodes share sectors (32-byte padded slots measured no faster, r01B)
 constexpr int kBinvGroupDoubles = 9 * 32;            // cached b^-1 of one group: [9][32 lanes]
 constexpr int kConnSlotDoubles = 3 * 32 / 2 + 2;               // connectivity of three groups in flight: [3][32 lanes] int; + the next chunk's skip-mask word
 constexpr int kWarpSmemBase   = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDoubles + kConnSlotDoubles;  // stages, K, C, shares, conn (+ staged b^-1)
@@ -54,7 +55,7 @@ struct ElemArgs
   const double* X[3];        // reference coordinates, SoA
   const double* u[3];        // displacement, SoA
   double*       f[3];        // nodal internal force, SoA (ATOMIC)
-  double*       ef;          // [n_elem][8][3] element nodal forces (ORDERED), already offset to the block
+  double*       ef;          // [n_elem][8][kEfStride] element nodal forces (ORDERED), already offset to the block
   double*       ipt;         // [n_elem][8][15] or nullptr
   double*       binv_cache;  // [n_groups][9][32] or nullptr, already offset to the block
   double        bulk, shear;
@@ -503,7 +504,7 @@ element_force_kernel(const ElemArgs p)
     }
     if (live) {
       if (ORDERED) {
-        double* o = p.ef + (e * 8 + q) * 3;
+        double* o = p.ef + (e * 8 + q) * kEfStride;
         o[0] = fx, o[1] = fy, o[2] = fz;
       } else {
         atomicAdd(p.f[0] + node, fx);
@@ -517,6 +518,38 @@ element_force_kernel(const ElemArgs p)
     g_nn   = g_nn < n_groups ? next_group() : n_groups;
     slot   = slot_next;
     stage ^= 1;
+  }
+}
+
+// ORDERED assembly: nodal force = sum of the node's element contributions in ascending (block, element) order
+// (the serial reference's order).  Lists of up to 8 entries (every node of a hex mesh but the odd irregular one)
+// load all slot ids first and then all 24 values, so that the loads overlap instead of forming a chain of 2 x 8
+// dependent round trips; the additions keep the list order.
+__device__ __forceinline__ void
+ordered_node_sum(const double* __restrict__ ef, const int64_t* __restrict__ adj_off, const uint32_t* __restrict__ adj_slot,
+                 int64_t node, double& f0, double& f1, double& f2)
+{
+  const int64_t b = adj_off[node], e = adj_off[node + 1];
+  f0 = 0.0, f1 = 0.0, f2 = 0.0;
+  if (e - b <= 8) {
+    const int n = (int)(e - b);
+    uint32_t  slot[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) slot[k] = k < n ? adj_slot[b + k] : 0u;
+    double v[8][3];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double* s = ef + (int64_t)slot[k] * kEfStride;
+      if (k < n) v[k][0] = s[0], v[k][1] = s[1], v[k][2] = s[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < n) f0 += v[k][0], f1 += v[k][1], f2 += v[k][2];
+  } else {
+    for (int64_t k = b; k < e; ++k) {
+      const double* s = ef + (int64_t)adj_slot[k] * kEfStride;
+      f0 += s[0], f1 += s[1], f2 += s[2];
+    }
   }
 }
 
@@ -554,11 +587,8 @@ gather_shared_nodes_kernel(int64_t n_shared, const int* __restrict__ shared_node
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_shared) return;
   const int nd = shared_node[i];
-  double    a = 0.0, b = 0.0, c = 0.0;
-  for (int64_t k = adj_off[nd]; k < adj_off[nd + 1]; ++k) {
-    const double* s = ef + (int64_t)adj_slot[k] * 3;
-    a += s[0], b += s[1], c += s[2];
-  }
+  double    a, b, c;
+  ordered_node_sum(ef, adj_off, adj_slot, nd, a, b, c);
   f0[nd] = a, f1[nd] = b, f2[nd] = c;
 }
 
@@ -644,7 +674,7 @@ struct NodeArgs
   const int*      bc_kind;
   const double*   bc_value;
   // ORDERED assembly
-  const double*   ef;         // [slots][3]
+  const double*   ef;         // [slots][kEfStride]
   const int64_t*  adj_off;    // [n_nodes+1]
   const uint32_t* adj_slot;   // slot = global element * 8 + local node, ascending per node
 };
@@ -696,14 +726,7 @@ node_correct_kernel(const NodeArgs p, double hdt, int update_velocity)
   if (i >= p.n_nodes) return;
   double f0, f1, f2;
   if (ORDERED) {
-    f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    const int64_t b = p.adj_off[i], e = p.adj_off[i + 1];
-    for (int64_t k = b; k < e; ++k) {
-      const double* s = p.ef + (int64_t)p.adj_slot[k] * 3;
-      f0 += s[0];
-      f1 += s[1];
-      f2 += s[2];
-    }
+    ordered_node_sum(p.ef, p.adj_off, p.adj_slot, i, f0, f1, f2);
     p.f[0][i] = f0, p.f[1][i] = f1, p.f[2][i] = f2;
   } else {
     f0 = p.f[0][i], f1 = p.f[1][i], f2 = p.f[2][i];
@@ -732,14 +755,7 @@ node_fused_kernel(const NodeArgs p, double hdt, double hdt_next, double dt_next)
   if (i >= p.n_nodes) return;
   double f[3];
   if (ORDERED) {
-    f[0] = 0.0, f[1] = 0.0, f[2] = 0.0;
-    const int64_t b = p.adj_off[i], e = p.adj_off[i + 1];
-    for (int64_t k = b; k < e; ++k) {
-      const double* s = p.ef + (int64_t)p.adj_slot[k] * 3;
-      f[0] += s[0];
-      f[1] += s[1];
-      f[2] += s[2];
-    }
+    ordered_node_sum(p.ef, p.adj_off, p.adj_slot, i, f[0], f[1], f[2]);
   } else {
     f[0] = p.f[0][i], f[1] = p.f[1][i], f[2] = p.f[2][i];
   }

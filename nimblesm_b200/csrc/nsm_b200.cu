@@ -74,7 +74,7 @@ struct nsm_b200_ctx
   // element data
   double* ipt  = nullptr;  // [n_elem_total][8][15], lazily allocated
   double* binv = nullptr;  // [n_elem_total][8][9]
-  double* ef   = nullptr;  // ORDERED: [n_elem_total][8][3]
+  double* ef   = nullptr;  // ORDERED: [n_elem_total][8][kEfStride]
   int64_t*  adj_off  = nullptr;
   uint32_t* adj_slot = nullptr;
 
@@ -243,7 +243,7 @@ elem_args(nsm_b200_ctx* c, const Block& b, int sched = kSchedAll)
   p.n_elem = b.n_elem;
   p.conn   = b.conn;
   for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.f[i] = c->f[i];
-  p.ef         = c->ef ? c->ef + b.elem_base * 24 : nullptr;
+  p.ef         = c->ef ? c->ef + b.elem_base * 8 * kEfStride : nullptr;
   p.ipt        = c->ipt ? c->ipt + b.elem_base * 120 : nullptr;
   p.binv_cache = c->binv ? c->binv + b.group_base * kBinvGroupDoubles : nullptr;
   p.bulk       = b.bulk;
@@ -644,8 +644,8 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
 
   if (assembly == NSM_ASSEMBLY_ORDERED) {
     // node -> (element, local node) adjacency, ascending slot == ascending (block id, element)
-    if ((rc = dev_alloc(c, &c->ef, c->n_elem_total * 24))) return rc;
-    NSM_CUDA(c, cudaMemsetAsync(c->ef, 0, (size_t)std::max<int64_t>(c->n_elem_total * 24, 1) * sizeof(double), c->stream));
+    if ((rc = dev_alloc(c, &c->ef, c->n_elem_total * 8 * kEfStride))) return rc;
+    NSM_CUDA(c, cudaMemsetAsync(c->ef, 0, (size_t)std::max<int64_t>(c->n_elem_total * 8 * kEfStride, 1) * sizeof(double), c->stream));
     if ((rc = dev_alloc(c, &c->adj_off, n + 1))) return rc;
     if ((rc = dev_alloc(c, &c->adj_slot, c->n_elem_total * 8))) return rc;
     unsigned long long* counts = nullptr;
