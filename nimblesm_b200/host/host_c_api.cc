@@ -274,6 +274,37 @@ nsmh_bc_table(const char* genesis_path, const char* deck_text, double t, int max
   }
 }
 
+// BoundaryConditionManager::GetDevicePrograms on a deck: JSON {active, n_programs, n_slots, n_code, entries_with_program,
+// slots_at_t: [...]}; the magnitudes the device would compute are checked on the GPU (tests/test_gpu_*), this exposes
+// the host-side decision (all time-dependent expressions compile -> device; otherwise or with NSM_B200_HOST_BC=1 -> host)
+int
+nsmh_bc_programs(const char* genesis_path, const char* deck_text, double t, char* out, int outlen, char* err, int errlen)
+{
+  try {
+    GenesisMesh m;
+    m.ReadFile(genesis_path);
+    Parser p;
+    p.InitializeFromString(deck_text);
+    BoundaryConditionManager bc;
+    bc.Initialize(m.GetNodeSetNames(), m.GetNodeSets(), {}, {}, p.GetBoundaryConditionStrings(), m.GetDim(), p.TimeIntegrationScheme());
+    const auto&        pr = bc.GetDevicePrograms();
+    std::ostringstream j;
+    j.precision(17);
+    int with = 0;
+    for (int v : pr.program_of_entry) with += v >= 0;
+    j << "{\"active\":" << (pr.active ? "true" : "false") << ",\"time_dependent\":" << (bc.HasTimeDependentMagnitudes() ? "true" : "false")
+      << ",\"n_programs\":" << (int)pr.offsets.size() - 1 << ",\"n_slots\":" << pr.slots.size() << ",\"n_code\":" << pr.code.size()
+      << ",\"n_entries\":" << bc.GetDeviceTable().node.size() << ",\"entries_with_program\":" << with << ",\"slots_at_t\":[";
+    std::vector<double> sv(pr.slots.size());
+    bc.EvaluateSlots(t, sv.data());
+    for (size_t k = 0; k < sv.size(); ++k) j << (k ? "," : "") << sv[k];
+    j << "]}";
+    return put(out, outlen, j.str(), err, errlen);
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
 // VectorCommunicator::Initialize on `n_ranks` threads: rank r holds global ids gids[off[r] .. off[r+1]).
 // Returns, for rank `query_rank`, its peers and shared local node lists (flattened).
 int

@@ -291,6 +291,38 @@ def test_boundary_condition_tables(host, tmp_path):
     assert np.allclose(np.array(val[len(want_nodes):n.value]), want, rtol=1e-15, atol=0)
 
 
+def test_bc_manager_chooses_device_programs(host, tmp_path, monkeypatch):
+    """BoundaryConditionManager::GetDevicePrograms: every time-dependent expression compiles -> the step loop evaluates
+    the magnitudes on the device (programs per BC, shared slots for the sub-expressions of t); one expression that needs
+    libm at a position (sin(x*t)) or NSM_B200_HOST_BC=1 -> the host evaluates per node, as the reference does."""
+    import math
+
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, _gold, _ref, _pieces = load_golden("wave_in_bar")
+    g = str(tmp_path / "w.g")
+    write_genesis(g, mesh)
+    n2, n1 = len(mesh["node_sets"][2]), len(mesh["node_sets"][1])
+    t = 3.0e-7
+    s = _call_json(host.nsmh_bc_programs, g.encode(), deck.encode(), C.c_double(t))
+    assert s["active"] is False and s["time_dependent"] is False and s["n_entries"] == 3 * n2  # constants only
+    td = deck + '\nboundary condition: prescribed_velocity nodelist_2 y "0.5*(1.0-cos(t*2.0e6))*(1.0+z)"\n' \
+              + 'boundary condition: prescribed_displacement nodelist_1 z "x*cos(t*2.0e6) + 1.0e-3*t"\n'
+    s = _call_json(host.nsmh_bc_programs, g.encode(), td.encode(), C.c_double(t))
+    assert s["active"] is True and s["n_programs"] == 2 and s["entries_with_program"] == n2 + n1
+    assert s["n_entries"] == 4 * n2 + n1
+    # slots: 0.5*(1.0-cos(t*2.0e6)), cos(t*2.0e6), 1.0e-3*t -- the cosine itself is NOT shared between the first two
+    # (the first slot is the whole t-only factor), the values are glibc's
+    assert s["n_slots"] == 3
+    assert s["slots_at_t"] == [0.5 * (1.0 - math.cos(t * 2.0e6)), math.cos(t * 2.0e6), 1.0e-3 * t]
+    bad = td + 'boundary condition: prescribed_velocity nodelist_2 x "sin(x*t)"\n'
+    s = _call_json(host.nsmh_bc_programs, g.encode(), bad.encode(), C.c_double(t))
+    assert s["active"] is False and s["time_dependent"] is True and s["n_programs"] == 0
+    monkeypatch.setenv("NSM_B200_HOST_BC", "1")
+    s = _call_json(host.nsmh_bc_programs, g.encode(), td.encode(), C.c_double(t))
+    assert s["active"] is False and s["time_dependent"] is True
+
+
 @pytest.mark.parametrize("case,P", [("wave_in_bar", 2), ("wave_in_bar", 4), ("brick_with_fibers", 4)])
 def test_vector_communicator_tables_match_python(host, case, P):
     """VectorCommunicator::Initialize on P rank threads == mesh.shared_node_tables (used by bench.py): for every
