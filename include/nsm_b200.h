@@ -189,6 +189,13 @@ int nsm_b200_apply_kinematic_bc(nsm_b200_ctx* ctx, double time_current, double t
  * with n_steps = 1).  store_ipt_last != 0 writes F/sigma on the final step and re-applies the BCs after
  * it, which is what the reference does on an output step (:266-275). */
 int nsm_b200_step(nsm_b200_ctx* ctx, int n_steps, double* time, double dt_user, int store_ipt_last);
+/* The same loop body on HOST-resident state, i.e. on the reference's Viewify<2> views as ExplicitTimeIntegrator holds
+ * them (src/integrators/explicit_time_integrator.cc:131-160): uploads displacement, velocity, acceleration
+ * ([n_nodes][3]), advances one step, returns displacement, velocity, acceleration and internal_force in place.
+ * With pinned buffers (nsm_b200_host_alloc) the displacement, which is final after the first half of the step,
+ * travels back over a second stream while the element kernels run. */
+int nsm_b200_step_host(nsm_b200_ctx* ctx, double* time, double dt_user, double* displacement, double* velocity,
+                       double* acceleration, double* internal_force);
 
 /* ---- element data / derived output (replaces ModelData::GetElementDataNew + Block::ComputeDerivedElementData,
  *      src/nimble_block.cc:438-497; HexElement::ComputeVolumeAverage, src/nimble_element.h:343-392) --- */

@@ -40,7 +40,7 @@ SYMBOLS = [
     "nsm_b200_comm_export", "nsm_b200_comm_attach", "nsm_b200_comm_ready", "nsm_b200_timer_start",
     "nsm_b200_timer_stop", "nsm_b200_launch_count", "nsm_b200_profile", "nsm_b200_profile_read",
     "nsm_b200_fp64_peak", "nsm_b200_cold_points", "nsm_b200_set_bc_values_steps", "nsm_b200_set_bc_programs",
-    "nsm_b200_set_bc_slots_steps", "nsm_b200_get_element_components",
+    "nsm_b200_set_bc_slots_steps", "nsm_b200_get_element_components", "nsm_b200_step_host",
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
         "nsm_b200_set_bc_slots_steps": (i32, [vp, i32, i32, dp]),
         "nsm_b200_apply_kinematic_bc": (i32, [vp, dbl, dbl]),
         "nsm_b200_step": (i32, [vp, i32, dp, dbl, i32]),
+        "nsm_b200_step_host": (i32, [vp, dp, dbl, vp, vp, vp, vp]),
         "nsm_b200_get_element_data": (i32, [vp, i32, dp]),
         "nsm_b200_derived_element_data": (i32, [vp, i32, dp]),
         "nsm_b200_get_element_components": (i32, [vp, i32, i32, ip, dp]),
@@ -304,6 +305,15 @@ class Context:
     def step(self, n_steps, time, dt_user, store_ipt_last=False) -> float:
         t = C.c_double(time)
         self._ck(self._L.nsm_b200_step(self._h, int(n_steps), C.byref(t), dt_user, 1 if store_ipt_last else 0))
+        return t.value
+
+    def step_host(self, time, dt_user, displacement, velocity, acceleration, internal_force) -> float:
+        """One explicit step on host-resident [n][3] float64 arrays, updated in place (pinned arrays overlap copies)."""
+        for a in (displacement, velocity, acceleration, internal_force):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n_nodes, 3)
+        t = C.c_double(time)
+        self._ck(self._L.nsm_b200_step_host(self._h, C.byref(t), dt_user, displacement.ctypes.data, velocity.ctypes.data,
+                                             acceleration.ctypes.data, internal_force.ctypes.data))
         return t.value
 
     def element_data(self, block_id):

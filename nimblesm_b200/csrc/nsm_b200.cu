@@ -69,6 +69,12 @@ struct nsm_b200_ctx
   double* fext[3] = {nullptr, nullptr, nullptr};
   double* mass    = nullptr;
   double* staging = nullptr;  // [n][3] AoS bounce buffer for host views
+  // nsm_b200_step_host: the displacement is final after the first half of the step, so it travels back to the host
+  // on a second stream (own bounce buffer) while the element kernels run
+  double*      staging_u      = nullptr;
+  cudaStream_t io_stream      = nullptr;
+  cudaEvent_t  ev_u_staged    = nullptr;
+  double*      early_u_host   = nullptr;  // set for the duration of one nsm_b200_step call
   bool    has_fext = false;
 
   // element data
@@ -542,7 +548,9 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   for (int i = 0; i < 3; ++i) {
     fr(c->X[i]), fr(c->u[i]), fr(c->v[i]), fr(c->a[i]), fr(c->f[i]), fr(c->fext[i]), fr(c->bc_of_dof[i]);
   }
-  fr(c->mass), fr(c->staging), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
+  fr(c->mass), fr(c->staging), fr(c->staging_u), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
+  if (c->io_stream) cudaStreamDestroy(c->io_stream);
+  if (c->ev_u_staged) cudaEventDestroy(c->ev_u_staged);
   fr(c->bc_kind), fr(c->bc_value), fr(c->bc_node), fr(c->d_flags), fr(c->d_min_dt), fr(c->d_ticket);
   free_bc_programs(c);
   for (auto& kv : c->blocks) fr(kv.second.conn), fr(kv.second.group_bits), fr(kv.second.group_list);
@@ -1076,6 +1084,14 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
           node_predict_kernel<false, true><<<ngrid, 256, 0, c->stream>>>(na, hdt, dt);
       }
       c->launches++;
+      if (c->early_u_host) {  // nsm_b200_step_host: u is final from here on; send it home while the elements compute
+        soa_to_aos_kernel<<<ngrid, 256, 0, c->stream>>>(n, c->u[0], c->u[1], c->u[2], c->staging_u);
+        c->launches++;
+        NSM_CUDA(c, cudaEventRecord(c->ev_u_staged, c->stream));
+        NSM_CUDA(c, cudaStreamWaitEvent(c->io_stream, c->ev_u_staged, 0));
+        NSM_CUDA(c, cudaMemcpyAsync(c->early_u_host, c->staging_u, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->io_stream));
+        c->early_u_host = nullptr;
+      }
     }
     if (c->profiling) prof_event(c);
     int rc;
@@ -1166,6 +1182,38 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
   *time = t;
   if (c->profiling) prof_resolve(c);
   return check_flags(c);
+}
+
+int
+nsm_b200_step_host(nsm_b200_ctx* c, double* time, double dt_user, double* displacement, double* velocity, double* acceleration,
+                   double* internal_force)
+{
+  NSM_REQUIRE(c, c && c->finalized, "step_host: context not finalized");
+  NSM_REQUIRE(c, time && displacement && velocity && acceleration && internal_force, "step_host: null argument");
+  const int64_t n = c->n_nodes;
+  if (!c->io_stream) {
+    int rc = dev_alloc(c, &c->staging_u, std::max<int64_t>(n * 3, 1));
+    if (rc) return rc;
+    NSM_CUDA(c, cudaStreamCreateWithFlags(&c->io_stream, cudaStreamNonBlocking));
+    NSM_CUDA(c, cudaEventCreateWithFlags(&c->ev_u_staged, cudaEventDisableTiming));
+  }
+  int rc;
+  if ((rc = upload_field(c, NSM_FIELD_DISPLACEMENT, displacement, false))) return rc;
+  if ((rc = upload_field(c, NSM_FIELD_VELOCITY, velocity, false))) return rc;
+  if ((rc = upload_field(c, NSM_FIELD_ACCELERATION, acceleration, false))) return rc;
+  c->early_u_host = n > 0 ? displacement : nullptr;
+  rc              = nsm_b200_step(c, 1, time, dt_user, 0);
+  c->early_u_host = nullptr;
+  if (rc) {
+    cudaStreamSynchronize(c->io_stream);
+    return rc;
+  }
+  if ((rc = download_field(c, NSM_FIELD_INTERNAL_FORCE, internal_force, false))) return rc;
+  if ((rc = download_field(c, NSM_FIELD_VELOCITY, velocity, false))) return rc;
+  if ((rc = download_field(c, NSM_FIELD_ACCELERATION, acceleration, false))) return rc;
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->io_stream));
+  return NSM_OK;
 }
 
 int

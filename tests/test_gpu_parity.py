@@ -499,3 +499,51 @@ def test_element_components_equal_full_download():
     with pytest.raises(capi.NsmError):
         c.element_components(2, [120])
     c.close()
+
+
+def test_step_host_equals_upload_step_download():
+    """nsm_b200_step_host (host-resident state, displacement download overlapped with the element kernels) returns
+    the bits of upload + nsm_b200_step(1) + download, over several steps, with boundary conditions, on pinned and on
+    pageable arrays."""
+    from nimblesm_b200 import capi
+
+    mesh, ref, _ = perturbed_cube(7, 0.0)
+    dt = 0.2 * (1.0 / 7) / np.sqrt(K / RHO)
+    face = mesh["node_sets"][2]
+    v0 = np.zeros_like(ref)
+    v0[:, 0] = 1000.0 * ref[:, 0]
+
+    def make():
+        c = _ctx(mesh, "neohookean", capi.ASSEMBLY_ORDERED, 2)
+        c.compute_lumped_mass()
+        c.set_bc_table(np.repeat(face, 3), np.tile(np.arange(3, dtype=np.int32), len(face)), np.zeros(3 * len(face), np.int32))
+        c.set_bc_values(np.zeros(3 * len(face)))
+        return c
+
+    c = make()
+    u, v, a = np.zeros_like(ref), v0.copy(), np.zeros_like(ref)
+    t = 0.0
+    for _ in range(4):
+        c.upload("displacement", u), c.upload("velocity", v), c.upload("acceleration", a)
+        t = c.step(1, t, dt)
+        u, v, a, f = (c.download(l) for l in ("displacement", "velocity", "acceleration", "internal_force"))
+    c.close()
+    for pinned in (True, False):
+        c = make()
+        if pinned:
+            bufs = [capi.PinnedArray(ref.shape) for _ in range(4)]
+            U, V, A, Fo = (b.array for b in bufs)
+        else:
+            U, V, A, Fo = (np.empty_like(ref) for _ in range(4))
+        U[:], V[:], A[:], Fo[:] = 0.0, v0, 0.0, 0.0
+        t2 = 0.0
+        for _ in range(4):
+            t2 = c.step_host(t2, dt, U, V, A, Fo)
+        assert t2 == t
+        for got, want in ((U, u), (V, v), (A, a), (Fo, f)):
+            assert np.array_equal(np.asarray(got).view(np.int64), want.view(np.int64))
+        c.close()
+        if pinned:
+            for b in bufs:
+                b.free()
+    assert np.abs(u).max() > 0
