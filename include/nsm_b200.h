@@ -185,8 +185,9 @@ int nsm_b200_apply_kinematic_bc(nsm_b200_ctx* ctx, double time_current, double t
  *      src/integrators/explicit_time_integrator.cc:177-278, contact disabled) ----------------------
  * Advances n_steps steps from *time (in/out): per step t_prev = t; t += dt_user; dt = t - t_prev;
  * v += dt/2 a; BC; u += dt v; BC; f_int(u); a = (1/m)(f_int + f_ext); v += dt/2 a.
- * BC magnitudes are those of the last nsm_b200_set_bc_values call (time-dependent expressions: call
- * with n_steps = 1).  store_ipt_last != 0 writes F/sigma on the final step and re-applies the BCs after
+ * BC magnitudes: the row of the last nsm_b200_set_bc_values call; for time-dependent expressions either one
+ * host-evaluated row per step (nsm_b200_set_bc_values_steps) or device programs with per-step slots
+ * (nsm_b200_set_bc_programs + nsm_b200_set_bc_slots_steps).  store_ipt_last != 0 writes F/sigma on the final step and re-applies the BCs after
  * it, which is what the reference does on an output step (:266-275). */
 int nsm_b200_step(nsm_b200_ctx* ctx, int n_steps, double* time, double dt_user, int store_ipt_last);
 /* The same loop body on HOST-resident state, i.e. on the reference's Viewify<2> views as ExplicitTimeIntegrator holds
