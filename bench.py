@@ -171,7 +171,7 @@ def workload_config(args, n_edge):
     return {"workload": "synthetic structured hex8 cube %d^3 = %d elements per GPU, %s, explicit central difference"
                         % (n_edge, n_edge ** 3, mat),
             "elements_per_gpu": n_edge ** 3, "material": "elastic+neohookean" if two else args.material,
-            "assembly": args.assembly,
+            "assembly": args.assembly, "numbering": "random (shuffled)" if getattr(args, "shuffle", False) else "lattice order",
             "l2_policy": "inputs larger than L2 (per-step traffic >> 126 MB)" if n_edge ** 3 * 234 > 4e8
                          else "small workload: L2-resident"}
 
@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--assembly", default="atomic", choices=["atomic", "ordered"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--flags", type=int, default=2, help="nsm_b200_finalize flags (2 = cache the reference Jacobians)")
+    ap.add_argument("--shuffle", action="store_true",
+                    help="random node numbering and element order (an unstructured mesh's worst case for gather locality)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -222,6 +224,18 @@ def main():
     rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
     mesh = weak_brick(n, (px, py, pz), (rx, ry, rz), args.workload == "twoblock")
     n_elem, n_nodes = sum(len(cn) for cn in mesh["conn"].values()), len(mesh["x"])
+    if args.shuffle:
+        assert world == 1, "--shuffle is a single-GPU experiment"
+        rng = np.random.default_rng(7)
+        perm = rng.permutation(n_nodes)           # new id of old node i
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(n_nodes)
+        for k in ("x", "y", "z"):
+            mesh[k] = np.ascontiguousarray(mesh[k][inv])
+        for bid in list(mesh["conn"]):
+            cn = perm[mesh["conn"][bid]].astype(np.int32)
+            mesh["conn"][bid] = np.ascontiguousarray(cn[rng.permutation(len(cn))])
+        mesh["node_sets"] = {k: np.sort(perm[v]).astype(np.int32) for k, v in mesh["node_sets"].items()}
 
     c = capi.Context(local_rank)
     c.set_nodes(mesh["x"], mesh["y"], mesh["z"])

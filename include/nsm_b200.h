@@ -72,6 +72,11 @@ typedef enum { NSM_ASSEMBLY_ATOMIC = 0, NSM_ASSEMBLY_ORDERED = 1 } nsm_assembly;
                                              default: only when a call asks for it (output steps)          */
 #define NSM_FLAG_CACHE_REF_JACOBIAN 0x2   /* keep inverse reference Jacobians (576 B/elem) instead of      \
                                              recomputing them each step; bit-identical either way          */
+#define NSM_FLAG_REORDER_ELEMENTS 0x4     /* walk each block's elements along a Morton curve of their       \
+                                             centroids instead of in file order (internal schedule only:    \
+                                             element data, outputs and the ORDERED summation keep the file  \
+                                             order).  For meshes whose element order has no locality: a     \
+                                             randomly ordered 8 M-element cube runs 3.4x slower without it. */
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 /* Creates a context bound to CUDA device `device` (one context per GPU, one host thread drives it:

@@ -51,7 +51,8 @@ constexpr int kWarpSmemBase   = 2 * kStageDoubles + 2 * kCoordDoubles + kShareDo
 struct ElemArgs
 {
   int64_t       n_elem;
-  const int*    conn;        // [n_elem][8]
+  const int*    conn;        // [n_elem][8], in SCHEDULE order (== file order unless the block was reordered)
+  const int*    orig;        // schedule position -> element index in file order (nullptr: identity)
   const double* X[3];        // reference coordinates, SoA
   const double* u[3];        // displacement, SoA
   double*       f[3];        // nodal internal force, SoA (ATOMIC)
@@ -444,7 +445,6 @@ element_force_kernel(const ElemArgs p)
       prefetch_l2(p.binv_cache + (int64_t)g_nn * kBinvGroupDoubles + lane * 16);  // DRAM -> L2 a full pass before the cp.async
 #endif
 
-    const int64_t e    = (int64_t)g * kElemsPerWarp + ew;
     const double* sX   = wsm + stage * kStageDoubles;
     const double* sU   = sX + kCoordDoubles;
     const double* binv_row  = (MODE & kModeReadBinv) ? p.binv_cache + (int64_t)g * kBinvGroupDoubles + lane : nullptr;
@@ -484,8 +484,14 @@ element_force_kernel(const ElemArgs p)
     const bool live = node >= 0;
     if (live && (st & 2u)) atomicOr(p.flags, 1);
 
+    // element data (F / sigma, ORDERED forces) live in FILE order: looked up where it is stored, so that the
+    // index does not occupy registers through the pass
+    auto file_element = [&]() -> int64_t {
+      const int64_t e_sched = (int64_t)g * kElemsPerWarp + ew;
+      return p.orig ? (int64_t)__ldg(p.orig + e_sched) : e_sched;
+    };
     if ((MODE & kModeStoreIpt) && live) {
-      double* d = p.ipt + (e * 8 + q) * 15;
+      double* d = p.ipt + (file_element() * 8 + q) * 15;
 #pragma unroll
       for (int i = 0; i < 9; ++i) d[i] = F[i];
 #pragma unroll
@@ -504,7 +510,7 @@ element_force_kernel(const ElemArgs p)
     }
     if (live) {
       if (ORDERED) {
-        double* o = p.ef + (e * 8 + q) * kEfStride;
+        double* o = p.ef + (file_element() * 8 + q) * kEfStride;
         o[0] = fx, o[1] = fy, o[2] = fz;
       } else {
         atomicAdd(p.f[0] + node, fx);

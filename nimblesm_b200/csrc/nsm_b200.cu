@@ -31,7 +31,9 @@ struct Block
   int              material = 0;
   double           bulk = 0, shear = 0, density = 0;
   std::vector<int> conn_host;  // dropped after finalize
-  int*             conn      = nullptr;
+  int*             conn      = nullptr;  // file order (mass, adjacency, derived data)
+  int*             conn_sched = nullptr; // the element kernel's walk: == conn, or Morton-ordered (NSM_FLAG_REORDER_ELEMENTS)
+  int*             orig      = nullptr;  // schedule position -> file-order element (nullptr: identity)
   int64_t          elem_base = 0;  // first global element (ascending block id order)
   int64_t          group_base = 0; // first 4-element group of the block in the b^-1 cache
   // boundary-first schedule (peer exchange attached): groups touching a node shared with another rank
@@ -247,7 +249,8 @@ elem_args(nsm_b200_ctx* c, const Block& b, int sched = kSchedAll)
   p.group_list = b.group_list;
   p.n_list     = b.n_list;
   p.n_elem = b.n_elem;
-  p.conn   = b.conn;
+  p.orig   = b.orig;
+  p.conn   = b.conn_sched;
   for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.f[i] = c->f[i];
   p.ef         = c->ef ? c->ef + b.elem_base * 8 * kEfStride : nullptr;
   p.ipt        = c->ipt ? c->ipt + b.elem_base * 120 : nullptr;
@@ -553,7 +556,10 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   if (c->ev_u_staged) cudaEventDestroy(c->ev_u_staged);
   fr(c->bc_kind), fr(c->bc_value), fr(c->bc_node), fr(c->d_flags), fr(c->d_min_dt), fr(c->d_ticket);
   free_bc_programs(c);
-  for (auto& kv : c->blocks) fr(kv.second.conn), fr(kv.second.group_bits), fr(kv.second.group_list);
+  for (auto& kv : c->blocks) {
+    if (kv.second.conn_sched != kv.second.conn) fr(kv.second.conn_sched);
+    fr(kv.second.conn), fr(kv.second.orig), fr(kv.second.group_bits), fr(kv.second.group_list);
+  }
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
   if (c->ev_packed) cudaEventDestroy(c->ev_packed);
@@ -643,6 +649,50 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
     if ((rc = dev_alloc(c, &b.conn, b.n_elem * 8))) return rc;
     NSM_CUDA(c, cudaMemcpyAsync(b.conn, b.conn_host.data(), (size_t)b.n_elem * 8 * sizeof(int), cudaMemcpyHostToDevice,
                                 c->stream));
+    b.conn_sched = b.conn;
+    if ((flags & NSM_FLAG_REORDER_ELEMENTS) && b.n_elem > 1) {
+      // schedule = elements sorted along a Morton curve of their centroids (21 bits per axis of the block's box):
+      // consecutive groups touch neighbouring nodes again, whatever the file order was
+      const int64_t ne = b.n_elem;
+      double        lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      std::vector<double> cen((size_t)ne * 3);
+      const double* xyz[3] = {c->hx.data(), c->hy.data(), c->hz.data()};
+      for (int64_t e = 0; e < ne; ++e)
+        for (int d = 0; d < 3; ++d) {
+          double s = 0.0;
+          for (int j = 0; j < 8; ++j) s += xyz[d][b.conn_host[e * 8 + j]];
+          cen[e * 3 + d] = s;
+          lo[d] = std::min(lo[d], s), hi[d] = std::max(hi[d], s);
+        }
+      auto spread = [](uint64_t v) {  // 21 bits -> every third bit
+        v &= 0x1fffffULL;
+        v = (v | v << 32) & 0x1f00000000ffffULL;
+        v = (v | v << 16) & 0x1f0000ff0000ffULL;
+        v = (v | v << 8) & 0x100f00f00f00f00fULL;
+        v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+        v = (v | v << 2) & 0x1249249249249249ULL;
+        return v;
+      };
+      std::vector<std::pair<uint64_t, int>> key((size_t)ne);
+      for (int64_t e = 0; e < ne; ++e) {
+        uint64_t k = 0;
+        for (int d = 0; d < 3; ++d) {
+          const double w = hi[d] > lo[d] ? (cen[e * 3 + d] - lo[d]) / (hi[d] - lo[d]) : 0.0;
+          k |= spread((uint64_t)(w * 2097151.0)) << d;
+        }
+        key[e] = {k, (int)e};
+      }
+      std::sort(key.begin(), key.end());
+      std::vector<int> orig((size_t)ne), conn_s((size_t)ne * 8);
+      for (int64_t s = 0; s < ne; ++s) {
+        orig[s] = key[s].second;
+        for (int j = 0; j < 8; ++j) conn_s[s * 8 + j] = b.conn_host[(int64_t)key[s].second * 8 + j];
+      }
+      if ((rc = dev_alloc(c, &b.conn_sched, ne * 8))) return rc;
+      if ((rc = dev_alloc(c, &b.orig, ne))) return rc;
+      NSM_CUDA(c, cudaMemcpy(b.conn_sched, conn_s.data(), (size_t)ne * 8 * sizeof(int), cudaMemcpyHostToDevice));
+      NSM_CUDA(c, cudaMemcpy(b.orig, orig.data(), (size_t)ne * sizeof(int), cudaMemcpyHostToDevice));
+    }
   }
   c->n_elem_total = base;
   NSM_REQUIRE(c, base * 8 < (int64_t)4294967295LL, "too many elements for 32-bit assembly slots on one GPU");
@@ -1354,7 +1404,7 @@ nsm_b200_comm_ready(nsm_b200_ctx* c)
       if ((rc = dev_alloc(c, &b.group_list, ng))) return rc;
       NSM_CUDA(c, cudaMemsetAsync(b.group_bits, 0, (size_t)words * sizeof(unsigned), c->stream));
       NSM_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(unsigned), c->stream));
-      flag_groups_kernel<<<grid_for(ng, 256), 256, 0, c->stream>>>(b.n_elem, b.conn, node_flag, b.group_bits, b.group_list, d_count);
+      flag_groups_kernel<<<grid_for(ng, 256), 256, 0, c->stream>>>(b.n_elem, b.conn_sched, node_flag, b.group_bits, b.group_list, d_count);
       c->launches++;
       unsigned h = 0;
       NSM_CUDA(c, cudaMemcpyAsync(&h, d_count, sizeof h, cudaMemcpyDeviceToHost, c->stream));
