@@ -77,6 +77,11 @@ typedef enum { NSM_ASSEMBLY_ATOMIC = 0, NSM_ASSEMBLY_ORDERED = 1 } nsm_assembly;
                                              element data, outputs and the ORDERED summation keep the file  \
                                              order).  For meshes whose element order has no locality: a     \
                                              randomly ordered 8 M-element cube runs 3.4x slower without it. */
+#define NSM_FLAG_RENUMBER_NODES 0x8       /* number the nodes along a Morton curve of their coordinates     \
+                                             INSIDE the context; every entry point keeps speaking the        \
+                                             caller's node ids (fields, BC table, shared-node lists are      \
+                                             mapped at the boundary).  For meshes whose node numbering has   \
+                                             no locality; use together with NSM_FLAG_REORDER_ELEMENTS.       */
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 /* Creates a context bound to CUDA device `device` (one context per GPU, one host thread drives it:

@@ -25,7 +25,7 @@ FIELDS = {"lumped_mass": 0, "reference_coordinate": 1, "displacement": 2, "veloc
           "internal_force": 5, "external_force": 6}
 BC_PRESCRIBED_VELOCITY, BC_PRESCRIBED_DISPLACEMENT = 0, 1
 ASSEMBLY_ATOMIC, ASSEMBLY_ORDERED = 0, 1
-FLAG_STORE_IPT_EVERY_STEP, FLAG_CACHE_REF_JACOBIAN, FLAG_REORDER_ELEMENTS = 0x1, 0x2, 0x4
+FLAG_STORE_IPT_EVERY_STEP, FLAG_CACHE_REF_JACOBIAN, FLAG_REORDER_ELEMENTS, FLAG_RENUMBER_NODES = 0x1, 0x2, 0x4, 0x8
 COMM_HANDLE_BYTES = 192
 
 # every symbol include/nsm_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)

@@ -883,22 +883,37 @@ apply_bc_kernel(const NodeArgs p, double dt)
   }
 }
 
-// host AoS [n][3] staging <-> device SoA
+// host AoS [n][3] staging (the caller's node order) <-> device SoA (internal node order: perm[caller id], or the
+// same when perm == nullptr)
 __global__ void __launch_bounds__(256)
-aos_to_soa_kernel(int64_t n, const double* __restrict__ aos, double* x, double* y, double* z)
+aos_to_soa_kernel(int64_t n, const double* __restrict__ aos, double* x, double* y, double* z, const int* __restrict__ perm)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  x[i] = aos[3 * i], y[i] = aos[3 * i + 1], z[i] = aos[3 * i + 2];
+  const int64_t j = perm ? perm[i] : i;
+  x[j] = aos[3 * i], y[j] = aos[3 * i + 1], z[j] = aos[3 * i + 2];
 }
 
 __global__ void __launch_bounds__(256)
 soa_to_aos_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                  double* aos)
+                  double* aos, const int* __restrict__ perm)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  aos[3 * i] = x[i], aos[3 * i + 1] = y[i], aos[3 * i + 2] = z[i];
+  const int64_t j = perm ? perm[i] : i;
+  aos[3 * i] = x[j], aos[3 * i + 1] = y[j], aos[3 * i + 2] = z[j];
+}
+
+// scalar nodal field between the caller's order (staging) and the internal order
+__global__ void __launch_bounds__(256)
+permute_scalar_kernel(int64_t n, const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ perm, int to_internal)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (to_internal)
+    out[perm[i]] = in[i];
+  else
+    out[i] = in[perm[i]];
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -59,6 +59,9 @@ struct nsm_b200_ctx
   unsigned flags_   = 0;
 
   std::vector<double> hx, hy, hz;  // host copies until finalize
+  // NSM_FLAG_RENUMBER_NODES: caller's node id -> internal id (Morton order of the coordinates); empty = identity
+  std::vector<int> node_perm_host;
+  int*             node_perm = nullptr;
   std::map<int, Block> blocks;     // ascending id == reference processing order
   int64_t              n_elem_total = 0;
 
@@ -448,12 +451,19 @@ upload_field(nsm_b200_ctx* c, int field, const double* host, bool sync)
   int     rc = field_ptrs(c, field, p, &nc);
   if (rc) return rc;
   const int64_t n = c->n_nodes;
-  if (nc == 1) {
+  if (nc == 1 && !c->node_perm) {
     NSM_CUDA(c, cudaMemcpyAsync(p[0], host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  } else if (nc == 1) {
+    NSM_CUDA(c, cudaMemcpyAsync(c->staging, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (n > 0) {
+      permute_scalar_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, c->staging, p[0], c->node_perm, 1);
+      c->launches++;
+      NSM_CUDA(c, cudaGetLastError());
+    }
   } else {
     NSM_CUDA(c, cudaMemcpyAsync(c->staging, host, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (n > 0) {
-      aos_to_soa_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, c->staging, p[0], p[1], p[2]);
+      aos_to_soa_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, c->staging, p[0], p[1], p[2], c->node_perm);
       c->launches++;
       NSM_CUDA(c, cudaGetLastError());
     }
@@ -473,11 +483,18 @@ download_field(nsm_b200_ctx* c, int field, double* host, bool sync)
   int     rc = field_ptrs(c, field, p, &nc);
   if (rc) return rc;
   const int64_t n = c->n_nodes;
-  if (nc == 1) {
+  if (nc == 1 && !c->node_perm) {
     NSM_CUDA(c, cudaMemcpyAsync(host, p[0], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else if (nc == 1) {
+    if (n > 0) {
+      permute_scalar_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, p[0], c->staging, c->node_perm, 0);
+      c->launches++;
+      NSM_CUDA(c, cudaGetLastError());
+    }
+    NSM_CUDA(c, cudaMemcpyAsync(host, c->staging, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   } else {
     if (n > 0) {
-      soa_to_aos_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, p[0], p[1], p[2], c->staging);
+      soa_to_aos_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, p[0], p[1], p[2], c->staging, c->node_perm);
       c->launches++;
       NSM_CUDA(c, cudaGetLastError());
     }
@@ -551,7 +568,7 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   for (int i = 0; i < 3; ++i) {
     fr(c->X[i]), fr(c->u[i]), fr(c->v[i]), fr(c->a[i]), fr(c->f[i]), fr(c->fext[i]), fr(c->bc_of_dof[i]);
   }
-  fr(c->mass), fr(c->staging), fr(c->staging_u), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
+  fr(c->node_perm), fr(c->mass), fr(c->staging), fr(c->staging_u), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
   if (c->io_stream) cudaStreamDestroy(c->io_stream);
   if (c->ev_u_staged) cudaEventDestroy(c->ev_u_staged);
   fr(c->bc_kind), fr(c->bc_value), fr(c->bc_node), fr(c->d_flags), fr(c->d_min_dt), fr(c->d_ticket);
@@ -635,6 +652,45 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
   if ((rc = dev_alloc(c, &c->d_min_dt, 1))) return rc;
   if ((rc = dev_alloc(c, &c->d_ticket, 1))) return rc;
   NSM_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(int), c->stream));
+  if ((flags & NSM_FLAG_RENUMBER_NODES) && n > 1) {
+    // internal node order = Morton order of the coordinates (21 bits per axis of the bounding box); the caller's
+    // ids are mapped at every entry point that takes or returns nodal data
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    const std::vector<double>* xyz[3] = {&c->hx, &c->hy, &c->hz};
+    for (int d = 0; d < 3; ++d)
+      for (int64_t i = 0; i < n; ++i) lo[d] = std::min(lo[d], (*xyz[d])[i]), hi[d] = std::max(hi[d], (*xyz[d])[i]);
+    auto spread = [](uint64_t v) {
+      v &= 0x1fffffULL;
+      v = (v | v << 32) & 0x1f00000000ffffULL;
+      v = (v | v << 16) & 0x1f0000ff0000ffULL;
+      v = (v | v << 8) & 0x100f00f00f00f00fULL;
+      v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+      v = (v | v << 2) & 0x1249249249249249ULL;
+      return v;
+    };
+    std::vector<std::pair<uint64_t, int>> key((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      uint64_t k = 0;
+      for (int d = 0; d < 3; ++d) {
+        const double w = hi[d] > lo[d] ? ((*xyz[d])[i] - lo[d]) / (hi[d] - lo[d]) : 0.0;
+        k |= spread((uint64_t)(w * 2097151.0)) << d;
+      }
+      key[i] = {k, (int)i};
+    }
+    std::sort(key.begin(), key.end());
+    c->node_perm_host.resize((size_t)n);
+    std::vector<double> nx((size_t)n), ny((size_t)n), nz((size_t)n);
+    for (int64_t k = 0; k < n; ++k) {
+      const int i                = key[k].second;
+      c->node_perm_host[i]       = (int)k;
+      nx[k] = c->hx[i], ny[k] = c->hy[i], nz[k] = c->hz[i];
+    }
+    c->hx.swap(nx), c->hy.swap(ny), c->hz.swap(nz);
+    for (auto& kv : c->blocks)
+      for (int& nd : kv.second.conn_host) nd = c->node_perm_host[nd];
+    if ((rc = dev_alloc(c, &c->node_perm, n))) return rc;
+    NSM_CUDA(c, cudaMemcpyAsync(c->node_perm, c->node_perm_host.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
   NSM_CUDA(c, cudaMemcpyAsync(c->X[0], c->hx.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemcpyAsync(c->X[1], c->hy.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemcpyAsync(c->X[2], c->hz.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -950,8 +1006,11 @@ nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int
         (kind[k] != NSM_BC_PRESCRIBED_VELOCITY && kind[k] != NSM_BC_PRESCRIBED_DISPLACEMENT))
       return fail(c, NSM_ERR_ARG, "set_bc_table: entry %lld invalid (node %d comp %d kind %d)", (long long)k, node[k],
                   comp[k], kind[k]);
-    map[comp[k]][node[k]] = (int)k;
+    map[comp[k]][c->node_perm_host.empty() ? node[k] : c->node_perm_host[node[k]]] = (int)k;
   }
+  std::vector<int> node_internal(node, node + n);
+  if (!c->node_perm_host.empty())
+    for (int& nd : node_internal) nd = c->node_perm_host[nd];
   int rc;
   for (int i = 0; i < 3; ++i) {
     if ((rc = dev_alloc(c, &c->bc_of_dof[i], c->n_nodes))) return rc;
@@ -961,7 +1020,7 @@ nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int
   if ((rc = dev_alloc(c, &c->bc_kind, n))) return rc;
   if ((rc = dev_alloc(c, &c->bc_value, n))) return rc;
   if ((rc = dev_alloc(c, &c->bc_node, n))) return rc;
-  NSM_CUDA(c, cudaMemcpyAsync(c->bc_node, node, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemcpyAsync(c->bc_node, node_internal.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   c->bc_rows = 1, c->bc_rows_cap = 1;
   NSM_CUDA(c, cudaMemcpyAsync(c->bc_kind, kind, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemsetAsync(c->bc_value, 0, (size_t)n * sizeof(double), c->stream));
@@ -1135,7 +1194,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
       }
       c->launches++;
       if (c->early_u_host) {  // nsm_b200_step_host: u is final from here on; send it home while the elements compute
-        soa_to_aos_kernel<<<ngrid, 256, 0, c->stream>>>(n, c->u[0], c->u[1], c->u[2], c->staging_u);
+        soa_to_aos_kernel<<<ngrid, 256, 0, c->stream>>>(n, c->u[0], c->u[1], c->u[2], c->staging_u, c->node_perm);
         c->launches++;
         NSM_CUDA(c, cudaEventRecord(c->ev_u_staged, c->stream));
         NSM_CUDA(c, cudaStreamWaitEvent(c->io_stream, c->ev_u_staged, 0));
@@ -1355,7 +1414,10 @@ nsm_b200_comm_init(nsm_b200_ctx* c, int rank, int world_size, int n_peers, const
   for (int64_t k = 0; k < pair_offsets[n_peers]; ++k)
     if (pair_local_nodes[k] < 0 || pair_local_nodes[k] >= c->n_nodes)
       return fail(c, NSM_ERR_ARG, "comm_init: shared node id out of range");
-  if (c->comm.init(c->device, rank, world_size, n_peers, peer_ranks, pair_offsets, pair_local_nodes))
+  std::vector<int32_t> internal(pair_local_nodes, pair_local_nodes + pair_offsets[n_peers]);
+  if (!c->node_perm_host.empty())
+    for (int32_t& nd : internal) nd = c->node_perm_host[nd];
+  if (c->comm.init(c->device, rank, world_size, n_peers, peer_ranks, pair_offsets, internal.data()))
     return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
   return NSM_OK;
 }

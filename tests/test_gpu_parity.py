@@ -549,10 +549,11 @@ def test_step_host_equals_upload_step_download():
     assert np.abs(u).max() > 0
 
 
-@pytest.mark.parametrize("flags", [4, 6])
+@pytest.mark.parametrize("flags", [4, 6, 8, 12, 14])
 def test_reordered_schedule_is_invisible(oracle, flags):
     """NSM_FLAG_REORDER_ELEMENTS walks the elements along a Morton curve of their centroids; element data, outputs and
-    the ORDERED summation keep the file order.  On a mesh whose nodes AND elements are randomly numbered: ORDERED
+    the ORDERED summation keep the file order.  NSM_FLAG_RENUMBER_NODES numbers the nodes along a Morton curve inside
+    the context; fields, the BC table and the lumped mass keep the caller's numbering at the boundary.  On a mesh whose nodes AND elements are randomly numbered: ORDERED
     forces equal the oracle's bit for bit, integration-point data and derived data equal the un-reordered run's, on
     two ragged blocks; a multi-step ATOMIC run stays within 1e-12 of the un-reordered one."""
     from nimblesm_b200 import capi
@@ -576,12 +577,16 @@ def test_reordered_schedule_is_invisible(oracle, flags):
     out = {}
     for fl in (flags & 2, flags):
         with _ctx(m, None, capi.ASSEMBLY_ORDERED, fl, blocks) as c:
+            c.compute_lumped_mass()
+            mass = c.download("lumped_mass")
             c.upload("displacement", disp)
             c.internal_force(store_ipt=True)
-            out[fl] = (c.download("internal_force"), {b: c.element_data(b) for b in (2, 5)}, {b: c.derived_element_data(b) for b in (2, 5)})
-    f0, ipt0, der0 = out[flags & 2]
-    f1, ipt1, der1 = out[flags]
+            out[fl] = (c.download("internal_force"), {b: c.element_data(b) for b in (2, 5)}, {b: c.derived_element_data(b) for b in (2, 5)},
+                       mass, c.download("reference_coordinate"))
+    f0, ipt0, der0, m0, x0 = out[flags & 2]
+    f1, ipt1, der1, m1, x1 = out[flags]
     assert np.array_equal(f0.view(np.int64), f1.view(np.int64))
+    assert np.array_equal(m0.view(np.int64), m1.view(np.int64)) and np.array_equal(x1, ref)
     assert np.abs(f1 - f_want).max() <= 1e-12 * np.abs(f_want).max()
     for b in (2, 5):
         assert np.array_equal(ipt0[b].view(np.int64), ipt1[b].view(np.int64))
@@ -589,11 +594,15 @@ def test_reordered_schedule_is_invisible(oracle, flags):
     dt = 0.2 * (1.0 / 6) / np.sqrt(K / RHO)
     v0 = np.zeros_like(ref)
     v0[:, 0] = 1000.0 * ref[:, 0]
+    face = perm[mesh["node_sets"][2]].astype(np.int32)  # the x = 0 face in the shuffled numbering
     us = []
     for fl in (flags & 2, flags):
         with _ctx(m, None, capi.ASSEMBLY_ATOMIC, fl, blocks) as c:
             c.compute_lumped_mass()
             c.upload("velocity", v0)
+            c.set_bc_table(np.repeat(face, 3), np.tile(np.arange(3, dtype=np.int32), len(face)), np.zeros(3 * len(face), np.int32))
+            c.set_bc_values(np.zeros(3 * len(face)))
             c.step(7, 0.0, dt)
-            us.append(c.download("displacement"))
-    assert _rel(us[1], us[0]) <= 1e-12
+            us.append((c.download("displacement"), c.download("velocity")))
+    assert _rel(us[1][0], us[0][0]) <= 1e-12 and _rel(us[1][1], us[0][1]) <= 1e-12
+    assert np.abs(us[1][0]).max() > 0 and np.all(us[1][0][face] == 0.0)  # the clamped face never moved
