@@ -28,12 +28,11 @@ sys.path.insert(0, ROOT)
 
 RHO, BULK, SHEAR = 7.8, 1.6e12, 0.8e12  # test/dynamics/notched_plate_native_neohookean deck constants
 MATERIAL_2 = (1.333e12, 0.1379e12, 5.0)  # bulk, shear, density of test/dynamics/brick_with_fibers material_2
-# executed DADD+DMUL+DFMA+DSETP lane-instructions per element, from the ncu source page of the profiled kernel
-# (sm__inst_executed_pipe_fp64.sum x 32 / elements, profiles/r01q_dp_counts.txt): [flags & 2 == 0 (b^-1 recomputed),
-# flags & 2 (b^-1 cached)]
-DP_INSTR_PER_ELEMENT = {"neohookean": (10640, 8968), "elastic": (5984, 4312)}
-# dram__bytes_read.sum + dram__bytes_write.sum of one element-kernel launch / elements, same captures (200^3 cube)
-DRAM_TRAFFIC_PER_ELEMENT = {"neohookean": (127.4, 721.4), "elastic": (128.2, 706.2)}
+# DP instruction counts are NOT constants of this file: they come from nsm_b200_kernel_info(), i.e. from the SASS of
+# the library that runs (scripts/sass_hot_loop.py at build time).  The ncu DRAM-traffic figure cannot be derived
+# from the binary; it is read from profiles/ncu_traffic.json, which records the kernel-source hash it was captured
+# at, and is reported only while that hash equals the running library's (otherwise `traffic` is null and says why).
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
 
 def env_int(k, d):
@@ -41,7 +40,8 @@ def env_int(k, d):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md).  start() returns once
+    the first sample has arrived; stop() keeps the samples taken between mark_begin() and mark_end()."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -49,36 +49,46 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.time() + 3.0
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        t0, t1 = self.t0 or 0.0, (self.t1 or time.time()) + 0.06  # a row is stamped when read, up to one period late
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 and len(r) >= 9]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+        for r in rows:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
@@ -99,14 +109,16 @@ def initial_velocity(mesh):
     return v
 
 
-def cpu_baseline(material, cores, budget_s=15.0, single_core=False):
+CPU_SAMPLE_EDGE = 128  # the CPU arms time a 128^3-element cube: 2.1 M elements, ~0.5 GB of state, well out of L3
+
+
+def cpu_baseline(material, cores, budget_s=15.0, single_core=False, n=CPU_SAMPLE_EDGE):
     """The reference's own serial per-element code (oracle/_ref, compiled from /root/reference/src) on `cores`
     host threads, bounded sample; falls back to the plain-C port when the reference objects are absent."""
     from nimblesm_b200.mesh import structured_cube
     from oracle import hex8 as port
     from oracle import refdrive
 
-    n = 64 if cores <= 16 else 96
     mesh = structured_cube(n)
     conn = mesh["conn"][1]
     ref = np.ascontiguousarray(np.stack([mesh["x"], mesh["y"], mesh["z"]], 1))
@@ -114,66 +126,197 @@ def cpu_baseline(material, cores, budget_s=15.0, single_core=False):
     dt = 0.2 * (1.0 / n) / np.sqrt(BULK / RHO)
     kind = "reference" if refdrive.available() else "port"
 
-    def run(steps):
+    def run(steps, threads):
         u, v, a = np.zeros_like(ref), initial_velocity(mesh), np.zeros_like(ref)
         if kind == "reference":
             ms = "%s density %r bulk_modulus %r shear_modulus %r" % (material, RHO, BULK, SHEAR)
-            t, _ = refdrive.bench_steps(ms, ref, conn, mass, u, v, a, dt, steps, cores)
+            t, _ = refdrive.bench_steps(ms, ref, conn, mass, u, v, a, dt, steps, threads)
         else:
             t, _ = port.bench_steps(port.NEOHOOKEAN if material == "neohookean" else port.ELASTIC, BULK, SHEAR, ref,
-                                    conn, mass, u, v, a, dt, steps, cores)
+                                    conn, mass, u, v, a, dt, steps, threads)
         return t
 
-    t1 = run(1)
+    t1 = run(1, cores)
     steps = int(max(2, min(400, budget_s / max(t1, 1e-3))))
-    t = run(steps)
+    t = run(steps, cores)
     out = {"value": len(conn) * steps / t, "unit": "element-updates/s", "cores": cores, "kind": kind,
            "sample": "%d^3 hex8 cube (%d elements), %s, %d explicit steps, %d threads over element chunks, %.1f s"
                      % (n, len(conn), material, steps, cores, t)}
     if single_core:
-        # the reference's own build is serial (its only multi-core path is Kokkos-OpenMP): one thread
-        cores_all, cores = cores, 1
-        ts = run(2)
-        out["single_core_value"] = len(conn) * 2 / ts
-        cores = cores_all
+        # the reference's own build is serial (its only multi-core path is Kokkos-OpenMP): one thread,
+        # on a smaller sample so that it stays within the budget
+        out["single_core_value"] = len(conn) * 1 / run(1, 1)
     return out, t / steps
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref = its serial sources compiled
+    in place; the plain-C port only if those objects are missing) on all host threads.  `config` is the workload of
+    the B200 arm (same dict); what is actually timed each step is the bounded sample named in `cpu_baseline.sample`
+    and `sample_config`, and `ms_per_step` is that measurement extrapolated to one step of the full workload
+    (elements of the workload / measured element-updates per second; the per-element cost does not depend on the
+    mesh size once the sample is out of cache)."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    world = env_int("WORLD_SIZE", args.gpus)
+    material = "neohookean" if args.workload == "twoblock" else args.material
     # K timed "steps", each a bounded sample of the workload
     per = max(3.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
-    vals, last = [], None
+    vals, sample_ms, last = [], [], None
     for i in range(args.warmup + args.steps):
-        cb, sec_per_step = cpu_baseline(args.material, cores, budget_s=per)
+        cb, sec_per_step = cpu_baseline(material, cores, budget_s=per)
         if i >= args.warmup:
             vals.append(cb["value"])
+            sample_ms.append(sec_per_step * 1e3)
         last = cb
     v = float(np.mean(vals))
     last["value"] = v
-    n_edge = args.n
+    cfg = workload_config(args, args.n, world)
     print(json.dumps({
         "impl": "reference", "metric": "hex8 element-updates/sec per explicit step", "value": v,
-        "unit": "element-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, n_edge),
+        "unit": "element-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": cfg["elements_per_gpu"] * world / v * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "sample_config": {"workload": "%d^3-element sample of config.workload per timed step (bounded CPU time); "
+                                      "ms_per_step is extrapolated to the full workload" % CPU_SAMPLE_EDGE,
+                          "elements": CPU_SAMPLE_EDGE ** 3, "sample_ms_per_step": float(np.mean(sample_ms))},
         "cpu_baseline": last,
         "e2e": {"value": v, "unit": "element-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(args, n_edge):
+def workload_config(args, n_edge, world=1):
+    """The workload, from the command line alone: both arms print the same dict."""
+    from nimblesm_b200.mesh import brick_grid
+
     two = getattr(args, "workload", "cube") == "twoblock"
     mat = "elastic block 1 (x < mid) + neohookean block 2, prescribed velocity on both x faces" if two else args.material
+    px, py, pz = brick_grid(world)
     return {"workload": "synthetic structured hex8 cube %d^3 = %d elements per GPU, %s, explicit central difference"
                         % (n_edge, n_edge ** 3, mat),
             "elements_per_gpu": n_edge ** 3, "material": "elastic+neohookean" if two else args.material,
             "assembly": args.assembly, "numbering": "random (shuffled)" if getattr(args, "shuffle", False) else "lattice order",
             "l2_policy": "inputs larger than L2 (per-step traffic >> 126 MB)" if n_edge ** 3 * 234 > 4e8
-                         else "small workload: L2-resident"}
+                         else "small workload: L2-resident",
+            "grid": [px, py, pz], "nodes_per_gpu": (n_edge + 1) ** 3,
+            "dt": 0.2 * (1.0 / (n_edge * px)) / float(np.sqrt(BULK / RHO)),
+            "cpu_reference_sample": "the reference arm (--impl reference) and cpu_baseline time a %d^3-element sample "
+                                    "of this workload on the host cores" % CPU_SAMPLE_EDGE}
+
+
+def dram_traffic(kernel_key, source_sha, n_elem):
+    """ncu DRAM bytes per element of the element kernel, valid only for the kernel sources it was captured at."""
+    try:
+        rec = json.load(open(TRAFFIC_FILE))
+    except Exception:
+        return None, "no ncu capture on file (%s)" % os.path.relpath(TRAFFIC_FILE, ROOT)
+    if rec.get("source_sha") != source_sha:
+        return None, ("stale: %s was captured at kernel-source hash %s, the running library is %s; re-run "
+                      "scripts/ncu_traffic.sh" % (os.path.relpath(TRAFFIC_FILE, ROOT), rec.get("source_sha"), source_sha))
+    e = rec.get("kernels", {}).get(kernel_key)
+    if not e:
+        return None, "no capture of %s in %s" % (kernel_key, os.path.relpath(TRAFFIC_FILE, ROOT))
+    return e["dram_bytes_per_element"] * n_elem, ("ncu --set full capture of this kernel build (%s, %s elements), "
+                                                 "dram__bytes_read.sum + dram__bytes_write.sum per launch scaled per "
+                                                 "element" % (rec.get("report", "profiles/"), e.get("elements")))
+
+
+def parity_check(c, mesh, args, n, grid, pos, rank, world, dist):
+    """CHECKER, after every timed region (the oracle is test infrastructure; nothing timed goes through it).
+    (1) N > 1: every replica of every shared node carries bit-identical u, v, f_int on all its holders (the
+        reference pins its reducer the same way: np2/np4 runs against the serial gold, test/run_exodiff_test.py:
+        103-111,164-190).
+    (2) A 2w^3-element window around the point where the partitions meet (the cube centre at N = 1), gathered from
+        all ranks by global lattice position: with the GPUs' own displacement the CPU oracle's internal force must
+        match the device's on every node the window determines, to 1e-12 (max-norm) -- across partition faces this
+        checks the shared-node sum itself."""
+    from nimblesm_b200.mesh import HEX_CORNERS
+
+    px, py, pz = grid
+    N = (n * px, n * py, n * pz)
+    u, v, f = (c.download(k) for k in ("displacement", "velocity", "internal_force"))
+    out = {"checked": True}
+    # ---- (1) replicas
+    if world > 1:
+        surf = mesh["surface_idx"]
+        blob = (mesh["node_gid"][surf], u[surf], v[surf], f[surf])
+        allb = [None] * world
+        dist.all_gather_object(allb, blob)
+        if rank == 0:
+            gid = np.concatenate([b[0] for b in allb])
+            order = np.argsort(gid, kind="stable")
+            gid = gid[order]
+            same = gid[1:] == gid[:-1]
+            ok = True
+            for k in (1, 2, 3):
+                val = np.concatenate([b[k] for b in allb])[order].view(np.int64)
+                ok = ok and bool(np.all(val[1:][same] == val[:-1][same]))
+            out["replicas_bit_equal"] = ok
+            out["shared_node_replicas_compared"] = int(same.sum())
+    # ---- (2) window vs oracle
+    w = 8 if min(N) >= 32 else max(1, min(N) // 4)
+    cen = [n if p > 1 else (n // 2) for p in (px, py, pz)]  # global element index of the meeting point
+    lo = [max(0, min(cen[d] - w, N[d] - 2 * w)) for d in range(3)]
+    W = 2 * w
+    nn = n + 1
+    off = [pos[d] * n for d in range(3)]
+    # this rank's nodes inside the window's node range [lo, lo + W] per axis
+    rng_ax = [np.arange(max(lo[d], off[d]), min(lo[d] + W, off[d] + n) + 1, dtype=np.int64) for d in range(3)]
+    if all(len(r) for r in rng_ax):
+        K, J, I = np.meshgrid(rng_ax[2], rng_ax[1], rng_ax[0], indexing="ij")
+        loc = ((I - off[0]) + nn * ((J - off[1]) + nn * (K - off[2]))).ravel()
+        wid = ((I - lo[0]) + (W + 1) * ((J - lo[1]) + (W + 1) * (K - lo[2]))).ravel()
+        X = np.stack([mesh["x"][loc], mesh["y"][loc], mesh["z"][loc]], 1)
+        part = (wid, X, u[loc], f[loc])
+    else:
+        part = (np.zeros(0, np.int64), np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 3)))
+    parts = [part]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, part)
+    if rank != 0:
+        return None
+    from oracle import hex8 as oracle
+
+    nw = (W + 1) ** 3
+    Xw, uw, fw, seen = np.zeros((nw, 3)), np.zeros((nw, 3)), np.zeros((nw, 3)), np.zeros(nw, bool)
+    for wid, X, uu, ff in parts:
+        Xw[wid], uw[wid], fw[wid] = X, uu, ff
+        seen[wid] = True
+    assert seen.all(), "window nodes missing from every rank"
+    e = np.arange(W ** 3, dtype=np.int64)
+    ei, ej, ek = e % W, (e // W) % W, e // (W * W)
+    conn = np.empty((W ** 3, 8), dtype=np.int32)
+    for k_, (di, dj, dk) in enumerate(HEX_CORNERS):
+        conn[:, k_] = (ei + di) + (W + 1) * ((ej + dj) + (W + 1) * (ek + dk))
+    if args.workload == "twoblock":  # block 1 = elastic where the brick-local element index i < n/2, else block 2
+        first = ((ei + lo[0]) % n) < n // 2
+        f_or = np.zeros((nw, 3))
+        for sel, kind, k_, g_ in ((first, oracle.ELASTIC, BULK, SHEAR), (~first, oracle.NEOHOOKEAN, MATERIAL_2[0], MATERIAL_2[1])):
+            if sel.any():
+                fb, _ = oracle.internal_force(kind, k_, g_, Xw, uw, np.ascontiguousarray(conn[sel]), False)
+                f_or += fb
+    else:
+        kind = oracle.NEOHOOKEAN if args.material == "neohookean" else oracle.ELASTIC
+        f_or, _ = oracle.internal_force(kind, BULK, SHEAR, Xw, uw, conn, False)
+    a = np.arange(W + 1)
+    Kn, Jn, In = np.meshgrid(a, a, a, indexing="ij")
+    complete = np.ones(nw, bool)
+    for loc_ax, d in ((In, 0), (Jn, 1), (Kn, 2)):
+        g = loc_ax.ravel() + lo[d]
+        complete &= ((g > lo[d]) | (g == 0)) & ((g < lo[d] + W) | (g == N[d]))
+    scale = np.abs(f_or).max()
+    out["max_rel_f"] = float(np.abs(fw[complete] - f_or[complete]).max() / scale) if scale > 0 else None
+    out["window"] = "%d^3 elements at global element (%d, %d, %d) of the %dx%dx%d lattice, %d nodes compared, %s" % (
+        W, lo[0], lo[1], lo[2], N[0], N[1], N[2], int(complete.sum()),
+        "straddling the partition faces" if world > 1 else "cube centre")
+    out["force_scale"] = float(scale)
+    out["ok"] = bool(out["max_rel_f"] is not None and out["max_rel_f"] <= 1e-12 and out.get("replicas_bit_equal", True))
+    out["what"] = ("after the timed regions: oracle (oracle/hex8_oracle.c, pinned to the reference's compiled serial code) "
+                   "internal force of the window with the GPUs' own displacement vs the device force; bar 1e-12 max-norm")
+    return out
 
 
 def main():
@@ -195,6 +338,7 @@ def main():
                     help="random node numbering and element order (an unstructured mesh's worst case for gather locality)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run oracle / replica check")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -290,13 +434,15 @@ def main():
     # ---- device-resident throughput ------------------------------------------------------------------
     t = c.step(args.warmup, 0.0, dt_user)
     sampler = ClockSampler(local_rank)
+    sampler.start()
     c.profile(True)
     launches0 = c.launch_count
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     c.timer_start()
     t = c.step(args.steps, t, dt_user)
     ms = c.timer_stop()
+    sampler.mark_end()
     barrier()
     clocks = sampler.stop()
     launches = c.launch_count - launches0
@@ -343,6 +489,14 @@ def main():
         for p_ in pin.values():
             p_.free()
 
+    # ---- parity of what was just timed (checker; all ranks take part, rank 0 reports) ------------------
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(c, mesh, args, n, (px, py, pz), (rx, ry, rz), rank, world, dist)
+        except Exception as ex:  # the checker is test infrastructure; report, do not hide
+            parity = {"checked": False, "error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -356,17 +510,20 @@ def main():
     step_bytes = 32.0 + 200.0 * r  # + node kernel: f 24, m 8, v 24, u 24 read, v 24, u 24 write (SURVEY §8d B_min)
     ach = elem_bytes * n_elem / (elem_ms * 1e-3) / 1e9 if elem_ms > 0 else None
     dadd, dfma = c.fp64_peak()
-    fi = 1 if args.flags & 2 else 0
+    # FP64 work per element-update: the static DP instruction count of one warp pass of the kernel instance that
+    # ran, from the library's own SASS (nsm_b200_kernel_info)
+    kinfo = capi.kernel_info()
+    mode = 2 if args.flags & 2 else 0
+    kkey = lambda mat: "mat%d_ordered%d_mode%d" % (1 if mat == "neohookean" else 0, 1 if args.assembly == "ordered" else 0, mode)
     if args.workload == "twoblock":  # the two blocks' element kernels run back to back; figures are per-element means
-        dp = 0.5 * (DP_INSTR_PER_ELEMENT["elastic"][fi] + DP_INSTR_PER_ELEMENT["neohookean"][fi])
+        keys = [kkey("elastic"), kkey("neohookean")]
     else:
-        dp = DP_INSTR_PER_ELEMENT[args.material][fi]
+        keys = [kkey(args.material)]
+    dp = float(np.mean([kinfo["kernels"][k]["dp_lane_instr_per_element"] for k in keys]))
+    traffic, traffic_source = dram_traffic(keys[-1], kinfo["source_sha"], n_elem) if len(keys) == 1 else (None, "two kernels per step")
     roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": (ach / peaks["hbm_gbs"]) if ach else None,
-            "traffic": DRAM_TRAFFIC_PER_ELEMENT[args.material][fi] * n_elem,
-            "traffic_source": "ncu --set full capture of the same kernel on a 200^3 cube (profiles/), scaled per element; "
-                              "flags & 2 adds the cached inverse reference Jacobians (576 B/element) to the 105 B/element "
-                              "of algorithmic traffic",
+            "traffic": traffic, "traffic_source": traffic_source,
             "peak_source": how,
             "kernel": "element_force_kernel", "kernel_ms": elem_ms, "kernel_share_of_step": elem_ms * nprof / ms if ms else None,
             "algorithmic_bytes_per_element": elem_bytes,
@@ -374,20 +531,24 @@ def main():
                            "achieved": step_bytes * n_elem * args.steps / (ms * 1e-3) / 1e9,
                            "frac": step_bytes * n_elem * args.steps / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     fp64 = {"note": "the kernel is FP64-issue bound (SURVEY.md §0.5); fraction of the measured DADD/DMUL issue peak",
-            "dp_instr_per_element": dp, "achieved_tera_lane_ops": dp * n_elem / (elem_ms * 1e-3) / 1e12 if elem_ms else None,
+            "dp_instr_per_element": dp, "dp_source": "nsm_b200_kernel_info(): static SASS count of the running binary, kernel "
+            + "+".join(keys) + ", sources " + kinfo["source_sha"],
+            "hot_loop": {k: {x: kinfo["kernels"][k][x] for x in ("dp", "other", "hot_instructions", "reg", "stack")} for k in keys},
+            "achieved_tera_lane_ops": dp * n_elem / (elem_ms * 1e-3) / 1e12 if elem_ms else None,
             "peak_dadd_dmul_tera_lane_ops": dadd, "peak_dfma_tera_lane_ops": dfma,
             "frac": (dp * n_elem / (elem_ms * 1e-3) / 1e12 / dadd) if elem_ms and dadd else None}
     out = {
         "metric": "hex8 element-updates/sec per explicit step", "value": value, "unit": "element-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args, n), grid=[px, py, pz], nodes_per_gpu=n_nodes, dt=dt_user,
-                       critical_dt=crit, device_bytes=c.device_bytes),
+        "config": workload_config(args, n, world), "critical_dt": crit, "device_bytes": c.device_bytes,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "fp64": fp64, "node_kernels_ms": node_ms,
         "cold_points": c.cold_points,
     }
     if e2e:
         out["e2e"] = e2e
+    if parity is not None:
+        out["parity"] = parity
     if not args.no_cpu and world == 1:
         try:
             out["cpu_baseline"], _ = cpu_baseline(args.material, os.cpu_count() or 1, single_core=True)
@@ -397,6 +558,14 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    bad = []
+    if not clocks.get("samples"):
+        bad.append("no nvidia-smi clock sample fell inside the timed region: this line is not a valid measurement")
+    if parity is not None and not parity.get("ok", False):
+        bad.append("parity check failed: %r" % (parity,))
+    if bad:
+        sys.stderr.write("bench.py: " + "; ".join(bad) + "\n")
+        sys.exit(3)
 
 
 def weak_brick(n, grid, pos, twoblock=False):
@@ -435,6 +604,7 @@ def weak_brick(n, grid, pos, twoblock=False):
             surf |= loc == 0
         if r_ < p_ - 1:
             surf |= loc == n
+    mesh["surface_idx"] = np.flatnonzero(surf)
     mesh["surface_gid"] = mesh["node_gid"][surf]
     return mesh
 

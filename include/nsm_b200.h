@@ -219,6 +219,12 @@ int nsm_b200_derived_element_data(nsm_b200_ctx* ctx, int block_id, double* out);
  * only the requested columns cross the bus (8 B per element and component instead of 960 B per element). */
 int nsm_b200_get_element_components(nsm_b200_ctx* ctx, int block_id, int n_components, const int32_t* offsets, double* out);
 
+/* Full integration-point records of a LIST of elements of one block (file-order element indices), gathered on
+ * the device: out[i] = the [8][15] record of elements[i].  For checks and probes on meshes whose whole
+ * [n_elem][8][15] array (61 GB at 64 M elements) should not cross the bus; same data as
+ * ModelData::GetElementDataNew (src/nimble_model_data.cc:557-596) restricted to those elements. */
+int nsm_b200_get_element_data_subset(nsm_b200_ctx* ctx, int block_id, int64_t n, const int64_t* elements, double* out);
+
 /* ---- shared-node exchange over NVLink peer memory (replaces VectorCommunicator::VectorReduction /
  *      ReductionClique_t MPI_Iallreduce, src/nimble_vector_communicator.h:104-157,
  *      src/nimble.mpi.rank_clique_reducer.h:130-257) -----------------------------------------------
@@ -238,6 +244,11 @@ int nsm_b200_comm_attach(nsm_b200_ctx* ctx, int peer_rank, const unsigned char h
  * shared-node sum.  Every rank must be past comm_attach of all its peers before any rank steps. */
 int nsm_b200_comm_ready(nsm_b200_ctx* ctx);
 
+/* How long a rank waits inside the step for a peer's shared-node data before the step fails with NSM_ERR_COMM
+ * (default 20 s; the reference's MPI_Wait has no bound, src/nimble.mpi.rank_clique_reducer.h:230-257).  Raise it
+ * when ranks may drift apart by more than that between two steps (a rank blocked in file output). */
+int nsm_b200_comm_set_timeout(nsm_b200_ctx* ctx, double seconds);
+
 /* ---- measurement helpers (CUDA events on the context stream) ---------------------------------- */
 int nsm_b200_timer_start(nsm_b200_ctx* ctx);
 int nsm_b200_timer_stop(nsm_b200_ctx* ctx, float* milliseconds);
@@ -252,6 +263,13 @@ int nsm_b200_profile_read(nsm_b200_ctx* ctx, double* elem_kernel_ms_avg, double*
 int64_t nsm_b200_cold_points(nsm_b200_ctx* ctx);
 /* FP64 pipe micro-benchmark: sustained DADD+DMUL (no FMA) and DFMA issue rates in 1e12 lane-ops/s. */
 int nsm_b200_fp64_peak(nsm_b200_ctx* ctx, double* dadd_dmul_tops, double* dfma_tops);
+
+/* Build-time description of the element kernels of THIS binary (JSON text): for every element_force_kernel
+ * instance the static instruction mix of one warp pass over 4 elements, read off the SASS of the object the
+ * library was linked from (scripts/sass_hot_loop.py): "dp" (DADD + DMUL + DFMA + DSETP), "other",
+ * "dp_lane_instr_per_element" = dp * 8, registers, stack bytes, and "source_sha", a hash of the kernel sources.
+ * bench.py derives its FP64-pipe figures from this text, so they cannot go stale against the code. */
+const char* nsm_b200_kernel_info(void);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ SYMBOLS = [
     "nsm_b200_timer_stop", "nsm_b200_launch_count", "nsm_b200_profile", "nsm_b200_profile_read",
     "nsm_b200_fp64_peak", "nsm_b200_cold_points", "nsm_b200_set_bc_values_steps", "nsm_b200_set_bc_programs",
     "nsm_b200_set_bc_slots_steps", "nsm_b200_get_element_components", "nsm_b200_step_host",
+    "nsm_b200_get_element_data_subset", "nsm_b200_comm_set_timeout", "nsm_b200_kernel_info",
 ]
 
 
@@ -114,6 +115,9 @@ def lib():
         "nsm_b200_profile_read": (i32, [vp, dp, dp, lp]),
         "nsm_b200_fp64_peak": (i32, [vp, dp, dp]),
         "nsm_b200_cold_points": (i64, [vp]),
+        "nsm_b200_get_element_data_subset": (i32, [vp, i32, i64, lp, dp]),
+        "nsm_b200_comm_set_timeout": (i32, [vp, dbl]),
+        "nsm_b200_kernel_info": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -328,6 +332,13 @@ class Context:
         self._ck(self._L.nsm_b200_get_element_components(self._h, block_id, len(offsets), _iptr(offsets), _dptr(out)))
         return out
 
+    def element_data_subset(self, block_id, elements):
+        """[len(elements)][8][15] integration-point records of the listed elements (file-order indices in the block)."""
+        el = np.ascontiguousarray(elements, dtype=np.int64)
+        out = np.empty((len(el), 8, 15))
+        self._ck(self._L.nsm_b200_get_element_data_subset(self._h, block_id, len(el), _lptr(el), _dptr(out)))
+        return out
+
     def derived_element_data(self, block_id):
         out = np.empty((16, self.block_nelem[block_id]))
         self._ck(self._L.nsm_b200_derived_element_data(self._h, block_id, _dptr(out)))
@@ -351,6 +362,9 @@ class Context:
 
     def comm_ready(self):
         self._ck(self._L.nsm_b200_comm_ready(self._h))
+
+    def comm_set_timeout(self, seconds):
+        self._ck(self._L.nsm_b200_comm_set_timeout(self._h, float(seconds)))
 
     # -- measurement --------------------------------------------------------------------------------
     def timer_start(self):
@@ -385,3 +399,10 @@ class Context:
 
 def version() -> str:
     return lib().nsm_b200_version().decode()
+
+
+def kernel_info() -> dict:
+    """nsm_b200_kernel_info(): the element kernels' static instruction mix, read off this binary's SASS at build time."""
+    import json
+
+    return json.loads(lib().nsm_b200_kernel_info().decode())

@@ -1073,6 +1073,16 @@ select_ipt_components_kernel(int64_t e0, int64_t n, int n_comp, const int* __res
   out[i]          = ipt[(e0 + e) * 120 + off[k]];
 }
 
+// Output / checks: full integration-point records of a list of elements, out[i] = ipt[elems[i]]
+__global__ void __launch_bounds__(256)
+gather_ipt_records_kernel(int64_t n, const int64_t* __restrict__ elems, const double* __restrict__ ipt, double* __restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 120) return;
+  const int64_t k = i / 120;
+  out[i]          = ipt[elems[k] * 120 + (i - k * 120)];
+}
+
 // F = identity, sigma = 0 (Block::InitializeElementData, src/nimble_block.cc:148-207)
 __global__ void __launch_bounds__(256)
 init_ipt_kernel(int64_t n_points, double* ipt)

@@ -154,6 +154,27 @@ fail(nsm_b200_ctx* c, int code, const char* fmt, ...)
     if (!(cond)) return fail((c), NSM_ERR_ARG, "%s", msg); \
   } while (0)
 
+// Every entry point that touches the GPU runs with the context's device current and puts the caller's device back
+// on return: a host thread may drive several contexts, or use another device through torch / its own CUDA code.
+struct DeviceGuard
+{
+  int prev = -1, dev = -1;
+  explicit DeviceGuard(int device) : dev(device)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&)            = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define NSM_ENTER(c)                                   \
+  NSM_REQUIRE((c), (c) != nullptr, "null context");    \
+  DeviceGuard device_guard_((c)->device)
+
 template <class T>
 int
 dev_alloc(nsm_b200_ctx* c, T** p, int64_t count)
@@ -444,7 +465,8 @@ field_ptrs(nsm_b200_ctx* c, int field, double** p, int* ncomp)
 int
 upload_field(nsm_b200_ctx* c, int field, const double* host, bool sync)
 {
-  NSM_REQUIRE(c, c && c->finalized, "upload_field: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "upload_field: context not finalized");
   NSM_REQUIRE(c, host != nullptr, "upload_field: null host pointer");
   double* p[3];
   int     nc;
@@ -476,7 +498,8 @@ upload_field(nsm_b200_ctx* c, int field, const double* host, bool sync)
 int
 download_field(nsm_b200_ctx* c, int field, double* host, bool sync)
 {
-  NSM_REQUIRE(c, c && c->finalized, "download_field: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "download_field: context not finalized");
   NSM_REQUIRE(c, host != nullptr, "download_field: null host pointer");
   double* p[3];
   int     nc;
@@ -543,14 +566,21 @@ nsm_b200_create(int device, nsm_b200_ctx** out)
   if (prop.major != 10)
     return fail(nullptr, NSM_ERR_CUDA, "device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major,
                 prop.minor);
-  NSM_CUDA(nullptr, cudaSetDevice(device));
+  DeviceGuard device_guard_(device);  // the caller's current device is put back on return
   auto* c   = new nsm_b200_ctx;
   c->device = device;
-  NSM_CUDA(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  NSM_CUDA(nullptr, cudaEventCreate(&c->ev_start));
-  NSM_CUDA(nullptr, cudaEventCreate(&c->ev_stop));
+  cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev_start);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev_stop);
   static const ShapeTables tables = make_shape_tables();
-  NSM_CUDA(nullptr, cudaMemcpyToSymbol(c_shape, &tables, sizeof tables));
+  if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(c_shape, &tables, sizeof tables);
+  if (ce != cudaSuccess) {  // nothing of a half-built context survives
+    if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return fail(nullptr, NSM_ERR_CUDA, "nsm_b200_create: %s", cudaGetErrorString(ce));
+  }
   *out = c;
   return NSM_OK;
 }
@@ -559,7 +589,7 @@ void
 nsm_b200_destroy(nsm_b200_ctx* c)
 {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard device_guard_(c->device);
   cudaStreamSynchronize(c->stream);
   c->comm.destroy();
   auto fr = [](void* p) {
@@ -627,10 +657,9 @@ nsm_b200_add_block(nsm_b200_ctx* c, int block_id, int64_t n_elem, const int32_t*
 int
 nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
 {
-  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_ENTER(c);
   NSM_REQUIRE(c, !c->finalized, "finalize called twice");
   NSM_REQUIRE(c, assembly == NSM_ASSEMBLY_ATOMIC || assembly == NSM_ASSEMBLY_ORDERED, "unknown assembly mode");
-  NSM_CUDA(c, cudaSetDevice(c->device));
   c->assembly = assembly;
   c->flags_   = flags;
   const int64_t n = c->n_nodes;
@@ -868,7 +897,7 @@ nsm_b200_download_field_async(nsm_b200_ctx* c, int field, double* host)
 int
 nsm_b200_sync(nsm_b200_ctx* c)
 {
-  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_ENTER(c);
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   return NSM_OK;
 }
@@ -890,7 +919,8 @@ nsm_b200_host_free(void* p)
 int
 nsm_b200_compute_lumped_mass(nsm_b200_ctx* c, double* critical_dt)
 {
-  NSM_REQUIRE(c, c && c->finalized, "compute_lumped_mass: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "compute_lumped_mass: context not finalized");
   const bool ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
   const int64_t n    = c->n_nodes;
   const unsigned long long inf_bits = 0x7ff0000000000000ULL;
@@ -937,7 +967,8 @@ nsm_b200_compute_lumped_mass(nsm_b200_ctx* c, double* critical_dt)
 int
 nsm_b200_internal_force(nsm_b200_ctx* c, int store_ipt)
 {
-  NSM_REQUIRE(c, c && c->finalized, "internal_force: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "internal_force: context not finalized");
   int rc = enqueue_internal_force(c, store_ipt != 0 || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP));
   if (rc) return rc;
   return check_flags(c);
@@ -959,12 +990,11 @@ int
 nsm_b200_compute_stress(nsm_b200_ctx* c, int material_kind, double bulk, double shear, int64_t n_points,
                         const double* def_grad, double* stress)
 {
-  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_ENTER(c);
   NSM_REQUIRE(c, n_points >= 0 && (n_points == 0 || (def_grad && stress)), "compute_stress: bad arguments");
   if (material_kind != NSM_MAT_ELASTIC && material_kind != NSM_MAT_NEOHOOKEAN)
     return fail(c, NSM_ERR_MATERIAL, "unknown material kind %d", material_kind);
   if (n_points == 0) return NSM_OK;
-  NSM_CUDA(c, cudaSetDevice(c->device));
   double *dF = nullptr, *dS = nullptr;
   NSM_CUDA(c, cudaMalloc((void**)&dF, (size_t)n_points * 9 * sizeof(double)));
   NSM_CUDA(c, cudaMalloc((void**)&dS, (size_t)n_points * 6 * sizeof(double)));
@@ -985,7 +1015,8 @@ nsm_b200_compute_stress(nsm_b200_ctx* c, int material_kind, double bulk, double 
 int
 nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int32_t* comp, const int32_t* kind)
 {
-  NSM_REQUIRE(c, c && c->finalized, "set_bc_table: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "set_bc_table: context not finalized");
   NSM_REQUIRE(c, n >= 0 && (n == 0 || (node && comp && kind)), "set_bc_table: bad arguments");
   for (int i = 0; i < 3; ++i) {
     if (c->bc_of_dof[i]) cudaFree(c->bc_of_dof[i]);
@@ -1031,7 +1062,8 @@ nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int
 int
 nsm_b200_set_bc_values(nsm_b200_ctx* c, int64_t n, const double* value)
 {
-  NSM_REQUIRE(c, c && c->finalized, "set_bc_values: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "set_bc_values: context not finalized");
   NSM_REQUIRE(c, n == c->n_bc, "set_bc_values: length differs from the BC table");
   if (n == 0) return NSM_OK;
   c->bc_rows = 1;
@@ -1043,7 +1075,8 @@ nsm_b200_set_bc_values(nsm_b200_ctx* c, int64_t n, const double* value)
 int
 nsm_b200_set_bc_values_steps(nsm_b200_ctx* c, int n_rows, int64_t n, const double* value)
 {
-  NSM_REQUIRE(c, c && c->finalized, "set_bc_values_steps: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "set_bc_values_steps: context not finalized");
   NSM_REQUIRE(c, n == c->n_bc && n_rows >= 1, "set_bc_values_steps: bad arguments");
   if (n == 0) return NSM_OK;
   if (n_rows > c->bc_rows_cap) {
@@ -1064,7 +1097,8 @@ int
 nsm_b200_set_bc_programs(nsm_b200_ctx* c, int n_programs, const int32_t* program_offsets, const int32_t* code, int n_consts,
                          const double* consts, int n_slots, int64_t n_entries, const int32_t* program_of_entry)
 {
-  NSM_REQUIRE(c, c && c->finalized, "set_bc_programs: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "set_bc_programs: context not finalized");
   NSM_REQUIRE(c, n_programs >= 0 && n_consts >= 0 && n_slots >= 0, "set_bc_programs: negative count");
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   free_bc_programs(c);
@@ -1119,7 +1153,8 @@ nsm_b200_set_bc_programs(nsm_b200_ctx* c, int n_programs, const int32_t* program
 int
 nsm_b200_set_bc_slots_steps(nsm_b200_ctx* c, int n_rows, int n_slots, const double* slots)
 {
-  NSM_REQUIRE(c, c && c->finalized, "set_bc_slots_steps: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "set_bc_slots_steps: context not finalized");
   NSM_REQUIRE(c, c->bcp_programs > 0, "set_bc_slots_steps: no boundary-condition programs set");
   NSM_REQUIRE(c, n_rows >= 1 && n_slots == c->bcp_slots && (n_slots == 0 || slots), "set_bc_slots_steps: bad arguments");
   if (n_slots == 0) {
@@ -1143,7 +1178,8 @@ nsm_b200_set_bc_slots_steps(nsm_b200_ctx* c, int n_rows, int n_slots, const doub
 int
 nsm_b200_apply_kinematic_bc(nsm_b200_ctx* c, double time_current, double time_previous)
 {
-  NSM_REQUIRE(c, c && c->finalized, "apply_kinematic_bc: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "apply_kinematic_bc: context not finalized");
   if (c->n_bc == 0 || c->n_nodes == 0) return NSM_OK;
   int rc_p = enqueue_bc_programs(c, 0);
   if (rc_p) return rc_p;
@@ -1158,7 +1194,8 @@ nsm_b200_apply_kinematic_bc(nsm_b200_ctx* c, double time_current, double time_pr
 int
 nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int store_ipt_last)
 {
-  NSM_REQUIRE(c, c && c->finalized, "step: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "step: context not finalized");
   NSM_REQUIRE(c, time != nullptr && n_steps >= 0, "step: bad arguments");
   NSM_REQUIRE(c, c->bc_rows <= 1 || n_steps <= c->bc_rows, "step: more steps than per-step boundary-condition rows");
   NSM_REQUIRE(c, c->bcp_programs == 0 || c->bcp_rows <= 1 || n_steps <= c->bcp_rows, "step: more steps than per-step boundary-condition slot rows");
@@ -1297,7 +1334,8 @@ int
 nsm_b200_step_host(nsm_b200_ctx* c, double* time, double dt_user, double* displacement, double* velocity, double* acceleration,
                    double* internal_force)
 {
-  NSM_REQUIRE(c, c && c->finalized, "step_host: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "step_host: context not finalized");
   NSM_REQUIRE(c, time && displacement && velocity && acceleration && internal_force, "step_host: null argument");
   const int64_t n = c->n_nodes;
   if (!c->io_stream) {
@@ -1328,7 +1366,8 @@ nsm_b200_step_host(nsm_b200_ctx* c, double* time, double dt_user, double* displa
 int
 nsm_b200_get_element_data(nsm_b200_ctx* c, int block_id, double* out)
 {
-  NSM_REQUIRE(c, c && c->finalized, "get_element_data: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "get_element_data: context not finalized");
   auto it = c->blocks.find(block_id);
   NSM_REQUIRE(c, it != c->blocks.end(), "get_element_data: unknown block id");
   int rc = ensure_ipt(c);
@@ -1343,7 +1382,8 @@ nsm_b200_get_element_data(nsm_b200_ctx* c, int block_id, double* out)
 int
 nsm_b200_derived_element_data(nsm_b200_ctx* c, int block_id, double* out)
 {
-  NSM_REQUIRE(c, c && c->finalized, "derived_element_data: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "derived_element_data: context not finalized");
   auto it = c->blocks.find(block_id);
   NSM_REQUIRE(c, it != c->blocks.end(), "derived_element_data: unknown block id");
   int rc = ensure_ipt(c);
@@ -1365,7 +1405,8 @@ nsm_b200_derived_element_data(nsm_b200_ctx* c, int block_id, double* out)
 int
 nsm_b200_get_element_components(nsm_b200_ctx* c, int block_id, int n_components, const int32_t* offsets, double* out)
 {
-  NSM_REQUIRE(c, c && c->finalized, "get_element_components: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "get_element_components: context not finalized");
   auto it = c->blocks.find(block_id);
   NSM_REQUIRE(c, it != c->blocks.end(), "get_element_components: unknown block id");
   NSM_REQUIRE(c, n_components >= 0 && (n_components == 0 || (offsets && out)), "get_element_components: bad arguments");
@@ -1401,14 +1442,47 @@ nsm_b200_get_element_components(nsm_b200_ctx* c, int block_id, int n_components,
   return NSM_OK;
 }
 
+int
+nsm_b200_get_element_data_subset(nsm_b200_ctx* c, int block_id, int64_t n, const int64_t* elements, double* out)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "get_element_data_subset: context not finalized");
+  auto it = c->blocks.find(block_id);
+  NSM_REQUIRE(c, it != c->blocks.end(), "get_element_data_subset: unknown block id");
+  NSM_REQUIRE(c, n >= 0 && (n == 0 || (elements && out)), "get_element_data_subset: bad arguments");
+  const Block& b = it->second;
+  for (int64_t i = 0; i < n; ++i)
+    if (elements[i] < 0 || elements[i] >= b.n_elem)
+      return fail(c, NSM_ERR_ARG, "get_element_data_subset: element %lld outside [0, %lld)", (long long)elements[i], (long long)b.n_elem);
+  int rc = ensure_ipt(c);
+  if (rc) return rc;
+  if (n == 0) return NSM_OK;
+  int64_t* d_el  = nullptr;
+  double*  d_out = nullptr;
+  NSM_CUDA(c, cudaMalloc((void**)&d_el, (size_t)n * sizeof(int64_t)));
+  cudaError_t e = cudaMalloc((void**)&d_out, (size_t)n * 120 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_el, elements, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    gather_ipt_records_kernel<<<grid_for(n * 120, 256), 256, 0, c->stream>>>(n, d_el, c->ipt + b.elem_base * 120, d_out);
+    c->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 120 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_el);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(c, NSM_ERR_CUDA, "get_element_data_subset: %s", cudaGetErrorString(e));
+  return NSM_OK;
+}
+
 // ---- peer exchange ---------------------------------------------------------------------------------
 int
 nsm_b200_comm_init(nsm_b200_ctx* c, int rank, int world_size, int n_peers, const int32_t* peer_ranks,
                    const int64_t* pair_offsets, const int32_t* pair_local_nodes)
 {
-  NSM_REQUIRE(c, c && c->finalized, "comm_init: context not finalized");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "comm_init: context not finalized");
   NSM_REQUIRE(c, n_peers >= 0 && (n_peers == 0 || (peer_ranks && pair_offsets)), "comm_init: bad arguments");
-  NSM_CUDA(c, cudaSetDevice(c->device));
   static const int64_t zero = 0;
   if (n_peers == 0) pair_offsets = &zero;
   for (int64_t k = 0; k < pair_offsets[n_peers]; ++k)
@@ -1425,8 +1499,8 @@ nsm_b200_comm_init(nsm_b200_ctx* c, int rank, int world_size, int n_peers, const
 int
 nsm_b200_comm_export(nsm_b200_ctx* c, unsigned char handle[NSM_COMM_HANDLE_BYTES])
 {
-  NSM_REQUIRE(c, c && c->finalized, "comm_export: context not finalized");
-  NSM_CUDA(c, cudaSetDevice(c->device));
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "comm_export: context not finalized");
   if (c->comm.export_handle(handle)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
   return NSM_OK;
 }
@@ -1434,8 +1508,8 @@ nsm_b200_comm_export(nsm_b200_ctx* c, unsigned char handle[NSM_COMM_HANDLE_BYTES
 int
 nsm_b200_comm_attach(nsm_b200_ctx* c, int peer_rank, const unsigned char handle[NSM_COMM_HANDLE_BYTES])
 {
-  NSM_REQUIRE(c, c && c->finalized, "comm_attach: context not finalized");
-  NSM_CUDA(c, cudaSetDevice(c->device));
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "comm_attach: context not finalized");
   if (c->comm.attach(peer_rank, handle)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
   return NSM_OK;
 }
@@ -1443,8 +1517,8 @@ nsm_b200_comm_attach(nsm_b200_ctx* c, int peer_rank, const unsigned char handle[
 int
 nsm_b200_comm_ready(nsm_b200_ctx* c)
 {
-  NSM_REQUIRE(c, c && c->finalized, "comm_ready: context not finalized");
-  NSM_CUDA(c, cudaSetDevice(c->device));
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "comm_ready: context not finalized");
   if (c->comm.ready(c->stream)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
   // boundary-first element schedule: flag and list the groups that touch a shared node
   const int64_t ns = c->comm.num_shared_nodes();
@@ -1485,11 +1559,20 @@ nsm_b200_comm_ready(nsm_b200_ctx* c)
 
 }
 
+int
+nsm_b200_comm_set_timeout(nsm_b200_ctx* c, double seconds)
+{
+  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_REQUIRE(c, seconds > 0.0, "comm_set_timeout: the timeout must be positive");
+  c->comm.set_timeout_seconds(seconds);
+  return NSM_OK;
+}
+
 // ---- measurement ------------------------------------------------------------------------------------
 int
 nsm_b200_timer_start(nsm_b200_ctx* c)
 {
-  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_ENTER(c);
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   NSM_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
   return NSM_OK;
@@ -1498,7 +1581,8 @@ nsm_b200_timer_start(nsm_b200_ctx* c)
 int
 nsm_b200_timer_stop(nsm_b200_ctx* c, float* ms)
 {
-  NSM_REQUIRE(c, c != nullptr && ms != nullptr, "timer_stop: bad arguments");
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, ms != nullptr, "timer_stop: bad arguments");
   NSM_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
   NSM_CUDA(c, cudaEventSynchronize(c->ev_stop));
   NSM_CUDA(c, cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
@@ -1525,7 +1609,7 @@ nsm_b200_profile(nsm_b200_ctx* c, int enable)
 int
 nsm_b200_profile_read(nsm_b200_ctx* c, double* elem_ms, double* node_ms, int64_t* n)
 {
-  NSM_REQUIRE(c, c != nullptr, "null context");
+  NSM_ENTER(c);
   prof_resolve(c);
   const double k = c->prof_steps ? 1.0 / (double)c->prof_steps : 0.0;
   if (elem_ms) *elem_ms = c->prof_elem_ms * k;
@@ -1538,6 +1622,7 @@ int64_t
 nsm_b200_cold_points(nsm_b200_ctx* c)
 {
   if (!c || !c->finalized) return -1;
+  DeviceGuard device_guard_(c->device);
   int h = 0;
   if (cudaMemcpyAsync(&h, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
@@ -1547,8 +1632,7 @@ nsm_b200_cold_points(nsm_b200_ctx* c)
 int
 nsm_b200_fp64_peak(nsm_b200_ctx* c, double* dadd_dmul_tops, double* dfma_tops)
 {
-  NSM_REQUIRE(c, c != nullptr, "null context");
-  NSM_CUDA(c, cudaSetDevice(c->device));
+  NSM_ENTER(c);
   cudaDeviceProp prop;
   NSM_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
   const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;

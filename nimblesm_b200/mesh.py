@@ -200,3 +200,36 @@ def reference_shared_sum(values_by_rank, gids_by_rank):
             acc[g] = v.copy() if g not in acc else acc[g] + v
     return [np.stack([acc[g] for g in np.asarray(gids).tolist()]) if len(gids) else np.asarray(vals)
             for vals, gids in zip(values_by_rank, gids_by_rank)]
+
+
+def lattice_window(n_elem_axes, lo, w, at_global_lo=(True, True, True), at_global_hi=(True, True, True)):
+    """A w^3-element window of a structured brick (local node id i + nx (j + ny k), local element id
+    ei + ex (ej + ey ek), as structured_brick / bench.weak_brick number them) with its lower corner at local
+    element (lo[0], lo[1], lo[2]).
+
+    Returns (node_ids [(w+1)^3], elem_ids [w^3], conn [w^3, 8] into node_ids, complete [(w+1)^3] bool): `complete`
+    marks the window nodes ALL of whose elements lie inside the window -- strictly inside it, or on a window face
+    that coincides with a face of the whole body (at_global_lo / at_global_hi say whether the brick's own faces are
+    such) -- i.e. the nodes whose assembled internal force the window alone determines.  Used by the sampled parity
+    checks at sizes where the CPU oracle cannot run the whole mesh (tests/test_gpu_parity.py, bench.py)."""
+    ex, ey, ez = (int(v) for v in n_elem_axes)
+    nx, ny = ex + 1, ey + 1
+    a = np.arange(w + 1, dtype=np.int64)
+    K, J, I = np.meshgrid(a + lo[2], a + lo[1], a + lo[0], indexing="ij")
+    node_ids = (I + nx * (J + ny * K)).ravel()
+    e = np.arange(w, dtype=np.int64)
+    EK, EJ, EI = np.meshgrid(e, e, e, indexing="ij")
+    EI, EJ, EK = EI.ravel(), EJ.ravel(), EK.ravel()
+    elem_ids = (EI + lo[0]) + ex * ((EJ + lo[1]) + ey * (EK + lo[2]))
+    conn = np.empty((w ** 3, 8), dtype=np.int32)
+    for c, (di, dj, dk) in enumerate(HEX_CORNERS):
+        conn[:, c] = (EI + di) + (w + 1) * ((EJ + dj) + (w + 1) * (EK + dk))
+    complete = np.ones(node_ids.shape, dtype=bool)
+    for loc, l0, n_ax, glo, ghi in ((I, lo[0], ex, at_global_lo[0], at_global_hi[0]), (J, lo[1], ey, at_global_lo[1], at_global_hi[1]),
+                                    (K, lo[2], ez, at_global_lo[2], at_global_hi[2])):
+        loc = loc.ravel()
+        inside = (loc > l0) & (loc < l0 + w)
+        inside |= (loc == l0) & (l0 == 0) & bool(glo)
+        inside |= (loc == l0 + w) & (l0 + w == n_ax) & bool(ghi)
+        complete &= inside
+    return node_ids, elem_ids, conn, complete

@@ -68,10 +68,12 @@ def _check_against_reference(mesh, gold, ref, res):
 
 
 @pytest.mark.parametrize("case", CASES)
-def test_driver_runs_reference_decks(case, tmp_path):
+@pytest.mark.parametrize("assembly", ["ordered", "atomic"])
+def test_driver_runs_reference_decks(case, assembly, tmp_path):
+    """Both assembly modes at the same bars: ORDERED is the driver's default, ATOMIC is what bench.py times."""
     from nimblesm_b200.exodus_py import read_results
 
-    _deck, mesh, gold, ref, _pieces, out = _run(tmp_path, case)
+    _deck, mesh, gold, ref, _pieces, out = _run(tmp_path, case, extra=("--assembly", assembly))
     _check_against_reference(mesh, gold, ref, read_results(out))
 
 

@@ -266,15 +266,17 @@ def test_multi_step_call_equals_single_steps(flags, with_bc):
 @pytest.mark.parametrize("case", ["wave_in_bar", "notched_plate_native_neohookean", "notched_plate_native_hypoelastic",
                                   "brick_with_fibers", "single_elem_complex_displacement",
                                   "single_elem_native_neohookean", "rigid_body_motion", "simple_deformation_modes"])
-def test_reference_decks_vs_reference_snapshots(case):
+@pytest.mark.parametrize("assembly", ["ordered", "atomic"])
+def test_reference_decks_vs_reference_snapshots(case, assembly):
     """The reference's own regression decks end to end (deck parse -> BCs -> N steps -> output-step data) against
     (1) snapshots the reference's serial code produced on the same deck (tests/golden, ref_*: bar 1e-9 * max) and
-    (2) the reference's gold Exodus files (exodiff bar of the reference: 1e-6 * max)."""
+    (2) the reference's gold Exodus files (exodiff bar of the reference: 1e-6 * max) -- in BOTH assembly modes:
+    ORDERED is the C++ driver's default, ATOMIC is what bench.py times."""
     from nimblesm_b200 import capi
     from nimblesm_b200.model import ExplicitModel
 
     deck, mesh, gold, ref, _ = load_golden(case)
-    m = ExplicitModel(deck, mesh, assembly=capi.ASSEMBLY_ORDERED)
+    m = ExplicitModel(deck, mesh, assembly=capi.ASSEMBLY_ORDERED if assembly == "ordered" else capi.ASSEMBLY_ATOMIC)
     crit = m.begin(keep_snapshots=True)
     assert crit == float(ref["critical_dt"])
     m.advance(m.deck.num_load_steps)
@@ -349,6 +351,56 @@ def test_full_size_properties(material, flags):
     with _ctx(mesh, material, capi.ASSEMBLY_ORDERED, flags) as c:
         f1o = c.internal_force_host(u1)
     assert np.abs(f1o - f1).max() <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("n,material", [(400, "neohookean"), (200, "elastic")])
+def test_headline_size_sampled_parity(oracle, n, material):
+    """The BENCHMARKED configurations against the oracle: the context is built exactly as bench.py builds it (the
+    64 M-element Neohookean cube = BASELINE configs[2], the 8 M-element elastic cube = configs[1]; ATOMIC assembly,
+    flags = NSM_FLAG_CACHE_REF_JACOBIAN, x-stretch initial velocity, clamped x = 0 face), stepped 10 times, and then
+    checked on 16^3-element windows the CPU oracle can afford: with the GPU's own displacement of the window's
+    nodes, F and sigma of every integration point of the window must equal the oracle's bit for bit, and the
+    assembled internal force of every node the window determines completely must agree to 1e-12 (max-norm).
+    Windows: the clamped corner, the centre, the far corner, an edge of the free x = L face."""
+    import bench
+    from nimblesm_b200 import capi
+    from nimblesm_b200.mesh import lattice_window
+
+    mesh = bench.weak_brick(n, (1, 1, 1), (0, 0, 0))
+    conn = mesh["conn"][1]
+    c = capi.Context(0)
+    c.set_nodes(mesh["x"], mesh["y"], mesh["z"])
+    c.add_block(1, conn, material, bench.BULK, bench.SHEAR, bench.RHO)
+    c.finalize(capi.ASSEMBLY_ATOMIC, capi.FLAG_CACHE_REF_JACOBIAN)
+    del conn
+    mesh["conn"] = None
+    dt = 0.2 * (1.0 / n) / np.sqrt(bench.BULK / bench.RHO)
+    c.compute_lumped_mass()
+    c.upload("velocity", bench.initial_velocity(mesh))
+    face = mesh["node_sets"][2]
+    c.set_bc_table(np.repeat(face, 3), np.tile(np.arange(3, dtype=np.int32), len(face)), np.zeros(3 * len(face), np.int32))
+    c.set_bc_values(np.zeros(3 * len(face)))
+    c.step(10, 0.0, dt, store_ipt_last=True)
+    assert c.cold_points == 0
+    u = c.download("displacement")
+    f = c.download("internal_force")
+    assert np.abs(u).max() > 0
+    kind = oracle.NEOHOOKEAN if material == "neohookean" else oracle.ELASTIC
+    w = 16
+    worst = 0.0
+    for lo in ((0, 0, 0), (n // 2 - 8, n // 2 - 8, n // 2 - 8), (n - w, n - w, n - w), (n - w, 0, n // 3)):
+        nodes, elems, conn_w, complete = lattice_window((n, n, n), lo, w)
+        X = np.ascontiguousarray(np.stack([mesh["x"][nodes], mesh["y"][nodes], mesh["z"][nodes]], 1))
+        uw = np.ascontiguousarray(u[nodes])
+        f_want, ed_want = oracle.internal_force(kind, bench.BULK, bench.SHEAR, X, uw, conn_w, True)
+        ed = c.element_data_subset(1, elems)
+        assert np.array_equal(ed.view(np.int64), ed_want.view(np.int64)), "F / sigma differ from the oracle in window %r" % (lo,)
+        assert complete.sum() >= (w - 1) ** 3
+        rel = np.abs(f[nodes][complete] - f_want[complete]).max() / np.abs(f_want).max()
+        worst = max(worst, rel)
+        assert np.abs(f_want[complete]).max() > 0
+    assert worst <= 1e-12, worst
+    c.close()
 
 
 def _host_lib():

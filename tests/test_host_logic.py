@@ -187,3 +187,100 @@ def test_shared_node_sum_world_size_2_gloo():
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True]
     assert res[0][2] == 1 and res[0][3] == (n + 1) ** 2  # one peer, one shared face of (n+1)^2 nodes
+
+
+def test_lattice_window_determines_its_complete_nodes(oracle):
+    """mesh.lattice_window (the sampled parity checks of the 64 M-element runs): the oracle force of a window equals
+    the oracle force of the whole mesh on every node the window marks `complete`, bit for bit."""
+    from nimblesm_b200.mesh import lattice_window
+    from tests.conftest import perturbed_cube
+
+    mesh, ref, disp = perturbed_cube(7, 1e-2)
+    conn = mesh["conn"][1]
+    f_all, ed_all = oracle.internal_force(oracle.NEOHOOKEAN, 1.6e12, 0.8e12, ref, disp, conn, True)
+    for lo, w in (((0, 0, 0), 3), ((2, 1, 3), 4), ((4, 4, 4), 3), ((0, 3, 4), 3)):
+        nodes, elems, conn_w, complete = lattice_window((7, 7, 7), lo, w)
+        assert np.array_equal(nodes[conn_w], conn[elems])
+        f_w, ed_w = oracle.internal_force(oracle.NEOHOOKEAN, 1.6e12, 0.8e12, np.ascontiguousarray(ref[nodes]),
+                                          np.ascontiguousarray(disp[nodes]), conn_w, True)
+        assert np.array_equal(ed_w.view(np.int64), ed_all[elems].view(np.int64))
+        assert complete.any() and not complete.all()
+        assert np.array_equal(f_w[complete].view(np.int64), f_all[nodes][complete].view(np.int64))
+        assert not np.array_equal(f_w[~complete], f_all[nodes][~complete])
+
+
+class _FakeContext:
+    """Stands in for capi.Context.download in bench.parity_check (no GPU in the CPU suite)."""
+
+    def __init__(self, fields):
+        self.fields = fields
+
+    def download(self, name):
+        return self.fields[name]
+
+
+def _parity_worker(rank, world, port, n, corrupt, q):
+    sys.path.insert(0, ROOT)
+    import argparse
+
+    import torch.distributed as dist
+
+    import bench
+    from oracle import hex8 as oracle
+
+    dist_mod = None
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dist_mod = dist
+    grid = (world, 1, 1)
+    bricks = [bench.weak_brick(n, grid, (r, 0, 0)) for r in range(world)]
+    # the global mesh, joined by global node id, and a smooth displacement of the global coordinates
+    n_glob = int(max(b["node_gid"].max() for b in bricks)) + 1
+    X = np.zeros((n_glob, 3))
+    conn = []
+    for b in bricks:
+        X[b["node_gid"]] = np.stack([b["x"], b["y"], b["z"]], 1)
+        conn.append(b["node_gid"][b["conn"][1]])
+    conn = np.ascontiguousarray(np.concatenate(conn), dtype=np.int32)
+    u = 1e-3 * np.stack([np.sin(3 * X[:, 1]) * X[:, 0], X[:, 2] * X[:, 0] ** 2, np.cos(2 * X[:, 0]) * X[:, 1]], 1)
+    f, _ = oracle.internal_force(oracle.NEOHOOKEAN, bench.BULK, bench.SHEAR, X, u, conn, False)
+    mine = bricks[rank]
+    g = mine["node_gid"]
+    fields = {"displacement": u[g].copy(), "velocity": (2.0 * u[g]).copy(), "internal_force": f[g].copy()}
+    if corrupt == "replica" and rank == world - 1:
+        fields["velocity"][mine["surface_idx"][0], 1] += 1e-300  # one replica of one shared node, one bit pattern off
+    if corrupt == "force":  # every rank alike: replicas stay equal, the oracle comparison must catch it
+        fields["internal_force"] *= 1.0 + 1e-9
+    args = argparse.Namespace(workload="cube", material="neohookean")
+    res = bench.parity_check(_FakeContext(fields), mine, args, n, grid, (rank, 0, 0), rank, world, dist_mod)
+    q.put((rank, res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,corrupt,ok", [(1, None, True), (2, None, True), (2, "replica", False), (2, "force", False)])
+def test_bench_parity_block(world, corrupt, ok):
+    """bench.parity_check (the `parity` object of the bench line, N = 1 and N = 2 over gloo): passes on the oracle's
+    own forces distributed over the ranks' bricks, fails when one replica of a shared node differs by one bit
+    pattern or when the forces are off by 1e-9."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_parity_worker, args=(r, world, port, 12, corrupt, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    res = got[0]
+    assert res["checked"] and res["ok"] is ok, res
+    if world > 1:
+        assert res["shared_node_replicas_compared"] == 13 * 13 and res["replicas_bit_equal"] is (corrupt != "replica")
+        assert "straddling" in res["window"]
+    if corrupt is None:
+        assert res["max_rel_f"] <= 1e-13
+    assert got.get(1) is None
