@@ -42,8 +42,22 @@ class RankGroup
   AllGather(int rank, const std::vector<char>& mine);
   double
   MinAll(int rank, double value);
+  // Ranks that share one GPU (NimbleSM_b200 --devices 0,0: the multi-rank path on a single-GPU box) must enter
+  // every device call that contains a shared-node exchange together: a rank's in-kernel wait for its peer's data
+  // would otherwise sit in front of a device-synchronising call (cudaFree, a pageable copy) of that peer's thread.
+  void
+  SetLockstep(bool on)
+  {
+    lockstep_ = on;
+  }
+  bool
+  Lockstep() const
+  {
+    return lockstep_;
+  }
 
  private:
+  bool                           lockstep_ = false;
   int                            num_ranks_;
   std::mutex                     mutex_;
   std::condition_variable        cv_;

@@ -178,7 +178,16 @@ NimbleApplication::Run(int argc, char** argv)
     const std::string a = argv[i];
     if (a == "--gpus" && i + 1 < argc)
       o.num_ranks = std::atoi(argv[++i]);
-    else if (a == "--assembly" && i + 1 < argc)
+    else if (a == "--devices" && i + 1 < argc) {
+      // CUDA device per rank; naming a device twice runs those ranks on one GPU in lockstep (RankGroup::SetLockstep)
+      o.devices.clear();
+      std::string list = argv[++i];
+      for (size_t p = 0; p <= list.size();) {
+        const size_t q = std::min(list.find(',', p), list.size());
+        o.devices.push_back(std::atoi(list.substr(p, q - p).c_str()));
+        p = q + 1;
+      }
+    } else if (a == "--assembly" && i + 1 < argc)
       o.assembly = std::string(argv[++i]) == "atomic" ? NSM_ASSEMBLY_ATOMIC : NSM_ASSEMBLY_ORDERED;
     else if (a == "--flags" && i + 1 < argc)
       o.flags = (unsigned)std::atoi(argv[++i]);
@@ -196,7 +205,7 @@ NimbleApplication::Run(int argc, char** argv)
       o.input_file = a;
   }
   if (o.input_file.empty()) {
-    std::cerr << "Usage: NimbleSM_b200 [--gpus N] [--assembly atomic|ordered] [--reference_sequence] [--quiet] <input deck>\n";
+    std::cerr << "Usage: NimbleSM_b200 [--gpus N] [--devices a,b,...] [--assembly atomic|ordered] [--flags F] [--reference_sequence] [--quiet] <input deck>\n";
     return 1;
   }
   return Run(o);
@@ -207,7 +216,16 @@ NimbleApplication::Run(const RunOptions& options)
 {
   options_ = options;
   if (options_.num_ranks < 1) options_.num_ranks = 1;
+  if (options_.devices.empty())
+    for (int r = 0; r < options_.num_ranks; ++r) options_.devices.push_back(r);
+  if ((int)options_.devices.size() != options_.num_ranks) {
+    std::cerr << "NimbleSM_b200: --devices names " << options_.devices.size() << " devices for " << options_.num_ranks << " ranks\n";
+    return 1;
+  }
   auto             group = std::make_shared<RankGroup>(options_.num_ranks);
+  for (int r = 0; r < options_.num_ranks; ++r)
+    for (int q = 0; q < r; ++q)
+      if (options_.devices[q] == options_.devices[r]) group->SetLockstep(true);
   std::vector<int> status(options_.num_ranks, 0);
   if (options_.num_ranks == 1) {
     status[0] = ExecRank(0, group);
@@ -247,9 +265,9 @@ NimbleApplication::ExecRank(int rank, std::shared_ptr<RankGroup> group)
     } else {
       mesh.ReadFile(piece);
     }
-    // one GPU per rank.  (Ranks cannot share a device: a rank's in-kernel wait for its peer would sit in front of
-    // every device-synchronising call of that peer's host thread.)
-    DataManager data_manager(*parser, mesh, rank, options_.assembly, options_.flags, group);
+    // one GPU per rank by default.  Ranks may share a device only in lockstep (--devices 0,0; RankGroup::SetLockstep):
+    // a rank's in-kernel wait for its peer must not sit in front of a device-synchronising call of that peer's thread.
+    DataManager data_manager(*parser, mesh, options_.devices[rank], options_.assembly, options_.flags, group);
     data_manager.SetBlockMaterialInterfaceFactory(CreateBlockMaterialInterfaceFactory());
     data_manager.GetModelData()->InitializeBlocks(data_manager, CreateMaterialFactory());
     data_manager.InitializeOutput(IOFileName(parser->ExodusFileName(), "e", "out", rank, options_.num_ranks));

@@ -75,6 +75,7 @@ struct RunOptions
 {
   std::string input_file;
   int         num_ranks          = 1;     // one thread + one GPU per rank
+  std::vector<int> devices;               // CUDA device of every rank (--devices a,b,...); default: rank r -> device r
   int         assembly           = NSM_ASSEMBLY_ORDERED;
   unsigned    flags              = NSM_FLAG_CACHE_REF_JACOBIAN;
   bool        reference_sequence = false;

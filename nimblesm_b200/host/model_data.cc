@@ -240,9 +240,21 @@ ModelData::SpecifyOutputFields(const std::string& output_field_string)
   }
 }
 
+namespace {
+// see RankGroup::SetLockstep
 void
-ModelData::ComputeLumpedMass(DataManager&)
+enter_exchange_call(DataManager& data_manager)
 {
+  auto vc    = data_manager.GetVectorCommunicator();
+  auto group = vc ? vc->Group() : nullptr;
+  if (group && group->Lockstep()) group->Barrier();
+}
+}  // namespace
+
+void
+ModelData::ComputeLumpedMass(DataManager& data_manager)
+{
+  enter_exchange_call(data_manager);
   // ModelData::ComputeLumpedMass (src/nimble_model_data.cc:495-530): mass from the reference configuration, critical
   // time step from the current one (displacement as it stands on the host), shared-node sum on the device
   DeviceContext& d = *device_;
@@ -252,6 +264,7 @@ ModelData::ComputeLumpedMass(DataManager&)
   d.check(nsm_b200_compute_lumped_mass(d.get(), &dt), "ModelData::ComputeLumpedMass");
   d.check(nsm_b200_download_field(d.get(), NSM_FIELD_LUMPED_MASS, fields_.at(GetFieldIdChecked("lumped_mass")).data),
           "ModelData::ComputeLumpedMass (download)");
+  enter_exchange_call(data_manager);
   SetCriticalTimeStep(dt);
 }
 
@@ -265,12 +278,14 @@ ModelData::ComputeExternalForce(DataManager&, double, double, bool)
 }
 
 void
-ModelData::ComputeInternalForce(DataManager&, double, double, bool is_output_step, const Viewify<2>& displacement,
+ModelData::ComputeInternalForce(DataManager& data_manager, double, double, bool is_output_step, const Viewify<2>& displacement,
                                 Viewify<2>& force)
 {
   DeviceContext& d = *device_;
+  enter_exchange_call(data_manager);
   d.check(nsm_b200_internal_force_host(d.get(), displacement.data(), force.data(), is_output_step ? 1 : 0),
           "ModelData::ComputeInternalForce");
+  enter_exchange_call(data_manager);
 }
 
 void
@@ -371,7 +386,9 @@ ModelData::AdvanceOnDevice(DataManager& data_manager, int n_steps, double& time_
       d.check(nsm_b200_set_bc_values(d.get(), n_bc, bc_values_.data()), "ModelData::AdvanceOnDevice (magnitudes)");
     }
   }
+  enter_exchange_call(data_manager);
   d.check(nsm_b200_step(d.get(), n_steps, &time_current, user_time_step, store_ipt_last ? 1 : 0), "ModelData::AdvanceOnDevice");
+  enter_exchange_call(data_manager);
 }
 
 std::vector<double>&
