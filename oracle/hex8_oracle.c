@@ -150,6 +150,64 @@ h8o_stress_elastic(double bulk, double shear, const double F[9], double sig[6])
   sig[SZX] = two_mu * e[SZX];
 }
 
+/* The history-dependent material of the state-variable slot ("j2_plasticity": small-strain J2, linear isotropic
+ * hardening, incremental form).  The reference ships no material with state, so the operation sequence is DEFINED by
+ * the test-only nimble::Material subclass that plugs into the reference's own block / element-data plumbing
+ * (oracle/ref_state_material.cc, J2PlasticityMaterial::GetStress); this is its restatement, bit for bit
+ * (tests/test_oracle.py).  params = {bulk, shear, yield_stress, hardening_modulus}; state = {equivalent plastic
+ * strain, von Mises stress}. */
+void
+h8o_stress_j2(const double params[4], const double Fn[9], const double Fnp1[9], const double sn[6], const double state_n[2],
+              double snp1[6], double state_np1[2])
+{
+  const double bulk = params[0], shear = params[1], yield = params[2], hard = params[3];
+  const double two_mu = 2.0 * shear;
+  const double lambda = bulk - 2.0 * shear / 3.0;
+  double       de[6], t[6];
+  de[SXX] = Fnp1[FXX] - Fn[FXX];
+  de[SYY] = Fnp1[FYY] - Fn[FYY];
+  de[SZZ] = Fnp1[FZZ] - Fn[FZZ];
+  de[SXY] = 0.5 * ((Fnp1[FXY] + Fnp1[FYX]) - (Fn[FXY] + Fn[FYX]));
+  de[SYZ] = 0.5 * ((Fnp1[FYZ] + Fnp1[FZY]) - (Fn[FYZ] + Fn[FZY]));
+  de[SZX] = 0.5 * ((Fnp1[FZX] + Fnp1[FXZ]) - (Fn[FZX] + Fn[FXZ]));
+  const double tr = de[SXX] + de[SYY] + de[SZZ];
+  t[SXX] = sn[SXX] + (two_mu * de[SXX] + lambda * tr);
+  t[SYY] = sn[SYY] + (two_mu * de[SYY] + lambda * tr);
+  t[SZZ] = sn[SZZ] + (two_mu * de[SZZ] + lambda * tr);
+  t[SXY] = sn[SXY] + two_mu * de[SXY];
+  t[SYZ] = sn[SYZ] + two_mu * de[SYZ];
+  t[SZX] = sn[SZX] + two_mu * de[SZX];
+  const double p  = (t[SXX] + t[SYY] + t[SZZ]) / 3.0;
+  const double s0 = t[SXX] - p, s1 = t[SYY] - p, s2 = t[SZZ] - p;
+  const double s3 = t[SXY], s4 = t[SYZ], s5 = t[SZX];
+  const double j2 = 0.5 * (s0 * s0 + s1 * s1 + s2 * s2) + (s3 * s3 + s4 * s4 + s5 * s5);
+  const double q  = sqrt(3.0 * j2);
+  const double eqps_n = state_n[0];
+  const double f      = q - (yield + hard * eqps_n);
+  if (f > 0.0) { /* radial return */
+    const double dgamma = f / (3.0 * shear + hard);
+    const double scale  = 1.0 - (3.0 * shear * dgamma) / q;
+    snp1[SXX]    = p + scale * s0;
+    snp1[SYY]    = p + scale * s1;
+    snp1[SZZ]    = p + scale * s2;
+    snp1[SXY]    = scale * s3;
+    snp1[SYZ]    = scale * s4;
+    snp1[SZX]    = scale * s5;
+    state_np1[0] = eqps_n + dgamma;
+    state_np1[1] = scale * q;
+  } else {
+    for (int i = 0; i < 6; ++i) snp1[i] = t[i];
+    state_np1[0] = eqps_n;
+    state_np1[1] = q;
+  }
+}
+
+int
+h8o_num_state(int material)
+{
+  return material == H8O_J2_PLASTICITY ? 2 : 0;
+}
+
 /* Cos_Of_Acos_Divided_By_3 (src/nimble_utils.h:650-665): rational (6,5) fit on [0,1]. */
 static double
 cos_third_acos(double x)
@@ -525,6 +583,58 @@ h8o_block_internal_force(int material, double bulk, double shear, const double* 
     h8o_nodal_forces(x, sig, fe);
     for (int j = 0; j < 8; ++j)
       for (int i = 0; i < 3; ++i) f[3L * en[j] + i] += fe[3 * j + i];
+  }
+}
+
+/* The same functor for any material, with the state plumbing of src/nimble_block.cc:297-307, 324-337, 355-368:
+ * records are [8][15 + n_state] per element (F 9, sigma 6, state scalars; src/nimble_block.cc:84-108); F_n, sigma_n
+ * and state_n are read from elem_data_n, the new record goes to elem_data_np1 (both required when n_state > 0).
+ * params = {bulk, shear, material-specific...}. */
+void
+h8o_block_internal_force_state(int material, const double* params, const double* ref, const double* disp, long n_elem,
+                               const int* conn, double* f, const double* elem_data_n, double* elem_data_np1)
+{
+  const int ns = h8o_num_state(material), stride = 15 + ns;
+  for (long e = 0; e < n_elem; ++e) {
+    const int* en = &conn[8 * e];
+    double     X[24], x[24], F[72], sig[48], fe[24];
+    gather(ref, disp, en, X, x);
+    h8o_def_grad(X, x, F);
+    for (int q = 0; q < 8; ++q) {
+      if (material == H8O_ELASTIC)
+        h8o_stress_elastic(params[0], params[1], &F[9 * q], &sig[6 * q]);
+      else if (material == H8O_NEOHOOKEAN)
+        h8o_stress_neohookean(params[0], params[1], &F[9 * q], &sig[6 * q]);
+      else {
+        const double* rn = &elem_data_n[(8 * e + q) * stride];
+        double*       rp = &elem_data_np1[(8 * e + q) * stride];
+        h8o_stress_j2(params, &rn[0], &F[9 * q], &rn[9], &rn[15], &sig[6 * q], &rp[15]);
+      }
+    }
+    if (elem_data_np1) {
+      for (int q = 0; q < 8; ++q) {
+        double* d = &elem_data_np1[(8 * e + q) * stride];
+        memcpy(&d[0], &F[9 * q], 9 * sizeof(double));
+        memcpy(&d[9], &sig[6 * q], 6 * sizeof(double));
+      }
+    }
+    h8o_nodal_forces(x, sig, fe);
+    for (int j = 0; j < 8; ++j)
+      for (int i = 0; i < 3; ++i) f[3L * en[j] + i] += fe[3 * j + i];
+  }
+}
+
+/* Block::ComputeDerivedElementData for records of `stride` doubles per point: out [(1 + stride)][n_elem]. */
+void
+h8o_block_derived_stride(const double* ref, const double* disp, long n_elem, const int* conn, const double* elem_data,
+                         int stride, double* out)
+{
+  for (long e = 0; e < n_elem; ++e) {
+    double X[24], x[24], vol, avg[64];
+    gather(ref, disp, &conn[8 * e], X, x);
+    h8o_volume_average(x, stride, &elem_data[8L * stride * e], &vol, avg);
+    out[e] = vol;
+    for (int k = 0; k < stride; ++k) out[(long)(k + 1) * n_elem + e] = avg[k];
   }
 }
 

@@ -33,6 +33,7 @@
 #include "nimble_parser.h"
 #include "nimble_vector_communicator.h"
 #include "nimble_view.h"
+#include "ref_state_material.h"
 
 // ---------------------------------------------------------------------------------------------
 // DataManager out-of-line members (follows src/nimble_data_manager.cc:70-198; serial ModelData)
@@ -257,7 +258,7 @@ nsmref_open(
     r->mesh.Initialize("in_memory.g", gid, vx, vy, vz, egid, bids, bnames, belem, bnpe, bconn);
     r->mesh.SetNodeSets(n_nodesets, ns_ids, ns_sizes, ns_nodes);
     r->dm.reset(new nimble::DataManager(r->parser, r->mesh));
-    r->factory = std::make_shared<nimble::MaterialFactory>();
+    r->factory = std::make_shared<nsm_oracle::StateMaterialFactory>();  // nimble::MaterialFactory + the test-only state material
     r->md      = dynamic_cast<nimble::ModelData*>(r->dm->GetModelData().get());
     r->md->InitializeBlocks(*r->dm, r->factory);  // src/nimble.cc:362
     r->md->InitializeExodusOutput(*r->dm);
@@ -382,6 +383,33 @@ nsmref_elem_data(void* h, int block_id, int which, double* out)
   return static_cast<long>(v.size());
 }
 
+// doubles per integration point of a block: 15 (F 9, sigma 6) + the material's state variables
+int
+nsmref_elem_stride(void* h, int block_id)
+{
+  auto& r = *static_cast<RefRun*>(h);
+  return static_cast<int>(r.md->GetElementDataLabels().at(block_id).size()) / 8;
+}
+
+// The material seam alone, through the reference's Material virtual (src/nimble_material.h:241-256): n_points
+// integration points, state arrays [n_points][n_state].  Returns the material's state-variable count, -1 on error.
+int
+nsmref_material_stress(const char* material_string, int n_points, const double* F_n, const double* F_np1, const double* s_n,
+                       double* s_np1, const double* state_n, double* state_np1)
+{
+  try {
+    nsm_oracle::StateMaterialFactory factory;
+    factory.parse_and_create(material_string);
+    auto mat = factory.get_material();
+    alignas(16) static char dm_storage[sizeof(nimble::DataManager)];
+    nimble::DataManager&    dm = *reinterpret_cast<nimble::DataManager*>(dm_storage);  // forwarded, never dereferenced
+    mat->GetStress(0, n_points, 0.0, 0.0, F_n, F_np1, s_n, s_np1, state_n, state_np1, dm, false);
+    return mat->NumStateVariables();
+  } catch (...) {
+    return -1;
+  }
+}
+
 int
 nsmref_num_snapshots(void* h)
 {
@@ -467,7 +495,7 @@ nsmref_bench_steps(
     std::vector<double> data_n, data_np1, force;
     std::vector<int>    gids;
   };
-  nimble::MaterialFactory             factory;
+  nsm_oracle::StateMaterialFactory    factory;
   std::vector<std::unique_ptr<Chunk>> chunks;
   std::vector<std::string>            labels(120, "x");
   nimble::Parser                      parser;
@@ -482,8 +510,6 @@ nsmref_bench_steps(
     c->e1  = static_cast<int>(static_cast<long>(n_elem) * (t + 1) / threads);
     c->block.Initialize(material_string, factory);
     int ne = c->e1 - c->e0;
-    c->data_n.assign(static_cast<size_t>(ne) * 120, 0.0);
-    c->data_np1.assign(static_cast<size_t>(ne) * 120, 0.0);
     c->n0 = n_nodes;
     c->n1 = 0;
     for (long i = 8L * c->e0; i < 8L * c->e1; ++i) {
@@ -503,6 +529,8 @@ nsmref_bench_steps(
       comp.insert(comp.end(), cl.begin(), cl.end());
     }
     labels = comp;
+    c->data_n.assign(static_cast<size_t>(ne) * comp.size(), 0.0);
+    c->data_np1.assign(static_cast<size_t>(ne) * comp.size(), 0.0);
     std::vector<std::string> none;
     c->block.InitializeElementData(ne, c->gids, comp, none, c->data_n, c->data_np1, factory, dm);
     chunks.push_back(std::move(c));

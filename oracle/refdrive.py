@@ -60,6 +60,10 @@ def lib():
         L.nsmref_derived_labels.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_long]
         L.nsmref_snapshot_derived.restype = C.c_long
         L.nsmref_snapshot_derived.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.nsmref_elem_stride.restype = C.c_int
+        L.nsmref_elem_stride.argtypes = [C.c_void_p, C.c_int]
+        L.nsmref_material_stress.restype = C.c_int
+        L.nsmref_material_stress.argtypes = [C.c_char_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
         L.nsmref_bench_steps.restype = C.c_double
         L.nsmref_bench_steps.argtypes = [C.c_char_p, C.c_int, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp,
                                          C.c_double, C.c_int, C.c_int]
@@ -131,7 +135,11 @@ class RefRun:
         n = lib().nsmref_elem_data(self.h, block_id, which, None)
         out = np.empty(n)
         lib().nsmref_elem_data(self.h, block_id, which, out.ctypes.data)
-        return out.reshape(-1, 8, 15)
+        return out.reshape(-1, 8, self.elem_stride(block_id))
+
+    def elem_stride(self, block_id: int) -> int:
+        """doubles per integration point: 15 + the material's state variables"""
+        return lib().nsmref_elem_stride(self.h, block_id)
 
     def snapshots(self):
         L = lib()
@@ -150,7 +158,7 @@ class RefRun:
                 n = L.nsmref_snapshot_elem(self.h, i, int(b), None)
                 a = np.empty(n)
                 L.nsmref_snapshot_elem(self.h, i, int(b), a.ctypes.data)
-                s["elem"][int(b)] = a.reshape(-1, 8, 15)
+                s["elem"][int(b)] = a.reshape(-1, 8, self.elem_stride(int(b)))
                 buf = C.create_string_buffer(65536)
                 L.nsmref_derived_labels(self.h, int(b), buf, 65536)
                 labels = [x for x in buf.value.decode().split("\n") if x]
@@ -163,6 +171,20 @@ class RefRun:
                 s["derived"][int(b)] = d
             res.append(s)
         return res
+
+
+def material_stress(material_string: str, F_n, F_np1, s_n, state_n):
+    """nimble::Material::GetStress of the reference (incl. the test-only state material) on n points ->
+    (sigma_np1 [n,6], state_np1 [n,n_state])."""
+    F_n, F_np1, s_n = (np.ascontiguousarray(a, dtype=np.float64) for a in (F_n, F_np1, s_n))
+    state_n = np.ascontiguousarray(state_n, dtype=np.float64)
+    s = np.empty((len(F_n), 6))
+    st = np.zeros_like(state_n) if state_n.size else np.zeros((len(F_n), 0))
+    ns = lib().nsmref_material_stress(material_string.encode(), len(F_n), F_n, F_np1, s_n, s,
+                                      state_n if state_n.size else np.zeros(1), st if st.size else np.zeros(1))
+    if ns < 0:
+        raise RuntimeError("reference material failed: " + material_string)
+    return s, st
 
 
 def bench_steps(material: str, ref_coord, conn, lumped_mass, u, v, a, dt: float, steps: int, threads: int):
