@@ -40,8 +40,14 @@ typedef enum {
   NSM_ERR_COMM    = 5  /* peer exchange not set up / peer failure                         */
 } nsm_status;
 
-/* nimble material models on the path (src/nimble_material.cc:60,218; both carry 0 state variables). */
-typedef enum { NSM_MAT_ELASTIC = 0, NSM_MAT_NEOHOOKEAN = 1 } nsm_material_kind;
+/* Material models.  ELASTIC and NEOHOOKEAN are the reference's (src/nimble_material.cc:60,218; both carry 0 state
+ * variables).  J2_PLASTICITY fills the reference's state-variable slot (Material::NumStateVariables /
+ * GetStateVariableLabel / GetStateVariableInitialValue, src/nimble_material.h:214-225; N / N+1 element data,
+ * src/nimble_block.cc:297-368): small-strain J2 plasticity with linear isotropic hardening in incremental form,
+ * sigma_np1 = radial_return(sigma_n + C : (sym F_np1 - sym F_n)), two state variables per integration point
+ * (equivalent_plastic_strain, von_mises_stress).  Its operation sequence is pinned by a nimble::Material subclass
+ * that the checker plugs into the reference's unmodified block code (oracle/ref_state_material.cc). */
+typedef enum { NSM_MAT_ELASTIC = 0, NSM_MAT_NEOHOOKEAN = 1, NSM_MAT_J2_PLASTICITY = 2, NSM_MAT_COUNT = 3 } nsm_material_kind;
 
 /* nodal fields allocated by DataManager::Initialize (src/nimble_data_manager.cc:135-158). */
 typedef enum {
@@ -101,6 +107,19 @@ int nsm_b200_set_nodes(nsm_b200_ctx* ctx, int64_t n_nodes, const double* x, cons
  * (src/nimble_material_factory.cc:56-69): bulk_modulus, shear_modulus, density. */
 int nsm_b200_add_block(nsm_b200_ctx* ctx, int block_id, int64_t n_elem, const int32_t* conn, int material_kind,
                        double bulk_modulus, double shear_modulus, double density);
+/* The same with the material's full parameter list: params = {bulk_modulus, shear_modulus, density} followed by the
+ * model's own parameters (J2_PLASTICITY: yield_stress, hardening_modulus); n_params must equal
+ * nsm_b200_material_num_params(kind).  A block whose material has state variables keeps two integration-point
+ * record arrays [n_elem][8][15 + n_state] on the device (N and N+1, Block::InitializeElementData gives both the
+ * initial values, src/nimble_block.cc:148-207) and writes F / sigma / state every step. */
+int nsm_b200_add_block_params(nsm_b200_ctx* ctx, int block_id, int64_t n_elem, const int32_t* conn, int material_kind,
+                              int n_params, const double* params);
+/* Material::NumStateVariables / GetStateVariableLabel / GetStateVariableInitialValue (src/nimble_material.h:214-225)
+ * and the parameter count of a kind (-1 / NULL for an unknown kind or index). */
+int         nsm_b200_material_num_state(int material_kind);
+int         nsm_b200_material_num_params(int material_kind);
+const char* nsm_b200_material_state_label(int material_kind, int index);
+double      nsm_b200_material_state_initial_value(int material_kind, int index);
 /* Uploads the mesh, builds assembly tables, allocates fields (zeroed; F = identity, sigma = 0 like
  * Block::InitializeElementData, src/nimble_block.cc:148-207). */
 int nsm_b200_finalize(nsm_b200_ctx* ctx, int assembly, unsigned flags);
@@ -141,9 +160,20 @@ int nsm_b200_internal_force_host(nsm_b200_ctx* ctx, const double* displacement, 
 /* ---- stress seam (replaces BlockMaterialInterface::ComputeStress, the MDRange(elem, ipt) loop of
  *      src/nimble_kokkos_block_material_interface.cc:65-119 -> Material::GetStress,
  *      src/nimble_material.cc:95-126, 252-310) ----------------------------------------------------- */
-/* Host arrays: def_grad [n_points][9] -> stress [n_points][6], evaluated on the device. */
+/* Host arrays: def_grad [n_points][9] -> stress [n_points][6], evaluated on the device.  PARITY / PLUG-IN SEAM, not a
+ * performance path: it allocates, copies and frees per call (the reference re-creates and calls this seam every step,
+ * src/nimble_kokkos_model_data.cc:1230-1234; here the step itself never leaves the device). */
 int nsm_b200_compute_stress(nsm_b200_ctx* ctx, int material_kind, double bulk_modulus, double shear_modulus,
                             int64_t n_points, const double* def_grad, double* stress);
+
+/* The full seam for a material with state variables: (F_n, F_np1, sigma_n, state_n) -> (sigma_np1, state_np1), host
+ * arrays [n_points][9], [n_points][6], [n_points][n_state] (the four views compute_block_stress hands to
+ * Material::GetStress, src/nimble_kokkos_block_material_interface.cc:86-118).  Materials without state ignore the N
+ * inputs.  PARITY / PLUG-IN SEAM, not a performance path: it allocates, copies and frees per call; the step keeps
+ * everything on the device. */
+int nsm_b200_compute_stress_state(nsm_b200_ctx* ctx, int material_kind, int n_params, const double* params, int64_t n_points,
+                                  const double* def_grad_n, const double* def_grad_np1, const double* stress_n,
+                                  const double* state_n, double* stress_np1, double* state_np1);
 
 /* ---- boundary conditions (replaces BoundaryConditionManager::ApplyKinematicBC,
  *      src/nimble_boundary_condition_manager.h:136-204) -------------------------------------------- */
@@ -210,11 +240,27 @@ int nsm_b200_step_host(nsm_b200_ctx* ctx, double* time, double dt_user, double* 
 
 /* ---- element data / derived output (replaces ModelData::GetElementDataNew + Block::ComputeDerivedElementData,
  *      src/nimble_block.cc:438-497; HexElement::ComputeVolumeAverage, src/nimble_element.h:343-392) --- */
-int nsm_b200_get_element_data(nsm_b200_ctx* ctx, int block_id, double* out /*[n_elem][8][15]*/);
-/* out [16][n_elem]: volume, then volume averages of F (9) and sigma (6) in storage order. */
+int nsm_b200_get_element_data(nsm_b200_ctx* ctx, int block_id, double* out /*[n_elem][8][stride]*/);
+/* doubles per integration point of a block's records: 15 + the state variables of its material (label order of
+ * Block::GetDataLabelsAndLengths, src/nimble_block.cc:84-108: F 9, sigma 6, then the state scalars) */
+int nsm_b200_element_data_stride(const nsm_b200_ctx* ctx, int block_id);
+/* ModelData::UpdateStates (src/nimble_model_data.h:104-107; end of the loop body, explicit_time_integrator.cc:277):
+ * the records written by the last force evaluation become the N records of the next one.  The swap is applied when
+ * that next evaluation starts, so nsm_b200_get_element_data keeps returning the most recently computed records
+ * (what the reference writes on an output step, before its swap).  nsm_b200_step does this after every step;
+ * callers sequencing nsm_b200_internal_force themselves call it where the reference calls UpdateStates. */
+int nsm_b200_update_states(nsm_b200_ctx* ctx);
+/* Overwrites a block's records from a host array [n_elem][8][stride]: previous = 0 the current (N+1) records,
+ * previous != 0 the N records the next force evaluation reads (blocks with state variables only).  This is how
+ * Block::ComputeInternalForce receives the caller's elem_data_n (src/nimble_block.cc:297-337), and how a run is
+ * resumed from saved element data. */
+int nsm_b200_set_element_data(nsm_b200_ctx* ctx, int block_id, int previous, const double* in);
+/* The N records of a block whose material has state variables (element_data_n of the reference). */
+int nsm_b200_get_element_data_previous(nsm_b200_ctx* ctx, int block_id, double* out /*[n_elem][8][stride]*/);
+/* out [1 + stride][n_elem]: volume, then volume averages of F (9), sigma (6) and the state scalars in storage order. */
 int nsm_b200_derived_element_data(nsm_b200_ctx* ctx, int block_id, double* out);
 /* Selected integration-point components of one block, split on the device: out[k][e] = ipt[e][offsets[k]],
- * offsets in 0..119 = 15 * point + field (the reference's per-element label order, src/nimble_block.cc:84-108).
+ * offsets in 0..8*stride-1 = stride * point + field (the reference's per-element label order, src/nimble_block.cc:84-108).
  * Replaces the host loop of ModelData::WriteExodusOutput over GetElementDataNew (src/nimble_model_data.cc:557-596):
  * only the requested columns cross the bus (8 B per element and component instead of 960 B per element). */
 int nsm_b200_get_element_components(nsm_b200_ctx* ctx, int block_id, int n_components, const int32_t* offsets, double* out);

@@ -17,8 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NSM_B200_LIB") or os.path.join(_HERE, "lib", "libnsm_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_JACOBIAN, ERR_MATERIAL, ERR_COMM = range(6)
-MAT_ELASTIC, MAT_NEOHOOKEAN = 0, 1
-MATERIAL_KINDS = {"elastic": MAT_ELASTIC, "neohookean": MAT_NEOHOOKEAN}
+MAT_ELASTIC, MAT_NEOHOOKEAN, MAT_J2_PLASTICITY = 0, 1, 2
+MATERIAL_KINDS = {"elastic": MAT_ELASTIC, "neohookean": MAT_NEOHOOKEAN, "j2_plasticity": MAT_J2_PLASTICITY}
 (FIELD_LUMPED_MASS, FIELD_REFERENCE_COORDINATE, FIELD_DISPLACEMENT, FIELD_VELOCITY, FIELD_ACCELERATION,
  FIELD_INTERNAL_FORCE, FIELD_EXTERNAL_FORCE) = range(7)
 FIELDS = {"lumped_mass": 0, "reference_coordinate": 1, "displacement": 2, "velocity": 3, "acceleration": 4,
@@ -42,6 +42,10 @@ SYMBOLS = [
     "nsm_b200_fp64_peak", "nsm_b200_cold_points", "nsm_b200_set_bc_values_steps", "nsm_b200_set_bc_programs",
     "nsm_b200_set_bc_slots_steps", "nsm_b200_get_element_components", "nsm_b200_step_host",
     "nsm_b200_get_element_data_subset", "nsm_b200_comm_set_timeout", "nsm_b200_kernel_info",
+    "nsm_b200_add_block_params", "nsm_b200_material_num_state", "nsm_b200_material_num_params",
+    "nsm_b200_material_state_label", "nsm_b200_material_state_initial_value", "nsm_b200_compute_stress_state",
+    "nsm_b200_element_data_stride", "nsm_b200_update_states", "nsm_b200_get_element_data_previous",
+    "nsm_b200_set_element_data",
 ]
 
 
@@ -118,6 +122,16 @@ def lib():
         "nsm_b200_get_element_data_subset": (i32, [vp, i32, i64, lp, dp]),
         "nsm_b200_comm_set_timeout": (i32, [vp, dbl]),
         "nsm_b200_kernel_info": (C.c_char_p, []),
+        "nsm_b200_add_block_params": (i32, [vp, i32, i64, ip, i32, i32, dp]),
+        "nsm_b200_material_num_state": (i32, [i32]),
+        "nsm_b200_material_num_params": (i32, [i32]),
+        "nsm_b200_material_state_label": (C.c_char_p, [i32, i32]),
+        "nsm_b200_material_state_initial_value": (dbl, [i32, i32]),
+        "nsm_b200_compute_stress_state": (i32, [vp, i32, i32, dp, i64, dp, dp, dp, dp, dp, dp]),
+        "nsm_b200_element_data_stride": (i32, [vp, i32]),
+        "nsm_b200_update_states": (i32, [vp]),
+        "nsm_b200_get_element_data_previous": (i32, [vp, i32, dp]),
+        "nsm_b200_set_element_data": (i32, [vp, i32, i32, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -177,6 +191,7 @@ class Context:
         self.n_nodes = 0
         self.block_ids = []
         self.block_nelem = {}
+        self.block_stride = {}  # doubles per integration point: 15 + the material's state variables
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -206,13 +221,15 @@ class Context:
         self.n_nodes = len(x)
         self._ck(self._L.nsm_b200_set_nodes(self._h, len(x), _dptr(x), _dptr(y), _dptr(z)))
 
-    def add_block(self, block_id, conn, material, bulk_modulus, shear_modulus, density):
+    def add_block(self, block_id, conn, material, bulk_modulus, shear_modulus, density, *extra):
+        """extra: the model's own parameters after (bulk, shear, density) -- j2_plasticity: yield_stress, hardening_modulus"""
         conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 8)
         kind = MATERIAL_KINDS[material] if isinstance(material, str) else int(material)
-        self._ck(self._L.nsm_b200_add_block(self._h, int(block_id), len(conn), _iptr(conn), kind,
-                                             float(bulk_modulus), float(shear_modulus), float(density)))
+        params = np.array([bulk_modulus, shear_modulus, density, *extra], dtype=np.float64)
+        self._ck(self._L.nsm_b200_add_block_params(self._h, int(block_id), len(conn), _iptr(conn), kind, len(params), _dptr(params)))
         self.block_ids.append(int(block_id))
         self.block_nelem[int(block_id)] = len(conn)
+        self.block_stride[int(block_id)] = 15 + int(self._L.nsm_b200_material_num_state(kind))
 
     def finalize(self, assembly=ASSEMBLY_ATOMIC, flags=0):
         self._ck(self._L.nsm_b200_finalize(self._h, assembly, flags))
@@ -320,10 +337,30 @@ class Context:
                                              acceleration.ctypes.data, internal_force.ctypes.data))
         return t.value
 
-    def element_data(self, block_id):
-        out = np.empty((self.block_nelem[block_id], 8, 15))
-        self._ck(self._L.nsm_b200_get_element_data(self._h, block_id, _dptr(out)))
+    def element_data(self, block_id, previous=False):
+        """[n_elem][8][15 + n_state] records: the most recently computed ones, or (previous) the N records."""
+        out = np.empty((self.block_nelem[block_id], 8, self.block_stride[block_id]))
+        fn = self._L.nsm_b200_get_element_data_previous if previous else self._L.nsm_b200_get_element_data
+        self._ck(fn(self._h, block_id, _dptr(out)))
         return out
+
+    def set_element_data(self, block_id, data, previous=False):
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        assert data.shape == (self.block_nelem[block_id], 8, self.block_stride[block_id])
+        self._ck(self._L.nsm_b200_set_element_data(self._h, block_id, 1 if previous else 0, _dptr(data)))
+
+    def update_states(self):
+        self._ck(self._L.nsm_b200_update_states(self._h))
+
+    def compute_stress_state(self, material, params, F_n, F_np1, s_n, state_n):
+        """Full material seam: params = [bulk, shear, density, model-specific...] -> (sigma_np1, state_np1)."""
+        kind = MATERIAL_KINDS[material] if isinstance(material, str) else int(material)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        F_n, F_np1, s_n, state_n = (np.ascontiguousarray(a, dtype=np.float64) for a in (F_n, F_np1, s_n, state_n))
+        s, st = np.empty((len(F_np1), 6)), np.empty_like(state_n)
+        self._ck(self._L.nsm_b200_compute_stress_state(self._h, kind, len(params), _dptr(params), len(F_np1), _dptr(F_n), _dptr(F_np1),
+                                                        _dptr(s_n), _dptr(state_n), _dptr(s), _dptr(st)))
+        return s, st
 
     def element_components(self, block_id, offsets):
         """out[k][e] = integration-point value offsets[k] (0..119 = 15*point + field) of element e, split on the device."""
@@ -335,12 +372,12 @@ class Context:
     def element_data_subset(self, block_id, elements):
         """[len(elements)][8][15] integration-point records of the listed elements (file-order indices in the block)."""
         el = np.ascontiguousarray(elements, dtype=np.int64)
-        out = np.empty((len(el), 8, 15))
+        out = np.empty((len(el), 8, self.block_stride[block_id]))
         self._ck(self._L.nsm_b200_get_element_data_subset(self._h, block_id, len(el), _lptr(el), _dptr(out)))
         return out
 
     def derived_element_data(self, block_id):
-        out = np.empty((16, self.block_nelem[block_id]))
+        out = np.empty((1 + self.block_stride[block_id], self.block_nelem[block_id]))
         self._ck(self._L.nsm_b200_derived_element_data(self._h, block_id, _dptr(out)))
         return out
 

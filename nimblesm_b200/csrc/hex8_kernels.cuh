@@ -57,7 +57,9 @@ struct ElemArgs
   const double* u[3];        // displacement, SoA
   double*       f[3];        // nodal internal force, SoA (ATOMIC)
   double*       ef;          // [n_elem][8][kEfStride] element nodal forces (ORDERED), already offset to the block
-  double*       ipt;         // [n_elem][8][15] or nullptr
+  double*       ipt;         // [n_elem][8][15 + n_state] or nullptr: the records this launch writes (N+1)
+  const double* ipt_n;       // history-dependent materials: the previous records (N), same layout
+  double        mat_a, mat_b;  // material-specific parameters (j2_plasticity: yield stress, hardening modulus)
   double*       binv_cache;  // [n_groups][9][32] or nullptr, already offset to the block
   double        bulk, shear;
   unsigned*     ticket;      // next unclaimed chunk of 4-element groups of this launch (zeroed by the host)
@@ -111,6 +113,11 @@ prefetch_l2(const void* g)
 {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
 }
+__device__ __forceinline__ void
+prefetch_l1(const void* g)
+{
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(g));
+}
 
 // Offset of node row j within a component of a coordinate set.  Rows 4..7 sit two doubles further: when lane
 // (q, ew) touches row q (gather copies, X / u reads, K / C stores) the 16 lanes of a half-warp then fall into 16
@@ -155,8 +162,9 @@ accumulate_one(const ShapeAtPoint& sh, const double* sC, int ew, double (&a)[3][
 enum { kSchedAll = 0, kSchedList = 1, kSchedSkipFlagged = 2 };
 static_assert(kTicketChunk == 8, "the skip mask holds the flag bits of one chunk of 8 groups in a byte");
 
-// MAT: nsm_material_kind; ORDERED: store element forces instead of atomics; MODE bit0: store F/sigma,
-// bit1: read cached b^-1 (filled once by binv_cache_kernel).
+// MAT: nsm_material_kind; ORDERED: store element forces instead of atomics; MODE bit0: store F/sigma (always set
+// for a material with state variables: its records are its memory), bit1: read cached b^-1 (filled once by
+// binv_cache_kernel).
 enum { kModeStoreIpt = 1, kModeReadBinv = 2 };
 
 // How the cached b^-1 reaches the lane.  Neohookean passes are long (~1130 DP instructions per lane), so the
@@ -197,7 +205,8 @@ template <int MAT, int MODE, bool FAST>
 __device__ __forceinline__ unsigned
 integration_point(const ShapeAtPoint& sh, const double* sX, const double* sK, const double* sC, int ew, int lane,
                   const double* binv_row, double* binv_slot, const double* binv_next, double bulk, double shear,
-                  double* share, double (&F)[9], double (&sig)[6])
+                  double* share, double (&F)[9], double (&sig)[6], const double* rec_n = nullptr, double mat_a = 0.0,
+                  double mat_b = 0.0, double* state_out = nullptr)
 {
   unsigned bad = 0u, jac = 0u;
   double   a[3][3], binv[3][3];
@@ -258,10 +267,24 @@ integration_point(const ShapeAtPoint& sh, const double* sX, const double* sK, co
   const double det = invert3x3<FAST>(a, ai, bad);
   jac |= !(det > 0.0) ? 2u : 0u;
 
-  if (MAT == 0)
+  if (MAT == 0) {
     stress_elastic(bulk, shear, F, sig);
-  else
+  } else if (MAT == 1) {
     stress_neohookean<FAST>(bulk, shear, F, sig, bad);
+  } else {
+    // history-dependent material: F_n, sigma_n, state_n of this point from the previous record (the lines were
+    // prefetched into L1 at the top of the pass); lanes beyond the block's last element see a virgin point
+    double Fn[9], sn[6], stn[kMaxStateVars], st[kMaxStateVars];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Fn[i] = rec_n ? rec_n[i] : (i < 3 ? 1.0 : 0.0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sn[i] = rec_n ? rec_n[9 + i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < kMaxStateVars; ++i) stn[i] = rec_n ? rec_n[15 + i] : 0.0;
+    stress_j2<FAST>(bulk, shear, mat_a, mat_b, Fn, F, sn, stn, sig, st, bad);
+#pragma unroll
+    for (int i = 0; i < kMaxStateVars; ++i) state_out[i] = st[i];
+  }
 
   GradProducts gp;
   gp.init(sh, ai);
@@ -470,32 +493,42 @@ element_force_kernel(const ElemArgs p)
     const bool jacobians_differ = __any_sync(0xffffffffu, differs);
     __syncwarp();
 
-    double   F[9], sig[6];
-    // (the fast pass always runs: it also refills the b^-1 staging slots and closes their copy group)
-    unsigned st = integration_point<MAT, MODE, true>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear,
-                                                     share, F, sig);
-    if (jacobians_differ) st |= 1u;
-    if (st & 1u) {  // cold: some operand outside the fast window (or distinct Jacobians): plain IEEE operators
-      atomicAdd(p.flags + 1, 1);  // statistics: integration points redone (nsm_b200_cold_points)
-      st = integration_point<MAT, MODE, false>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear, share,
-                                               F, sig);
-    }
-    const int  node = sN[slot * 32];
-    const bool live = node >= 0;
-    if (live && (st & 2u)) atomicOr(p.flags, 1);
-
-    // element data (F / sigma, ORDERED forces) live in FILE order: looked up where it is stored, so that the
+    // element data (F / sigma / state, ORDERED forces) live in FILE order: looked up where it is used, so that the
     // index does not occupy registers through the pass
     auto file_element = [&]() -> int64_t {
       const int64_t e_sched = (int64_t)g * kElemsPerWarp + ew;
       return p.orig ? (int64_t)__ldg(p.orig + e_sched) : e_sched;
     };
+    constexpr int kRecord = 15 + MaterialState<MAT>::n;  // doubles per integration point (src/nimble_block.cc:84-108)
+    const double* rec_n = nullptr;
+    if (MaterialState<MAT>::n > 0 && sN[slot * 32] >= 0) {
+      rec_n = p.ipt_n + (file_element() * 8 + q) * kRecord;
+      prefetch_l1(rec_n);  // 136 bytes per point: both lines are in L1 by the time F is formed
+      prefetch_l1(rec_n + kRecord - 1);
+    }
+
+    double   F[9], sig[6], state[kMaxStateVars];
+    // (the fast pass always runs: it also refills the b^-1 staging slots and closes their copy group)
+    unsigned st = integration_point<MAT, MODE, true>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear,
+                                                     share, F, sig, rec_n, p.mat_a, p.mat_b, state);
+    if (jacobians_differ) st |= 1u;
+    if (st & 1u) {  // cold: some operand outside the fast window (or distinct Jacobians): plain IEEE operators
+      atomicAdd(p.flags + 1, 1);  // statistics: integration points redone (nsm_b200_cold_points)
+      st = integration_point<MAT, MODE, false>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear, share,
+                                               F, sig, rec_n, p.mat_a, p.mat_b, state);
+    }
+    const int  node = sN[slot * 32];
+    const bool live = node >= 0;
+    if (live && (st & 2u)) atomicOr(p.flags, 1);
+
     if ((MODE & kModeStoreIpt) && live) {
-      double* d = p.ipt + (file_element() * 8 + q) * 15;
+      double* d = p.ipt + (file_element() * 8 + q) * kRecord;
 #pragma unroll
       for (int i = 0; i < 9; ++i) d[i] = F[i];
 #pragma unroll
       for (int i = 0; i < 6; ++i) d[9 + i] = sig[i];
+#pragma unroll
+      for (int i = 0; i < MaterialState<MAT>::n; ++i) d[15 + i] = state[i];
     }
     __syncwarp();
 
@@ -662,6 +695,30 @@ stress_kernel(int64_t n, const double* __restrict__ Fin, double* __restrict__ so
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) sout[i * 6 + k] = s[k];
+}
+
+// the same seam for a material with state variables: (F_n, F_np1, sigma_n, state_n) -> (sigma_np1, state_np1)
+__global__ void __launch_bounds__(128)
+stress_state_kernel(int64_t n, const double* __restrict__ Fn_in, const double* __restrict__ F_in, const double* __restrict__ sn_in,
+                    const double* __restrict__ stn_in, double* __restrict__ s_out, double* __restrict__ st_out, double bulk,
+                    double shear, double mat_a, double mat_b)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double Fn[9], F[9], sn[6], stn[kMaxStateVars], s[6], st[kMaxStateVars];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Fn[k] = Fn_in[i * 9 + k], F[k] = F_in[i * 9 + k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) sn[k] = sn_in[i * 6 + k];
+#pragma unroll
+  for (int k = 0; k < kMaxStateVars; ++k) stn[k] = stn_in[i * kMaxStateVars + k];
+  unsigned bad = 0u;
+  stress_j2<true>(bulk, shear, mat_a, mat_b, Fn, F, sn, stn, s, st, bad);
+  if (bad) stress_j2<false>(bulk, shear, mat_a, mat_b, Fn, F, sn, stn, s, st, bad);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s_out[i * 6 + k] = s[k];
+#pragma unroll
+  for (int k = 0; k < kMaxStateVars; ++k) st_out[i * kMaxStateVars + k] = st[k];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1036,7 +1093,7 @@ node_gather_scalar_kernel(int64_t n_nodes, const double* __restrict__ es, const 
 // current configuration; averages of the 15 integration-point fields.  out [16][n_elem].
 __global__ void __launch_bounds__(128)
 derived_kernel(int64_t n_elem, const int* __restrict__ conn, const double* X0, const double* X1, const double* X2,
-               const double* u0, const double* u1, const double* u2, const double* __restrict__ ipt, double* out)
+               const double* u0, const double* u1, const double* u2, const double* __restrict__ ipt, double* out, int record)
 {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_elem) return;
@@ -1047,51 +1104,53 @@ derived_kernel(int64_t n_elem, const int* __restrict__ conn, const double* X0, c
     const int nd = conn[e * 8 + j];
     for (int i = 0; i < 3; ++i) x[3 * j + i] = (Xs[i][nd] + us[i][nd]) + 0.0;
   }
-  double vol = 0.0, avg[15];
-  for (int i = 0; i < 15; ++i) avg[i] = 0.0;
-  const double* qd = ipt + e * 120;
+  double vol = 0.0, avg[15 + kMaxStateVars];  // record = 15 + the material's state variables
+  for (int i = 0; i < 15 + kMaxStateVars; ++i) avg[i] = 0.0;
+  const double* qd = ipt + e * 8 * record;
   for (int g = 0; g < 8; ++g) {
     double a[3][3], ai[3][3];
     param_gradient_tbl(x, g, a);
     unsigned     unused = 0u;
     const double det    = invert3x3<false>(a, ai, unused);
     vol += det;
-    for (int i = 0; i < 15; ++i) avg[i] += qd[g * 15 + i] * 1.0 * det;
+    for (int i = 0; i < 15 + kMaxStateVars; ++i)
+      if (i < record) avg[i] += qd[g * record + i] * 1.0 * det;
   }
   out[e] = vol;
-  for (int i = 0; i < 15; ++i) out[(int64_t)(i + 1) * n_elem + e] = avg[i] / vol;
+  for (int i = 0; i < record; ++i) out[(int64_t)(i + 1) * n_elem + e] = avg[i] / vol;
 }
 
 // Output: component split of the integration-point data, out[k][e - e0] = ipt[e][off[k]] for a range of elements
 __global__ void __launch_bounds__(256)
 select_ipt_components_kernel(int64_t e0, int64_t n, int n_comp, const int* __restrict__ off, const double* __restrict__ ipt,
-                             double* __restrict__ out)
+                             double* __restrict__ out, int per_element)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * n_comp) return;
   const int64_t k = i / n, e = i - k * n;
-  out[i]          = ipt[(e0 + e) * 120 + off[k]];
+  out[i]          = ipt[(e0 + e) * per_element + off[k]];
 }
 
 // Output / checks: full integration-point records of a list of elements, out[i] = ipt[elems[i]]
 __global__ void __launch_bounds__(256)
-gather_ipt_records_kernel(int64_t n, const int64_t* __restrict__ elems, const double* __restrict__ ipt, double* __restrict__ out)
+gather_ipt_records_kernel(int64_t n, const int64_t* __restrict__ elems, const double* __restrict__ ipt, double* __restrict__ out,
+                          int per_element)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * 120) return;
-  const int64_t k = i / 120;
-  out[i]          = ipt[elems[k] * 120 + (i - k * 120)];
+  if (i >= n * per_element) return;
+  const int64_t k = i / per_element;
+  out[i]          = ipt[elems[k] * per_element + (i - k * per_element)];
 }
 
 // F = identity, sigma = 0 (Block::InitializeElementData, src/nimble_block.cc:148-207)
+// (state variables start from the material's initial values, 0 for the built-in history-dependent material)
 __global__ void __launch_bounds__(256)
-init_ipt_kernel(int64_t n_points, double* ipt)
+init_ipt_kernel(int64_t n_points, double* ipt, int record)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
-  double* d = ipt + i * 15;
-#pragma unroll
-  for (int k = 0; k < 15; ++k) d[k] = (k < 3) ? 1.0 : 0.0;
+  double* d = ipt + i * record;
+  for (int k = 0; k < record; ++k) d[k] = (k < 3) ? 1.0 : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -30,6 +30,14 @@ struct Block
   int64_t          n_elem   = 0;
   int              material = 0;
   double           bulk = 0, shear = 0, density = 0;
+  double           mat_a = 0, mat_b = 0;  // material-specific parameters (j2_plasticity: yield stress, hardening modulus)
+  // history-dependent material: integration-point records N and N+1, [n_elem][8][15 + n_state] each, owned by the
+  // block; rec[cur] is the one the element kernel writes.  roll_pending: ModelData::UpdateStates was requested, the
+  // roles swap at the next force evaluation (src/nimble_model_data.h:104-107)
+  int              n_state = 0;
+  double*          rec[2]  = {nullptr, nullptr};
+  int              cur     = 0;
+  bool             roll_pending = false;
   std::vector<int> conn_host;  // dropped after finalize
   int*             conn      = nullptr;  // file order (mass, adjacency, derived data)
   int*             conn_sched = nullptr; // the element kernel's walk: == conn, or Morton-ordered (NSM_FLAG_REORDER_ELEMENTS)
@@ -277,7 +285,10 @@ elem_args(nsm_b200_ctx* c, const Block& b, int sched = kSchedAll)
   p.conn   = b.conn_sched;
   for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.f[i] = c->f[i];
   p.ef         = c->ef ? c->ef + b.elem_base * 8 * kEfStride : nullptr;
-  p.ipt        = c->ipt ? c->ipt + b.elem_base * 120 : nullptr;
+  p.ipt        = b.n_state ? b.rec[b.cur] : (c->ipt ? c->ipt + b.elem_base * 120 : nullptr);
+  p.ipt_n      = b.n_state ? b.rec[b.cur ^ 1] : nullptr;
+  p.mat_a      = b.mat_a;
+  p.mat_b      = b.mat_b;
   p.binv_cache = c->binv ? c->binv + b.group_base * kBinvGroupDoubles : nullptr;
   p.bulk       = b.bulk;
   p.shear      = b.shear;
@@ -338,18 +349,61 @@ launch_element_any(const ElemArgs& p, int material, bool ordered, int mode, cuda
 {
   if (material == NSM_MAT_ELASTIC)
     return ordered ? launch_element_mode<0, true>(p, mode, s) : launch_element_mode<0, false>(p, mode, s);
+  if (material == NSM_MAT_J2_PLASTICITY) {  // a material with state always writes its records
+    if (mode & kModeReadBinv) return ordered ? launch_element<2, true, 3>(p, s) : launch_element<2, false, 3>(p, s);
+    return ordered ? launch_element<2, true, 1>(p, s) : launch_element<2, false, 1>(p, s);
+  }
   return ordered ? launch_element_mode<1, true>(p, mode, s) : launch_element_mode<1, false>(p, mode, s);
+}
+
+int
+num_state_of(int material_kind)
+{
+  return material_kind == NSM_MAT_J2_PLASTICITY ? 2 : 0;
+}
+
+// records of a block: pointer, doubles per element
+const double*
+block_records(nsm_b200_ctx* c, const Block& b, int* per_element)
+{
+  *per_element = 8 * (15 + b.n_state);
+  return b.n_state ? b.rec[b.cur] : c->ipt + b.elem_base * 120;
+}
+
+// ModelData::UpdateStates requested earlier: the records written last become the N records of this evaluation
+void
+roll_states(nsm_b200_ctx* c)
+{
+  for (auto& kv : c->blocks) {
+    Block& b = kv.second;
+    if (b.n_state && b.roll_pending) b.cur ^= 1;
+    b.roll_pending = false;
+  }
+}
+
+void
+mark_states_for_roll(nsm_b200_ctx* c)
+{
+  for (auto& kv : c->blocks)
+    if (kv.second.n_state) kv.second.roll_pending = true;
 }
 
 int
 ensure_ipt(nsm_b200_ctx* c)
 {
   if (c->ipt) return NSM_OK;
-  int rc = dev_alloc(c, &c->ipt, c->n_elem_total * 120);
-  if (rc) return rc;
+  bool any_stateless = false;  // blocks of a material with state variables own their records (Block::rec)
+  for (auto& kv : c->blocks) any_stateless = any_stateless || kv.second.n_state == 0;
+  if (!any_stateless) return NSM_OK;
+  // stream-ordered allocation: this may run in the middle of a call whose earlier steps are already queued, and a
+  // cudaMalloc would wait for the whole device -- including a peer's in-kernel wait for OUR next shared-node data
+  // when ranks share one GPU (RankGroup lockstep mode)
+  const int64_t count = std::max<int64_t>(c->n_elem_total * 120, 1);
+  NSM_CUDA(c, cudaMallocAsync((void**)&c->ipt, (size_t)count * sizeof(double), c->stream));
+  c->device_bytes += count * (int64_t)sizeof(double);
   const int64_t np = c->n_elem_total * 8;
   if (np > 0) {
-    init_ipt_kernel<<<grid_for(np, 256), 256, 0, c->stream>>>(np, c->ipt);
+    init_ipt_kernel<<<grid_for(np, 256), 256, 0, c->stream>>>(np, c->ipt, 15);
     c->launches++;
     NSM_CUDA(c, cudaGetLastError());
   }
@@ -429,6 +483,7 @@ enqueue_internal_force(nsm_b200_ctx* c, bool store_ipt)
   if (!ordered) {
     for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->f[i], 0, (size_t)c->n_nodes * sizeof(double), c->stream));
   }
+  roll_states(c);
   int rc = enqueue_element_kernels(c, store_ipt);
   if (rc) return rc;
   if (ordered) {
@@ -606,6 +661,7 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   for (auto& kv : c->blocks) {
     if (kv.second.conn_sched != kv.second.conn) fr(kv.second.conn_sched);
     fr(kv.second.conn), fr(kv.second.orig), fr(kv.second.group_bits), fr(kv.second.group_list);
+    fr(kv.second.rec[0]), fr(kv.second.rec[1]);
   }
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
@@ -635,13 +691,52 @@ int
 nsm_b200_add_block(nsm_b200_ctx* c, int block_id, int64_t n_elem, const int32_t* conn, int material_kind,
                    double bulk_modulus, double shear_modulus, double density)
 {
+  const double params[3] = {bulk_modulus, shear_modulus, density};
+  return nsm_b200_add_block_params(c, block_id, n_elem, conn, material_kind, 3, params);
+}
+
+int
+nsm_b200_material_num_state(int material_kind)
+{
+  return (material_kind >= 0 && material_kind < NSM_MAT_COUNT) ? num_state_of(material_kind) : -1;
+}
+
+int
+nsm_b200_material_num_params(int material_kind)
+{
+  if (material_kind < 0 || material_kind >= NSM_MAT_COUNT) return -1;
+  return material_kind == NSM_MAT_J2_PLASTICITY ? 5 : 3;
+}
+
+const char*
+nsm_b200_material_state_label(int material_kind, int index)
+{
+  static const char* const j2[2] = {"equivalent_plastic_strain", "von_mises_stress"};
+  if (material_kind == NSM_MAT_J2_PLASTICITY && index >= 0 && index < 2) return j2[index];
+  return nullptr;
+}
+
+double
+nsm_b200_material_state_initial_value(int, int)
+{
+  return 0.0;
+}
+
+int
+nsm_b200_add_block_params(nsm_b200_ctx* c, int block_id, int64_t n_elem, const int32_t* conn, int material_kind, int n_params,
+                          const double* params)
+{
   NSM_REQUIRE(c, c != nullptr, "null context");
+  if (material_kind < 0 || material_kind >= NSM_MAT_COUNT)
+    return fail(c, NSM_ERR_MATERIAL, "unknown material kind %d (0 = elastic, 1 = neohookean, 2 = j2_plasticity)", material_kind);
+  if (n_params != nsm_b200_material_num_params(material_kind) || !params)
+    return fail(c, NSM_ERR_MATERIAL, "material kind %d takes %d parameters, %d given", material_kind,
+                nsm_b200_material_num_params(material_kind), n_params);
+  const double bulk_modulus = params[0], shear_modulus = params[1], density = params[2];
   NSM_REQUIRE(c, !c->finalized, "add_block after finalize");
   NSM_REQUIRE(c, n_elem >= 0 && (n_elem == 0 || conn), "bad element count / null connectivity");
   NSM_REQUIRE(c, n_elem <= ((int64_t)1 << 32), "a block holds at most 2^32 elements (32-bit group indices)");
   NSM_REQUIRE(c, c->blocks.find(block_id) == c->blocks.end(), "duplicate block id");
-  if (material_kind != NSM_MAT_ELASTIC && material_kind != NSM_MAT_NEOHOOKEAN)
-    return fail(c, NSM_ERR_MATERIAL, "unknown material kind %d (0 = elastic, 1 = neohookean)", material_kind);
   for (int64_t i = 0; i < n_elem * 8; ++i)
     if (conn[i] < 0 || conn[i] >= c->n_nodes)
       return fail(c, NSM_ERR_ARG, "block %d: connectivity entry %lld = %d outside [0, %lld)", block_id, (long long)i,
@@ -649,6 +744,8 @@ nsm_b200_add_block(nsm_b200_ctx* c, int block_id, int64_t n_elem, const int32_t*
   Block b;
   b.id = block_id, b.n_elem = n_elem, b.material = material_kind;
   b.bulk = bulk_modulus, b.shear = shear_modulus, b.density = density;
+  b.n_state = num_state_of(material_kind);
+  if (material_kind == NSM_MAT_J2_PLASTICITY) b.mat_a = params[3], b.mat_b = params[4];
   b.conn_host.assign(conn, conn + n_elem * 8);
   c->blocks[block_id] = std::move(b);
   return NSM_OK;
@@ -826,6 +923,20 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
     cudaFree(counts);
   }
 
+  for (auto& kv : c->blocks) {  // Block::InitializeElementData (src/nimble_block.cc:148-207): N and N+1 start alike
+    Block& b = kv.second;
+    if (!b.n_state) continue;
+    const int     record = 15 + b.n_state;
+    const int64_t np     = b.n_elem * 8;
+    for (int k = 0; k < 2; ++k) {
+      if ((rc = dev_alloc(c, &b.rec[k], np * record))) return rc;
+      if (np > 0) {
+        init_ipt_kernel<<<grid_for(np, 256), 256, 0, c->stream>>>(np, b.rec[k], record);
+        c->launches++;
+      }
+    }
+    NSM_CUDA(c, cudaGetLastError());
+  }
   c->finalized = true;
   if (flags & NSM_FLAG_STORE_IPT_EVERY_STEP) {
     if ((rc = ensure_ipt(c))) return rc;
@@ -926,8 +1037,8 @@ nsm_b200_compute_lumped_mass(nsm_b200_ctx* c, double* critical_dt)
   const unsigned long long inf_bits = 0x7ff0000000000000ULL;
   NSM_CUDA(c, cudaMemcpyAsync(c->d_min_dt, &inf_bits, sizeof inf_bits, cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemsetAsync(c->mass, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->stream));
-  double* em = nullptr;
-  if (ordered) NSM_CUDA(c, cudaMalloc((void**)&em, (size_t)std::max<int64_t>(c->n_elem_total * 8, 1) * sizeof(double)));
+  double* em = nullptr;  // (stream-ordered: see ensure_ipt)
+  if (ordered) NSM_CUDA(c, cudaMallocAsync((void**)&em, (size_t)std::max<int64_t>(c->n_elem_total * 8, 1) * sizeof(double), c->stream));
   for (auto& kv : c->blocks) {
     const Block& b = kv.second;
     if (b.n_elem == 0) continue;
@@ -957,8 +1068,8 @@ nsm_b200_compute_lumped_mass(nsm_b200_ctx* c, double* critical_dt)
   }
   unsigned long long bits = 0;
   NSM_CUDA(c, cudaMemcpyAsync(&bits, c->d_min_dt, sizeof bits, cudaMemcpyDeviceToHost, c->stream));
+  if (em) cudaFreeAsync(em, c->stream);
   int rc = check_flags(c);
-  if (em) cudaFree(em);
   if (rc) return rc;
   if (critical_dt) memcpy(critical_dt, &bits, sizeof bits);
   return NSM_OK;
@@ -1009,6 +1120,45 @@ nsm_b200_compute_stress(nsm_b200_ctx* c, int material_kind, double bulk, double 
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   cudaFree(dF);
   cudaFree(dS);
+  return NSM_OK;
+}
+
+int
+nsm_b200_compute_stress_state(nsm_b200_ctx* c, int material_kind, int n_params, const double* params, int64_t n_points,
+                              const double* def_grad_n, const double* def_grad_np1, const double* stress_n, const double* state_n,
+                              double* stress_np1, double* state_np1)
+{
+  NSM_ENTER(c);
+  if (material_kind < 0 || material_kind >= NSM_MAT_COUNT) return fail(c, NSM_ERR_MATERIAL, "unknown material kind %d", material_kind);
+  if (n_params != nsm_b200_material_num_params(material_kind) || !params)
+    return fail(c, NSM_ERR_MATERIAL, "material kind %d takes %d parameters, %d given", material_kind,
+                nsm_b200_material_num_params(material_kind), n_params);
+  const int ns = num_state_of(material_kind);
+  if (ns == 0)  // F_n, sigma_n and the state arrays are not read by a material without state
+    return nsm_b200_compute_stress(c, material_kind, params[0], params[1], n_points, def_grad_np1, stress_np1);
+  NSM_REQUIRE(c, n_points >= 0 && (n_points == 0 || (def_grad_n && def_grad_np1 && stress_n && state_n && stress_np1 && state_np1)),
+              "compute_stress_state: bad arguments");
+  if (n_points == 0) return NSM_OK;
+  // one device buffer: F_n 9, F_np1 9, sigma_n 6, state_n ns | sigma_np1 6, state_np1 ns
+  const size_t n = (size_t)n_points;
+  double*      d = nullptr;
+  NSM_CUDA(c, cudaMalloc((void**)&d, n * (size_t)(30 + 2 * ns) * sizeof(double)));
+  double *dFn = d, *dF = dFn + 9 * n, *dsn = dF + 9 * n, *dstn = dsn + 6 * n, *ds = dstn + ns * n, *dst = ds + 6 * n;
+  cudaError_t e = cudaMemcpyAsync(dFn, def_grad_n, 9 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dF, def_grad_np1, 9 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dsn, stress_n, 6 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dstn, state_n, ns * n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    stress_state_kernel<<<grid_for(n_points, 128), 128, 0, c->stream>>>(n_points, dFn, dF, dsn, dstn, ds, dst, params[0], params[1],
+                                                                        params[3], params[4]);
+    c->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(stress_np1, ds, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(state_np1, dst, ns * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(c, NSM_ERR_CUDA, "compute_stress_state: %s", cudaGetErrorString(e));
   return NSM_OK;
 }
 
@@ -1240,6 +1390,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
       }
     }
     if (c->profiling) prof_event(c);
+    roll_states(c);  // UpdateStates of the previous step (explicit_time_integrator.cc:277)
     int rc;
     if (c->overlap) {
       // boundary-first: the groups that touch shared nodes run first, their nodal forces travel to the peers on
@@ -1260,6 +1411,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
       if ((rc = enqueue_element_kernels(c, store))) return rc;
     }
     if (c->profiling) prof_event(c);
+    mark_states_for_roll(c);
     if (n > 0) {
       const NodeArgs na = node_args(c, s + 1);  // boundary-condition magnitudes of the step the fused pass opens
       if (c->comm.active()) {
@@ -1373,8 +1525,63 @@ nsm_b200_get_element_data(nsm_b200_ctx* c, int block_id, double* out)
   int rc = ensure_ipt(c);
   if (rc) return rc;
   const Block& b = it->second;
-  NSM_CUDA(c, cudaMemcpyAsync(out, c->ipt + b.elem_base * 120, (size_t)b.n_elem * 120 * sizeof(double),
-                              cudaMemcpyDeviceToHost, c->stream));
+  int           per_element = 0;
+  const double* rec         = block_records(c, b, &per_element);
+  NSM_CUDA(c, cudaMemcpyAsync(out, rec, (size_t)b.n_elem * per_element * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
+nsm_b200_element_data_stride(const nsm_b200_ctx* c, int block_id)
+{
+  if (!c) return -1;
+  auto it = c->blocks.find(block_id);
+  return it == c->blocks.end() ? -1 : 15 + it->second.n_state;
+}
+
+int
+nsm_b200_update_states(nsm_b200_ctx* c)
+{
+  NSM_REQUIRE(c, c != nullptr && c->finalized, "update_states: context not finalized");
+  mark_states_for_roll(c);
+  return NSM_OK;
+}
+
+int
+nsm_b200_set_element_data(nsm_b200_ctx* c, int block_id, int previous, const double* in)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "set_element_data: context not finalized");
+  auto it = c->blocks.find(block_id);
+  NSM_REQUIRE(c, it != c->blocks.end() && in, "set_element_data: unknown block id / null data");
+  Block& b = it->second;
+  NSM_REQUIRE(c, b.n_state > 0 || !previous, "set_element_data: the block's material carries no state (no N records are kept)");
+  roll_states(c);  // a pending UpdateStates is applied first, so that `previous` names the records the next evaluation reads
+  double* dst = nullptr;
+  if (b.n_state) {
+    dst = b.rec[previous ? (b.cur ^ 1) : b.cur];
+  } else {
+    int rc = ensure_ipt(c);
+    if (rc) return rc;
+    dst = c->ipt + b.elem_base * 120;
+  }
+  NSM_CUDA(c, cudaMemcpyAsync(dst, in, (size_t)b.n_elem * 8 * (15 + b.n_state) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
+nsm_b200_get_element_data_previous(nsm_b200_ctx* c, int block_id, double* out)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "get_element_data_previous: context not finalized");
+  auto it = c->blocks.find(block_id);
+  NSM_REQUIRE(c, it != c->blocks.end(), "get_element_data_previous: unknown block id");
+  const Block& b = it->second;
+  NSM_REQUIRE(c, b.n_state > 0, "get_element_data_previous: the block's material carries no state (no N records are kept)");
+  NSM_CUDA(c, cudaMemcpyAsync(out, b.rec[b.cur ^ 1], (size_t)b.n_elem * 8 * (15 + b.n_state) * sizeof(double), cudaMemcpyDeviceToHost,
+                              c->stream));
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   return NSM_OK;
 }
@@ -1390,13 +1597,16 @@ nsm_b200_derived_element_data(nsm_b200_ctx* c, int block_id, double* out)
   if (rc) return rc;
   const Block& b = it->second;
   if (b.n_elem == 0) return NSM_OK;
-  double* d = nullptr;
-  NSM_CUDA(c, cudaMalloc((void**)&d, (size_t)b.n_elem * 16 * sizeof(double)));
+  double*       d           = nullptr;
+  int           per_element = 0;
+  const double* rec         = block_records(c, b, &per_element);
+  const int     record      = per_element / 8;
+  NSM_CUDA(c, cudaMalloc((void**)&d, (size_t)b.n_elem * (1 + record) * sizeof(double)));
   derived_kernel<<<grid_for(b.n_elem, 128), 128, 0, c->stream>>>(b.n_elem, b.conn, c->X[0], c->X[1], c->X[2], c->u[0],
-                                                                 c->u[1], c->u[2], c->ipt + b.elem_base * 120, d);
+                                                                 c->u[1], c->u[2], rec, d, record);
   c->launches++;
   NSM_CUDA(c, cudaGetLastError());
-  NSM_CUDA(c, cudaMemcpyAsync(out, d, (size_t)b.n_elem * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NSM_CUDA(c, cudaMemcpyAsync(out, d, (size_t)b.n_elem * (1 + record) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   cudaFree(d);
   return NSM_OK;
@@ -1410,11 +1620,14 @@ nsm_b200_get_element_components(nsm_b200_ctx* c, int block_id, int n_components,
   auto it = c->blocks.find(block_id);
   NSM_REQUIRE(c, it != c->blocks.end(), "get_element_components: unknown block id");
   NSM_REQUIRE(c, n_components >= 0 && (n_components == 0 || (offsets && out)), "get_element_components: bad arguments");
+  const Block& b = it->second;
   for (int k = 0; k < n_components; ++k)
-    if (offsets[k] < 0 || offsets[k] >= 120) return fail(c, NSM_ERR_ARG, "get_element_components: offset %d out of 0..119", offsets[k]);
+    if (offsets[k] < 0 || offsets[k] >= 8 * (15 + b.n_state))
+      return fail(c, NSM_ERR_ARG, "get_element_components: offset %d out of 0..%d", offsets[k], 8 * (15 + b.n_state) - 1);
   int rc = ensure_ipt(c);
   if (rc) return rc;
-  const Block& b = it->second;
+  int           per_element = 0;
+  const double* rec         = block_records(c, b, &per_element);
   if (b.n_elem == 0 || n_components == 0) return NSM_OK;
   // bounded staging: ranges of elements, [n_components][range] on the device, one strided copy per range
   const int64_t range = std::min<int64_t>(b.n_elem, std::max<int64_t>(((int64_t)32 << 20) / n_components, 1024));
@@ -1430,7 +1643,7 @@ nsm_b200_get_element_components(nsm_b200_ctx* c, int block_id, int n_components,
   for (int64_t e0 = 0; e0 < b.n_elem && e == cudaSuccess; e0 += range) {
     const int64_t n = std::min(range, b.n_elem - e0);
     select_ipt_components_kernel<<<grid_for(n * n_components, 256), 256, 0, c->stream>>>(e0, n, n_components, d_off,
-                                                                                         c->ipt + b.elem_base * 120, d_out);
+                                                                                         rec, d_out, per_element);
     c->launches++;
     e = cudaMemcpy2DAsync(out + e0, (size_t)b.n_elem * sizeof(double), d_out, (size_t)n * sizeof(double), (size_t)n * sizeof(double),
                           (size_t)n_components, cudaMemcpyDeviceToHost, c->stream);
@@ -1457,17 +1670,19 @@ nsm_b200_get_element_data_subset(nsm_b200_ctx* c, int block_id, int64_t n, const
   int rc = ensure_ipt(c);
   if (rc) return rc;
   if (n == 0) return NSM_OK;
-  int64_t* d_el  = nullptr;
-  double*  d_out = nullptr;
+  int64_t*      d_el        = nullptr;
+  double*       d_out       = nullptr;
+  int           per_element = 0;
+  const double* rec         = block_records(c, b, &per_element);
   NSM_CUDA(c, cudaMalloc((void**)&d_el, (size_t)n * sizeof(int64_t)));
-  cudaError_t e = cudaMalloc((void**)&d_out, (size_t)n * 120 * sizeof(double));
+  cudaError_t e = cudaMalloc((void**)&d_out, (size_t)n * per_element * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_el, elements, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) {
-    gather_ipt_records_kernel<<<grid_for(n * 120, 256), 256, 0, c->stream>>>(n, d_el, c->ipt + b.elem_base * 120, d_out);
+    gather_ipt_records_kernel<<<grid_for(n * per_element, 256), 256, 0, c->stream>>>(n, d_el, rec, d_out, per_element);
     c->launches++;
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 120 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * per_element * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(d_el);
   cudaFree(d_out);

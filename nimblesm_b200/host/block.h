@@ -55,8 +55,15 @@ class BlockBase
   virtual double
   ComputeCriticalTimeStep(const Viewify<2>& node_reference_coordinates, const Viewify<2>& node_displacements, int num_elem,
                           const int* elem_conn) const;
+  // CUDA device of the per-block entry points below (the owning ModelData's; default 0)
+  void
+  SetDeviceIndex(int device)
+  {
+    device_index_ = device;
+  }
 
  protected:
+  int                       device_index_ = 0;
   std::string               model_material_parameters_ = "none";
   std::shared_ptr<Material> material_;
   // block-private device context for the per-block entry points
@@ -89,17 +96,25 @@ class Block : public BlockBase
   {
     return 8;
   }
-  // iptNN_deformation_gradient (FULL_TENSOR), iptNN_stress (SYMMETRIC_TENSOR) for NN = 01..08 (src/nimble_block.cc:84-108)
+  // iptNN_deformation_gradient (FULL_TENSOR), iptNN_stress (SYMMETRIC_TENSOR), then the material's state variables
+  // (SCALAR) for NN = 01..08 (src/nimble_block.cc:84-108)
   void
   GetDataLabelsAndLengths(std::vector<std::pair<std::string, Length>>& data_labels_and_lengths) const;
   // lumped_mass[node] += element contribution (src/nimble_block.cc:110-146)
   void
   ComputeLumpedMassMatrix(const double* reference_coordinates, int num_elem, const int* elem_conn, double* lumped_mass) const;
-  // F = identity, sigma = 0 in both states (src/nimble_block.cc:148-207)
+  // doubles per integration point: 15 + the material's state variables
+  int
+  NumDataPerIntegrationPoint() const
+  {
+    return 15 + material_->NumStateVariables();
+  }
+  // F = identity, sigma = 0, state variables at their initial values, in both states (src/nimble_block.cc:148-207)
   void
   InitializeElementData(int num_elem_in_block, std::vector<double>& elem_data_n, std::vector<double>& elem_data_np1) const;
-  // internal_force[3*node+i] += f; elem_data_np1 receives F / sigma of every integration point
-  // (src/nimble_block.cc:388-436).  reference_coordinates / displacement / internal_force are [n][3] AoS.
+  // internal_force[3*node+i] += f; elem_data_np1 receives F / sigma / state of every integration point; a material
+  // with state variables reads F_n / sigma_n / state_n from elem_data_n (src/nimble_block.cc:297-368, 388-436).
+  // reference_coordinates / displacement / internal_force are [n][3] AoS.
   void
   ComputeInternalForce(const double* reference_coordinates, const double* displacement, const double* velocity,
                        double* internal_force, double time_previous, double time_current, int num_elem, const int* elem_conn,
@@ -107,7 +122,7 @@ class Block : public BlockBase
                        std::vector<double> const& elem_data_n, std::vector<double>& elem_data_np1, DataManager* data_manager,
                        bool is_output_step, bool compute_stress_only = false) const;
   // volume and volume averages of the integration-point fields (src/nimble_block.cc:438-497);
-  // derived_elem_data[k][elem], k: 0 = volume, 1..9 = F components, 10..15 = sigma components
+  // derived_elem_data[k][elem], k: 0 = volume, 1..9 = F components, 10..15 = sigma components, 16.. = state variables
   void
   ComputeDerivedElementData(const double* reference_coordinates, const double* displacement, int num_elem, const int* elem_conn,
                             std::vector<double> const& elem_data_np1, std::vector<std::vector<double>>& derived_elem_data) const;
@@ -149,6 +164,12 @@ class BlockMaterialInterface : public BlockMaterialInterfaceBase
   {
     const double* deformation_gradient_np1;  // [num_elems][num_points][9]
     double*       stress_np1;                // [num_elems][num_points][6]
+    // read by materials with state variables only (the other views of compute_block_stress,
+    // src/nimble_kokkos_block_material_interface.cc:86-118)
+    const double* deformation_gradient_n = nullptr;  // [num_elems][num_points][9]
+    const double* stress_n               = nullptr;  // [num_elems][num_points][6]
+    const double* state_n                = nullptr;  // [num_elems][num_points][n_state]
+    double*       state_np1              = nullptr;
   };
   BlockMaterialInterface(double time_n_, double time_np1_, const std::vector<BlockData>& blocks_,
                          const std::map<int, Arrays>& arrays_, DeviceContext& device_)

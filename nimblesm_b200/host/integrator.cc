@@ -226,6 +226,9 @@ NimbleApplication::Run(const RunOptions& options)
   for (int r = 0; r < options_.num_ranks; ++r)
     for (int q = 0; q < r; ++q)
       if (options_.devices[q] == options_.devices[r]) group->SetLockstep(true);
+  // Ranks on one GPU wait for each other INSIDE kernels; a kernel's code must therefore never be loaded lazily at
+  // its first launch (module loading synchronises the device and would wait for the peer's spinning kernel).
+  if (group->Lockstep()) setenv("CUDA_MODULE_LOADING", "EAGER", 1);
   std::vector<int> status(options_.num_ranks, 0);
   if (options_.num_ranks == 1) {
     status[0] = ExecRank(0, group);

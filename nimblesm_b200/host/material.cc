@@ -36,11 +36,21 @@ Material::Material(const MaterialParameters& params, nsm_material_kind kind) : p
 }
 
 void
-Material::GetStress(int, int num_pts, double, double, const double*, const double* deformation_gradient_np1, const double*,
-                    double* stress_np1, const double*, double*, DeviceContext& device, bool) const
+Material::GetStateVariableLabel(int index, char label[MaterialParameters::MAX_MAT_MODEL_STR_LEN]) const
 {
-  device.check(nsm_b200_compute_stress(device.get(), kind_, bulk_modulus_, shear_modulus_, num_pts, deformation_gradient_np1,
-                                       stress_np1),
+  const char* l = nsm_b200_material_state_label(kind_, index);
+  if (!l) throw std::invalid_argument("Material::GetStateVariableLabel: bad index " + std::to_string(index));
+  std::snprintf(label, MaterialParameters::MAX_MAT_MODEL_STR_LEN, "%s", l);
+}
+
+void
+Material::GetStress(int, int num_pts, double, double, const double* deformation_gradient_n, const double* deformation_gradient_np1,
+                    const double* stress_n, double* stress_np1, const double* state_data_n, double* state_data_np1,
+                    DeviceContext& device, bool) const
+{
+  const std::vector<double> params = DeviceParameters();
+  device.check(nsm_b200_compute_stress_state(device.get(), kind_, (int)params.size(), params.data(), num_pts, deformation_gradient_n,
+                                             deformation_gradient_np1, stress_n, state_data_n, stress_np1, state_data_np1),
                "Material::GetStress");
 }
 
@@ -50,6 +60,9 @@ MaterialFactoryBase::MaterialFactoryBase()
   add_valid_double_parameter_name("bulk_modulus");
   add_valid_double_parameter_name("shear_modulus");
   add_valid_double_parameter_name("density");
+  // the history-dependent model of the state-variable slot
+  add_valid_double_parameter_name("yield_stress");
+  add_valid_double_parameter_name("hardening_modulus");
 }
 
 std::shared_ptr<MaterialParameters>
@@ -79,6 +92,8 @@ MaterialFactory::create()
     material = std::make_shared<NeohookeanMaterial>(*material_params);
   else if (name == "elastic")
     material = std::make_shared<ElasticMaterial>(*material_params);
+  else if (name == "j2_plasticity")
+    material = std::make_shared<J2PlasticityMaterial>(*material_params);
   else
     throw std::invalid_argument("\nError in Block::InstantiateMaterialModel(), invalid material model name.\n");
 }

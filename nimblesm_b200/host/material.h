@@ -21,6 +21,8 @@ class DeviceContext;
 class MaterialParameters
 {
  public:
+  static const int MAX_NUM_MAT_PARAM     = 64;  // src/nimble_material.h:64-65
+  static const int MAX_MAT_MODEL_STR_LEN = 64;
   MaterialParameters() = default;
   MaterialParameters(const std::string& material_name, const std::map<std::string, std::string>& string_params,
                      const std::map<std::string, double>& double_params, int num_material_points = 0)
@@ -75,19 +77,25 @@ class Material
   {
     return false;
   }
+  // Material::NumStateVariables / GetStateVariableLabel / GetStateVariableInitialValue (src/nimble_material.h:214-225):
+  // answered by the device library for the material kind (0 for the reference's two models, src/nimble_material.cc:60,218)
   virtual int
   NumStateVariables() const
   {
-    return 0;  // src/nimble_material.cc:60,218
+    return nsm_b200_material_num_state(kind_);
   }
   virtual void
-  GetStateVariableLabel(int, char*) const
-  {
-  }
+  GetStateVariableLabel(int index, char label[MaterialParameters::MAX_MAT_MODEL_STR_LEN]) const;
   virtual double
-  GetStateVariableInitialValue(int) const
+  GetStateVariableInitialValue(int index) const
   {
-    return 0.0;
+    return nsm_b200_material_state_initial_value(kind_, index);
+  }
+  // {bulk_modulus, shear_modulus, density, model-specific...} in the order nsm_b200_add_block_params takes them
+  virtual std::vector<double>
+  DeviceParameters() const
+  {
+    return {bulk_modulus_, shear_modulus_, density_};
   }
   double
   GetDensity() const
@@ -114,8 +122,9 @@ class Material
   {
     return params_;
   }
-  // Material::GetStress (src/nimble_material.h:196-214): deformation_gradient_np1 [num_pts][9] ->
-  // stress_np1 [num_pts][6]; the N-state arguments are accepted and unused, as in both reference models.
+  // Material::GetStress (src/nimble_material.h:241-256): (F_n, F_np1, sigma_n, state_n) [num_pts][9 / 9 / 6 / n_state]
+  // -> (stress_np1 [num_pts][6], state_np1); the reference's two models ignore the N arguments, a material with
+  // state variables reads them all.
   void
   GetStress(int elem_id, int num_pts, double time_previous, double time_current, const double* deformation_gradient_n,
             const double* deformation_gradient_np1, const double* stress_n, double* stress_np1, const double* state_data_n,
@@ -137,6 +146,26 @@ class NeohookeanMaterial : public Material
 {
  public:
   explicit NeohookeanMaterial(const MaterialParameters& p) : Material(p, NSM_MAT_NEOHOOKEAN) {}
+};
+
+// The history-dependent model of the state-variable slot (include/nsm_b200.h, NSM_MAT_J2_PLASTICITY): small-strain
+// J2 plasticity with linear isotropic hardening; parameters density, bulk_modulus, shear_modulus, yield_stress,
+// hardening_modulus; state equivalent_plastic_strain, von_mises_stress.
+class J2PlasticityMaterial : public Material
+{
+ public:
+  explicit J2PlasticityMaterial(const MaterialParameters& p)
+      : Material(p, NSM_MAT_J2_PLASTICITY), yield_stress_(p.GetParameterValue("yield_stress")), hardening_modulus_(p.GetParameterValue("hardening_modulus"))
+  {
+  }
+  std::vector<double>
+  DeviceParameters() const override
+  {
+    return {bulk_modulus_, shear_modulus_, density_, yield_stress_, hardening_modulus_};
+  }
+
+ private:
+  double yield_stress_, hardening_modulus_;
 };
 
 class MaterialFactoryBase

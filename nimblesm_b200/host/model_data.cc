@@ -157,6 +157,7 @@ ModelData::InitializeBlocks(DataManager& data_manager, const std::shared_ptr<Mat
     if (mesh.GetElementType(block_id) != "HEX")
       throw std::invalid_argument("\nError: the B200 path handles hex8 blocks only (block " + std::to_string(block_id) + ")\n");
     auto block = std::make_shared<Block>();
+    block->SetDeviceIndex(device_index_);
     block->Initialize(params, *material_factory_base);
     std::vector<std::pair<std::string, Length>> labels;
     block->GetDataLabelsAndLengths(labels);
@@ -176,9 +177,10 @@ ModelData::InitializeBlocks(DataManager& data_manager, const std::shared_ptr<Mat
   d.check(nsm_b200_set_nodes(d.get(), mesh.GetNumNodes(), mesh.GetCoordinatesX(), mesh.GetCoordinatesY(), mesh.GetCoordinatesZ()),
           "ModelData::InitializeBlocks (nodes)");
   for (auto const& kv : blocks_) {
-    const Material& m = *kv.second->GetMaterialPointer();
-    d.check(nsm_b200_add_block(d.get(), kv.first, mesh.GetNumElementsInBlock(kv.first), mesh.GetConnectivity(kv.first), m.Kind(),
-                               m.GetBulkModulus(), m.GetShearModulus(), m.GetDensity()),
+    const Material&           m  = *kv.second->GetMaterialPointer();
+    const std::vector<double> mp = m.DeviceParameters();
+    d.check(nsm_b200_add_block_params(d.get(), kv.first, mesh.GetNumElementsInBlock(kv.first), mesh.GetConnectivity(kv.first), m.Kind(),
+                                      (int)mp.size(), mp.data()),
             "ModelData::InitializeBlocks (block)");
   }
   d.check(nsm_b200_finalize(d.get(), assembly_, flags_), "ModelData::InitializeBlocks (finalize)");
@@ -200,8 +202,20 @@ ModelData::SpecifyOutputFields(const std::string& output_field_string)
     length_of[f.label] = f.length;
     for (auto const& c : component_labels(f.label, f.length)) node_components.push_back(c);
   }
+  // per-point fields: F, sigma and the state variables of the blocks' materials (ELEMENT fields with an integration
+  // point prefix in the reference's data_fields_, src/nimble_model_data.cc:233-260)
+  std::vector<std::pair<std::string, Length>> point_fields = {{"deformation_gradient", FULL_TENSOR}, {"stress", SYMMETRIC_TENSOR}};
+  for (auto const& kv : blocks_) {
+    const Material& m = *kv.second->GetMaterialPointer();
+    for (int i = 0; i < m.NumStateVariables(); ++i) {
+      char label[MaterialParameters::MAX_MAT_MODEL_STR_LEN];
+      m.GetStateVariableLabel(i, label);
+      if (std::find_if(point_fields.begin(), point_fields.end(), [&](auto const& pf) { return pf.first == label; }) == point_fields.end())
+        point_fields.emplace_back(label, SCALAR);
+    }
+  }
   for (int q = 1; q <= 8; ++q)
-    for (auto const& base : {std::make_pair(std::string("deformation_gradient"), FULL_TENSOR), std::make_pair(std::string("stress"), SYMMETRIC_TENSOR)}) {
+    for (auto const& base : point_fields) {
       char prefix[16];
       snprintf(prefix, sizeof prefix, "ipt%02d_", q);
       const std::string label = prefix + base.first;
@@ -214,6 +228,13 @@ ModelData::SpecifyOutputFields(const std::string& output_field_string)
         for (auto const& c : component_labels(base.first, base.second)) elem_components.push_back(c);
       }
     }
+  // a label is output for a block only if the block carries it (src/nimble_model_data.cc:284-306): `c` without the
+  // integration-point prefix (volume averages) or with it
+  auto on_block = [&](int id, const std::string& c, bool averaged) {
+    for (auto const& have : element_component_labels_.at(id))
+      if ((averaged ? have.substr(6) : have) == c) return true;  // "iptNN_" is six characters
+    return false;
+  };
   std::istringstream ss(output_field_string);
   std::string        req;
   while (ss >> req) {
@@ -222,16 +243,19 @@ ModelData::SpecifyOutputFields(const std::string& output_field_string)
     } else if (contains(node_fields, req)) {
       for (auto const& c : component_labels(req, length_of[req])) output_node_component_labels_.push_back(c);
     } else if (contains(elem_components, req)) {
-      for (int id : block_ids_) derived_output_element_data_labels_[id].push_back(req);
+      for (int id : block_ids_)
+        if (on_block(id, req, true)) derived_output_element_data_labels_[id].push_back(req);
     } else if (contains(ipt_components, req)) {
-      for (int id : block_ids_) output_element_component_labels_[id].push_back(req);
+      for (int id : block_ids_)
+        if (on_block(id, req, false)) output_element_component_labels_[id].push_back(req);
     } else if (contains(elem_fields, req)) {
       for (auto const& c : component_labels(req, length_of[req]))
         for (int id : block_ids_)
-          if (!contains(derived_output_element_data_labels_[id], c)) derived_output_element_data_labels_[id].push_back(c);
+          if (on_block(id, c, true) && !contains(derived_output_element_data_labels_[id], c)) derived_output_element_data_labels_[id].push_back(c);
     } else if (contains(ipt_fields, req)) {
       for (auto const& c : component_labels(req, length_of[req]))
-        for (int id : block_ids_) output_element_component_labels_[id].push_back(c);
+        for (int id : block_ids_)
+          if (on_block(id, c, false)) output_element_component_labels_[id].push_back(c);
     } else if (req == "volume") {
       for (int id : block_ids_) derived_output_element_data_labels_[id].push_back(req);
     } else {
@@ -391,12 +415,19 @@ ModelData::AdvanceOnDevice(DataManager& data_manager, int n_steps, double& time_
   enter_exchange_call(data_manager);
 }
 
+void
+ModelData::UpdateStates(const DataManager&)
+{
+  DeviceContext& d = *device_;
+  d.check(nsm_b200_update_states(d.get()), "ModelData::UpdateStates");
+}
+
 std::vector<double>&
 ModelData::GetElementDataNew(int block_id)
 {
   DeviceContext&       d = *device_;
   std::vector<double>& v = element_data_np1_[block_id];
-  v.resize((size_t)nsm_b200_num_elements(d.get(), block_id) * 120);
+  v.resize((size_t)nsm_b200_num_elements(d.get(), block_id) * 8 * nsm_b200_element_data_stride(d.get(), block_id));
   d.check(nsm_b200_get_element_data(d.get(), block_id, v.data()), "ModelData::GetElementDataNew");
   return v;
 }
@@ -448,14 +479,12 @@ ModelData::WriteExodusOutput(DataManager& data_manager, double time_current)
       for (size_t k = 0; k < want_e.size(); ++k) eo[k].assign(flat.begin() + k * (size_t)ne, flat.begin() + (k + 1) * (size_t)ne);
     }
     if (!want_d.empty()) {
-      std::vector<double> flat((size_t)16 * ne);
+      const int           record = nsm_b200_element_data_stride(d.get(), id);
+      std::vector<double> flat((size_t)(1 + record) * ne);
       d.check(nsm_b200_derived_element_data(d.get(), id, flat.data()), "ModelData::WriteExodusOutput (derived)");
-      static const std::vector<std::string> order = [] {
-        std::vector<std::string> o{"volume"};
-        for (auto const& c : component_labels("deformation_gradient", FULL_TENSOR)) o.push_back(c);
-        for (auto const& c : component_labels("stress", SYMMETRIC_TENSOR)) o.push_back(c);
-        return o;
-      }();
+      // rows: volume, then the block's per-point labels of point 1 without their prefix (F 9, sigma 6, state scalars)
+      std::vector<std::string> order{"volume"};
+      for (int k = 0; k < record; ++k) order.push_back(element_component_labels_.at(id)[k].substr(6));
       dv.resize(want_d.size());
       for (size_t k = 0; k < want_d.size(); ++k) {
         const size_t row = std::find(order.begin(), order.end(), want_d[k]) - order.begin();

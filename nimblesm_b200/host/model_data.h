@@ -157,10 +157,11 @@ class ModelData : public ModelDataBase
   GetFieldId(const std::string& field_label) const override;
   void
   InitializeBlocks(DataManager& data_manager, const std::shared_ptr<MaterialFactoryBase>& material_factory_base) override;
+  // N <- N+1 (src/nimble_model_data.h:104-107): a record swap on the device for blocks whose material has state
+  // variables (nsm_b200_update_states); nothing to roll for the reference's two stateless models, whose F / sigma are
+  // written once per requesting call
   void
-  UpdateStates(const DataManager&) override
-  {
-  }  // neither material carries state and F / sigma are written once per call: nothing to roll
+  UpdateStates(const DataManager&) override;
   using ModelDataBase::GetScalarNodeData;
   using ModelDataBase::GetVectorNodeData;
   Viewify<1>
@@ -206,7 +207,7 @@ class ModelData : public ModelDataBase
   void
   PullNodalFields();  // device (u, v, a, f_int) -> host mirrors
   std::vector<double>&
-  GetElementDataNew(int block_id);  // [elem][8][15], refreshed from the device
+  GetElementDataNew(int block_id);  // [elem][8][15 + n_state], refreshed from the device
   void
   SpecifyOutputFields(const std::string& output_field_string);
 

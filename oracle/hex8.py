@@ -63,15 +63,18 @@ def internal_force(material, bulk, shear, ref, disp, conn, want_elem_data=True):
     return f, ed
 
 
-def internal_force_state(material, params, ref, disp, conn, elem_data_n=None):
+def internal_force_state(material, params, ref, disp, conn, elem_data_n=None, f=None):
     """Any material incl. the history-dependent one -> (f [n,3], elem_data_np1 [ne,8,15+n_state]).  params =
-    [bulk, shear, material-specific...]; elem_data_n is the previous record array (required when n_state > 0)."""
+    [bulk, shear, material-specific...]; elem_data_n is the previous record array (required when n_state > 0).
+    f: accumulate into this array (the serial reference adds block after block into one array,
+    src/nimble_model_data.cc:636-659) instead of a fresh zero one."""
     ref = np.ascontiguousarray(ref, dtype=np.float64)
     disp = np.ascontiguousarray(disp, dtype=np.float64)
     conn = np.ascontiguousarray(conn, dtype=np.int32)
     params = np.ascontiguousarray(params, dtype=np.float64)
     ns = lib().h8o_num_state(material)
-    f = np.zeros_like(ref)
+    if f is None:
+        f = np.zeros_like(ref)
     ed = np.empty((len(conn), 8, 15 + ns))
     if ns:
         elem_data_n = np.ascontiguousarray(elem_data_n, dtype=np.float64)

@@ -154,9 +154,65 @@ def load_case(name):
     return str(z["deck"]), mesh, gold, ref, pieces
 
 
+STATE_CUBE_DECK = """genesis input file:               state_cube.g
+exodus output file:               state_cube.e
+final time:                       4.4e-6
+number of load steps:             60
+output frequency:                 20
+output fields:                    displacement velocity internal_force stress equivalent_plastic_strain ipt03_equivalent_plastic_strain ipt08_von_mises_stress ipt01_stress volume
+material parameters:              material_1 j2_plasticity density 7.8 bulk_modulus 1.6e12 shear_modulus 0.8e12 yield_stress 5.0e8 hardening_modulus 2.0e10
+material parameters:              material_2 neohookean density 7.8 bulk_modulus 1.6e12 shear_modulus 0.8e12
+element block:                    block_1 material_1
+element block:                    block_2 material_2
+boundary condition:               initial_velocity nodelist_1 x "1000.0*x"
+boundary condition:               prescribed_velocity nodelist_2 x 0.0
+boundary condition:               prescribed_velocity nodelist_2 y 0.0
+boundary condition:               prescribed_velocity nodelist_2 z 0.0
+"""
+
+
+def make_state_case():
+    """state_cube: NOT a deck of the reference (it ships no material with state variables).  A 6^3 cube whose lower
+    half (block 1) is the history-dependent test material behind the reference's own Material virtuals
+    (oracle/ref_state_material.cc) and whose upper half (block 2) is neohookean; the snapshots come from the
+    reference's unmodified block / element-data / UpdateStates code, so they pin the B200 state-variable slot."""
+    from nimblesm_b200.mesh import structured_cube
+    from oracle import refdrive
+
+    mesh = structured_cube(6, block_of_element=lambda i, j, k: np.where(k < 3, 1, 2))
+    out = {}
+    pack_mesh("mesh_", mesh, out)
+    out["deck"] = np.array(STATE_CUBE_DECK)
+    out["exodiff"] = np.array("")
+    out["gold_times"] = np.zeros(0)
+    run = refdrive.RefRun(STATE_CUBE_DECK, mesh, keep_snapshots=True)
+    out["ref_critical_dt"] = np.array(run.begin())
+    run.advance(60)
+    snaps = run.snapshots()
+    out["ref_times"] = np.array([s["time"] for s in snaps])
+    for lbl in snaps[0]["node"]:
+        out["ref_node_" + lbl] = np.stack([s["node"][lbl] for s in snaps])
+    for b in mesh["block_ids"]:
+        out["ref_elem_%d" % b] = np.stack([s["elem"][b] for s in snaps])  # every output step: [times][ne][8][stride]
+        out["ref_elem_last_%d" % b] = snaps[-1]["elem"][b]
+        for lbl in snaps[0]["derived"][b]:
+            out["ref_derived_%d_%s" % (b, lbl)] = np.stack([s["derived"][b][lbl] for s in snaps])
+    run.close()
+    path = os.path.join(HERE, "state_cube.npz")
+    np.savez_compressed(path, **out)
+    eqps = out["ref_elem_last_1"][:, :, 15]
+    print("%-40s %8.1f kB  nodes=%d elems=%d  yielded points %.0f%%  max eqps %.3e" % (
+        "state_cube.npz", os.path.getsize(path) / 1e3, len(mesh["x"]), sum(len(c) for c in mesh["conn"].values()),
+        100.0 * (eqps > 0).mean(), eqps.max()))
+
+
 def main():
     refroot = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     from oracle import refdrive
+
+    make_state_case()
+    if "--state-only" in sys.argv:
+        return
 
     for d, deck, g in CASES:
         base = os.path.join(refroot, "test", "dynamics", d)
