@@ -485,9 +485,11 @@ element_force_kernel(const ElemArgs p)
     sK[0 * kCoordComp + own] = k0;
     sK[1 * kCoordComp + own] = k1;
     sK[2 * kCoordComp + own] = k2;
+#ifndef NSM_LAZY_SC  // A/B (scripts/build_variants.sh): the force-path coordinates are read by the cold path only
     sC[0 * kCoordComp + own] = c0;
     sC[1 * kCoordComp + own] = c1;
     sC[2 * kCoordComp + own] = c2;
+#endif
     // The F-path and force-path Jacobians coincide unless ref + ((ref+d) - ref) != ref + d for some node of
     // the warp's elements (possible only when |d| is comparable to |ref|); decided warp-uniformly.
     const bool jacobians_differ = __any_sync(0xffffffffu, differs);
@@ -512,6 +514,14 @@ element_force_kernel(const ElemArgs p)
     unsigned st = integration_point<MAT, MODE, true>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear,
                                                      share, F, sig, rec_n, p.mat_a, p.mat_b, state);
     if (jacobians_differ) st |= 1u;
+#ifdef NSM_LAZY_SC
+    if (__any_sync(0xffffffffu, (st & 1u) != 0u)) {  // some lane goes cold: every lane files its node's coordinates
+      sC[0 * kCoordComp + own] = c0;
+      sC[1 * kCoordComp + own] = c1;
+      sC[2 * kCoordComp + own] = c2;
+      __syncwarp();
+    }
+#endif
     if (st & 1u) {  // cold: some operand outside the fast window (or distinct Jacobians): plain IEEE operators
       atomicAdd(p.flags + 1, 1);  // statistics: integration points redone (nsm_b200_cold_points)
       st = integration_point<MAT, MODE, false>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear, share,

@@ -34,6 +34,9 @@
 #include "nimble_vector_communicator.h"
 #include "nimble_view.h"
 #include "ref_state_material.h"
+#ifdef NSM_REF_BINDING  // tests/ref_binding: the same glue with the B200 binding class as the model data
+#include "b200_model_data.h"
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // DataManager out-of-line members (follows src/nimble_data_manager.cc:70-198; serial ModelData)
@@ -63,7 +66,11 @@ DataManager::Initialize()
   for (int n = 0; n < num_nodes; ++n) global_node_ids[n] = gids[n];
   vector_communicator_->Initialize(global_node_ids);
 
+#ifdef NSM_REF_BINDING
+  model_data_ = std::make_shared<nsm_binding::B200ModelData>();  // the one-line selection of INTEGRATION.md §2
+#else
   model_data_ = std::make_shared<nimble::ModelData>();  // serial path (reference: nimble_kokkos::ModelData)
+#endif
   model_data_->SetDimension(dim);
 
   boundary_condition_->Initialize(
@@ -161,6 +168,7 @@ struct RefRun
   double                time_current = 0.0, time_previous = 0.0, dt_user = 0.0;
   int                   step = 0, num_load_steps = 0, output_frequency = 0;
   bool                  keep_snapshots = false;
+  bool                  write_output   = false;  // also through the reference's own ExodusOutput (text form in this build)
   std::vector<Snapshot> snaps;
   std::string           err;
 };
@@ -202,6 +210,7 @@ take_snapshot(RefRun& r)
     s.derived[bid] = derived;
   }
   r.snaps.push_back(std::move(s));
+  if (r.write_output) r.dm->WriteOutput(r.time_current);  // data_manager.WriteOutput (explicit_time_integrator.cc:149, 270)
 }
 
 }  // namespace
@@ -267,6 +276,35 @@ nsmref_open(
     r->err = e.what();
   }
   return r;
+}
+
+// Route every snapshot through ModelData::WriteExodusOutput -> nimble::ExodusOutput as well (without
+// NIMBLE_HAVE_EXODUS the reference writes a text file, src/nimble_exodus_output.cc:86-88, 326-549).  Call before begin.
+int
+nsmref_enable_output(void* h, const char* filename)
+{
+  auto& r = *static_cast<RefRun*>(h);
+  try {
+    r.dm->InitializeOutput(filename);
+    r.write_output = true;
+    return 0;
+  } catch (std::exception const& e) {
+    r.err = e.what();
+    return 1;
+  }
+}
+
+// kernels launched by the device library behind the model data (0 for the serial reference): proof of which path ran
+long
+nsmref_device_launches(void* h)
+{
+#ifdef NSM_REF_BINDING
+  auto* md = dynamic_cast<nsm_binding::B200ModelData*>(static_cast<RefRun*>(h)->md);
+  return md ? md->DeviceLaunches() : -1;
+#else
+  (void)h;
+  return 0;
+#endif
 }
 
 void

@@ -24,13 +24,19 @@ def available() -> bool:
     return os.path.exists(REF_LIB)
 
 
-_lib = None
+# tests/ref_binding/_build/libref_binding.so: the SAME glue compiled with the B200 binding class as the model data
+BINDING_LIB = os.path.join(os.path.dirname(_HERE), "tests", "ref_binding", "_build", "libref_binding.so")
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(REF_LIB)
+def binding_available() -> bool:
+    return os.path.exists(BINDING_LIB)
+
+
+def lib(path=None):
+    path = path or REF_LIB
+    if path not in _libs:
+        L = C.CDLL(path)
         L.nsmref_open.restype = C.c_void_p
         L.nsmref_open.argtypes = [C.c_char_p, C.c_int, _ip, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip, _ip,
                                   C.c_int, _ip, _ip, _ip, C.c_int]
@@ -67,15 +73,21 @@ def lib():
         L.nsmref_bench_steps.restype = C.c_double
         L.nsmref_bench_steps.argtypes = [C.c_char_p, C.c_int, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp,
                                          C.c_double, C.c_int, C.c_int]
-        _lib = L
-    return _lib
+        L.nsmref_enable_output.restype = C.c_int
+        L.nsmref_enable_output.argtypes = [C.c_void_p, C.c_char_p]
+        L.nsmref_device_launches.restype = C.c_long
+        L.nsmref_device_launches.argtypes = [C.c_void_p]
+        _libs[path] = L
+    return _libs[path]
 
 
 class RefRun:
     """One reference run: deck text + mesh dict (see meshio.py for the mesh dict layout)."""
 
-    def __init__(self, deck_text: str, mesh: dict, keep_snapshots: bool = True):
-        L = lib()
+    def __init__(self, deck_text: str, mesh: dict, keep_snapshots: bool = True, lib_path: str = None):
+        """lib_path: None = the serial reference (libnimble_ref.so); BINDING_LIB = the same glue over the B200 binding."""
+        self._lib_path = lib_path
+        L = lib(lib_path)
         self._tmp = tempfile.NamedTemporaryFile("w", suffix=".in", delete=False)
         self._tmp.write(deck_text)
         self._tmp.close()
@@ -103,7 +115,7 @@ class RefRun:
 
     def close(self):
         if self.h:
-            lib().nsmref_close(self.h)
+            lib(self._lib_path).nsmref_close(self.h)
             self.h = None
             os.unlink(self._tmp.name)
 
@@ -113,18 +125,26 @@ class RefRun:
         except Exception:
             pass
 
+    def enable_output(self, filename: str):
+        """every snapshot also goes through ModelData::WriteExodusOutput -> the reference's ExodusOutput (text form)"""
+        if lib(self._lib_path).nsmref_enable_output(self.h, filename.encode()):
+            raise RuntimeError(lib(self._lib_path).nsmref_last_error(self.h).decode())
+
+    def device_launches(self) -> int:
+        return int(lib(self._lib_path).nsmref_device_launches(self.h))
+
     def begin(self) -> float:
-        return lib().nsmref_begin(self.h)
+        return lib(self._lib_path).nsmref_begin(self.h)
 
     def advance(self, n: int = 1) -> float:
-        return lib().nsmref_advance(self.h, n)
+        return lib(self._lib_path).nsmref_advance(self.h, n)
 
     def internal_force(self):
-        lib().nsmref_internal_force(self.h)
+        lib(self._lib_path).nsmref_internal_force(self.h)
 
     def field(self, label: str) -> np.ndarray:
         """Live (writable) view of a nodal field, AoS [n,3] (or [n] for lumped_mass)."""
-        p = lib().nsmref_node_field(self.h, label.encode())
+        p = lib(self._lib_path).nsmref_node_field(self.h, label.encode())
         if not p:
             raise KeyError(label)
         n = self.n_nodes * (1 if label == "lumped_mass" else 3)
@@ -132,14 +152,14 @@ class RefRun:
         return a if label == "lumped_mass" else a.reshape(-1, 3)
 
     def elem_data(self, block_id: int, which: int = 0) -> np.ndarray:
-        n = lib().nsmref_elem_data(self.h, block_id, which, None)
+        n = lib(self._lib_path).nsmref_elem_data(self.h, block_id, which, None)
         out = np.empty(n)
-        lib().nsmref_elem_data(self.h, block_id, which, out.ctypes.data)
+        lib(self._lib_path).nsmref_elem_data(self.h, block_id, which, out.ctypes.data)
         return out.reshape(-1, 8, self.elem_stride(block_id))
 
     def elem_stride(self, block_id: int) -> int:
         """doubles per integration point: 15 + the material's state variables"""
-        return lib().nsmref_elem_stride(self.h, block_id)
+        return lib(self._lib_path).nsmref_elem_stride(self.h, block_id)
 
     def snapshots(self):
         L = lib()
