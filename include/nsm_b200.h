@@ -196,6 +196,7 @@ int nsm_b200_set_bc_values_steps(nsm_b200_ctx* ctx, int n_rows, int64_t n, const
  *   NSM_BCOP_CONST arg -> consts[arg]     NSM_BCOP_X / _Y / _Z -> reference coordinate of the entry's node
  *   NSM_BCOP_SLOT arg  -> slots[step][arg], a scalar the HOST evaluated for that step (the time, and every
  *                         sub-expression of t alone -- cos(t*pi/T) keeps glibc's bits that way)
+ *   NSM_BCOP_ENTRYCONST arg -> entry_constants[arg][entry], see nsm_b200_set_bc_entry_constants
  *   ADD SUB MUL DIV FMOD NEG SQRT ABS FLOOR CEIL ROUND, LT LE GT GE EQ AND OR XOR NOT (1.0 / 0.0 results),
  *   SELECT (a b c -> a != 0 ? b : c): all correctly rounded / exact on both sides, hence bit-identical to the
  *   host evaluation.
@@ -207,7 +208,8 @@ typedef enum {
   NSM_BCOP_SQRT = 11, NSM_BCOP_ABS = 12, NSM_BCOP_FLOOR = 13, NSM_BCOP_CEIL = 14, NSM_BCOP_ROUND = 15,
   NSM_BCOP_LT = 16, NSM_BCOP_LE = 17, NSM_BCOP_GT = 18, NSM_BCOP_GE = 19, NSM_BCOP_EQ = 20,
   NSM_BCOP_AND = 21, NSM_BCOP_OR = 22, NSM_BCOP_XOR = 23, NSM_BCOP_NOT = 24, NSM_BCOP_SELECT = 25,
-  NSM_BCOP_COUNT = 26
+  NSM_BCOP_ENTRYCONST = 26, /* arg -> entry_constants[arg][k]: a value the HOST evaluated once for table entry k */
+  NSM_BCOP_COUNT = 27
 } nsm_bc_op;
 #define NSM_BC_STACK_DEPTH 16
 /* Call after nsm_b200_set_bc_table.  program_offsets has n_programs + 1 entries into code; n_entries must equal
@@ -215,6 +217,13 @@ typedef enum {
 int nsm_b200_set_bc_programs(nsm_b200_ctx* ctx, int n_programs, const int32_t* program_offsets, const int32_t* code,
                              int n_consts, const double* consts, int n_slots, int64_t n_entries,
                              const int32_t* program_of_entry);
+/* Per-entry constants of the programs (NSM_BCOP_ENTRYCONST): values[j][k] = sub-expression j at the node of table
+ * entry k.  For sub-trees of the POSITION alone that go through libm or pow (sin(3*x), x^2, exp(-y)): they do not
+ * change in time, so the host evaluates them once at set-up with glibc's bits -- where the reference re-evaluates them
+ * per node per step (src/nimble_boundary_condition_manager.h:166-201, src/nimble_expression_parser.h:323) -- and the
+ * device reads them back every step.  Call after nsm_b200_set_bc_programs; stepping fails with NSM_ERR_ARG while a
+ * program names a constant that has not been supplied. */
+int nsm_b200_set_bc_entry_constants(nsm_b200_ctx* ctx, int n_constants, int64_t n_entries, const double* values);
 /* slots[r][s] for step r of the next nsm_b200_step call (r = 0 .. n_rows-1; that call must not ask for more steps
  * than rows); row 0 also serves nsm_b200_apply_kinematic_bc. */
 int nsm_b200_set_bc_slots_steps(nsm_b200_ctx* ctx, int n_rows, int n_slots, const double* slots);
@@ -290,6 +299,12 @@ int nsm_b200_comm_attach(nsm_b200_ctx* ctx, int peer_rank, const unsigned char h
  * shared-node sum.  Every rank must be past comm_attach of all its peers before any rank steps. */
 int nsm_b200_comm_ready(nsm_b200_ctx* ctx);
 
+/* Ranks that SHARE one GPU (several contexts on a device: the multi-rank path on a single-GPU box) cannot wait for each
+ * other inside a kernel.  With a host barrier set, every exchange becomes pack -> host waits for its own pack ->
+ * barrier(arg) (must return once ALL ranks of the run have called it for this exchange) -> rank-ordered unpack; the
+ * sums are the same bits.  One GPU per rank keeps the in-kernel wait (no host round trip per step).  Call on every
+ * rank before the first exchange; barrier = NULL restores the in-kernel wait. */
+int nsm_b200_comm_set_host_barrier(nsm_b200_ctx* ctx, void (*barrier)(void*), void* arg);
 /* How long a rank waits inside the step for a peer's shared-node data before the step fails with NSM_ERR_COMM
  * (default 20 s; the reference's MPI_Wait has no bound, src/nimble.mpi.rank_clique_reducer.h:230-257).  Raise it
  * when ranks may drift apart by more than that between two steps (a rank blocked in file output). */

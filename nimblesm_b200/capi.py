@@ -45,7 +45,7 @@ SYMBOLS = [
     "nsm_b200_add_block_params", "nsm_b200_material_num_state", "nsm_b200_material_num_params",
     "nsm_b200_material_state_label", "nsm_b200_material_state_initial_value", "nsm_b200_compute_stress_state",
     "nsm_b200_element_data_stride", "nsm_b200_update_states", "nsm_b200_get_element_data_previous",
-    "nsm_b200_set_element_data",
+    "nsm_b200_set_element_data", "nsm_b200_set_bc_entry_constants", "nsm_b200_comm_set_host_barrier",
 ]
 
 
@@ -132,6 +132,8 @@ def lib():
         "nsm_b200_update_states": (i32, [vp]),
         "nsm_b200_get_element_data_previous": (i32, [vp, i32, dp]),
         "nsm_b200_set_element_data": (i32, [vp, i32, i32, dp]),
+        "nsm_b200_set_bc_entry_constants": (i32, [vp, i32, i64, dp]),
+        "nsm_b200_comm_set_host_barrier": (i32, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -313,6 +315,12 @@ class Context:
         consts = np.ascontiguousarray(consts, dtype=np.float64)
         self._ck(self._L.nsm_b200_set_bc_programs(self._h, len(offsets) - 1, _iptr(offsets), _iptr(code), len(consts),
                                                    _dptr(consts), int(n_slots), len(poe), _iptr(poe)))
+
+    def set_bc_entry_constants(self, values):
+        """values[j][k]: host-evaluated per-entry constant j (a function of the position alone) for table entry k."""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        assert values.ndim == 2
+        self._ck(self._L.nsm_b200_set_bc_entry_constants(self._h, values.shape[0], values.shape[1], _dptr(values)))
 
     def set_bc_slots_steps(self, slots):
         """slots[r][s]: host-evaluated scalar s (a function of t alone) at the time of step r of the next step() call."""

@@ -868,6 +868,7 @@ struct BcProgramArgs
   const int*    code;
   const double* consts;
   const double* slots;             // this step's row
+  const double* entry_consts;      // [n_entry_consts][n_entries]: host-evaluated functions of the entry's position
   const double* X[3];
   double*       value;             // [n_entries]
 };
@@ -884,14 +885,15 @@ bc_program_kernel(const BcProgramArgs p)
   int       sp = 0;
   for (int pc = p.offsets[prog]; pc < p.offsets[prog + 1]; ++pc) {
     const int word = p.code[pc], op = word & 0xff, arg = word >> 8;
-    if (op <= 4) {  // pushes
+    if (op <= 4 || op == 26) {  // pushes
       double v;
       switch (op) {
         case 0: v = p.consts[arg]; break;
         case 1: v = p.X[0][nd]; break;
         case 2: v = p.X[1][nd]; break;
         case 3: v = p.X[2][nd]; break;
-        default: v = p.slots[arg]; break;
+        case 4: v = p.slots[arg]; break;
+        default: v = p.entry_consts[(int64_t)arg * p.n_entries + k]; break;
       }
       st[sp++] = v;
     } else if (op == 10 || (op >= 11 && op <= 15) || op == 24) {  // unary

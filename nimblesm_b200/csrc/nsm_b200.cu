@@ -15,6 +15,7 @@
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler is attached
 
 #include "../../include/nsm_b200.h"
 #include "hex8_kernels.cuh"
@@ -51,6 +52,18 @@ struct Block
 };
 
 thread_local std::string g_create_error;
+
+// NVTX range over the host code that enqueues one phase of the step, named after the reference's own timer regions
+// (src/integrators/explicit_time_integrator.cc:197-274: "Time Integration Scheme", "BC enforcement", "Force
+// calculation", "Output"; the shared-node sum is timed as vector reduction, src/nimble_vector_communicator.h:144-157).
+// A profiler's CUDA-launch correlation ties the kernels to the range they were launched from.
+struct NvtxRange
+{
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&)            = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 }  // namespace
 
@@ -111,6 +124,8 @@ struct nsm_b200_ctx
   double* bcp_consts  = nullptr;
   int*    bcp_of_entry = nullptr;
   double* bcp_slot_values = nullptr;  // [bcp_rows][bcp_slots]
+  double* bcp_entry_consts = nullptr; // [bcp_n_entry_consts][n_bc] (NSM_BCOP_ENTRYCONST)
+  int     bcp_n_entry_consts = 0, bcp_entry_consts_needed = 0;
 
   int*                d_flags  = nullptr;
   unsigned*        d_ticket = nullptr;  // element-kernel work counter
@@ -253,6 +268,10 @@ enqueue_bc_programs(nsm_b200_ctx* c, int64_t row)
   p.code             = c->bcp_code;
   p.consts           = c->bcp_consts;
   p.slots            = c->bcp_slot_values + (c->bcp_rows > 1 ? row : 0) * c->bcp_slots;
+  p.entry_consts     = c->bcp_entry_consts;
+  if (c->bcp_n_entry_consts < c->bcp_entry_consts_needed)
+    return fail(c, NSM_ERR_ARG, "boundary-condition programs name %d per-entry constants, %d supplied (nsm_b200_set_bc_entry_constants)",
+                c->bcp_entry_consts_needed, c->bcp_n_entry_consts);
   for (int i = 0; i < 3; ++i) p.X[i] = c->X[i];
   p.value = c->bc_value;
   bc_program_kernel<<<grid_for(c->n_bc, 128), 128, 0, c->stream>>>(p);
@@ -268,8 +287,9 @@ free_bc_programs(nsm_b200_ctx* c)
     if (p) cudaFree(p);
     p = nullptr;
   };
-  fr(c->bcp_offsets), fr(c->bcp_code), fr(c->bcp_consts), fr(c->bcp_of_entry), fr(c->bcp_slot_values);
+  fr(c->bcp_offsets), fr(c->bcp_code), fr(c->bcp_consts), fr(c->bcp_of_entry), fr(c->bcp_slot_values), fr(c->bcp_entry_consts);
   c->bcp_programs = c->bcp_slots = c->bcp_rows = c->bcp_rows_cap = 0;
+  c->bcp_n_entry_consts = c->bcp_entry_consts_needed = 0;
 }
 
 ElemArgs
@@ -1080,6 +1100,7 @@ nsm_b200_internal_force(nsm_b200_ctx* c, int store_ipt)
 {
   NSM_ENTER(c);
   NSM_REQUIRE(c, c->finalized, "internal_force: context not finalized");
+  NvtxRange range("Force calculation");
   int rc = enqueue_internal_force(c, store_ipt != 0 || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP));
   if (rc) return rc;
   return check_flags(c);
@@ -1258,13 +1279,18 @@ nsm_b200_set_bc_programs(nsm_b200_ctx* c, int n_programs, const int32_t* program
   NSM_REQUIRE(c, program_offsets[0] == 0, "set_bc_programs: offsets must start at 0");
   // validate: every program leaves exactly one value, never underflows or exceeds the device stack, and only
   // names constants / slots that exist
+  int entry_consts_needed = 0;
   for (int p = 0; p < n_programs; ++p) {
     NSM_REQUIRE(c, program_offsets[p + 1] > program_offsets[p], "set_bc_programs: empty program");
     int depth = 0;
     for (int pc = program_offsets[p]; pc < program_offsets[p + 1]; ++pc) {
       const int op = code[pc] & 0xff, arg = code[pc] >> 8;
       int       pops = 2;
-      if (op <= NSM_BCOP_SLOT) {
+      if (op == NSM_BCOP_ENTRYCONST) {
+        pops = 0;
+        if (arg < 0) return fail(c, NSM_ERR_ARG, "set_bc_programs: negative per-entry constant index");
+        entry_consts_needed = std::max(entry_consts_needed, arg + 1);
+      } else if (op <= NSM_BCOP_SLOT) {
         pops = 0;
         if (op == NSM_BCOP_CONST && (arg < 0 || arg >= n_consts)) return fail(c, NSM_ERR_ARG, "set_bc_programs: constant %d out of range", arg);
         if (op == NSM_BCOP_SLOT && (arg < 0 || arg >= n_slots)) return fail(c, NSM_ERR_ARG, "set_bc_programs: slot %d out of range", arg);
@@ -1297,6 +1323,27 @@ nsm_b200_set_bc_programs(nsm_b200_ctx* c, int n_programs, const int32_t* program
   NSM_CUDA(c, cudaMemsetAsync(c->bcp_slot_values, 0, (size_t)std::max(n_slots, 1) * sizeof(double), c->stream));
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   c->bcp_programs = n_programs, c->bcp_slots = n_slots, c->bcp_rows = 1, c->bcp_rows_cap = 1;
+  c->bcp_entry_consts_needed = entry_consts_needed;
+  return NSM_OK;
+}
+
+int
+nsm_b200_set_bc_entry_constants(nsm_b200_ctx* c, int n_constants, int64_t n_entries, const double* values)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "set_bc_entry_constants: context not finalized");
+  NSM_REQUIRE(c, c->bcp_programs > 0, "set_bc_entry_constants: no boundary-condition programs set");
+  NSM_REQUIRE(c, n_constants >= 0 && n_entries == c->n_bc && (n_constants == 0 || values), "set_bc_entry_constants: bad arguments");
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->bcp_entry_consts) cudaFree(c->bcp_entry_consts);
+  c->bcp_entry_consts   = nullptr;
+  c->bcp_n_entry_consts = 0;
+  if (n_constants == 0) return NSM_OK;
+  int rc = dev_alloc(c, &c->bcp_entry_consts, (int64_t)n_constants * n_entries);
+  if (rc) return rc;
+  NSM_CUDA(c, cudaMemcpyAsync(c->bcp_entry_consts, values, (size_t)n_constants * n_entries * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->bcp_n_entry_consts = n_constants;
   return NSM_OK;
 }
 
@@ -1331,6 +1378,7 @@ nsm_b200_apply_kinematic_bc(nsm_b200_ctx* c, double time_current, double time_pr
   NSM_ENTER(c);
   NSM_REQUIRE(c, c->finalized, "apply_kinematic_bc: context not finalized");
   if (c->n_bc == 0 || c->n_nodes == 0) return NSM_OK;
+  NvtxRange range("BC enforcement");
   int rc_p = enqueue_bc_programs(c, 0);
   if (rc_p) return rc_p;
   const double dt = time_current - time_previous;
@@ -1365,6 +1413,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     const bool   store =
         (store_ipt_last && s == n_steps - 1) || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP);
     if (n > 0 && s == 0) {  // later first halves ride in the previous step's fused node pass
+      NvtxRange range("Time Integration Scheme");
       int rc_p = enqueue_bc_programs(c, 0);
       if (rc_p) return rc_p;
       const NodeArgs na = node_args(c, 0);
@@ -1392,6 +1441,8 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     if (c->profiling) prof_event(c);
     roll_states(c);  // UpdateStates of the previous step (explicit_time_integrator.cc:277)
     int rc;
+    {
+    NvtxRange range("Force calculation");
     if (c->overlap) {
       // boundary-first: the groups that touch shared nodes run first, their nodal forces travel to the peers on
       // the exchange stream while the interior groups compute on this one
@@ -1410,11 +1461,13 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     } else {
       if ((rc = enqueue_element_kernels(c, store))) return rc;
     }
+    }
     if (c->profiling) prof_event(c);
     mark_states_for_roll(c);
     if (n > 0) {
       const NodeArgs na = node_args(c, s + 1);  // boundary-condition magnitudes of the step the fused pass opens
       if (c->comm.active()) {
+        NvtxRange range("Vector Reduction");
         if (c->overlap) NSM_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_packed, 0));  // the pack has read f before it changes
         if (ordered) {
           node_correct_kernel<true, false><<<ngrid, 256, 0, c->stream>>>(na, 0.0, 0);
@@ -1426,6 +1479,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
           return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
         }
       }
+      NvtxRange range("Time Integration Scheme");
       if (s + 1 < n_steps) {
         int rc_p = enqueue_bc_programs(c, s + 1);  // magnitudes of the step the fused pass opens
         if (rc_p) return rc_p;
@@ -1593,6 +1647,7 @@ nsm_b200_derived_element_data(nsm_b200_ctx* c, int block_id, double* out)
   NSM_REQUIRE(c, c->finalized, "derived_element_data: context not finalized");
   auto it = c->blocks.find(block_id);
   NSM_REQUIRE(c, it != c->blocks.end(), "derived_element_data: unknown block id");
+  NvtxRange nvtx_range("Output");
   int rc = ensure_ipt(c);
   if (rc) return rc;
   const Block& b = it->second;
@@ -1619,6 +1674,7 @@ nsm_b200_get_element_components(nsm_b200_ctx* c, int block_id, int n_components,
   NSM_REQUIRE(c, c->finalized, "get_element_components: context not finalized");
   auto it = c->blocks.find(block_id);
   NSM_REQUIRE(c, it != c->blocks.end(), "get_element_components: unknown block id");
+  NvtxRange nvtx_range("Output");
   NSM_REQUIRE(c, n_components >= 0 && (n_components == 0 || (offsets && out)), "get_element_components: bad arguments");
   const Block& b = it->second;
   for (int k = 0; k < n_components; ++k)
@@ -1772,6 +1828,14 @@ nsm_b200_comm_ready(nsm_b200_ctx* c)
   }
   return NSM_OK;
 
+}
+
+int
+nsm_b200_comm_set_host_barrier(nsm_b200_ctx* c, void (*barrier)(void*), void* arg)
+{
+  NSM_ENTER(c);
+  if (c->comm.set_host_barrier(barrier, arg)) return fail(c, NSM_ERR_COMM, "%s", c->comm.error());
+  return NSM_OK;
 }
 
 int

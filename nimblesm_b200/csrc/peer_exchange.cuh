@@ -298,6 +298,7 @@ class PeerExchange
     p.done_counter = d_counter_;
     const unsigned grid = (unsigned)std::max<int64_t>((total_ + 255) / 256, 1);
     comm_pack_kernel<<<grid, 256, 0, stream>>>(p);
+    if (host_barrier_) cudaEventRecord(packed_, stream);
     if (launches) *launches += 1;
     if (cudaGetLastError() != cudaSuccess) return set_err("peer exchange kernel launch failed");
     return 0;
@@ -309,8 +310,15 @@ class PeerExchange
     if (!ready_) return set_err("reduce before comm_ready");
     if (peers_.empty()) return 0;
     const int parity = (int)(seq_ & 1);
-    comm_wait_kernel<<<1, 32, 0, stream>>>((const volatile unsigned long long*)buf_, d_peer_ranks_, (int)peers_.size(),
-                                           seq_, timeout_ns_, d_err_);
+    if (host_barrier_) {
+      // ranks that share one GPU must not wait for each other inside a kernel (the waiting kernel can sit in front of
+      // the peer's pack in a hardware queue): the host waits for this rank's pack, meets the peers, then unpacks
+      if (cudaEventSynchronize(packed_) != cudaSuccess) return set_err("peer exchange: waiting for the pack failed");
+      host_barrier_(host_barrier_arg_);
+    } else {
+      comm_wait_kernel<<<1, 32, 0, stream>>>((const volatile unsigned long long*)buf_, d_peer_ranks_, (int)peers_.size(),
+                                             seq_, timeout_ns_, d_err_);
+    }
     UnpackArgs u{};
     u.n_shared = n_shared_, u.ncomp = ncomp, u.node = d_node_, u.src_off = d_src_off_, u.src = d_src_;
     u.recv = (const double*)((unsigned char*)buf_ + kFlagWords * sizeof(unsigned long long)) +
@@ -365,6 +373,8 @@ class PeerExchange
                     (void*)d_src_off_, (void*)d_src_, (void*)d_peer_ranks_, (void*)d_counter_, (void*)d_err_})
       if (p) cudaFree(p);
     buf_ = nullptr;
+    if (packed_) cudaEventDestroy(packed_);
+    packed_ = nullptr;
     ready_ = inited_ = false;
   }
 
@@ -372,6 +382,14 @@ class PeerExchange
   set_timeout_seconds(double s)
   {
     timeout_ns_ = (long long)(s * 1e9);
+  }
+  // see finish(): replaces the in-kernel wait by a host rendezvous of all ranks (called once per exchange by every rank)
+  int
+  set_host_barrier(void (*barrier)(void*), void* arg)
+  {
+    host_barrier_ = barrier, host_barrier_arg_ = arg;
+    if (barrier && !packed_ && cudaEventCreateWithFlags(&packed_, cudaEventDisableTiming) != cudaSuccess) return set_err("cudaEventCreate failed");
+    return 0;
   }
 
  private:
@@ -408,6 +426,9 @@ class PeerExchange
   int*                 d_err_     = nullptr;
   unsigned long long   seq_       = 0;
   long long            timeout_ns_ = 20LL * 1000000000LL;
+  void (*host_barrier_)(void*)     = nullptr;
+  void*                host_barrier_arg_ = nullptr;
+  cudaEvent_t          packed_     = nullptr;
 };
 
 }  // namespace nsm

@@ -122,7 +122,7 @@ BoundaryConditionManager::Initialize(std::map<int, std::string> const& node_set_
       if (bc.bc_type_ != BoundaryCondition::PRESCRIBED_VELOCITY && bc.bc_type_ != BoundaryCondition::PRESCRIBED_DISPLACEMENT)
         continue;
       if (!bc.has_expression_ || !bc.expression_.depends_on_time()) continue;
-      ok = bc.expression_.compile(p.code, p.consts, p.slots, 16);
+      ok = bc.expression_.compile(p.code, p.consts, p.slots, p.entry_constants, 16);
       if (ok) {
         program_of_bc[b] = (int)p.offsets.size() - 1;
         p.offsets.push_back((int)p.code.size());
@@ -174,6 +174,18 @@ BoundaryConditionManager::ApplyKinematicBC(double time_current, double time_prev
       }
     }
   }
+}
+
+void
+BoundaryConditionManager::EvaluateEntryConstants(const Viewify<2>& X, double* values) const
+{
+  // values[j][k]: entry constant j (a function of the position alone) at the node of table entry k
+  const size_t n = table_.node.size();
+  for (size_t j = 0; j < programs_.entry_constants.size(); ++j)
+    for (size_t k = 0; k < n; ++k) {
+      const int nd      = table_.node[k];
+      values[j * n + k] = programs_.entry_constants[j].eval(X(nd, 0), X(nd, 1), dim_ == 3 ? X(nd, 2) : 0.0, 0.0);
+    }
 }
 
 void

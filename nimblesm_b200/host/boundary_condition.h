@@ -112,7 +112,8 @@ class BoundaryConditionManager
     std::vector<int>     offsets{0};        // [n_programs + 1]
     std::vector<int32_t> code;
     std::vector<double>  consts;
-    std::vector<Expression> slots;
+    std::vector<Expression> slots;            // functions of t alone: one host value per step
+    std::vector<Expression> entry_constants;  // functions of (x, y, z) alone through libm / pow: one host value per entry
     std::vector<int>     program_of_entry;  // [table entries], -1 = host magnitude
   };
   const DevicePrograms&
@@ -120,6 +121,9 @@ class BoundaryConditionManager
   {
     return programs_;
   }
+  // values [entry_constants.size()][table entries] (NSM_BCOP_ENTRYCONST)
+  void
+  EvaluateEntryConstants(const Viewify<2>& X, double* values) const;
   void
   EvaluateSlots(double t, double* values) const
   {

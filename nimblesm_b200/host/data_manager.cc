@@ -105,6 +105,9 @@ VectorCommunicator::ConnectDevices(DeviceContext& device)
   for (int p : peer_ranks_)
     device.check(nsm_b200_comm_attach(device.get(), p, (const unsigned char*)all[p].data()), "VectorCommunicator: comm_attach");
   device.check(nsm_b200_comm_ready(device.get()), "VectorCommunicator: comm_ready");
+  if (group_->Lockstep())  // ranks share a GPU: rendezvous on the host instead of waiting inside a kernel
+    device.check(nsm_b200_comm_set_host_barrier(device.get(), [](void* g) { static_cast<RankGroup*>(g)->Barrier(); }, group_.get()),
+                 "VectorCommunicator: host barrier");
   group_->Barrier();  // every rank is attached before any rank exchanges
 }
 

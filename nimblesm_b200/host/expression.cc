@@ -372,6 +372,8 @@ struct Emitter
   std::vector<double>                  consts;
   std::vector<NodeP>                   slot_nodes;
   std::vector<std::string>             slot_keys;
+  std::vector<NodeP>                   entry_nodes;  // sub-trees of (x, y, z) alone that need libm: one value per BC entry
+  std::vector<std::string>             entry_keys;
   int                                  depth = 0, max_seen = 0;
   void
   push(int op, int arg)
@@ -390,7 +392,40 @@ struct Emitter
 // op codes of include/nsm_b200.h (nsm_bc_op); kept numeric here: the host layer does not include the CUDA ABI
 enum { OP_CONST = 0, OP_X = 1, OP_SLOT = 4, OP_ADD = 5, OP_SUB = 6, OP_MUL = 7, OP_DIV = 8, OP_FMOD = 9, OP_NEG = 10, OP_SQRT = 11,
        OP_ABS = 12, OP_FLOOR = 13, OP_CEIL = 14, OP_ROUND = 15, OP_LT = 16, OP_LE = 17, OP_GT = 18, OP_GE = 19, OP_EQ = 20,
-       OP_AND = 21, OP_OR = 22, OP_XOR = 23, OP_NOT = 24, OP_SELECT = 25 };
+       OP_AND = 21, OP_OR = 22, OP_XOR = 23, OP_NOT = 24, OP_SELECT = 25, OP_ENTRYCONST = 26 };
+
+// every operation of the sub-tree has a correctly rounded / exact device counterpart
+bool
+exact_on_device(const Expression::Node* n)
+{
+  if (!n) return true;
+  switch (n->kind) {
+    case Kind::CONST:
+    case Kind::BCONST:
+    case Kind::VAR: return true;
+    case Kind::ADD:
+    case Kind::SUB:
+    case Kind::MUL:
+    case Kind::DIV:
+    case Kind::MOD:
+    case Kind::NEG:
+    case Kind::LT:
+    case Kind::LE:
+    case Kind::GT:
+    case Kind::GE:
+    case Kind::EQ:
+    case Kind::AND:
+    case Kind::OR:
+    case Kind::XOR:
+    case Kind::NOT:
+    case Kind::COND: break;
+    case Kind::FUNC:
+      if (n->index != 6 && n->index != 10 && n->index != 13 && n->index != 14 && n->index != 15) return false;
+      break;
+    default: return false;  // POW / IPOW
+  }
+  return exact_on_device(n->a.get()) && exact_on_device(n->b.get()) && exact_on_device(n->c.get());
+}
 
 bool
 emit(const NodeP& n, Emitter& e)
@@ -409,6 +444,21 @@ emit(const NodeP& n, Emitter& e)
       e.slot_nodes.push_back(n);
     }
     e.push(OP_SLOT, (int)k);
+    return true;
+  }
+  if (!uses(n.get(), 3, 3) && !exact_on_device(n.get())) {
+    // a function of the position alone that goes through libm or pow (sin(3*x), x^2, exp(-y)): it does not change in
+    // time, so the host evaluates it ONCE per boundary-condition entry at set-up -- with glibc's bits, exactly where the
+    // reference evaluates it every step (src/nimble_boundary_condition_manager.h:166-201) -- and the device program
+    // reads it as a per-entry constant
+    const std::string key = show(n.get());
+    size_t            k   = 0;
+    while (k < e.entry_keys.size() && e.entry_keys[k] != key) ++k;
+    if (k == e.entry_keys.size()) {
+      e.entry_keys.push_back(key);
+      e.entry_nodes.push_back(n);
+    }
+    e.push(OP_ENTRYCONST, (int)k);
     return true;
   }
   auto binary = [&](int op) {
@@ -451,20 +501,25 @@ emit(const NodeP& n, Emitter& e)
         case 15: return unary(OP_FLOOR);
         default: return false;
       }
-    default: return false;  // POW / IPOW of a position: glibc's pow is not reproducible on the device
+    default: return false;  // POW / IPOW mixing position and time: glibc's pow is not reproducible on the device
   }
 }
 
 }  // namespace
 
 bool
-Expression::compile(std::vector<int32_t>& code, std::vector<double>& consts, std::vector<Expression>& slots, int max_depth) const
+Expression::compile(std::vector<int32_t>& code, std::vector<double>& consts, std::vector<Expression>& slots,
+                    std::vector<Expression>& entry_constants, int max_depth) const
 {
   if (!root_) return false;
   Emitter e;
   for (const Expression& s : slots) {
     e.slot_keys.push_back(show(s.root_.get()));
     e.slot_nodes.push_back(s.root_);
+  }
+  for (const Expression& s : entry_constants) {
+    e.entry_keys.push_back(show(s.root_.get()));
+    e.entry_nodes.push_back(s.root_);
   }
   const size_t const_base = consts.size();
   if (!emit(root_, e) || e.max_seen > max_depth) return false;
@@ -474,6 +529,7 @@ Expression::compile(std::vector<int32_t>& code, std::vector<double>& consts, std
   }
   consts.insert(consts.end(), e.consts.begin(), e.consts.end());
   for (size_t k = slots.size(); k < e.slot_nodes.size(); ++k) slots.push_back(Expression(e.slot_nodes[k], e.slot_keys[k]));
+  for (size_t k = entry_constants.size(); k < e.entry_nodes.size(); ++k) entry_constants.push_back(Expression(e.entry_nodes[k], e.entry_keys[k]));
   return true;
 }
 

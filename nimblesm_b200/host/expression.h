@@ -44,8 +44,12 @@ class Expression
   // host-evaluated sub-expressions of t to `slots` (shared between programs: an identical text reuses its slot).
   // Returns false, leaving the outputs untouched, when some position-dependent node has no bit-exact device
   // counterpart (transcendental functions and pow of x, y, z) or the value stack would exceed `max_depth`.
+  // entry_constants: sub-trees of (x, y, z) alone that need libm or pow; the caller evaluates each once per
+  // boundary-condition entry (NSM_BCOP_ENTRYCONST).  Only sub-trees that MIX position and time through such a
+  // function (sin(x*t)) leave the expression without a device form.
   bool
-  compile(std::vector<int32_t>& code, std::vector<double>& consts, std::vector<Expression>& slots, int max_depth) const;
+  compile(std::vector<int32_t>& code, std::vector<double>& consts, std::vector<Expression>& slots,
+          std::vector<Expression>& entry_constants, int max_depth) const;
 
  private:
   Expression(std::shared_ptr<Node> root, std::string text) : text_(std::move(text)), root_(std::move(root)) {}

@@ -55,13 +55,34 @@ nsmh_expression_compile(const char* text, double t, int max_words, int* n_words,
     Expression              e(text);
     std::vector<int32_t>    c;
     std::vector<double>     k;
-    std::vector<Expression> s;
-    if (!e.compile(c, k, s, 16)) return 2;
+    std::vector<Expression> s, ec;
+    if (!e.compile(c, k, s, ec, 16)) return 2;
     if ((int)c.size() > max_words || (int)k.size() > max_consts || (int)s.size() > max_slots) return fail(err, errlen, "buffers too small");
     *n_words = (int)c.size(), *n_consts = (int)k.size(), *n_slots = (int)s.size();
     for (size_t i = 0; i < c.size(); ++i) code[i] = c[i];
     for (size_t i = 0; i < k.size(); ++i) consts[i] = k[i];
     for (size_t i = 0; i < s.size(); ++i) slot_values[i] = s[i].eval(0.0, 0.0, 0.0, t);
+    return 0;
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
+// The entry constants of the same compilation (sub-trees of the position alone that need libm / pow, NSM_BCOP_ENTRYCONST)
+// evaluated at one point.  Returns 0 and their count, 2 when the expression has no device form, 1 on a parse error.
+int
+nsmh_expression_entry_constants(const char* text, double x, double y, double z, int max_values, int* n_values, double* values,
+                                char* err, int errlen)
+{
+  try {
+    Expression              e(text);
+    std::vector<int32_t>    c;
+    std::vector<double>     k;
+    std::vector<Expression> s, ec;
+    if (!e.compile(c, k, s, ec, 16)) return 2;
+    if ((int)ec.size() > max_values) return fail(err, errlen, "buffers too small");
+    *n_values = (int)ec.size();
+    for (size_t i = 0; i < ec.size(); ++i) values[i] = ec[i].eval(x, y, z, 0.0);
     return 0;
   } catch (std::exception const& e) {
     return fail(err, errlen, e.what());

@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <iostream>
 #include <thread>
@@ -92,6 +93,10 @@ ExplicitTimeIntegrator::Integrate()
       std::cout << "  100% complete\n" << std::endl;
   };
 
+  // the reference's timer regions (explicit_time_integrator.cc:172-279): host wall clock per region in the
+  // call-by-call sequence; in the fused path the device reports the split of a run of steps (CUDA events)
+  double     total_dynamics_time = 0.0, total_force_time = 0.0, total_exodus_write_time = 0.0, total_vector_reduction_time = 0.0;
+  auto       seconds_since       = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
   const auto t0 = std::chrono::steady_clock::now();
   if (!reference_sequence_) {
     // ---- fused: one device call per run of steps that ends at an output step (or at a 10 % progress mark)
@@ -109,11 +114,15 @@ ExplicitTimeIntegrator::Integrate()
       for (int s = 0; s < run; ++s) progress(step + s);
       step += run;
       if (out) {
+        const auto t_out = std::chrono::steady_clock::now();
         model_data->PullNodalFields();
         data_manager.WriteOutput(time_current);
+        total_exodus_write_time += seconds_since(t_out);
       }
     }
     model_data->PullNodalFields();
+    total_force_time    = model_data->DeviceForceSeconds();
+    total_dynamics_time = model_data->DeviceUpdateSeconds();
   } else {
     // ---- reference sequence (explicit_time_integrator.cc:177-278), host-sequenced through the ModelData virtuals
     for (int step = 0; step < num_load_steps; ++step) {
@@ -122,32 +131,63 @@ ExplicitTimeIntegrator::Integrate()
       time_previous             = time_current;
       time_current += user_specified_time_step;
       const double delta_time = time_current - time_previous, half_delta_time = 0.5 * delta_time;
+      auto t_region = std::chrono::steady_clock::now();
       axpy(velocity, half_delta_time, acceleration);
       model_data->UpdateWithNewVelocity(data_manager, half_delta_time);
       model_data->ApplyKinematicConditions(data_manager, time_current, time_previous);
       axpy(displacement, delta_time, velocity);
       model_data->UpdateWithNewDisplacement(data_manager, delta_time);
       model_data->ApplyKinematicConditions(data_manager, time_current, time_previous);
+      total_dynamics_time += seconds_since(t_region);
+      t_region = std::chrono::steady_clock::now();
       model_data->ComputeExternalForce(data_manager, time_previous, time_current, is_output_step);
       model_data->ComputeInternalForce(data_manager, time_previous, time_current, is_output_step, displacement, internal_force);
+      total_force_time += seconds_since(t_region);
+      t_region = std::chrono::steady_clock::now();
       for (int i = 0; i < num_nodes; ++i) {
         const double one_over_m = 1.0 / lumped_mass(i);
         for (int c = 0; c < 3; ++c) acceleration(i, c) = one_over_m * (internal_force(i, c) + external_force(i, c));
       }
       axpy(velocity, half_delta_time, acceleration);
       model_data->UpdateWithNewVelocity(data_manager, half_delta_time);
+      total_dynamics_time += seconds_since(t_region);
       if (is_output_step) {
+        const auto t_out = std::chrono::steady_clock::now();
         model_data->ApplyKinematicConditions(data_manager, time_current, time_previous);
         data_manager.WriteOutput(time_current);
+        total_exodus_write_time += seconds_since(t_out);
       }
       model_data->UpdateStates(data_manager);
     }
   }
   step_loop_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (group) group->Barrier();
+  const int num_ranks = group ? group->NumRanks() : 1;
+  if (my_rank == 0 && parser.WriteTimingDataFile()) {
+    // TimingInfo::BinaryWrite (src/nimble_timing_utils.cc:70-94): nimble_timing_data_n<ranks>_<time stamp>.log, one
+    // tab-separated line: ranks, simulation, internal force, contact, exodus write, vector reduction
+    char        stamp[64];
+    const auto  now = std::chrono::system_clock::now();
+    std::time_t tt  = std::chrono::system_clock::to_time_t(now);
+    const long  us  = (long)(std::chrono::duration_cast<std::chrono::microseconds>(now.time_since_epoch()).count() % 1000000);
+    size_t      end = std::strftime(stamp, sizeof stamp, "%Y.%m.%d.%H.%M.%S.", std::localtime(&tt));
+    std::snprintf(stamp + end, sizeof stamp - end, "%06ld", us);
+    std::ofstream fs("nimble_timing_data_n" + std::to_string(num_ranks) + "_" + stamp + ".log", std::ios::binary | std::ios::trunc);
+    if (!fs.is_open())
+      std::cerr << "Failed to open timing data file" << std::endl;
+    else
+      fs << num_ranks << "\t" << step_loop_seconds_ << "\t" << total_force_time << "\t" << 0.0 << "\t" << total_exodus_write_time << "\t"
+         << total_vector_reduction_time << "\n";
+  }
   if (talk) {
+    // the reference's closing summary (explicit_time_integrator.cc:307-322)
     const double upd = (double)Mesh().GetNumElements() * num_load_steps / (step_loop_seconds_ > 0 ? step_loop_seconds_ : 1.0);
-    std::cout << " Total step time = " << step_loop_seconds_ << " s (" << upd << " element-updates/s on rank 0, output included)\n";
+    std::cout << "======== Timing data: ========\n";
+    std::cout << "Total step time = " << step_loop_seconds_ << " s (" << upd << " element-updates/s on rank 0, output included)\n";
+    std::cout << " --- Update A, V, U: " << total_dynamics_time << (reference_sequence_ ? "" : "  (device time; includes the shared-node exchange)") << '\n';
+    std::cout << " --- Force: " << total_force_time << (reference_sequence_ ? "" : "  (device time of the element kernels)") << "\n";
+    if (num_ranks > 1) std::cout << " --- Vector Reduction = " << total_vector_reduction_time << "  (on the device, inside the update time)\n";
+    std::cout << " --- Exodus Write = " << total_exodus_write_time << "\n";
   }
   return 0;
 }

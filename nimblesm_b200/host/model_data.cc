@@ -382,6 +382,12 @@ ModelData::AdvanceOnDevice(DataManager& data_manager, int n_steps, double& time_
                                          (int)programs.consts.size(), programs.consts.data(), (int)programs.slots.size(), n_bc,
                                          programs.program_of_entry.data()),
                 "ModelData::AdvanceOnDevice (boundary-condition programs)");
+        if (!programs.entry_constants.empty()) {
+          std::vector<double> ec(programs.entry_constants.size() * (size_t)n_bc);
+          bc->EvaluateEntryConstants(X, ec.data());
+          d.check(nsm_b200_set_bc_entry_constants(d.get(), (int)programs.entry_constants.size(), n_bc, ec.data()),
+                  "ModelData::AdvanceOnDevice (boundary-condition entry constants)");
+        }
         bc_programs_sent_ = true;
       }
       bc_values_.resize((size_t)n_bc);
@@ -411,7 +417,15 @@ ModelData::AdvanceOnDevice(DataManager& data_manager, int n_steps, double& time_
     }
   }
   enter_exchange_call(data_manager);
+  // device time of the element kernels ("Force calculation") and of the node passes + shared-node exchange ("Time
+  // Integration Scheme" / vector reduction), CUDA events on the context's stream: the figures of the timing summary
+  d.check(nsm_b200_profile(d.get(), 1), "ModelData::AdvanceOnDevice (profile)");
   d.check(nsm_b200_step(d.get(), n_steps, &time_current, user_time_step, store_ipt_last ? 1 : 0), "ModelData::AdvanceOnDevice");
+  double  elem_ms = 0.0, node_ms = 0.0;
+  int64_t n_prof  = 0;
+  d.check(nsm_b200_profile_read(d.get(), &elem_ms, &node_ms, &n_prof), "ModelData::AdvanceOnDevice (profile)");
+  device_force_seconds_ += 1e-3 * elem_ms * (double)n_prof;
+  device_update_seconds_ += 1e-3 * node_ms * (double)n_prof;
   enter_exchange_call(data_manager);
 }
 

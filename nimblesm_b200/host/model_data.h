@@ -202,6 +202,17 @@ class ModelData : public ModelDataBase
   // the run.  store_ipt_last: the last step is an output step.
   void
   AdvanceOnDevice(DataManager& data_manager, int n_steps, double& time_current, double user_time_step, bool store_ipt_last);
+  // accumulated device time of AdvanceOnDevice: element kernels / node passes incl. the shared-node exchange
+  double
+  DeviceForceSeconds() const
+  {
+    return device_force_seconds_;
+  }
+  double
+  DeviceUpdateSeconds() const
+  {
+    return device_update_seconds_;
+  }
   void
   PushNodalFields();  // host mirrors (u, v, a) -> device
   void
@@ -230,6 +241,7 @@ class ModelData : public ModelDataBase
   std::map<int, std::shared_ptr<Block>> blocks_;
   std::vector<int>                      block_ids_;
   std::map<int, std::vector<double>>    element_data_np1_;
+  double                                device_force_seconds_ = 0.0, device_update_seconds_ = 0.0;
   std::vector<double>                   bc_values_;
   std::vector<double>                   bc_slots_;
   bool                                  bc_table_sent_ = false, bc_programs_sent_ = false;

@@ -7,12 +7,16 @@ import math
 import numpy as np
 
 (CONST, X, Y, Z, SLOT, ADD, SUB, MUL, DIV, FMOD, NEG, SQRT, ABS, FLOOR, CEIL, ROUND, LT, LE, GT, GE, EQ, AND, OR, XOR, NOT,
- SELECT) = range(26)
+ SELECT, ENTRYCONST) = range(27)
 
 EXTRA_EXPRESSIONS = ["x*cos(t*3.0e5)", "cos(t*3.141592653589793/2.0e-4)*x + y/3", "sqrt(x*x+y*y)*exp(-0.2*t) - abs(z)*t",
                      "x % 0.3 + t", "t>1.0e-6 ? 10*x : -y", "(x+1)*(y+2)/(z+3)*log(t+2)", "floor(10*x)+ceil(y)+round(z)+t",
                      "0.01*t", "x<0.5 ? -t*y : 2*y+t", "1000.0*x*t"]
-NOT_COMPILABLE = ["sin(x*t)", "x^2*t", "exp(x)*t", "cbrt(x)+t", "e^x * t"]
+# position-only sub-trees through libm / pow: compiled, the host supplies one value per BC entry (NSM_BCOP_ENTRYCONST)
+ENTRY_CONSTANT_EXPRESSIONS = ["x^2*t", "exp(x)*t", "cbrt(x)+t", "e^x * t", "sin(3*x)*cos(t)", "exp(-y)*(1+t)",
+                              "sin(3*x)*cos(t) + x*sin(3*x)*t", "log(z+2)^2*t - y"]
+# libm / pow of a MIX of position and time has no bit-exact device form: the host evaluates these per node per step
+NOT_COMPILABLE = ["sin(x*t)", "(x*t)^2", "exp(x+t)", "cos(t+y)*x"]
 
 
 def compile_expression(host, text, t):
@@ -31,7 +35,18 @@ def compile_expression(host, text, t):
     return (np.array(code[:nw.value], dtype=np.int32), np.array(consts[:nc.value]), np.array(slots[:ns.value]))
 
 
-def interpret(code, consts, slots, x, y, z):
+def entry_constants(host, text, x, y, z):
+    """the per-entry constants of compile_expression(text) evaluated at one point (host, glibc)"""
+    host.nsmh_expression_entry_constants.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int),
+                                                     C.POINTER(C.c_double), C.c_char_p, C.c_int]
+    vals, n = (C.c_double * 64)(), C.c_int()
+    err = C.create_string_buffer(512)
+    rc = host.nsmh_expression_entry_constants(text.encode(), x, y, z, 64, C.byref(n), vals, err, 512)
+    assert rc == 0, (rc, err.value)
+    return np.array(vals[:n.value])
+
+
+def interpret(code, consts, slots, x, y, z, entry=()):
     st = []
     for w in code:
         op, arg = int(w) & 0xff, int(w) >> 8
@@ -41,6 +56,8 @@ def interpret(code, consts, slots, x, y, z):
             st.append(float((x, y, z)[op - X]))
         elif op == SLOT:
             st.append(float(slots[arg]))
+        elif op == ENTRYCONST:
+            st.append(float(entry[arg]))
         elif op in (NEG, SQRT, ABS, FLOOR, CEIL, ROUND, NOT):
             a = st.pop()
             st.append({NEG: lambda: -a, SQRT: lambda: math.sqrt(a) if a >= 0 else float("nan"), ABS: lambda: abs(a),

@@ -207,6 +207,8 @@ def test_driver_time_dependent_bc_on_device_equals_host_evaluation(tmp_path):
     deck = re.sub(r"\n*$", "\n", deck)
     deck += 'boundary condition:  prescribed_velocity nodelist_2 y "0.5*(1.0-cos(t*3.141592653589793/1.0e-6))*(1.0+z)"\n'
     deck += 'boundary condition:  prescribed_displacement nodelist_2 z "1.0e-3*t*(y+2)/(x+3)"\n'
+    # a position-only sub-tree through libm and pow: per-entry constants on the device (NSM_BCOP_ENTRYCONST)
+    deck += 'boundary condition:  prescribed_velocity nodelist_2 x "1.0e-2*sin(300*y)*cos(t*1.0e6) + z^2*t"\n'
     base = re.search(r"genesis input file:\s*(\S+)", deck).group(1)
     out = re.search(r"exodus output file:\s*(\S+)", deck).group(1)
     stem = out[:-2] if out.endswith(".e") else out
@@ -227,3 +229,29 @@ def test_driver_time_dependent_bc_on_device_equals_host_evaluation(tmp_path):
     ns2 = mesh["node_sets"][2]
     vy = res["nod"]["velocity_y"][:, ns2]
     assert np.abs(vy).max() > 0  # the prescribed velocity really acted (it returns to 0 at the final time)
+
+
+def test_driver_timing_summary_and_log(tmp_path):
+    """`write timing data file: on` (src/nimble_parser.cc): the driver prints the reference's closing timing summary
+    (explicit_time_integrator.cc:307-322) and writes nimble_timing_data_n<ranks>_<stamp>.log in the reference's
+    tab-separated layout (src/nimble_timing_utils.cc:70-94): ranks, simulation, force, contact, exodus write, reduction."""
+    import glob
+    import re
+
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, _gold, _ref, _pieces = load_golden("wave_in_bar")
+    deck = re.sub(r"\n*$", "\n", deck) + "write timing data file: on\n"
+    base = re.search(r"genesis input file:\s*(\S+)", deck).group(1)
+    write_genesis(str(tmp_path / base), mesh)
+    (tmp_path / "case.in").write_text(deck)
+    r = subprocess.run([EXE, "case.in"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for line in ("======== Timing data: ========", "Total step time = ", " --- Update A, V, U: ", " --- Force: ", " --- Exodus Write = "):
+        assert line in r.stdout, line
+    logs = glob.glob(str(tmp_path / "nimble_timing_data_n1_*.log"))
+    assert len(logs) == 1
+    cols = open(logs[0]).read().split()
+    assert len(cols) == 6 and int(cols[0]) == 1
+    sim, force, contact, exo, red = (float(c) for c in cols[1:])
+    assert sim > 0 and 0 < force <= sim and contact == 0.0 and exo >= 0.0 and red == 0.0

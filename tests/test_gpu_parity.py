@@ -422,6 +422,7 @@ def _bc_program_setup(c, mesh, ref, exprs, times, last_is_displacement=True):
     face = mesh["node_sets"][2]
     nodes, comps, kinds, prog_of = [], [], [], []
     offsets, code, consts = [0], [], []
+    entry_exprs = []  # (expression, index of its per-entry constant), one row of nsm_b200_set_bc_entry_constants each
     slot_rows = [[] for _ in times]
     for k, ex in enumerate(exprs):
         nodes += list(face)
@@ -430,10 +431,11 @@ def _bc_program_setup(c, mesh, ref, exprs, times, last_is_displacement=True):
         prog = bp.compile_expression(host, ex, times[0])
         assert prog is not None, ex
         pc, pk, _ = prog
-        base_c, base_s = len(consts), len(slot_rows[0])
-        for w in pc:  # relocate constant / slot indices into the shared pools
+        base_c, base_s, base_e = len(consts), len(slot_rows[0]), len(entry_exprs)
+        for w in pc:  # relocate constant / slot / per-entry constant indices into the shared pools
             op, arg = int(w) & 0xff, int(w) >> 8
-            code.append(op | ((arg + (base_c if op == bp.CONST else base_s if op == bp.SLOT else 0)) << 8))
+            code.append(op | ((arg + (base_c if op == bp.CONST else base_s if op == bp.SLOT else base_e if op == bp.ENTRYCONST else 0)) << 8))
+        entry_exprs += [(ex, j) for j in range(len(bp.entry_constants(host, ex, 0.1, 0.2, 0.3)))]
         consts += list(pk)
         for r, t in enumerate(times):
             slot_rows[r] += list(bp.compile_expression(host, ex, t)[2])
@@ -441,11 +443,18 @@ def _bc_program_setup(c, mesh, ref, exprs, times, last_is_displacement=True):
         prog_of += [k] * len(face)
     rows = np.array([[bp.host_eval(host, exprs[p], *ref[n], t) for n, p in zip(nodes, prog_of)] for t in times])
     c.set_bc_table(nodes, comps, kinds)
+    # per-entry constants: the host evaluates each position-only libm sub-tree at every table entry's node
+    entry_values = np.array([[bp.entry_constants(host, ex, *ref[n])[j] for n in nodes] for ex, j in entry_exprs]).reshape(len(entry_exprs), len(nodes))
+    c._test_entry_constants = entry_values
     return nodes, comps, kinds, rows, (offsets, code, consts, np.array(slot_rows).reshape(len(times), -1), prog_of)
 
 
 BC_EXPRESSIONS = ["cos(t*3.141592653589793/2.0e-6)*x + y/3", "sqrt(x*x+y*y)*exp(-0.2*t) - abs(z)*t", "t>1.0e-8 ? 10*y : -z",
                   "1.0e-3*(y+1)*(z+2)/(x+3)*log(t+2)", "floor(10*y)+ceil(z)+round(y*4)+1.0e6*t", "(y % 0.3)*t*1.0e5"]
+
+
+# position-only sub-trees through libm / pow (f-2 residue of round 1): per-entry constants, NSM_BCOP_ENTRYCONST
+BC_ENTRY_CONSTANT_EXPRESSIONS = ["sin(3*x)*cos(t)", "x^2*t", "exp(-y)*(1+t)"]
 
 
 def test_bc_programs_bitwise():
@@ -455,13 +464,16 @@ def test_bc_programs_bitwise():
     from nimblesm_b200 import capi
 
     mesh, ref, _ = perturbed_cube(5, 0.0)
-    exprs = BC_EXPRESSIONS[:3]  # one per component, all prescribed velocities
-    for t in (0.0, 3.0e-7, 2.5e-6):
+    for exprs, t in [(e, t) for e in (BC_EXPRESSIONS[:3], BC_ENTRY_CONSTANT_EXPRESSIONS) for t in (0.0, 3.0e-7, 2.5e-6)]:  # one per component, all prescribed velocities
         c = _ctx(mesh, "elastic", capi.ASSEMBLY_ATOMIC)
         nodes, comps, kinds, rows, (off, code, consts, slots, prog_of) = _bc_program_setup(c, mesh, ref, exprs, [t], False)
         c.set_bc_programs(off, code, consts, slots.shape[1], prog_of)
         c.set_bc_values(np.full(len(nodes), 123.0))  # must be overwritten for every entry that has a program
         c.set_bc_slots_steps(slots)
+        if len(c._test_entry_constants):
+            with pytest.raises(capi.NsmError):  # a program names a per-entry constant that was not supplied yet
+                c.apply_kinematic_bc(t, t)
+            c.set_bc_entry_constants(c._test_entry_constants)
         c.apply_kinematic_bc(t, t)
         v = c.download("velocity")
         n_face = len(mesh["node_sets"][2])

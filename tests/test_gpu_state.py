@@ -62,8 +62,9 @@ def test_state_material_seam_bitwise(oracle):
     assert L.nsm_b200_material_state_label(2, 1) == b"von_mises_stress" and L.nsm_b200_material_num_params(2) == 5
 
 
-def _oracle_loop(oracle, mesh, n_steps, dt_user, blocks):
-    """The explicit loop on the plain-C oracle with per-block records; yields after every step."""
+def _oracle_loop(oracle, mesh, n_steps, dt_user, blocks, is_output=lambda step: False):
+    """The explicit loop on the plain-C oracle with per-block records; yields after every step.  On an output step the
+    kinematic conditions are applied once more after the second half-kick (explicit_time_integrator.cc:266-269)."""
     L = oracle.lib()
     ref = np.ascontiguousarray(np.stack([mesh["x"], mesh["y"], mesh["z"]], 1))
     m = np.zeros(len(ref))
@@ -88,6 +89,8 @@ def _oracle_loop(oracle, mesh, n_steps, dt_user, blocks):
             f, ed[b] = oracle.internal_force_state(kind, params, ref, u, mesh["conn"][b], ed[b], f)
         L.h8o_accel(len(ref), m, f, None, a)
         L.h8o_axpy(u.size, 0.5 * d, a.ravel(), v.ravel())
+        if is_output(step):
+            v[face] = 0.0
         yield step, t, u, v, a, f, ed
 
 
@@ -133,8 +136,8 @@ def test_state_trajectory_bitwise_ordered(oracle, flags):
     assert c.block_stride == {1: 17, 2: 15}
     t = 0.0
     prev = None
-    for step, t_o, u, v, a, f, ed in _oracle_loop(oracle, mesh, 50, dt, blocks):
-        t = c.step(1, t, dt, store_ipt_last=(step % 10 == 9))
+    for step, t_o, u, v, a, f, ed in _oracle_loop(oracle, mesh, 50, dt, blocks, lambda s: s % 10 == 9):
+        t = c.step(1, t, dt, store_ipt_last=(step % 10 == 9))  # an output step: records stored, BCs re-applied
         assert t == t_o
         assert np.array_equal(_bits(c.download("internal_force")), _bits(f)), step
         if step % 10 == 9:
@@ -160,11 +163,12 @@ def test_state_trajectory_bitwise_ordered(oracle, flags):
     assert np.array_equal(_bits(sub), _bits(final[4][1][[0, 5, len(rec) - 1]]))
     c.close()
     # one call / chunks: the per-step roll inside nsm_b200_step
-    for chunks in ([50], [7, 1, 30, 12]):
+    for chunks in ([10] * 5, [3, 7, 10, 10, 1, 9, 10]):  # every call ends where the first run had its output steps
         c = _ctx(mesh, capi.ASSEMBLY_ORDERED, flags)
-        t = 0.0
+        t, done = 0.0, 0
         for k in chunks:
-            t = c.step(k, t, dt)
+            done += k
+            t = c.step(k, t, dt, store_ipt_last=(done % 10 == 0))
         for lbl, want in zip(("displacement", "velocity", "acceleration", "internal_force"), final[:4]):
             assert np.array_equal(_bits(c.download(lbl)), _bits(want)), (chunks, lbl)
         assert np.array_equal(_bits(c.element_data(1)), _bits(final[4][1])), chunks

@@ -77,17 +77,24 @@ def test_expression_programs_reproduce_host_evaluation(host):
     from tests import bc_program as bp
 
     compiled = 0
-    for ex in EXPRESSIONS + bp.EXTRA_EXPRESSIONS:
+    for ex in EXPRESSIONS + bp.EXTRA_EXPRESSIONS + bp.ENTRY_CONSTANT_EXPRESSIONS:
         for (x, y, z, t) in POINTS:
             prog = bp.compile_expression(host, ex, t)
             if prog is None:
+                assert ex not in bp.ENTRY_CONSTANT_EXPRESSIONS, ex
                 continue
             compiled += 1
-            got, want = bp.interpret(*prog, x, y, z), bp.host_eval(host, ex, x, y, z, t)
+            entry = bp.entry_constants(host, ex, x, y, z)
+            got, want = bp.interpret(*prog, x, y, z, entry), bp.host_eval(host, ex, x, y, z, t)
             assert np.float64(got).view(np.int64) == np.float64(want).view(np.int64) or (got != got and want != want), (ex, x, y, z, t)
-    assert compiled >= 4 * (len(bp.EXTRA_EXPRESSIONS) + 10)
+    assert compiled >= 4 * (len(bp.EXTRA_EXPRESSIONS) + len(bp.ENTRY_CONSTANT_EXPRESSIONS) + 10)
     for ex in bp.NOT_COMPILABLE:
         assert bp.compile_expression(host, ex, 0.5) is None, ex
+    # a position-only libm sub-tree is ONE per-entry constant, shared when it repeats
+    code, consts, slots = bp.compile_expression(host, "sin(3*x)*cos(t) + sin(3*x)*t", 0.25)
+    assert sum(1 for w in code if (int(w) & 0xff) == bp.ENTRYCONST) == 2 and len(bp.entry_constants(host, "sin(3*x)*cos(t) + sin(3*x)*t", 0.1, 0.2, 0.3)) == 1
+    # ... and the MAXIMAL position-only sub-tree is taken: x*sin(3*x) is one constant, not sin(3*x) times a device product
+    assert len(bp.entry_constants(host, "x*sin(3*x)*t", 0.1, 0.2, 0.3)) == 1
     # a function of t alone is ONE slot and nothing else crosses per step
     code, consts, slots = bp.compile_expression(host, " 0.0635 * (-0.5*cos(t*3.141592653589793/2.0e-4) + 0.5)", 1.0e-4)
     assert len(code) == 1 and (code[0] & 0xff) == bp.SLOT and len(slots) == 1
