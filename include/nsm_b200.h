@@ -242,10 +242,21 @@ int nsm_b200_step(nsm_b200_ctx* ctx, int n_steps, double* time, double dt_user, 
 /* The same loop body on HOST-resident state, i.e. on the reference's Viewify<2> views as ExplicitTimeIntegrator holds
  * them (src/integrators/explicit_time_integrator.cc:131-160): uploads displacement, velocity, acceleration
  * ([n_nodes][3]), advances one step, returns displacement, velocity, acceleration and internal_force in place.
- * With pinned buffers (nsm_b200_host_alloc) the displacement, which is final after the first half of the step,
- * travels back over a second stream while the element kernels run. */
+ * The call is PIPELINED over chunks of consecutive node ids (16 by default on meshes of a million nodes or more): chunk
+ * c is uploaded and integrated (first half of the step) while chunk c-1's elements run -- every 4-element group whose
+ * nodes all lie in the chunks uploaded so far -- and every chunk whose elements have all run is corrected and sent
+ * home while later chunks are still travelling up: upload, compute and download overlap (PCIe is full duplex).
+ * The dependency ranges come from the connectivity, so the overlap is as good as the mesh numbering is local (lattice
+ * or Morton order: a diagonal pipeline; random order: the plain upload -> step -> download schedule).  Per-node and
+ * per-element arithmetic and the ORDERED summation order are those of nsm_b200_step, hence the same bits.  Use pinned
+ * buffers (nsm_b200_host_alloc).  Contexts with a peer exchange, an internal node renumbering or per-step
+ * boundary-condition rows take the plain schedule. */
 int nsm_b200_step_host(nsm_b200_ctx* ctx, double* time, double dt_user, double* displacement, double* velocity,
                        double* acceleration, double* internal_force);
+
+/* Number of node chunks of the pipelined nsm_b200_step_host: -1 automatic (default), 0 or 1 the plain schedule.  Call
+ * before the first nsm_b200_step_host. */
+int nsm_b200_set_host_step_chunks(nsm_b200_ctx* ctx, int n_chunks);
 
 /* ---- element data / derived output (replaces ModelData::GetElementDataNew + Block::ComputeDerivedElementData,
  *      src/nimble_block.cc:438-497; HexElement::ComputeVolumeAverage, src/nimble_element.h:343-392) --- */

@@ -46,6 +46,7 @@ SYMBOLS = [
     "nsm_b200_material_state_label", "nsm_b200_material_state_initial_value", "nsm_b200_compute_stress_state",
     "nsm_b200_element_data_stride", "nsm_b200_update_states", "nsm_b200_get_element_data_previous",
     "nsm_b200_set_element_data", "nsm_b200_set_bc_entry_constants", "nsm_b200_comm_set_host_barrier",
+    "nsm_b200_set_host_step_chunks",
 ]
 
 
@@ -134,6 +135,7 @@ def lib():
         "nsm_b200_set_element_data": (i32, [vp, i32, i32, dp]),
         "nsm_b200_set_bc_entry_constants": (i32, [vp, i32, i64, dp]),
         "nsm_b200_comm_set_host_barrier": (i32, [vp, vp, vp]),
+        "nsm_b200_set_host_step_chunks": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -335,6 +337,10 @@ class Context:
         t = C.c_double(time)
         self._ck(self._L.nsm_b200_step(self._h, int(n_steps), C.byref(t), dt_user, 1 if store_ipt_last else 0))
         return t.value
+
+    def set_host_step_chunks(self, n_chunks):
+        """node chunks of the pipelined step_host (-1 automatic, <= 1 the plain schedule); before the first step_host"""
+        self._ck(self._L.nsm_b200_set_host_step_chunks(self._h, int(n_chunks)))
 
     def step_host(self, time, dt_user, displacement, velocity, acceleration, internal_force) -> float:
         """One explicit step on host-resident [n][3] float64 arrays, updated in place (pinned arrays overlap copies)."""

@@ -74,6 +74,9 @@ struct ElemArgs
   const unsigned char* chunk_mask;  // [chunks of kTicketChunk groups] bit i: group chunk*8+i touches a shared node
   const int*           group_list;
   int                  n_list;
+  // kSchedAll over a RANGE of groups [group_begin, group_begin + n_range) (n_range == 0: all groups): the pipelined
+  // host step launches the elements whose nodes have already been uploaded (nsm_b200_step_host)
+  int                  group_begin, n_range;
   int*          flags;       // [0] bit 0: non-positive Jacobian seen; [1]: integration points redone in IEEE mode
 };
 
@@ -394,7 +397,7 @@ element_force_kernel(const ElemArgs p)
   // is entered and first read kTicketChunk passes later, so the atomic's round trip (which queues behind every
   // other warp's on the one counter) never shows; groups are looked up two passes ahead (connectivity load).
   unsigned* const ticket_at = ticket_address(p.ticket, lane, p.zero);
-  const int n_tickets  = p.sched == kSchedList ? p.n_list : n_groups;  // positions the counter hands out
+  const int n_tickets  = p.sched == kSchedList ? p.n_list : (p.n_range > 0 ? p.n_range : n_groups);  // positions the counter hands out
   int       chunk_base = claim_group(ticket_at, lane) * kTicketChunk;  // chunk that holds the position two passes ahead
   int       chunk_off  = -1;
   unsigned  ticket     = 0;                                            // lane 0: the chunk after that one
@@ -425,7 +428,7 @@ element_force_kernel(const ElemArgs p)
       const int pos = chunk_base + chunk_off;
       if (pos >= n_tickets) return n_groups;
       if (p.sched == kSchedSkipFlagged && ((skip_mask >> chunk_off) & 1u)) continue;
-      return p.sched == kSchedList ? __ldg(p.group_list + pos) : pos;
+      return p.sched == kSchedList ? __ldg(p.group_list + pos) : pos + p.group_begin;
     }
   };
   int g = next_group();
@@ -736,7 +739,8 @@ stress_state_kernel(int64_t n, const double* __restrict__ Fn_in, const double* _
 // ---------------------------------------------------------------------------------------------------
 struct NodeArgs
 {
-  int64_t         n_nodes;
+  int64_t         n_nodes;     // end of the node range this launch covers
+  int64_t         node_begin;  // its start (0 except in the pipelined host step)
   double*         u[3];
   double*         v[3];
   double*         a[3];
@@ -767,7 +771,7 @@ template <bool HAS_BC, bool ZERO_F>
 __global__ void __launch_bounds__(256)
 node_predict_kernel(const NodeArgs p, double hdt, double dt)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = p.node_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n_nodes) return;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -795,7 +799,7 @@ template <bool ORDERED, bool HAS_FEXT>
 __global__ void __launch_bounds__(256)
 node_correct_kernel(const NodeArgs p, double hdt, int update_velocity)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = p.node_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n_nodes) return;
   double f0, f1, f2;
   if (ORDERED) {
@@ -824,7 +828,7 @@ template <bool ORDERED, bool HAS_FEXT, bool HAS_BC, bool ZERO_F>
 __global__ void __launch_bounds__(256)
 node_fused_kernel(const NodeArgs p, double hdt, double hdt_next, double dt_next)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = p.node_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n_nodes) return;
   double f[3];
   if (ORDERED) {
@@ -943,7 +947,7 @@ bc_program_kernel(const BcProgramArgs p)
 __global__ void __launch_bounds__(256)
 apply_bc_kernel(const NodeArgs p, double dt)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = p.node_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n_nodes) return;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -971,6 +975,41 @@ soa_to_aos_kernel(int64_t n, const double* __restrict__ x, const double* __restr
   if (i >= n) return;
   const int64_t j = perm ? perm[i] : i;
   aos[3 * i] = x[j], aos[3 * i + 1] = y[j], aos[3 * i + 2] = z[j];
+}
+
+// the same for a node range [i0, i0 + n) without a node permutation: staging rows are the range's own (pipelined host step)
+__global__ void __launch_bounds__(256)
+aos_to_soa_range_kernel(int64_t i0, int64_t n, const double* __restrict__ aos, double* x, double* y, double* z)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  x[i0 + k] = aos[3 * (i0 + k)], y[i0 + k] = aos[3 * (i0 + k) + 1], z[i0 + k] = aos[3 * (i0 + k) + 2];
+}
+
+__global__ void __launch_bounds__(256)
+soa_to_aos_range_kernel(int64_t i0, int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                        double* aos)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  aos[3 * (i0 + k)] = x[i0 + k], aos[3 * (i0 + k) + 1] = y[i0 + k], aos[3 * (i0 + k) + 2] = z[i0 + k];
+}
+
+// lowest and highest node id of every 4-element group (dependency ranges of the pipelined host step)
+__global__ void __launch_bounds__(256)
+group_node_range_kernel(int64_t n_elem, const int* __restrict__ conn, int* lo, int* hi)
+{
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (n_elem + kElemsPerWarp - 1) / kElemsPerWarp) return;
+  int a = 0x7fffffff, b = -1;
+  for (int k = 0; k < kElemsPerWarp * 8; ++k) {
+    const int64_t s = g * kElemsPerWarp * 8 + k;
+    if (s < n_elem * 8) {
+      const int nd = conn[s];
+      a = nd < a ? nd : a, b = nd > b ? nd : b;
+    }
+  }
+  lo[g] = a, hi[g] = b;
 }
 
 // scalar nodal field between the caller's order (staging) and the internal order

@@ -141,6 +141,22 @@ struct nsm_b200_ctx
   double                   prof_elem_ms = 0, prof_node_ms = 0;
   int64_t                  prof_steps   = 0;
 
+  // pipelined nsm_b200_step_host: node chunks travel up, are integrated, their elements run and the finished chunks
+  // travel down while later chunks are still on their way up (PCIe is full duplex); see build_host_pipe
+  struct HostPipe
+  {
+    int                  requested_chunks = -1;  // -1: automatic
+    bool                 built            = false;
+    int                  n_chunks         = 0;
+    std::vector<int64_t> node_end;                 // [C] end of node chunk c
+    std::map<int, std::vector<int>> up_end;        // block -> [C]: groups [0, up_end[c]) touch only nodes < node_end[c]
+    std::vector<int>     done_after;               // [C]: node chunk k is complete once element chunk done_after[k] has run
+    double*              stage[4] = {nullptr, nullptr, nullptr, nullptr};  // AoS bounce buffers of u, v, a, f
+    cudaStream_t         up = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_elem;
+    cudaEvent_t          ev_bc = nullptr;
+  } pipe;
+
   PeerExchange comm;
   // overlap of the shared-node exchange with the interior elements (nsm_b200_step)
   cudaStream_t comm_stream = nullptr;
@@ -346,7 +362,7 @@ launch_element(const ElemArgs& p, cudaStream_t s)
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     wave = wave_of_device[dev] = sms * per_sm;
   }
-  const int64_t positions = p.sched == kSchedList ? p.n_list : groups_of(p.n_elem);
+  const int64_t positions = p.sched == kSchedList ? p.n_list : (p.n_range > 0 ? p.n_range : groups_of(p.n_elem));
   const int64_t need      = std::max<int64_t>((positions + kElemWarps * kTicketChunk - 1) / (kElemWarps * kTicketChunk), 1);
   k<<<(unsigned)std::min<int64_t>(need, wave), kElemThreads, kElemSmemBytes, s>>>(p);
   return cudaGetLastError();
@@ -406,6 +422,20 @@ mark_states_for_roll(nsm_b200_ctx* c)
 {
   for (auto& kv : c->blocks)
     if (kv.second.n_state) kv.second.roll_pending = true;
+}
+
+// one block's element kernel over the groups [g0, g1) on stream s (the pipelined host step)
+int
+enqueue_element_range(nsm_b200_ctx* c, const Block& b, bool store_ipt, int g0, int g1, cudaStream_t s)
+{
+  if (g1 <= g0) return NSM_OK;
+  int mode = (store_ipt ? kModeStoreIpt : 0) | (c->binv ? kModeReadBinv : 0);
+  ElemArgs p    = elem_args(c, b, kSchedAll);
+  p.group_begin = g0, p.n_range = g1 - g0;
+  NSM_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned), s));
+  NSM_CUDA(c, launch_element_any(p, b.material, c->assembly == NSM_ASSEMBLY_ORDERED, mode, s));
+  c->launches++;
+  return NSM_OK;
 }
 
 int
@@ -683,6 +713,12 @@ nsm_b200_destroy(nsm_b200_ctx* c)
     fr(kv.second.conn), fr(kv.second.orig), fr(kv.second.group_bits), fr(kv.second.group_list);
     fr(kv.second.rec[0]), fr(kv.second.rec[1]);
   }
+  for (double* p : c->pipe.stage) fr(p);
+  if (c->pipe.up) cudaStreamDestroy(c->pipe.up);
+  if (c->pipe.down) cudaStreamDestroy(c->pipe.down);
+  if (c->pipe.ev_bc) cudaEventDestroy(c->pipe.ev_bc);
+  for (auto e : c->pipe.ev_up) cudaEventDestroy(e);
+  for (auto e : c->pipe.ev_elem) cudaEventDestroy(e);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
   if (c->ev_packed) cudaEventDestroy(c->ev_packed);
@@ -1536,6 +1572,212 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
   return check_flags(c);
 }
 
+}  // extern "C"
+
+namespace {
+
+// Dependency ranges of the pipelined host step.  Nodes travel in C chunks of consecutive ids.  Per block, with lo(g) /
+// hi(g) the lowest / highest node of group g: up_end[c] = number of leading groups whose nodes all lie below the end of
+// chunk c (prefix maximum of hi), so those groups can run as soon as chunk c has been uploaded and integrated; a node
+// chunk k is final once every group with a node below its end has run, i.e. after the element chunk done_after[k].
+// Meshes numbered with locality (lattice order, Morton order) give a diagonal pipeline; a randomly numbered mesh
+// degenerates gracefully into "everything after the last upload", which is the unpipelined schedule.
+int
+build_host_pipe(nsm_b200_ctx* c)
+{
+  auto&         P = c->pipe;
+  const int64_t n = c->n_nodes;
+  int           C = P.requested_chunks >= 0 ? P.requested_chunks : (n >= (int64_t)1 << 20 ? 16 : 1);
+  C               = (int)std::min<int64_t>(C, std::max<int64_t>(n, 1));
+  P.built         = true;
+  P.n_chunks      = 0;
+  if (C < 2 || c->comm.active() || c->node_perm || n == 0) return NSM_OK;  // the plain schedule
+  P.node_end.resize(C);
+  for (int k = 0; k < C; ++k) P.node_end[k] = n * (k + 1) / C;
+  std::vector<int> need(C, 0);  // over all blocks: the element chunk after which node chunk k is final
+  for (auto& kv : c->blocks) {
+    const Block&  b  = kv.second;
+    const int64_t ng = groups_of(b.n_elem);
+    std::vector<int> up(C, 0);
+    if (ng > 0) {
+      int *d_lo = nullptr, *d_hi = nullptr;
+      NSM_CUDA(c, cudaMalloc((void**)&d_lo, (size_t)ng * sizeof(int)));
+      NSM_CUDA(c, cudaMalloc((void**)&d_hi, (size_t)ng * sizeof(int)));
+      group_node_range_kernel<<<grid_for(ng, 256), 256, 0, c->stream>>>(b.n_elem, b.conn_sched, d_lo, d_hi);
+      c->launches++;
+      std::vector<int> lo((size_t)ng), hi((size_t)ng);
+      NSM_CUDA(c, cudaMemcpyAsync(lo.data(), d_lo, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      NSM_CUDA(c, cudaMemcpyAsync(hi.data(), d_hi, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+      cudaFree(d_lo), cudaFree(d_hi);
+      int64_t g = 0;
+      int     k = 0;
+      for (; k < C; ++k) {  // prefix maximum of hi: leading groups entirely below node_end[k]
+        while (g < ng && hi[g] < P.node_end[k]) ++g;
+        up[k] = (int)g;
+      }
+      up[C - 1] = (int)ng;
+      // last group with a node below node_end[k] -> the element chunk that contains it
+      std::vector<int64_t> last(C, -1);
+      for (int64_t gg = 0; gg < ng; ++gg) {
+        const int kk = (int)std::min<int64_t>(((int64_t)lo[gg] * C) / std::max<int64_t>(n, 1), C - 1);
+        // lo[gg] lies in node chunk >= kk' where node_end[kk'] > lo[gg]; mark every chunk from there on
+        int first = kk;
+        while (first > 0 && P.node_end[first - 1] > lo[gg]) --first;
+        while (P.node_end[first] <= lo[gg]) ++first;
+        if (gg > last[first]) last[first] = gg;
+      }
+      int64_t run = -1;  // chunk k needs every group whose lowest node is below node_end[k]: running maximum over k' <= k
+      for (int kk = 0; kk < C; ++kk) {
+        run = std::max(run, last[kk]);
+        if (run >= 0) {
+          int cc = 0;
+          while (up[cc] <= run) ++cc;  // the element chunk [up[cc-1], up[cc]) that holds group `run`
+          need[kk] = std::max(need[kk], cc);
+        }
+      }
+    }
+    P.up_end[kv.first] = up;
+  }
+  for (int k = 1; k < C; ++k) need[k] = std::max(need[k], need[k - 1]);  // chunks finish in order (one download queue)
+  for (int k = 0; k < C; ++k) need[k] = std::max(need[k], k);            // ... and never before their own upload
+  P.done_after = need;
+  for (double*& p : P.stage) {
+    int rc = dev_alloc(c, &p, std::max<int64_t>(n * 3, 1));
+    if (rc) return rc;
+  }
+  NSM_CUDA(c, cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
+  NSM_CUDA(c, cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
+  NSM_CUDA(c, cudaEventCreateWithFlags(&P.ev_bc, cudaEventDisableTiming));
+  P.ev_up.resize(C), P.ev_elem.resize(C);
+  for (int k = 0; k < C; ++k) {
+    NSM_CUDA(c, cudaEventCreateWithFlags(&P.ev_up[k], cudaEventDisableTiming));
+    NSM_CUDA(c, cudaEventCreateWithFlags(&P.ev_elem[k], cudaEventDisableTiming));
+  }
+  P.n_chunks = C;
+  return NSM_OK;
+}
+
+// One explicit step on host-resident state, pipelined over node chunks (see build_host_pipe).  Same kernels and the same
+// per-node / per-element operation order as nsm_b200_step: the results are bit-identical (ORDERED) to the plain path.
+int
+step_host_pipelined(nsm_b200_ctx* c, double* time, double dt_user, double* displacement, double* velocity, double* acceleration,
+                    double* internal_force)
+{
+  auto&         P       = c->pipe;
+  const int     C       = P.n_chunks;
+  const bool    ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
+  const bool    has_bc  = c->n_bc > 0;
+  const bool    store   = (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP) != 0;
+  const double  t_prev  = *time;
+  const double  t       = t_prev + dt_user;
+  const double  dt      = t - t_prev, hdt = 0.5 * dt;
+  double* const host[4] = {displacement, velocity, acceleration, internal_force};
+  double* const* const dev[4] = {c->u, c->v, c->a, c->f};
+  if (store) {
+    int rc = ensure_ipt(c);
+    if (rc) return rc;
+  }
+  {
+    NvtxRange range("BC enforcement");
+    int rc = enqueue_bc_programs(c, 0);  // this step's magnitudes, before any chunk is integrated
+    if (rc) return rc;
+    NSM_CUDA(c, cudaEventRecord(P.ev_bc, c->stream));
+    NSM_CUDA(c, cudaStreamWaitEvent(P.up, P.ev_bc, 0));
+  }
+  roll_states(c);
+  int next_done = 0;  // node chunks [0, next_done) have been sent home
+  for (int k = 0; k < C; ++k) {
+    const int64_t  i0 = k ? P.node_end[k - 1] : 0, i1 = P.node_end[k], m = i1 - i0;
+    const unsigned grid = grid_for(m, 256);
+    {  // ---- up: u, v, a of the chunk, AoS -> SoA, first half of the step
+      NvtxRange range("Time Integration Scheme");
+      for (int f = 0; f < 3; ++f) {
+        NSM_CUDA(c, cudaMemcpyAsync(P.stage[f] + 3 * i0, host[f] + 3 * i0, (size_t)m * 3 * sizeof(double), cudaMemcpyHostToDevice, P.up));
+        aos_to_soa_range_kernel<<<grid, 256, 0, P.up>>>(i0, m, P.stage[f], dev[f][0], dev[f][1], dev[f][2]);
+      }
+      NodeArgs na   = node_args(c, 0);
+      na.node_begin = i0, na.n_nodes = i1;
+      if (has_bc) {
+        if (ordered)
+          node_predict_kernel<true, false><<<grid, 256, 0, P.up>>>(na, hdt, dt);
+        else
+          node_predict_kernel<true, true><<<grid, 256, 0, P.up>>>(na, hdt, dt);
+      } else {
+        if (ordered)
+          node_predict_kernel<false, false><<<grid, 256, 0, P.up>>>(na, hdt, dt);
+        else
+          node_predict_kernel<false, true><<<grid, 256, 0, P.up>>>(na, hdt, dt);
+      }
+      c->launches += 4;
+      NSM_CUDA(c, cudaEventRecord(P.ev_up[k], P.up));
+    }
+    {  // ---- elements whose nodes are all on the device now
+      NvtxRange range("Force calculation");
+      NSM_CUDA(c, cudaStreamWaitEvent(c->stream, P.ev_up[k], 0));
+      for (auto& kv : c->blocks) {
+        const std::vector<int>& up = P.up_end.at(kv.first);
+        int rc = enqueue_element_range(c, kv.second, store, k ? up[k - 1] : 0, up[k], c->stream);
+        if (rc) return rc;
+      }
+      NSM_CUDA(c, cudaEventRecord(P.ev_elem[k], c->stream));
+    }
+    {  // ---- down: the displacement of this chunk is final; so is everything of the chunks whose elements have all run
+      NvtxRange range("Time Integration Scheme");
+      NSM_CUDA(c, cudaStreamWaitEvent(P.down, P.ev_up[k], 0));
+      soa_to_aos_range_kernel<<<grid, 256, 0, P.down>>>(i0, m, c->u[0], c->u[1], c->u[2], P.stage[0]);
+      c->launches++;
+      NSM_CUDA(c, cudaMemcpyAsync(host[0] + 3 * i0, P.stage[0] + 3 * i0, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, P.down));
+      for (; next_done < C && P.done_after[next_done] <= k; ++next_done) {
+        const int64_t  j0 = next_done ? P.node_end[next_done - 1] : 0, j1 = P.node_end[next_done], mm = j1 - j0;
+        const unsigned g2 = grid_for(mm, 256);
+        NSM_CUDA(c, cudaStreamWaitEvent(P.down, P.ev_elem[k], 0));
+        NodeArgs na   = node_args(c, 0);
+        na.node_begin = j0, na.n_nodes = j1;
+        if (ordered) {
+          if (c->has_fext)
+            node_correct_kernel<true, true><<<g2, 256, 0, P.down>>>(na, hdt, 1);
+          else
+            node_correct_kernel<true, false><<<g2, 256, 0, P.down>>>(na, hdt, 1);
+        } else {
+          if (c->has_fext)
+            node_correct_kernel<false, true><<<g2, 256, 0, P.down>>>(na, hdt, 1);
+          else
+            node_correct_kernel<false, false><<<g2, 256, 0, P.down>>>(na, hdt, 1);
+        }
+        // internal force, velocity, acceleration of the finished chunk (staging rows of v and a are free again: their
+        // upload was consumed on the up stream before ev_up of the chunk)
+        const int fields[3] = {3, 1, 2};
+        for (int f : fields) {
+          soa_to_aos_range_kernel<<<g2, 256, 0, P.down>>>(j0, mm, dev[f][0], dev[f][1], dev[f][2], P.stage[f]);
+          NSM_CUDA(c, cudaMemcpyAsync(host[f] + 3 * j0, P.stage[f] + 3 * j0, (size_t)mm * 3 * sizeof(double), cudaMemcpyDeviceToHost, P.down));
+        }
+        c->launches += 4;
+      }
+    }
+    NSM_CUDA(c, cudaGetLastError());
+  }
+  mark_states_for_roll(c);
+  *time = t;
+  NSM_CUDA(c, cudaStreamSynchronize(P.down));
+  NSM_CUDA(c, cudaStreamSynchronize(P.up));
+  return check_flags(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+int
+nsm_b200_set_host_step_chunks(nsm_b200_ctx* c, int n_chunks)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, n_chunks >= -1 && n_chunks <= 4096, "set_host_step_chunks: chunk count out of range");
+  NSM_REQUIRE(c, !c->pipe.built, "set_host_step_chunks: call before the first nsm_b200_step_host");
+  c->pipe.requested_chunks = n_chunks;
+  return NSM_OK;
+}
+
 int
 nsm_b200_step_host(nsm_b200_ctx* c, double* time, double dt_user, double* displacement, double* velocity, double* acceleration,
                    double* internal_force)
@@ -1543,6 +1785,12 @@ nsm_b200_step_host(nsm_b200_ctx* c, double* time, double dt_user, double* displa
   NSM_ENTER(c);
   NSM_REQUIRE(c, c->finalized, "step_host: context not finalized");
   NSM_REQUIRE(c, time && displacement && velocity && acceleration && internal_force, "step_host: null argument");
+  if (!c->pipe.built) {
+    int rc = build_host_pipe(c);
+    if (rc) return rc;
+  }
+  if (c->pipe.n_chunks >= 2 && c->bc_rows <= 1 && !c->comm.active())
+    return step_host_pipelined(c, time, dt_user, displacement, velocity, acceleration, internal_force);
   const int64_t n = c->n_nodes;
   if (!c->io_stream) {
     int rc = dev_alloc(c, &c->staging_u, std::max<int64_t>(n * 3, 1));

@@ -592,8 +592,9 @@ def test_step_host_equals_upload_step_download():
         t = c.step(1, t, dt)
         u, v, a, f = (c.download(l) for l in ("displacement", "velocity", "acceleration", "internal_force"))
     c.close()
-    for pinned in (True, False):
+    for pinned, chunks in ((True, -1), (False, -1), (True, 2), (True, 7), (False, 64), (True, 100000)):
         c = make()
+        c.set_host_step_chunks(chunks)  # -1: automatic (this small mesh takes the plain schedule); else the pipeline
         if pinned:
             bufs = [capi.PinnedArray(ref.shape) for _ in range(4)]
             U, V, A, Fo = (b.array for b in bufs)
@@ -611,6 +612,65 @@ def test_step_host_equals_upload_step_download():
             for b in bufs:
                 b.free()
     assert np.abs(u).max() > 0
+
+
+@pytest.mark.parametrize("assembly", ["ordered", "atomic"])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_pipelined_step_host_two_blocks(oracle, assembly, shuffle):
+    """The pipelined nsm_b200_step_host (node chunks up / elements / finished chunks down, all overlapped) on a
+    two-block mesh (state-carrying block + neohookean, ragged), lattice-numbered and randomly numbered (no locality:
+    the dependency ranges collapse, the result must not): equal to upload + nsm_b200_step + download bit for bit in
+    ORDERED mode, within 1e-12 in ATOMIC mode, and equal to the oracle's force on the final displacement."""
+    from nimblesm_b200 import capi
+    from nimblesm_b200.mesh import structured_cube
+
+    n = 9
+    mesh = structured_cube(n, block_of_element=lambda i, j, k: np.where(k < 4, 1, 2))
+    ref = np.stack([mesh["x"], mesh["y"], mesh["z"]], 1)
+    conn = {b: mesh["conn"][b] for b in (1, 2)}
+    face = mesh["node_sets"][2]
+    if shuffle:
+        rng = np.random.default_rng(5)
+        perm = rng.permutation(len(ref))
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(ref))
+        ref = np.ascontiguousarray(ref[inv])
+        conn = {b: np.ascontiguousarray(perm[conn[b]][rng.permutation(len(conn[b]))].astype(np.int32)) for b in conn}
+        face = perm[face].astype(np.int32)
+    dt = 0.2 * (1.0 / n) / np.sqrt(K / RHO)
+    v0 = np.zeros_like(ref)
+    v0[:, 0] = 1000.0 * ref[:, 0]
+    asm = capi.ASSEMBLY_ORDERED if assembly == "ordered" else capi.ASSEMBLY_ATOMIC
+
+    def make(chunks):
+        c = capi.Context(0)
+        c.set_nodes(ref[:, 0].copy(), ref[:, 1].copy(), ref[:, 2].copy())
+        c.add_block(1, conn[1], "j2_plasticity", K, G, RHO, 5.0e8, 2.0e10)
+        c.add_block(2, conn[2], "neohookean", K, G, RHO)
+        c.finalize(asm, 2)
+        c.compute_lumped_mass()
+        c.set_bc_table(np.repeat(face, 3), np.tile(np.arange(3, dtype=np.int32), len(face)), np.zeros(3 * len(face), np.int32))
+        c.set_bc_values(np.zeros(3 * len(face)))
+        c.set_host_step_chunks(chunks)
+        return c
+
+    results = []
+    for chunks in (0, 5, 23):
+        c = make(chunks)
+        U, V, A, Fo = np.zeros_like(ref), v0.copy(), np.zeros_like(ref), np.zeros_like(ref)
+        t = 0.0
+        for _ in range(6):
+            t = c.step_host(t, dt, U, V, A, Fo)
+        results.append((t, U.copy(), V.copy(), A.copy(), Fo.copy(), c.element_data(1)))
+        c.close()
+    for r in results[1:]:
+        assert r[0] == results[0][0]
+        for got, want in zip(r[1:], results[0][1:]):
+            if assembly == "ordered":
+                assert np.array_equal(got.view(np.int64), want.view(np.int64))
+            else:
+                assert _rel(got, want) <= 1e-12
+    assert np.abs(results[0][1]).max() > 0 and results[0][5][:, :, 15].max() >= 0.0
 
 
 @pytest.mark.parametrize("flags", [4, 6, 8, 12, 14])
