@@ -127,6 +127,10 @@ int nsm_b200_finalize(nsm_b200_ctx* ctx, int assembly, unsigned flags);
 int64_t nsm_b200_num_nodes(const nsm_b200_ctx* ctx);
 int64_t nsm_b200_num_elements(const nsm_b200_ctx* ctx, int block_id); /* block_id < 0: all blocks */
 int64_t nsm_b200_device_bytes(const nsm_b200_ctx* ctx);               /* HBM held by the context  */
+/* The flags in force after nsm_b200_finalize: NSM_FLAG_CACHE_REF_JACOBIAN is dropped (the reference Jacobians are
+ * recomputed every step, same bits) when the 576 B/element cache would not leave room for the integration-point
+ * records of an output step beside what is already resident. */
+unsigned nsm_b200_effective_flags(const nsm_b200_ctx* ctx);
 
 /* ---- nodal fields (replaces ModelData::GetNodeData / UpdateWithNewVelocity / UpdateWithNewDisplacement
  *      host<->device deep copies, src/nimble_kokkos_model_data.cc:1730-1740,1282) ------------------ */

@@ -46,7 +46,7 @@ SYMBOLS = [
     "nsm_b200_material_state_label", "nsm_b200_material_state_initial_value", "nsm_b200_compute_stress_state",
     "nsm_b200_element_data_stride", "nsm_b200_update_states", "nsm_b200_get_element_data_previous",
     "nsm_b200_set_element_data", "nsm_b200_set_bc_entry_constants", "nsm_b200_comm_set_host_barrier",
-    "nsm_b200_set_host_step_chunks",
+    "nsm_b200_set_host_step_chunks", "nsm_b200_effective_flags",
 ]
 
 
@@ -136,6 +136,7 @@ def lib():
         "nsm_b200_set_bc_entry_constants": (i32, [vp, i32, i64, dp]),
         "nsm_b200_comm_set_host_barrier": (i32, [vp, vp, vp]),
         "nsm_b200_set_host_step_chunks": (i32, [vp, i32]),
+        "nsm_b200_effective_flags": (C.c_uint, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -241,6 +242,10 @@ class Context:
     @property
     def n_elements(self):
         return int(self._L.nsm_b200_num_elements(self._h, -1))
+
+    @property
+    def effective_flags(self):
+        return int(self._L.nsm_b200_effective_flags(self._h))
 
     @property
     def device_bytes(self):

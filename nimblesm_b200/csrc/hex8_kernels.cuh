@@ -62,7 +62,9 @@ struct ElemArgs
   double        mat_a, mat_b;  // material-specific parameters (j2_plasticity: yield stress, hardening modulus)
   double*       binv_cache;  // [n_groups][9][32] or nullptr, already offset to the block
   double        bulk, shear;
-  unsigned*     ticket;      // next unclaimed chunk of 4-element groups of this launch (zeroed by the host)
+  unsigned*     ticket;      // next unclaimed chunk of 4-element groups of this launch (zero when the launch starts)
+  unsigned*     ticket_next; // the counter of the NEXT launch on this stream: zeroed here, so that no memset node sits
+                             // between two element launches (counters alternate; launches of a context are stream-ordered)
   int           zero;        // always 0: keeps ptxas from proving the ticket address warp-uniform (see draw_ticket)
   // Element schedule of this launch (multi-GPU overlap, nsm_b200_step): kSchedAll walks every group;
   // kSchedList walks group_list[0 .. n_list) (the groups that touch a node shared with another rank, run first so
@@ -390,6 +392,7 @@ element_force_kernel(const ElemArgs p)
 
   ShapeAtPoint sh;
   sh.init(q);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.ticket_next = 0u;
 
   // Groups are claimed from a grid-wide ticket counter in chunks of kTicketChunk consecutive groups: warps of
   // one scheduler advance at different rates, and a static stride left the slow ones to finish alone

@@ -128,11 +128,13 @@ struct nsm_b200_ctx
   int     bcp_n_entry_consts = 0, bcp_entry_consts_needed = 0;
 
   int*                d_flags  = nullptr;
-  unsigned*        d_ticket = nullptr;  // element-kernel work counter
+  unsigned*        d_ticket = nullptr;  // element-kernel work counters [2]: launches alternate, each zeroes the other's
+  int              ticket_parity = 0;
   unsigned long long* d_min_dt = nullptr;
 
   int64_t launches     = 0;
   int64_t device_bytes = 0;
+  std::map<const void*, int64_t> alloc_bytes;  // what dev_alloc handed out, so that dev_release keeps device_bytes true
 
   // per-launch profiling (CUDA events on the stream)
   bool                     profiling = false;
@@ -222,7 +224,23 @@ dev_alloc(nsm_b200_ctx* c, T** p, int64_t count)
   if (count <= 0) count = 1;
   NSM_CUDA(c, cudaMalloc((void**)p, (size_t)count * sizeof(T)));
   c->device_bytes += count * (int64_t)sizeof(T);
+  c->alloc_bytes[*p] = count * (int64_t)sizeof(T);
   return NSM_OK;
+}
+
+// frees a dev_alloc buffer that is being replaced during the context's life (tables, per-step rows)
+template <class T>
+void
+dev_release(nsm_b200_ctx* c, T*& p)
+{
+  if (!p) return;
+  auto it = c->alloc_bytes.find(p);
+  if (it != c->alloc_bytes.end()) {
+    c->device_bytes -= it->second;
+    c->alloc_bytes.erase(it);
+  }
+  cudaFree(p);
+  p = nullptr;
 }
 
 inline unsigned
@@ -299,11 +317,8 @@ enqueue_bc_programs(nsm_b200_ctx* c, int64_t row)
 void
 free_bc_programs(nsm_b200_ctx* c)
 {
-  auto fr = [](auto*& p) {
-    if (p) cudaFree(p);
-    p = nullptr;
-  };
-  fr(c->bcp_offsets), fr(c->bcp_code), fr(c->bcp_consts), fr(c->bcp_of_entry), fr(c->bcp_slot_values), fr(c->bcp_entry_consts);
+  dev_release(c, c->bcp_offsets), dev_release(c, c->bcp_code), dev_release(c, c->bcp_consts), dev_release(c, c->bcp_of_entry);
+  dev_release(c, c->bcp_slot_values), dev_release(c, c->bcp_entry_consts);
   c->bcp_programs = c->bcp_slots = c->bcp_rows = c->bcp_rows_cap = 0;
   c->bcp_n_entry_consts = c->bcp_entry_consts_needed = 0;
 }
@@ -329,7 +344,8 @@ elem_args(nsm_b200_ctx* c, const Block& b, int sched = kSchedAll)
   p.bulk       = b.bulk;
   p.shear      = b.shear;
   p.flags      = c->d_flags;
-  p.ticket     = c->d_ticket;
+  p.ticket      = c->d_ticket + c->ticket_parity;  // (the launch sites flip the parity after each launch)
+  p.ticket_next = c->d_ticket + (c->ticket_parity ^ 1);
   return p;
 }
 
@@ -432,8 +448,8 @@ enqueue_element_range(nsm_b200_ctx* c, const Block& b, bool store_ipt, int g0, i
   int mode = (store_ipt ? kModeStoreIpt : 0) | (c->binv ? kModeReadBinv : 0);
   ElemArgs p    = elem_args(c, b, kSchedAll);
   p.group_begin = g0, p.n_range = g1 - g0;
-  NSM_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned), s));
   NSM_CUDA(c, launch_element_any(p, b.material, c->assembly == NSM_ASSEMBLY_ORDERED, mode, s));
+  c->ticket_parity ^= 1;
   c->launches++;
   return NSM_OK;
 }
@@ -475,8 +491,8 @@ enqueue_element_kernels(nsm_b200_ctx* c, bool store_ipt, int sched = kSchedAll)
   for (auto& kv : c->blocks) {
     const Block& b = kv.second;
     if (b.n_elem == 0 || (sched == kSchedList && b.n_list == 0)) continue;
-    NSM_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned), c->stream));
     NSM_CUDA(c, launch_element_any(elem_args(c, b, sched), b.material, ordered, mode, c->stream));
+    c->ticket_parity ^= 1;
     c->launches++;
   }
   return NSM_OK;
@@ -817,6 +833,11 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
   c->flags_   = flags;
   const int64_t n = c->n_nodes;
   int           rc;
+  {  // size limits first: nothing is allocated for a model this build cannot index
+    int64_t total = 0;
+    for (auto& kv : c->blocks) total += kv.second.n_elem;
+    NSM_REQUIRE(c, total * 8 < (int64_t)4294967295LL, "too many elements for 32-bit assembly slots on one GPU");
+  }
   for (int i = 0; i < 3; ++i) {
     if ((rc = dev_alloc(c, &c->X[i], n))) return rc;
     if ((rc = dev_alloc(c, &c->u[i], n))) return rc;
@@ -832,7 +853,8 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
   if ((rc = dev_alloc(c, &c->staging, n * 3))) return rc;
   if ((rc = dev_alloc(c, &c->d_flags, 2))) return rc;
   if ((rc = dev_alloc(c, &c->d_min_dt, 1))) return rc;
-  if ((rc = dev_alloc(c, &c->d_ticket, 1))) return rc;
+  if ((rc = dev_alloc(c, &c->d_ticket, 2))) return rc;
+  NSM_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, 2 * sizeof(unsigned), c->stream));
   NSM_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(int), c->stream));
   if ((flags & NSM_FLAG_RENUMBER_NODES) && n > 1) {
     // internal node order = Morton order of the coordinates (21 bits per axis of the bounding box); the caller's
@@ -933,7 +955,6 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
     }
   }
   c->n_elem_total = base;
-  NSM_REQUIRE(c, base * 8 < (int64_t)4294967295LL, "too many elements for 32-bit assembly slots on one GPU");
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   for (auto& kv : c->blocks) std::vector<int>().swap(kv.second.conn_host);
   std::vector<double>().swap(c->hx), std::vector<double>().swap(c->hy), std::vector<double>().swap(c->hz);
@@ -945,6 +966,17 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
     if ((rc = dev_alloc(c, &c->adj_off, n + 1))) return rc;
     if ((rc = dev_alloc(c, &c->adj_slot, c->n_elem_total * 8))) return rc;
     unsigned long long* counts = nullptr;
+    void*               tmp    = nullptr;
+    struct Scratch  // freed on every return path
+    {
+      unsigned long long*& a;
+      void*&               b;
+      ~Scratch()
+      {
+        if (a) cudaFree(a);
+        if (b) cudaFree(b);
+      }
+    } scratch{counts, tmp};
     NSM_CUDA(c, cudaMalloc((void**)&counts, (size_t)(n + 1) * sizeof(unsigned long long)));
     NSM_CUDA(c, cudaMemsetAsync(counts, 0, (size_t)(n + 1) * sizeof(unsigned long long), c->stream));
     for (auto& kv : c->blocks) {
@@ -953,7 +985,6 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
       adj_count_kernel<<<grid_for(b.n_elem * 8, 256), 256, 0, c->stream>>>(b.n_elem * 8, b.conn, counts);
       c->launches++;
     }
-    void*  tmp      = nullptr;
     size_t tmp_size = 0;
     NSM_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_size, (const long long*)counts, (long long*)c->adj_off,
                                                (int)(n + 1), c->stream));
@@ -975,8 +1006,6 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
     }
     NSM_CUDA(c, cudaStreamSynchronize(c->stream));
     NSM_CUDA(c, cudaGetLastError());
-    cudaFree(tmp);
-    cudaFree(counts);
   }
 
   for (auto& kv : c->blocks) {  // Block::InitializeElementData (src/nimble_block.cc:148-207): N and N+1 start alike
@@ -996,6 +1025,25 @@ nsm_b200_finalize(nsm_b200_ctx* c, int assembly, unsigned flags)
   c->finalized = true;
   if (flags & NSM_FLAG_STORE_IPT_EVERY_STEP) {
     if ((rc = ensure_ipt(c))) return rc;
+  }
+  if (flags & NSM_FLAG_CACHE_REF_JACOBIAN) {
+    int64_t n_groups = 0;
+    for (auto& kv : c->blocks) n_groups += groups_of(kv.second.n_elem);
+    // The cache is a bytes-for-flops trade (576 B per element for 16 % fewer FP64 instructions) and the FIRST thing to
+    // give way when memory is short: it must leave room for the integration-point records of an output step
+    // (960 B per element, allocated on first use) next to what is already resident -- e.g. the N / N+1 records of a
+    // material with state variables, 2 x 1088 B per element.  64 M elements: 36.9 GB cache + 61.4 GB records fit beside
+    // 14 GB of mesh and fields; with 139 GB of state records they do not, and the reference Jacobians are recomputed.
+    size_t free_b = 0, total_b = 0;
+    NSM_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    int64_t stateless = 0;
+    for (auto& kv : c->blocks) stateless += kv.second.n_state ? 0 : kv.second.n_elem;
+    const int64_t need    = n_groups * kBinvGroupDoubles * (int64_t)sizeof(double);
+    const int64_t reserve = (c->ipt ? 0 : stateless * 120 * (int64_t)sizeof(double)) + (int64_t)(total_b / 20);
+    if (need + reserve > (int64_t)free_b) {
+      flags &= ~(unsigned)NSM_FLAG_CACHE_REF_JACOBIAN;
+      c->flags_ = flags;
+    }
   }
   if (flags & NSM_FLAG_CACHE_REF_JACOBIAN) {
     int64_t n_groups = 0;
@@ -1037,6 +1085,12 @@ int64_t
 nsm_b200_device_bytes(const nsm_b200_ctx* c)
 {
   return c ? c->device_bytes : -1;
+}
+
+unsigned
+nsm_b200_effective_flags(const nsm_b200_ctx* c)
+{
+  return c ? c->flags_ : 0u;
 }
 
 int
@@ -1225,14 +1279,8 @@ nsm_b200_set_bc_table(nsm_b200_ctx* c, int64_t n, const int32_t* node, const int
   NSM_ENTER(c);
   NSM_REQUIRE(c, c->finalized, "set_bc_table: context not finalized");
   NSM_REQUIRE(c, n >= 0 && (n == 0 || (node && comp && kind)), "set_bc_table: bad arguments");
-  for (int i = 0; i < 3; ++i) {
-    if (c->bc_of_dof[i]) cudaFree(c->bc_of_dof[i]);
-    c->bc_of_dof[i] = nullptr;
-  }
-  if (c->bc_kind) cudaFree(c->bc_kind);
-  if (c->bc_value) cudaFree(c->bc_value);
-  if (c->bc_node) cudaFree(c->bc_node);
-  c->bc_kind = nullptr, c->bc_value = nullptr, c->bc_node = nullptr;
+  for (int i = 0; i < 3; ++i) dev_release(c, c->bc_of_dof[i]);
+  dev_release(c, c->bc_kind), dev_release(c, c->bc_value), dev_release(c, c->bc_node);
   free_bc_programs(c);
   c->n_bc = n;
   if (n == 0) return NSM_OK;
@@ -1288,8 +1336,7 @@ nsm_b200_set_bc_values_steps(nsm_b200_ctx* c, int n_rows, int64_t n, const doubl
   if (n == 0) return NSM_OK;
   if (n_rows > c->bc_rows_cap) {
     NSM_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->bc_value) cudaFree(c->bc_value);
-    c->bc_value = nullptr;
+    dev_release(c, c->bc_value);
     int rc      = dev_alloc(c, &c->bc_value, (int64_t)n_rows * n);
     if (rc) return rc;
     c->bc_rows_cap = n_rows;
@@ -1371,8 +1418,7 @@ nsm_b200_set_bc_entry_constants(nsm_b200_ctx* c, int n_constants, int64_t n_entr
   NSM_REQUIRE(c, c->bcp_programs > 0, "set_bc_entry_constants: no boundary-condition programs set");
   NSM_REQUIRE(c, n_constants >= 0 && n_entries == c->n_bc && (n_constants == 0 || values), "set_bc_entry_constants: bad arguments");
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->bcp_entry_consts) cudaFree(c->bcp_entry_consts);
-  c->bcp_entry_consts   = nullptr;
+  dev_release(c, c->bcp_entry_consts);
   c->bcp_n_entry_consts = 0;
   if (n_constants == 0) return NSM_OK;
   int rc = dev_alloc(c, &c->bcp_entry_consts, (int64_t)n_constants * n_entries);
@@ -1396,8 +1442,7 @@ nsm_b200_set_bc_slots_steps(nsm_b200_ctx* c, int n_rows, int n_slots, const doub
   }
   if (n_rows > c->bcp_rows_cap) {
     NSM_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->bcp_slot_values) cudaFree(c->bcp_slot_values);
-    c->bcp_slot_values = nullptr;
+    dev_release(c, c->bcp_slot_values);
     int rc             = dev_alloc(c, &c->bcp_slot_values, (int64_t)n_rows * n_slots);
     if (rc) return rc;
     c->bcp_rows_cap = n_rows;
