@@ -469,6 +469,10 @@ element_force_kernel(const ElemArgs p)
     if (has_next) stage_gather(p, wsm + (stage ^ 1) * kStageDoubles, sN[slot_next * 32], q, ew);
     stage_group_node(p, sN + slot_nn * 32, g_nn, n_groups, ew, q);
     cp_async_commit();
+#ifdef NSM_BINV_PREFETCH_L1  // A/B: instances that load the cached b^-1 directly (elastic) pull the NEXT group's rows into L1
+    if ((MODE & kModeReadBinv) && !BinvStaged<MAT, MODE>::value && has_next && lane < (kBinvGroupDoubles * 8) / 128)
+      prefetch_l1(p.binv_cache + (int64_t)g_next * kBinvGroupDoubles + lane * 16);
+#endif
 #ifdef NSM_BINV_PREFETCH  // measured (r01y): the L2 prefetch a pass ahead of the copy costs 0.5 % instead of helping
     if ((MODE & kModeReadBinv) && g_nn < n_groups && lane < (kBinvGroupDoubles * 8) / 128)
       prefetch_l2(p.binv_cache + (int64_t)g_nn * kBinvGroupDoubles + lane * 16);  // DRAM -> L2 a full pass before the cp.async

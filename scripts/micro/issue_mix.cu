@@ -6,6 +6,7 @@
 // profiles/r01A_ncu_elem_neo_f2_summary.txt), run at the element kernel's occupancy (2 CTAs x 8 warps per SM =
 // 4 warps per scheduler).  Reported: scheduler cycles per loop body per warp = elapsed SM cycles / iterations /
 // (warps per scheduler).
+// (clock64 from the block's start to the finish of its LAST warp; the CUDA-event time of the launch is printed beside it.)
 //   issue-port model  : 2*NDP + NOTHER          (DP blocks the port for both cycles)
 //   pipe-only model   : max(2*NDP, NDP + NOTHER) (the second cycle of a DP issue is free for another warp's non-DP)
 // Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o issue_mix issue_mix.cu ; run: ./issue_mix
@@ -87,8 +88,10 @@ template <int NDP, int NOTHER, int KIND>
 __global__ void __launch_bounds__(256, 2)
 mix_kernel(double* out, long long* cycles, int iters, double m, double c, unsigned k)
 {
-  __shared__ unsigned sm[256];
+  __shared__ unsigned           sm[256];
+  __shared__ unsigned long long t_end;  // the LAST warp's finish time: warps of one scheduler do not advance in step
   sm[threadIdx.x] = threadIdx.x * k;
+  if (threadIdx.x == 0) t_end = 0ull;
   __syncthreads();
   double   x[8];
   unsigned y[8];
@@ -99,11 +102,13 @@ mix_kernel(double* out, long long* cycles, int iters, double m, double c, unsign
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) Body<NDP, NOTHER, KIND, 0, NDP + NOTHER>::run(x, y, z, m, c, k, sm);
   const long long t1 = clock64();
+  if ((threadIdx.x & 31) == 0) atomicMax(&t_end, (unsigned long long)t1);
+  __syncthreads();
   double s = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += x[i] + (double)y[i] + (double)z[i];
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
-  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = (long long)t_end - t0;
 }
 
 template <int NDP, int NOTHER, int KIND>
