@@ -339,6 +339,10 @@ int nsm_b200_profile_read(nsm_b200_ctx* ctx, double* elem_kernel_ms_avg, double*
 int64_t nsm_b200_cold_points(nsm_b200_ctx* ctx);
 /* FP64 pipe micro-benchmark: sustained DADD+DMUL (no FMA) and DFMA issue rates in 1e12 lane-ops/s. */
 int nsm_b200_fp64_peak(nsm_b200_ctx* ctx, double* dadd_dmul_tops, double* dfma_tops);
+/* The same DADD+DMUL stream back to back for `seconds` (<= 30): the rate of the last quarter, i.e. what an FP64-bound
+ * run of that length can sustain once power capping has settled the SM clock (the burst figure above is the
+ * denominator for a kernel timed alone, this one for a kernel timed inside a long run). */
+int nsm_b200_fp64_peak_sustained(nsm_b200_ctx* ctx, double seconds, double* dadd_dmul_tops);
 
 /* Build-time description of the element kernels of THIS binary (JSON text): for every element_force_kernel
  * instance the static instruction mix of one warp pass over 4 elements, read off the SASS of the object the

@@ -46,7 +46,7 @@ SYMBOLS = [
     "nsm_b200_material_state_label", "nsm_b200_material_state_initial_value", "nsm_b200_compute_stress_state",
     "nsm_b200_element_data_stride", "nsm_b200_update_states", "nsm_b200_get_element_data_previous",
     "nsm_b200_set_element_data", "nsm_b200_set_bc_entry_constants", "nsm_b200_comm_set_host_barrier",
-    "nsm_b200_set_host_step_chunks", "nsm_b200_effective_flags",
+    "nsm_b200_set_host_step_chunks", "nsm_b200_effective_flags", "nsm_b200_fp64_peak_sustained",
 ]
 
 
@@ -137,6 +137,7 @@ def lib():
         "nsm_b200_comm_set_host_barrier": (i32, [vp, vp, vp]),
         "nsm_b200_set_host_step_chunks": (i32, [vp, i32]),
         "nsm_b200_effective_flags": (C.c_uint, [vp]),
+        "nsm_b200_fp64_peak_sustained": (i32, [vp, dbl, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -451,6 +452,16 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._ck(self._L.nsm_b200_fp64_peak(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+def _fp64_peak_sustained(self, seconds=2.0):
+    """DADD+DMUL rate of the last quarter of `seconds` of back-to-back launches (1e12 lane-ops/s)"""
+    a = C.c_double()
+    self._ck(self._L.nsm_b200_fp64_peak_sustained(self._h, float(seconds), C.byref(a)))
+    return a.value
+
+
+Context.fp64_peak_sustained = _fp64_peak_sustained
 
 
 def version() -> str:

@@ -2238,4 +2238,42 @@ nsm_b200_fp64_peak(nsm_b200_ctx* c, double* dadd_dmul_tops, double* dfma_tops)
   return NSM_OK;
 }
 
+int
+nsm_b200_fp64_peak_sustained(nsm_b200_ctx* c, double seconds, double* dadd_dmul_tops)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, seconds > 0.0 && seconds <= 30.0 && dadd_dmul_tops, "fp64_peak_sustained: bad arguments");
+  cudaDeviceProp prop;
+  NSM_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double*   out = nullptr;
+  NSM_CUDA(c, cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  // back-to-back launches for `seconds`; the rate of the last quarter is what a long FP64-bound run can sustain
+  // (power capping lowers the SM clock after the first few hundred milliseconds)
+  std::vector<float> ms;
+  double             elapsed = 0.0;
+  while (elapsed < seconds * 1e3) {
+    cudaEventRecord(e0, c->stream);
+    for (int k = 0; k < 4; ++k) fp64_peak_kernel<false><<<blocks, threads, 0, c->stream>>>(out, iters, 1.0);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    ms.push_back(t / 4.0f);
+    elapsed += t;
+    c->launches += 4;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  cudaFree(out);
+  NSM_CUDA(c, cudaGetLastError());
+  double sum = 0.0;
+  size_t n0  = ms.size() - std::max<size_t>(ms.size() / 4, 1);
+  for (size_t i = n0; i < ms.size(); ++i) sum += ms[i];
+  const double avg = sum / (double)(ms.size() - n0);
+  *dadd_dmul_tops  = (double)blocks * threads * (double)iters * 8.0 / (avg * 1e-3) / 1e12;
+  return NSM_OK;
+}
+
 }  // extern "C"
