@@ -245,6 +245,44 @@ def dram_traffic(kernel_key, source_sha, n_elem):
                                                  "element" % (rec.get("report", "profiles/"), e.get("elements")))
 
 
+def copy_ceiling(device, world, dist, nbytes):
+    """All ranks at once, pinned host memory, no compute: one-way H2D, one-way D2H, and both directions together
+    (two streams).  Aggregate GB/s over the ranks = what bounds `e2e` on this box however the step is scheduled."""
+    import torch
+
+    torch.cuda.set_device(device)
+    h_up, h_dn = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_up, d_dn = torch.empty(nbytes, dtype=torch.uint8, device="cuda"), torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up, down, reps=3):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s_up):
+                    d_up.copy_(h_up, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_dn):
+                    h_dn.copy_(d_dn, non_blocking=True)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return (int(up) + int(down)) * nbytes * reps * world / dt / 1e9
+
+    run(True, True, 1)
+    return {"bytes_per_copy": nbytes, "h2d_only_gbs_all_ranks": run(True, False), "d2h_only_gbs_all_ranks": run(False, True),
+            "both_directions_gbs_all_ranks": run(True, True),
+            "what": "pinned-memory copies by every rank at the same time, nothing else running"}
+
+
 def parity_check(c, mesh, args, n, grid, pos, rank, world, dist):
     """CHECKER, after every timed region (the oracle is test infrastructure; nothing timed goes through it).
     (1) N > 1: every replica of every shared node carries bit-identical u, v, f_int on all its holders (the
@@ -362,6 +400,9 @@ def main():
                     help="random node numbering and element order (an unstructured mesh's worst case for gather locality)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs next to its GPU")
+    ap.add_argument("--copy-ceiling", action="store_true",
+                    help="also measure what the box's host<->device path sustains with all ranks copying at once (no compute): "
+                         "the ceiling of the end-to-end figure")
     ap.add_argument("--host-chunks", type=int, default=-1, help="node chunks of the pipelined nsm_b200_step_host (-1 auto, 0 off)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run oracle / replica check")
@@ -522,6 +563,8 @@ def main():
                        "clock, max over ranks"}
         for p_ in pin.values():
             p_.free()
+        if args.copy_ceiling:
+            e2e["copy_ceiling"] = copy_ceiling(local_rank, world, dist, int(24 * n_nodes))
 
     # ---- parity of what was just timed (checker; all ranks take part, rank 0 reports) ------------------
     parity = None

@@ -211,7 +211,7 @@ __device__ __forceinline__ unsigned
 integration_point(const ShapeAtPoint& sh, const double* sX, const double* sK, const double* sC, int ew, int lane,
                   const double* binv_row, double* binv_slot, const double* binv_next, double bulk, double shear,
                   double* share, double (&F)[9], double (&sig)[6], const double* rec_n = nullptr, double mat_a = 0.0,
-                  double mat_b = 0.0, double* state_out = nullptr)
+                  double mat_b = 0.0, double* state_out = nullptr, const double* rec_staged = nullptr)
 {
   unsigned bad = 0u, jac = 0u;
   double   a[3][3], binv[3][3];
@@ -277,15 +277,24 @@ integration_point(const ShapeAtPoint& sh, const double* sX, const double* sK, co
   } else if (MAT == 1) {
     stress_neohookean<FAST>(bulk, shear, F, sig, bad);
   } else {
-    // history-dependent material: F_n, sigma_n, state_n of this point from the previous record (the lines were
-    // prefetched into L1 at the top of the pass); lanes beyond the block's last element see a virgin point
-    double Fn[9], sn[6], stn[kMaxStateVars], st[kMaxStateVars];
+    // history-dependent material: F_n, sigma_n, state_n of this point from the previous record.  FAST: the warp's
+    // four records were copied into the (still unused) share buffer by coalesced cp.async at the top of the pass --
+    // the copy group before the gather's, hence wait_group 1; the IEEE redo reads the record itself (the fast pass has
+    // overwritten the buffer with its shares).  Lanes beyond the block's last element see a virgin point.
+    double        Fn[9], sn[6], stn[kMaxStateVars], st[kMaxStateVars];
+    const double* rec = rec_n;
+    if (FAST) {
+      cp_async_wait<1>();
+      __syncwarp();
+      if (rec_n) rec = rec_staged;
+    }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Fn[i] = rec_n ? rec_n[i] : (i < 3 ? 1.0 : 0.0);
+    for (int i = 0; i < 9; ++i) Fn[i] = rec ? rec[i] : (i < 3 ? 1.0 : 0.0);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) sn[i] = rec_n ? rec_n[9 + i] : 0.0;
+    for (int i = 0; i < 6; ++i) sn[i] = rec ? rec[9 + i] : 0.0;
 #pragma unroll
-    for (int i = 0; i < kMaxStateVars; ++i) stn[i] = rec_n ? rec_n[15 + i] : 0.0;
+    for (int i = 0; i < kMaxStateVars; ++i) stn[i] = rec ? rec[15 + i] : 0.0;
+    if (FAST) __syncwarp();  // every lane holds its record before any lane's shares overwrite the buffer
     stress_j2<FAST>(bulk, shear, mat_a, mat_b, Fn, F, sn, stn, sig, st, bad);
 #pragma unroll
     for (int i = 0; i < kMaxStateVars; ++i) state_out[i] = st[i];
@@ -466,6 +475,25 @@ element_force_kernel(const ElemArgs p)
     __syncwarp();
     const bool has_next  = g_next < n_groups;
     const int  slot_next = slot == 2 ? 0 : slot + 1, slot_nn = slot == 0 ? 2 : slot - 1;
+    // element data (F / sigma / state, ORDERED forces) live in FILE order: looked up where it is used, so that the
+    // index does not occupy registers through the pass
+    auto file_element = [&]() -> int64_t {
+      const int64_t e_sched = (int64_t)g * kElemsPerWarp + ew;
+      return p.orig ? (int64_t)__ldg(p.orig + e_sched) : e_sched;
+    };
+    constexpr int kRecord = 15 + MaterialState<MAT>::n;  // doubles per integration point (src/nimble_block.cc:84-108)
+    const double* rec_n = nullptr;
+    if (MaterialState<MAT>::n > 0) {
+      // previous records of the warp's four elements -> share buffer (free until the shares are stored): the 8 lanes of
+      // an element copy its 8 x kRecord contiguous doubles row by row, so every request is a full 64-byte run
+      if (sN[slot * 32] >= 0) {
+        const double* src = p.ipt_n + file_element() * (8 * kRecord);
+        rec_n             = src + q * kRecord;
+#pragma unroll
+        for (int i = 0; i < kRecord; ++i) cp_async8(share + ew * (8 * kRecord) + i * 8 + q, src + i * 8 + q);
+      }
+      cp_async_commit();
+    }
     if (has_next) stage_gather(p, wsm + (stage ^ 1) * kStageDoubles, sN[slot_next * 32], q, ew);
     stage_group_node(p, sN + slot_nn * 32, g_nn, n_groups, ew, q);
     cp_async_commit();
@@ -505,24 +533,10 @@ element_force_kernel(const ElemArgs p)
     const bool jacobians_differ = __any_sync(0xffffffffu, differs);
     __syncwarp();
 
-    // element data (F / sigma / state, ORDERED forces) live in FILE order: looked up where it is used, so that the
-    // index does not occupy registers through the pass
-    auto file_element = [&]() -> int64_t {
-      const int64_t e_sched = (int64_t)g * kElemsPerWarp + ew;
-      return p.orig ? (int64_t)__ldg(p.orig + e_sched) : e_sched;
-    };
-    constexpr int kRecord = 15 + MaterialState<MAT>::n;  // doubles per integration point (src/nimble_block.cc:84-108)
-    const double* rec_n = nullptr;
-    if (MaterialState<MAT>::n > 0 && sN[slot * 32] >= 0) {
-      rec_n = p.ipt_n + (file_element() * 8 + q) * kRecord;
-      prefetch_l1(rec_n);  // 136 bytes per point: both lines are in L1 by the time F is formed
-      prefetch_l1(rec_n + kRecord - 1);
-    }
-
     double   F[9], sig[6], state[kMaxStateVars];
     // (the fast pass always runs: it also refills the b^-1 staging slots and closes their copy group)
     unsigned st = integration_point<MAT, MODE, true>(sh, sX, sK, sC, ew, lane, binv_row, sB, binv_next, p.bulk, p.shear,
-                                                     share, F, sig, rec_n, p.mat_a, p.mat_b, state);
+                                                     share, F, sig, rec_n, p.mat_a, p.mat_b, state, share + lane * kRecord);
     if (jacobians_differ) st |= 1u;
 #ifdef NSM_LAZY_SC
     if (__any_sync(0xffffffffu, (st & 1u) != 0u)) {  // some lane goes cold: every lane files its node's coordinates
@@ -541,7 +555,7 @@ element_force_kernel(const ElemArgs p)
     const bool live = node >= 0;
     if (live && (st & 2u)) atomicOr(p.flags, 1);
 
-    if ((MODE & kModeStoreIpt) && live) {
+    if ((MODE & kModeStoreIpt) && MaterialState<MAT>::n == 0 && live) {  // (records of a material with state: below)
       double* d = p.ipt + (file_element() * 8 + q) * kRecord;
 #pragma unroll
       for (int i = 0; i < 9; ++i) d[i] = F[i];
@@ -569,6 +583,24 @@ element_force_kernel(const ElemArgs p)
         atomicAdd(p.f[0] + node, fx);
         atomicAdd(p.f[1] + node, fy);
         atomicAdd(p.f[2] + node, fz);
+      }
+    }
+    if (MaterialState<MAT>::n > 0) {
+      // the new records leave the way the old ones came: through the share buffer (the shares have been summed), as
+      // 64-byte runs per element row instead of 8-byte stores 136 bytes apart
+      __syncwarp();
+      double* rs = share + lane * kRecord;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) rs[i] = F[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rs[9 + i] = sig[i];
+#pragma unroll
+      for (int i = 0; i < MaterialState<MAT>::n; ++i) rs[15 + i] = state[i];
+      __syncwarp();
+      if (live) {
+        double* dst = p.ipt + file_element() * (8 * kRecord);
+#pragma unroll
+        for (int i = 0; i < kRecord; ++i) dst[i * 8 + q] = share[ew * (8 * kRecord) + i * 8 + q];
       }
     }
     // roll the pipeline
