@@ -112,13 +112,14 @@ struct UnpackArgs
   const int64_t* src;      // ascending holder rank; -1 = this rank's own partial, else receive entry index
   const double*  recv;     // my receive data of this parity
   double*        f[3];
+  const int*     err;      // set by a wait that timed out: the receive data is stale, leave the partial sums alone
 };
 
 __global__ void __launch_bounds__(256)
 comm_unpack_kernel(const UnpackArgs p)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_shared) return;
+  if (i >= p.n_shared || *p.err != 0) return;
   const int nd = p.node[i];
   for (int c = 0; c < p.ncomp; ++c) {
     double  s     = 0.0;
@@ -324,6 +325,7 @@ class PeerExchange
     u.recv = (const double*)((unsigned char*)buf_ + kFlagWords * sizeof(unsigned long long)) +
              (int64_t)parity * std::max<int64_t>(total_, 1) * kCommComps;
     for (int c = 0; c < 3; ++c) u.f[c] = c < ncomp ? f[c] : nullptr;
+    u.err = d_err_;
     if (n_shared_ > 0) comm_unpack_kernel<<<(unsigned)((n_shared_ + 255) / 256), 256, 0, stream>>>(u);
     if (launches) *launches += 2;
     if (cudaGetLastError() != cudaSuccess) return set_err("peer exchange kernel launch failed");

@@ -731,3 +731,28 @@ def test_reordered_schedule_is_invisible(oracle, flags):
             us.append((c.download("displacement"), c.download("velocity")))
     assert _rel(us[1][0], us[0][0]) <= 1e-12 and _rel(us[1][1], us[0][1]) <= 1e-12
     assert np.abs(us[1][0]).max() > 0 and np.all(us[1][0][face] == 0.0)  # the clamped face never moved
+
+
+def test_kernel_info_and_measurement_helpers():
+    """nsm_b200_kernel_info describes the kernels of the running binary (the FP64 figures bench.py reports come from it),
+    the FP64 peak helpers return plausible B200 rates, and the small control entry points validate their arguments."""
+    from nimblesm_b200 import capi
+
+    info = capi.kernel_info()
+    assert len(info["source_sha"]) == 16
+    # the reference's operation sequence, counted per warp pass over 4 elements (x 8 = lane-instructions per element)
+    assert info["kernels"]["mat1_ordered0_mode2"]["dp"] == 1121 and info["kernels"]["mat1_ordered0_mode0"]["dp"] == 1330
+    assert info["kernels"]["mat0_ordered0_mode2"]["dp"] == 539 and info["kernels"]["mat0_ordered0_mode0"]["dp"] == 748
+    for k, v in info["kernels"].items():
+        assert v["dp_lane_instr_per_element"] == 8 * v["dp"] and v["reg"] <= 128, k
+    mesh, ref, _ = perturbed_cube(4, 0.0)
+    with _ctx(mesh, "elastic", capi.ASSEMBLY_ATOMIC, 2) as c:
+        assert c.effective_flags == 2
+        dadd, dfma = c.fp64_peak()
+        sustained = c.fp64_peak_sustained(0.3)
+        assert 10.0 < dadd < 25.0 and 10.0 < dfma < 25.0 and 10.0 < sustained <= 1.05 * dadd
+        c.comm_set_timeout(5.0)
+        with pytest.raises(capi.NsmError):
+            c.comm_set_timeout(0.0)
+        with pytest.raises(capi.NsmError):
+            c.set_host_step_chunks(100000)
