@@ -561,6 +561,23 @@ def main():
                "what": "per step: nsm_b200_step_host on pinned host [n][3] views = upload u,v,a, one explicit step, download "
                        "u,v,a,f_int, pipelined over node chunks (upload, element kernels and download overlap); host wall "
                        "clock, max over ranks"}
+        # second figure: the reference's own crossing pattern.  Its Kokkos path keeps the integrator's axpys on the host
+        # and crosses once per step at ModelData::ComputeInternalForce (displacement up, internal force down;
+        # src/nimble_kokkos_model_data.cc:1730-1740, 1282) -- here nsm_b200_internal_force_host on the same pinned views,
+        # pipelined over node chunks.  The host-side axpys of that sequence are the caller's and are not timed.
+        if world == 1:
+            c.internal_force_host(pin["u"].array, out=pin["f"].array)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                c.internal_force_host(pin["u"].array, out=pin["f"].array)
+            barrier()
+            dt_seam = time.perf_counter() - t0
+            e2e["force_seam"] = {"value": total_elems * k_e2e / dt_seam, "unit": "element-updates/s", "ms_per_call": dt_seam / k_e2e * 1e3,
+                                 "h2d_bytes_per_step": int(24 * n_nodes), "d2h_bytes_per_step": int(24 * n_nodes),
+                                 "what": "per step: nsm_b200_internal_force_host = ModelData::ComputeInternalForce on pinned host "
+                                         "views (u up, f_int down, pipelined); the integrator's nodal updates stay with the caller, "
+                                         "as in the reference's Kokkos sequence"}
         for p_ in pin.values():
             p_.free()
         if args.copy_ceiling:

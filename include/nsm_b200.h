@@ -157,7 +157,12 @@ int nsm_b200_compute_lumped_mass(nsm_b200_ctx* ctx, double* critical_dt);
  * writes F/sigma of every integration point (is_output_step of the reference). */
 int nsm_b200_internal_force(nsm_b200_ctx* ctx, int store_ipt);
 /* Same through host views: uploads displacement [n][3], computes, downloads internal_force [n][3]
- * (the exact shape of the reference call with Viewify<2> arguments). */
+ * (the exact shape of the reference call with Viewify<2> arguments, src/nimble_model_data_base.h:208-215; the
+ * reference's Kokkos path crosses here every step: deep_copy of displacement and velocity up, internal force down,
+ * src/nimble_kokkos_model_data.cc:1730-1740, 1282).  PIPELINED over the node chunks of nsm_b200_step_host
+ * (nsm_b200_set_host_step_chunks): chunk k of the displacement travels up while the elements below it run and the
+ * force of every node chunk whose elements have all run travels down; same kernels, same bits as the plain schedule.
+ * Contexts with a peer exchange or an internal node renumbering take the plain schedule. */
 int nsm_b200_internal_force_host(nsm_b200_ctx* ctx, const double* displacement, double* internal_force,
                                  int store_ipt);
 

@@ -1197,18 +1197,6 @@ nsm_b200_internal_force(nsm_b200_ctx* c, int store_ipt)
 }
 
 int
-nsm_b200_internal_force_host(nsm_b200_ctx* c, const double* displacement, double* internal_force, int store_ipt)
-{
-  int rc = upload_field(c, NSM_FIELD_DISPLACEMENT, displacement, false);
-  if (rc) return rc;
-  rc = enqueue_internal_force(c, store_ipt != 0 || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP));
-  if (rc) return rc;
-  rc = download_field(c, NSM_FIELD_INTERNAL_FORCE, internal_force, false);
-  if (rc) return rc;
-  return check_flags(c);
-}
-
-int
 nsm_b200_compute_stress(nsm_b200_ctx* c, int material_kind, double bulk, double shear, int64_t n_points,
                         const double* def_grad, double* stress)
 {
@@ -1809,9 +1797,91 @@ step_host_pipelined(nsm_b200_ctx* c, double* time, double dt_user, double* displ
   return check_flags(c);
 }
 
+// ModelData::ComputeInternalForce on host views (displacement in, internal force out), pipelined over the same node
+// chunks: chunk k of u travels up while the elements below it run, and the force of every node chunk whose elements have
+// all run travels down while later chunks are still on their way up.  Same element kernels and (ORDERED) the same nodal
+// summation as nsm_b200_internal_force, hence the same bits.
+int
+internal_force_host_pipelined(nsm_b200_ctx* c, const double* displacement, double* internal_force, bool store)
+{
+  auto&      P       = c->pipe;
+  const int  C       = P.n_chunks;
+  const bool ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
+  if (store) {
+    int rc = ensure_ipt(c);
+    if (rc) return rc;
+  }
+  roll_states(c);
+  NvtxRange range("Force calculation");
+  // whatever the caller queued on the context stream (uploads, an earlier step) comes first
+  NSM_CUDA(c, cudaEventRecord(P.ev_bc, c->stream));
+  NSM_CUDA(c, cudaStreamWaitEvent(P.up, P.ev_bc, 0));
+  NSM_CUDA(c, cudaStreamWaitEvent(P.down, P.ev_bc, 0));
+  int next_done = 0;
+  for (int k = 0; k < C; ++k) {
+    const int64_t  i0 = k ? P.node_end[k - 1] : 0, i1 = P.node_end[k], m = i1 - i0;
+    const unsigned grid = grid_for(m, 256);
+    NSM_CUDA(c, cudaMemcpyAsync(P.stage[0] + 3 * i0, displacement + 3 * i0, (size_t)m * 3 * sizeof(double), cudaMemcpyHostToDevice, P.up));
+    aos_to_soa_range_kernel<<<grid, 256, 0, P.up>>>(i0, m, P.stage[0], c->u[0], c->u[1], c->u[2]);
+    c->launches++;
+    if (!ordered)  // the atomic assembly adds into a cleared force
+      for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->f[i] + i0, 0, (size_t)m * sizeof(double), P.up));
+    NSM_CUDA(c, cudaEventRecord(P.ev_up[k], P.up));
+    NSM_CUDA(c, cudaStreamWaitEvent(c->stream, P.ev_up[k], 0));
+    for (auto& kv : c->blocks) {
+      const std::vector<int>& up = P.up_end.at(kv.first);
+      int rc = enqueue_element_range(c, kv.second, store, k ? up[k - 1] : 0, up[k], c->stream);
+      if (rc) return rc;
+    }
+    NSM_CUDA(c, cudaEventRecord(P.ev_elem[k], c->stream));
+    for (; next_done < C && P.done_after[next_done] <= k; ++next_done) {
+      const int64_t  j0 = next_done ? P.node_end[next_done - 1] : 0, j1 = P.node_end[next_done], mm = j1 - j0;
+      const unsigned g2 = grid_for(mm, 256);
+      NSM_CUDA(c, cudaStreamWaitEvent(P.down, P.ev_elem[k], 0));
+      if (ordered) {
+        NodeArgs na   = node_args(c, 0);
+        na.node_begin = j0, na.n_nodes = j1;
+        node_correct_kernel<true, false><<<g2, 256, 0, P.down>>>(na, 0.0, 0);
+        c->launches++;
+      }
+      soa_to_aos_range_kernel<<<g2, 256, 0, P.down>>>(j0, mm, c->f[0], c->f[1], c->f[2], P.stage[3]);
+      c->launches++;
+      NSM_CUDA(c, cudaMemcpyAsync(internal_force + 3 * j0, P.stage[3] + 3 * j0, (size_t)mm * 3 * sizeof(double), cudaMemcpyDeviceToHost, P.down));
+    }
+    NSM_CUDA(c, cudaGetLastError());
+  }
+  // later work on the context stream sees the complete force field
+  NSM_CUDA(c, cudaEventRecord(P.ev_bc, P.down));
+  NSM_CUDA(c, cudaStreamWaitEvent(c->stream, P.ev_bc, 0));
+  NSM_CUDA(c, cudaStreamSynchronize(P.down));
+  NSM_CUDA(c, cudaStreamSynchronize(P.up));
+  return check_flags(c);
+}
+
 }  // namespace
 
 extern "C" {
+
+int
+nsm_b200_internal_force_host(nsm_b200_ctx* c, const double* displacement, double* internal_force, int store_ipt)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "internal_force_host: context not finalized");
+  NSM_REQUIRE(c, displacement && internal_force, "internal_force_host: null argument");
+  const bool store = store_ipt != 0 || (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP);
+  if (!c->pipe.built) {
+    int rc = build_host_pipe(c);
+    if (rc) return rc;
+  }
+  if (c->pipe.n_chunks >= 2 && !c->comm.active()) return internal_force_host_pipelined(c, displacement, internal_force, store);
+  int rc = upload_field(c, NSM_FIELD_DISPLACEMENT, displacement, false);
+  if (rc) return rc;
+  rc = enqueue_internal_force(c, store);
+  if (rc) return rc;
+  rc = download_field(c, NSM_FIELD_INTERNAL_FORCE, internal_force, false);
+  if (rc) return rc;
+  return check_flags(c);
+}
 
 int
 nsm_b200_set_host_step_chunks(nsm_b200_ctx* c, int n_chunks)
