@@ -52,6 +52,7 @@ class Deck:
     materials: dict = field(default_factory=dict)  # key -> Material
     blocks: dict = field(default_factory=dict)  # block id -> material key
     boundary_conditions: list = field(default_factory=list)
+    contact_string: str = ""  # `contact:` line (src/nimble_parser.cc: contact_string_); empty = no contact
 
     def block_material(self, block_id: int) -> Material:
         return self.materials[self.blocks[block_id]]
@@ -136,4 +137,6 @@ def parse_deck(text: str) -> Deck:
             d.blocks[int(bname.rsplit("_", 1)[1])] = mk.strip()
         elif key == "boundary condition":
             d.boundary_conditions.append(parse_boundary_condition(value))
+        elif key == "contact":
+            d.contact_string = value
     return d

@@ -12,6 +12,7 @@ import numpy as np
 from nimblesm_b200.deck import parse_deck
 from nimblesm_b200.model import IPT_F_LABELS, IPT_S_LABELS, eval_expression
 
+from . import contact as contact_oracle
 from . import hex8
 
 
@@ -26,6 +27,12 @@ class OracleModel:
         self.mass = np.zeros(n)
         self.elem = {b: None for b in mesh["block_ids"]}
         self.snapshots = []
+        # penalty contact (explicit_time_integrator.cc:76-92): block names of the `contact:` line -> entities
+        self.contact, self.fcontact, self.contact_pairs = None, np.zeros((n, 3)), 0
+        if getattr(self.deck, "contact_string", ""):
+            prim, sec, penalty = contact_oracle.parse_contact_command(self.deck.contact_string)
+            ids = lambda names: [int(nm.rsplit("_", 1)[1]) for nm in names]
+            self.contact = contact_oracle.ContactSetup(mesh, ids(prim), ids(sec), penalty)
 
     def _kind(self, b):
         return hex8.ELASTIC if self.deck.block_material(b).model == "elastic" else hex8.NEOHOOKEAN
@@ -97,7 +104,11 @@ class OracleModel:
             self._apply_bc(self.time, self.time_prev)
             self.fext[:] = 0.0
             self.internal_force()
-            L.h8o_accel(len(self.ref), self.mass, self.f, self.fext.ctypes.data, self.a)
+            if self.contact is not None:  # explicit_time_integrator.cc:232-249
+                self.fcontact, self.contact_pairs = self.contact.force(self.u)
+                contact_oracle.accel_contact(self.mass, self.f, self.fext, self.fcontact, self.a)
+            else:
+                L.h8o_accel(len(self.ref), self.mass, self.f, self.fext.ctypes.data, self.a)
             L.h8o_axpy(self.v.size, hdt, self.a.ravel(), self.v.ravel())
             if out:
                 self._apply_bc(self.time, self.time_prev)
@@ -110,7 +121,8 @@ class OracleModel:
         s = {"time": self.time, "node": {"lumped_mass": self.mass.copy(), "reference_coordinate": self.ref.copy(),
                                          "displacement": self.u.copy(), "velocity": self.v.copy(),
                                          "acceleration": self.a.copy(), "internal_force": self.f.copy(),
-                                         "external_force": self.fext.copy()}, "elem": {}, "derived": {}}
+                                         "external_force": self.fext.copy(), "contact_force": self.fcontact.copy()},
+             "elem": {}, "derived": {}}
         for b in self.mesh["block_ids"]:
             s["elem"][b] = self.elem[b].copy()
             dd = hex8.derived(self.ref, self.u, self.mesh["conn"][b], self.elem[b])

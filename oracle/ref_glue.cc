@@ -33,6 +33,7 @@
 #include "nimble_parser.h"
 #include "nimble_vector_communicator.h"
 #include "nimble_view.h"
+#include "ref_contact.h"
 #include "ref_state_material.h"
 #ifdef NSM_REF_BINDING  // tests/ref_binding: the same glue with the B200 binding class as the model data
 #include "b200_model_data.h"
@@ -171,6 +172,9 @@ struct RefRun
   bool                  write_output   = false;  // also through the reference's own ExodusOutput (text form in this build)
   std::vector<Snapshot> snaps;
   std::string           err;
+  // penalty contact (decks with a `contact:` line): the reference's own ContactEntity objects, see ref_contact.h
+  std::unique_ptr<nsm_oracle::RefContact> contact;
+  long                                    contact_pairs_last = 0;
 };
 
 void
@@ -180,7 +184,7 @@ take_snapshot(RefRun& r)
   s.time = r.time_current;
   for (const char* lbl :
        {"lumped_mass", "reference_coordinate", "displacement", "velocity", "acceleration", "internal_force",
-        "external_force"}) {
+        "external_force", "contact_force"}) {
     int id = r.md->GetFieldId(lbl);
     if (id < 0) continue;
     bool   scalar = std::string(lbl) == "lumped_mass";
@@ -272,6 +276,17 @@ nsmref_open(
     r->md->InitializeBlocks(*r->dm, r->factory);  // src/nimble.cc:362
     r->md->InitializeExodusOutput(*r->dm);
     r->keep_snapshots = keep_snapshots != 0;
+    if (r->parser.HasContact()) {
+      // explicit_time_integrator.cc:76-92: block names of the `contact:` line -> ids on this rank -> contact entities
+      std::vector<std::string> primary_names, secondary_names;
+      double                   penalty = 0.0;
+      nsm_oracle::RefContact::ParseCommand(r->parser.ContactString(), primary_names, secondary_names, penalty);
+      std::vector<int> primary_ids, secondary_ids;
+      r->mesh.BlockNamesToOnProcessorBlockIds(primary_names, primary_ids);
+      r->mesh.BlockNamesToOnProcessorBlockIds(secondary_names, secondary_ids);
+      r->contact.reset(new nsm_oracle::RefContact);
+      r->contact->Create(r->mesh, primary_ids, secondary_ids, penalty);
+    }
   } catch (std::exception const& e) {
     r->err = e.what();
   }
@@ -332,7 +347,8 @@ nsmref_begin(void* h)
   return r.md->GetCriticalTimeStep();
 }
 
-// n passes of the loop body (explicit_time_integrator.cc:177-278), contact disabled.
+// n passes of the loop body (explicit_time_integrator.cc:177-278); the contact branch (:232-249) runs when the deck has
+// a `contact:` line, through RefContact.
 double
 nsmref_advance(void* h, int n)
 {
@@ -367,11 +383,22 @@ nsmref_advance(void* h, int n)
     model_data.ComputeExternalForce(data_manager, r.time_previous, r.time_current, is_output_step);
     model_data.ComputeInternalForce(
         data_manager, r.time_previous, r.time_current, is_output_step, displacement, internal_force);
-    for (int k = 0; k < num_nodes; ++k) {
-      const double oneOverM = 1.0 / lumped_mass(k);
-      acceleration(k, 0)    = oneOverM * (internal_force(k, 0) + external_force(k, 0));
-      acceleration(k, 1)    = oneOverM * (internal_force(k, 1) + external_force(k, 1));
-      acceleration(k, 2)    = oneOverM * (internal_force(k, 2) + external_force(k, 2));
+    if (r.contact) {
+      auto contact_force   = model_data.GetVectorNodeData("contact_force");
+      r.contact_pairs_last = r.contact->Compute(displacement.data(), contact_force.data(), num_nodes);
+      for (int k = 0; k < num_nodes; ++k) {
+        const double oneOverM = 1.0 / lumped_mass(k);
+        acceleration(k, 0)    = oneOverM * (internal_force(k, 0) + external_force(k, 0) + contact_force(k, 0));
+        acceleration(k, 1)    = oneOverM * (internal_force(k, 1) + external_force(k, 1) + contact_force(k, 1));
+        acceleration(k, 2)    = oneOverM * (internal_force(k, 2) + external_force(k, 2) + contact_force(k, 2));
+      }
+    } else {
+      for (int k = 0; k < num_nodes; ++k) {
+        const double oneOverM = 1.0 / lumped_mass(k);
+        acceleration(k, 0)    = oneOverM * (internal_force(k, 0) + external_force(k, 0));
+        acceleration(k, 1)    = oneOverM * (internal_force(k, 1) + external_force(k, 1));
+        acceleration(k, 2)    = oneOverM * (internal_force(k, 2) + external_force(k, 2));
+      }
     }
     velocity += half_delta_time * acceleration;
     model_data.UpdateWithNewVelocity(data_manager, half_delta_time);
@@ -382,6 +409,45 @@ nsmref_advance(void* h, int n)
     model_data.UpdateStates(data_manager);
   }
   return r.time_current;
+}
+
+// ---- contact: what RefContact built and one evaluation on a given displacement -------------------------------
+// which: 0 primary quads (4 ints each), 1 secondary quads, 2 contact node ids; returns the count (quads / nodes) and
+// fills out when it is non-null
+long
+nsmref_contact_ints(void* h, int which, int* out)
+{
+  auto& r = *static_cast<RefRun*>(h);
+  if (!r.contact) return -1;
+  const std::vector<int>& v = which == 0 ? r.contact->primary_quads : which == 1 ? r.contact->secondary_quads : r.contact->contact_node_ids;
+  if (out) std::copy(v.begin(), v.end(), out);
+  return (long)v.size() / (which == 2 ? 1 : 4);
+}
+
+// which: 0 characteristic lengths of the primary quads, 1 of the contact nodes
+long
+nsmref_contact_doubles(void* h, int which, double* out)
+{
+  auto& r = *static_cast<RefRun*>(h);
+  if (!r.contact) return -1;
+  const std::vector<double>& v = which == 0 ? r.contact->primary_char_len : r.contact->contact_node_char_len;
+  if (out) std::copy(v.begin(), v.end(), out);
+  return (long)v.size();
+}
+
+// contact force of a displacement field ([n][3] in, [n][3] out); returns the number of enforced pairs
+long
+nsmref_contact_force(void* h, const double* displacement, double* contact_force)
+{
+  auto& r = *static_cast<RefRun*>(h);
+  if (!r.contact) return -1;
+  return r.contact->Compute(displacement, contact_force, static_cast<int>(r.mesh.GetNumNodes()));
+}
+
+long
+nsmref_contact_pairs_last(void* h)
+{
+  return static_cast<RefRun*>(h)->contact_pairs_last;
 }
 
 // ModelData::ComputeInternalForce alone on the current displacement (no state roll).

@@ -77,6 +77,14 @@ def lib(path=None):
         L.nsmref_enable_output.argtypes = [C.c_void_p, C.c_char_p]
         L.nsmref_device_launches.restype = C.c_long
         L.nsmref_device_launches.argtypes = [C.c_void_p]
+        L.nsmref_contact_ints.restype = C.c_long
+        L.nsmref_contact_ints.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.nsmref_contact_doubles.restype = C.c_long
+        L.nsmref_contact_doubles.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.nsmref_contact_force.restype = C.c_long
+        L.nsmref_contact_force.argtypes = [C.c_void_p, _dp, _dp]
+        L.nsmref_contact_pairs_last.restype = C.c_long
+        L.nsmref_contact_pairs_last.argtypes = [C.c_void_p]
         _libs[path] = L
     return _libs[path]
 
@@ -142,6 +150,36 @@ class RefRun:
     def internal_force(self):
         lib(self._lib_path).nsmref_internal_force(self.h)
 
+    def contact_entities(self):
+        """What the contact glue built from the deck's `contact:` line (oracle/ref_contact.cc) -> dict of the primary
+        quads [nf,4], secondary quads, contact node ids (mesh node ids) and the characteristic lengths; None without contact."""
+        L = lib(self._lib_path)
+        if L.nsmref_contact_ints(self.h, 0, None) < 0:
+            return None
+        out = {}
+        for which, key, width in ((0, "primary_quads", 4), (1, "secondary_quads", 4), (2, "contact_nodes", 1)):
+            n = L.nsmref_contact_ints(self.h, which, None)
+            a = np.empty(n * width, np.int32)
+            L.nsmref_contact_ints(self.h, which, a.ctypes.data)
+            out[key] = a.reshape(-1, 4) if width == 4 else a
+        for which, key in ((0, "primary_char_len"), (1, "contact_node_char_len")):
+            n = L.nsmref_contact_doubles(self.h, which, None)
+            a = np.empty(n)
+            L.nsmref_contact_doubles(self.h, which, a.ctypes.data)
+            out[key] = a
+        return out
+
+    def contact_force(self, displacement):
+        """-> (contact force [n,3], enforced node-face pairs) of a displacement field, through the reference's
+        ContactEntity objects"""
+        d = np.ascontiguousarray(displacement, dtype=np.float64)
+        f = np.zeros_like(d)
+        pairs = lib(self._lib_path).nsmref_contact_force(self.h, d, f)
+        return f, int(pairs)
+
+    def contact_pairs_last(self) -> int:
+        return int(lib(self._lib_path).nsmref_contact_pairs_last(self.h))
+
     def field(self, label: str) -> np.ndarray:
         """Live (writable) view of a nodal field, AoS [n,3] (or [n] for lumped_mass)."""
         p = lib(self._lib_path).nsmref_node_field(self.h, label.encode())
@@ -167,7 +205,7 @@ class RefRun:
         for i in range(L.nsmref_num_snapshots(self.h)):
             s = {"time": L.nsmref_snapshot_time(self.h, i), "node": {}, "elem": {}, "derived": {}}
             for lbl in ("lumped_mass", "reference_coordinate", "displacement", "velocity", "acceleration",
-                        "internal_force", "external_force"):
+                        "internal_force", "external_force", "contact_force"):
                 n = L.nsmref_snapshot_node(self.h, i, lbl.encode(), None)
                 if n < 0:
                     continue

@@ -33,6 +33,14 @@ CASES = [
     ("single_elem_complex_displacement", "single_elem_complex_displacement", "single_elem_complex_displacement"),
     ("single_elem_complex_displacement", "single_elem_native_neohookean", "single_elem"),
 ]
+# penalty-contact decks (test/contact; the reference runs them only in its Kokkos + ArborX / BVH builds).  Their ref_*
+# snapshots come from the reference's serial model data + the reference's own ContactEntity objects behind the
+# restated pair loop (oracle/ref_contact.cc); sliding_contact ships no gold file.
+CONTACT_CASES = [
+    ("cubes_contact", "cubes_contact", "cubes_contact"),
+    ("sphere_plate_contact", "sphere_plate_contact", "sphere_plate_contact"),
+    ("sliding_contact", "sliding_contact", "sliding_contact"),
+]
 
 
 def _names(var):
@@ -207,28 +215,36 @@ def make_state_case():
 
 
 def main():
-    refroot = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    refroot = args[0] if args else "/root/reference"
     from oracle import refdrive
 
-    make_state_case()
+    if "--contact-only" not in sys.argv:
+        make_state_case()
     if "--state-only" in sys.argv:
         return
 
-    for d, deck, g in CASES:
-        base = os.path.join(refroot, "test", "dynamics", d)
+    cases = [("dynamics",) + c for c in CASES] if "--contact-only" not in sys.argv else []
+    for sub, d, deck, g in cases + [("contact",) + c for c in CONTACT_CASES]:
+        base = os.path.join(refroot, "test", sub, d)
         out = {}
         mesh = read_genesis(os.path.join(base, g + ".g"))
         pack_mesh("mesh_", mesh, out)
         out["deck"] = np.array(open(os.path.join(base, deck + ".in")).read())
         # the reference's own per-variable tolerances for this case (exodiff -f <case>.exodiff)
         out["exodiff"] = np.array(open(os.path.join(base, deck + ".exodiff")).read())
-        times, nod, elem = read_results(os.path.join(base, deck + ".gold.e"))
+        if os.path.exists(os.path.join(base, deck + ".gold.e")):
+            times, nod, elem = read_results(os.path.join(base, deck + ".gold.e"))
+        else:
+            times, nod, elem = np.zeros(0), {}, {}
         out["gold_times"] = times
         for k, a in nod.items():
             out["gold_nod_" + k] = a
         for (k, b), a in elem.items():
+            if sub == "contact" and not k.startswith(("stress_xx", "deformation_gradient_xx")):
+                continue  # the contact .exodiff files compare nodal variables only; keep the fixture small
             out["gold_elem_%s_eb%d" % (k, b)] = a
-        for p in sorted(glob.glob(os.path.join(base, g + ".g.*.*"))):
+        for p in sorted(glob.glob(os.path.join(base, g + ".g.*.*"))) if sub != "contact" else []:
             tag = p.split(".g.")[1]
             pack_mesh("piece_%s_" % tag, read_genesis(p), out)
         # reference-code snapshots at the deck's output steps (tight oracle when /root/reference is absent)
@@ -238,14 +254,26 @@ def main():
         nsteps = int(re.search(r"number of load steps:\s*(\d+)", str(out["deck"])).group(1))
         run.advance(nsteps)
         snaps = run.snapshots()
+        if sub == "contact" and len(snaps) > 16:  # sliding_contact: 102 output steps; keep every tenth and the last
+            keep = sorted(set(range(0, len(snaps), 10)) | {len(snaps) - 1})
+            out["ref_snapshot_index"] = np.array(keep)
+            snaps = [snaps[i] for i in keep]
         out["ref_times"] = np.array([s["time"] for s in snaps])
         for lbl in snaps[0]["node"]:
-            out["ref_node_" + lbl] = np.stack([s["node"][lbl] for s in snaps])
+            if sub == "contact" and lbl in ("reference_coordinate", "external_force", "acceleration"):
+                continue
+            out["ref_node_" + lbl] = np.stack([s["node"][lbl] for s in snaps]) if lbl != "lumped_mass" else snaps[0]["node"][lbl][None]
         for b in mesh["block_ids"]:
             # full per-ipt F/sigma only at the final output step (keeps the fixture small)
             out["ref_elem_last_%d" % b] = snaps[-1]["elem"][b]
             for lbl in snaps[0]["derived"][b]:
+                if sub == "contact" and lbl not in ("stress_xx", "stress_zz", "volume"):
+                    continue
                 out["ref_derived_%d_%s" % (b, lbl)] = np.stack([s["derived"][b][lbl] for s in snaps])
+        ce = run.contact_entities()
+        if ce is not None:
+            for k, a in ce.items():
+                out["ref_contact_" + k] = a
         run.close()
         path = os.path.join(HERE, deck + ".npz")
         np.savez_compressed(path, **out)
