@@ -58,7 +58,8 @@ typedef enum {
   NSM_FIELD_ACCELERATION         = 4,
   NSM_FIELD_INTERNAL_FORCE       = 5,
   NSM_FIELD_EXTERNAL_FORCE       = 6,
-  NSM_FIELD_COUNT                = 7
+  NSM_FIELD_CONTACT_FORCE        = 7, /* zero until nsm_b200_set_contact; download only */
+  NSM_FIELD_COUNT                = 8
 } nsm_field;
 
 /* boundary-condition kinds applied inside the step (src/nimble_boundary_condition.h:62-69). */
@@ -266,6 +267,29 @@ int nsm_b200_step_host(nsm_b200_ctx* ctx, double* time, double dt_user, double* 
 /* Number of node chunks of the pipelined nsm_b200_step_host: -1 automatic (default), 0 or 1 the plain schedule.  Call
  * before the first nsm_b200_step_host. */
 int nsm_b200_set_host_step_chunks(nsm_b200_ctx* ctx, int n_chunks);
+
+/* ---- penalty contact (replaces ContactManager::CreateContactEntities' device arrays, ComputeContactForce and the
+ *      contact branch of the explicit loop: src/nimble_contact_manager.cc:184-393, 395-429,
+ *      src/contact/serial/arborx_serial_contact_manager.cc:147-196, src/integrators/explicit_time_integrator.cc:232-249) */
+/* Contact entities of this context: the skin faces of the primary blocks as quads of node ids (Exodus face order; each
+ * becomes four triangles around its centre, src/nimble_contact_manager.cc:1043-1190) with their characteristic
+ * lengths, and the contact nodes of the secondary blocks with theirs (the host layer's ContactManager computes both
+ * lists as the reference does, :184-330).  From then on every step evaluates the contact force after the internal
+ * force and the acceleration is (1/m)(f_int + f_ext + f_contact).  n_primary_faces == 0 && n_contact_nodes == 0
+ * switches contact off again.  Contexts with a peer exchange are refused (the reference's ghost-face exchange across
+ * ranks, src/contact/parallel, is outside this path). */
+int nsm_b200_set_contact(nsm_b200_ctx* ctx, double penalty_parameter, int64_t n_primary_faces, const int32_t* primary_face_nodes,
+                         const double* primary_face_char_len, int64_t n_contact_nodes, const int32_t* contact_node_ids,
+                         const double* contact_node_char_len);
+/* ContactManager::ComputeContactForce: from the device-resident displacement into the device-resident contact_force
+ * (NSM_FIELD_CONTACT_FORCE; zero away from the contact surfaces, ContactManager::GetForces :732-748). */
+int nsm_b200_contact_force(nsm_b200_ctx* ctx);
+/* The reference call shape (ComputeContactForce(step, debug_output, Viewify<2> contact_force) after the displacement
+ * reached the device): uploads displacement [n][3] when it is non-null, evaluates, downloads contact_force [n][3]. */
+int nsm_b200_contact_force_host(nsm_b200_ctx* ctx, const double* displacement, double* contact_force);
+/* Counters of the last evaluation: stats[0] node-face pairs enforced, [1] pairs that passed the bounding-box test,
+ * [2] triangles in contact (numActiveContactFaces, :692-702), [3] nodes in contact (numActiveContactNodes). */
+int nsm_b200_contact_stats(nsm_b200_ctx* ctx, int64_t stats[4]);
 
 /* ---- element data / derived output (replaces ModelData::GetElementDataNew + Block::ComputeDerivedElementData,
  *      src/nimble_block.cc:438-497; HexElement::ComputeVolumeAverage, src/nimble_element.h:343-392) --- */

@@ -20,9 +20,9 @@ OK, ERR_ARG, ERR_CUDA, ERR_JACOBIAN, ERR_MATERIAL, ERR_COMM = range(6)
 MAT_ELASTIC, MAT_NEOHOOKEAN, MAT_J2_PLASTICITY = 0, 1, 2
 MATERIAL_KINDS = {"elastic": MAT_ELASTIC, "neohookean": MAT_NEOHOOKEAN, "j2_plasticity": MAT_J2_PLASTICITY}
 (FIELD_LUMPED_MASS, FIELD_REFERENCE_COORDINATE, FIELD_DISPLACEMENT, FIELD_VELOCITY, FIELD_ACCELERATION,
- FIELD_INTERNAL_FORCE, FIELD_EXTERNAL_FORCE) = range(7)
+ FIELD_INTERNAL_FORCE, FIELD_EXTERNAL_FORCE, FIELD_CONTACT_FORCE) = range(8)
 FIELDS = {"lumped_mass": 0, "reference_coordinate": 1, "displacement": 2, "velocity": 3, "acceleration": 4,
-          "internal_force": 5, "external_force": 6}
+          "internal_force": 5, "external_force": 6, "contact_force": 7}
 BC_PRESCRIBED_VELOCITY, BC_PRESCRIBED_DISPLACEMENT = 0, 1
 ASSEMBLY_ATOMIC, ASSEMBLY_ORDERED = 0, 1
 FLAG_STORE_IPT_EVERY_STEP, FLAG_CACHE_REF_JACOBIAN, FLAG_REORDER_ELEMENTS, FLAG_RENUMBER_NODES = 0x1, 0x2, 0x4, 0x8
@@ -47,6 +47,7 @@ SYMBOLS = [
     "nsm_b200_element_data_stride", "nsm_b200_update_states", "nsm_b200_get_element_data_previous",
     "nsm_b200_set_element_data", "nsm_b200_set_bc_entry_constants", "nsm_b200_comm_set_host_barrier",
     "nsm_b200_set_host_step_chunks", "nsm_b200_effective_flags", "nsm_b200_fp64_peak_sustained",
+    "nsm_b200_set_contact", "nsm_b200_contact_force", "nsm_b200_contact_force_host", "nsm_b200_contact_stats",
 ]
 
 
@@ -138,6 +139,10 @@ def lib():
         "nsm_b200_set_host_step_chunks": (i32, [vp, i32]),
         "nsm_b200_effective_flags": (C.c_uint, [vp]),
         "nsm_b200_fp64_peak_sustained": (i32, [vp, dbl, dp]),
+        "nsm_b200_set_contact": (i32, [vp, dbl, i64, ip, dp, i64, ip, dp]),
+        "nsm_b200_contact_force": (i32, [vp]),
+        "nsm_b200_contact_force_host": (i32, [vp, vp, vp]),
+        "nsm_b200_contact_stats": (i32, [vp, lp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -293,6 +298,34 @@ class Context:
         self._ck(self._L.nsm_b200_internal_force_host(self._h, displacement.ctypes.data, out.ctypes.data,
                                                        1 if store_ipt else 0))
         return out
+
+    def set_contact(self, penalty, primary_quads, primary_char_len, contact_nodes, contact_node_char_len):
+        """Contact entities (ContactManager::CreateContactEntities): skin quads of the primary blocks and contact nodes
+        of the secondary blocks with their characteristic lengths; empty lists switch contact off."""
+        q = np.ascontiguousarray(primary_quads, dtype=np.int32).reshape(-1, 4)
+        ql = np.ascontiguousarray(primary_char_len, dtype=np.float64)
+        cn = np.ascontiguousarray(contact_nodes, dtype=np.int32)
+        cl = np.ascontiguousarray(contact_node_char_len, dtype=np.float64)
+        assert len(q) == len(ql) and len(cn) == len(cl)
+        self._ck(self._L.nsm_b200_set_contact(self._h, float(penalty), len(q), _iptr(q), _dptr(ql), len(cn), _iptr(cn), _dptr(cl)))
+
+    def contact_force(self):
+        self._ck(self._L.nsm_b200_contact_force(self._h))
+
+    def contact_force_host(self, displacement=None, out=None):
+        if displacement is not None:
+            displacement = np.ascontiguousarray(displacement, dtype=np.float64)
+        if out is None:
+            out = np.empty((self.n_nodes, 3))
+        self._ck(self._L.nsm_b200_contact_force_host(self._h, displacement.ctypes.data if displacement is not None else None,
+                                                      out.ctypes.data))
+        return out
+
+    def contact_stats(self):
+        """-> dict of the last evaluation's counters (pairs enforced / box-tested, active faces / nodes)"""
+        st = np.zeros(4, np.int64)
+        self._ck(self._L.nsm_b200_contact_stats(self._h, st.ctypes.data_as(C.POINTER(C.c_int64))))
+        return {"pairs": int(st[0]), "box_tested": int(st[1]), "active_faces": int(st[2]), "active_nodes": int(st[3])}
 
     def compute_stress(self, material, bulk_modulus, shear_modulus, def_grad):
         kind = MATERIAL_KINDS[material] if isinstance(material, str) else int(material)

@@ -1,0 +1,308 @@
+// nimblesm_b200/csrc/contact.cuh — penalty contact on the device (sm_100a, fp64, no FMA contraction): the
+// `contact_force` term of the explicit loop (src/integrators/explicit_time_integrator.cc:232-249).
+//
+// What the reference computes per step (ArborXSerialContactManager::ComputeSerialContactForce,
+// src/contact/serial/arborx_serial_contact_manager.cc:147-196): every secondary NODE against every primary TRIANGLE
+// (a skin quad split in four around its centre, ContactManager::CreateContactNodesAndFaces,
+// src/nimble_contact_manager.cc:1043-1190) whose inflated bounding boxes intersect (ArborX BVH on float boxes); pairs
+// that ContactManager::Projection (:1549-1620) places inside the facet, penetrating by less than the facet's
+// characteristic length, receive penalty * gap along the facet normal, spread over the facet's nodes by the barycentric
+// coordinates (the centre's share goes to the quad's four nodes in quarters) and, negated, to the node
+// (PenaltyContactEnforcement::EnforceContact, src/nimble_contact_manager.h:94-128).  The result is a sum over all
+// accepted pairs: the search structure decides only how fast the pairs are found.
+//
+// Execution plan (B200): the contact surfaces are 2-D, so the work is tiny next to the element kernel and latency, not
+// bandwidth, is what counts -- three launches per evaluation, no host synchronisation, no sort:
+//   contact_update_kernel   thread per quad / per contact node: current coordinates (X + u), the quad's centre, the four
+//                           triangles' inflated boxes (narrowed to float exactly as ArborX::Point does), a grid-wide
+//                           minimum corner and maximum box extent (warp reductions + one atomic per warp), contact
+//                           force of the touched nodes cleared, hash heads cleared
+//   contact_bin_kernel      thread per triangle: cell of the box's minimum corner on a uniform grid of pitch
+//                           h >= every box extent, pushed on the chain of its hash bucket (atomicExch, no scan)
+//   contact_pair_kernel     one WARP per contact node, lane l < 27 walks the chain of neighbour cell l: a box of extent
+//                           <= h anchored in cell n can only meet boxes anchored in n + {-1,0,1}^3; float box test,
+//                           projection and enforcement in the reference's operation order (so each pair's force has the
+//                           oracle's bits), red.global.add.f64 into the nodal contact force (the order of the sum over
+//                           pairs is not fixed: noise ~1e-16, as in the reference's own Kokkos::atomic_add scatter)
+#pragma once
+#include <float.h>
+#include <stdint.h>
+
+namespace nsm {
+
+struct ContactArgs
+{
+  int64_t       n_quads, n_sec;
+  const int*    quad;      // [n_quads][4] node ids (internal numbering), Exodus face order
+  const double* quad_len;  // [n_quads] characteristic length (largest edge in the model configuration)
+  const int*    sec_node;  // [n_sec]
+  const double* sec_len;   // [n_sec]
+  const double* X[3];
+  const double* u[3];
+  double*       fc[3];     // nodal contact force, SoA
+  double        penalty;
+  // per-evaluation scratch
+  double*    quad_xyz;  // [n_quads][15]: the four corners and the centre, current configuration
+  float*     tri_box;   // [4 n_quads][6]: lo xyz, hi xyz
+  long long* tri_cell;  // [4 n_quads][3]
+  int*       next;      // [4 n_quads] hash chain
+  int*       head;      // [table_mask + 1]
+  unsigned   table_mask;
+  unsigned*  red;       // [4] this evaluation: ordered-float min corner x, y, z; max box extent (float bits, >= 0)
+  unsigned*  red_next;  // [4] the next evaluation's, reset here
+  unsigned long long* counters;  // [0] enforced pairs, [1] pairs that passed the box test
+  unsigned char*      status;    // [4 n_quads + n_sec] contact_status flags of this evaluation
+};
+
+__device__ __forceinline__ unsigned
+ordered_float(float f)
+{  // monotone map float -> unsigned (so that min/max work through integer atomics)
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ float
+float_of_ordered(unsigned o)
+{
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// ContactEntity::SetBoundingBox (src/nimble_contact_entity.cc:76-125): vertex min/max inflated by 0.15 * char_len;
+// narrowed to float as ArborX::Point holds it (src/contact/arborx_utils.h:85-90)
+__device__ __forceinline__ void
+inflate_to_float(const double lo[3], const double hi[3], double char_len, float* out)
+{
+  const double inflation_length = 0.15 * char_len;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    out[d]     = (float)(lo[d] - inflation_length);
+    out[3 + d] = (float)(hi[d] + inflation_length);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+contact_update_kernel(const ContactArgs p)
+{
+  const int64_t t   = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = t; i <= (int64_t)p.table_mask; i += nth) p.head[i] = -1;
+  if (t < 4) p.red_next[t] = t < 3 ? 0xffffffffu : 0u;
+  if (t < 2) p.counters[t] = 0ull;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ext = 0.0f;
+  if (t < p.n_quads) {
+    // ContactManager::ApplyDisplacements (src/nimble_contact_manager.cc:750-786) + ContactEntity::SetCoordinates
+    // (src/nimble_contact_entity.h:236-258): the third vertex of every triangle is the mean of the quad's nodes
+    double c[4][3], ctr[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int nd = p.quad[4 * t + k];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        c[k][d]      = p.X[d][nd] + p.u[d][nd];
+        p.fc[d][nd]  = 0.0;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) ctr[d] = (c[0][d] + c[1][d] + c[2][d] + c[3][d]) / 4.0;
+    double* q = p.quad_xyz + 15 * t;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) q[3 * k + d] = c[k][d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) q[12 + d] = ctr[d];
+    const double len = p.quad_len[t];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int b = (k + 1) & 3;
+      double    blo[3], bhi[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        blo[d] = bhi[d] = c[k][d];
+        if (c[b][d] < blo[d]) blo[d] = c[b][d];
+        if (c[b][d] > bhi[d]) bhi[d] = c[b][d];
+        if (ctr[d] < blo[d]) blo[d] = ctr[d];
+        if (ctr[d] > bhi[d]) bhi[d] = ctr[d];
+      }
+      float box[6];
+      inflate_to_float(blo, bhi, len, box);
+      float* o = p.tri_box + 6 * (4 * t + k);
+#pragma unroll
+      for (int d = 0; d < 6; ++d) o[d] = box[d];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = fminf(lo[d], box[d]);
+        ext   = fmaxf(ext, box[3 + d] - box[d]);
+      }
+      p.status[4 * t + k] = 0;
+    }
+  }
+  if (t < p.n_sec) {
+    const int nd = p.sec_node[t];
+    double    x[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      x[d]        = p.X[d][nd] + p.u[d][nd];
+      p.fc[d][nd] = 0.0;
+    }
+    float box[6];
+    inflate_to_float(x, x, p.sec_len[t], box);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = fminf(lo[d], box[d]);
+      ext   = fmaxf(ext, box[3 + d] - box[d]);
+    }
+    p.status[4 * p.n_quads + t] = 0;
+  }
+  // grid-wide minimum corner and maximum extent: warp reduction, one atomic per warp and quantity
+  unsigned r[4] = {ordered_float(lo[0]), ordered_float(lo[1]), ordered_float(lo[2]), __float_as_uint(ext)};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) r[d] = __reduce_min_sync(0xffffffffu, r[d]);
+  r[3] = __reduce_max_sync(0xffffffffu, r[3]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) atomicMin(p.red + d, r[d]);
+    atomicMax(p.red + 3, r[3]);
+  }
+}
+
+// pitch of the uniform grid: a little more than the largest box extent, so that rounding in the cell computation can
+// never move a box corner across more than one cell boundary
+__device__ __forceinline__ double
+contact_pitch(const unsigned* red)
+{
+  const float ext = __uint_as_float(red[3]);
+  return ext > 0.0f ? 1.0001 * (double)ext : 1.0;
+}
+
+__device__ __forceinline__ void
+contact_cell(const float* lo, const unsigned* red, double pitch, long long cell[3])
+{
+#pragma unroll
+  for (int d = 0; d < 3; ++d) cell[d] = (long long)floor(((double)lo[d] - (double)float_of_ordered(red[d])) / pitch);
+}
+
+__device__ __forceinline__ unsigned
+contact_hash(long long cx, long long cy, long long cz)
+{
+  unsigned long long h = (unsigned long long)cx * 0x9E3779B97F4A7C15ull;
+  h ^= (unsigned long long)cy * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+  h ^= (unsigned long long)cz * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+  return (unsigned)(h ^ (h >> 32));
+}
+
+__global__ void __launch_bounds__(256)
+contact_bin_kernel(const ContactArgs p)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * p.n_quads) return;
+  const double pitch = contact_pitch(p.red);
+  long long    cell[3];
+  contact_cell(p.tri_box + 6 * t, p.red, pitch, cell);
+  p.tri_cell[3 * t] = cell[0], p.tri_cell[3 * t + 1] = cell[1], p.tri_cell[3 * t + 2] = cell[2];
+  const unsigned bucket = contact_hash(cell[0], cell[1], cell[2]) & p.table_mask;
+  p.next[t]             = atomicExch(p.head + bucket, (int)t);
+}
+
+__device__ __forceinline__ void
+contact_cross(const double* u, const double* v, double* r)
+{  // CrossProduct (src/nimble_utils.h:393-400)
+  r[0] = u[1] * v[2] - u[2] * v[1];
+  r[1] = u[2] * v[0] - u[0] * v[2];
+  r[2] = u[0] * v[1] - u[1] * v[0];
+}
+
+__device__ __forceinline__ void
+contact_add3(double* const fc[3], int node, double x, double y, double z)
+{
+  atomicAdd(fc[0] + node, x);
+  atomicAdd(fc[1] + node, y);
+  atomicAdd(fc[2] + node, z);
+}
+
+__global__ void __launch_bounds__(256)
+contact_pair_kernel(const ContactArgs p)
+{
+  const int64_t s    = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per contact node
+  const int     lane = threadIdx.x & 31;
+  if (s >= p.n_sec || lane >= 27) return;
+  const int nd = p.sec_node[s];
+  double    pt[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) pt[d] = p.X[d][nd] + p.u[d][nd];
+  float box[6];
+  inflate_to_float(pt, pt, p.sec_len[s], box);
+  const double pitch = contact_pitch(p.red);
+  long long    cell[3];
+  contact_cell(box, p.red, pitch, cell);
+  cell[0] += lane % 3 - 1, cell[1] += (lane / 3) % 3 - 1, cell[2] += lane / 9 - 1;
+  unsigned long long tested = 0, enforced = 0;
+  for (int t = p.head[contact_hash(cell[0], cell[1], cell[2]) & p.table_mask]; t >= 0; t = p.next[t]) {
+    const long long* tc = p.tri_cell + 3 * (int64_t)t;
+    if (tc[0] != cell[0] || tc[1] != cell[1] || tc[2] != cell[2]) continue;  // another cell of the same bucket
+    const float* tb = p.tri_box + 6 * (int64_t)t;
+    // ArborX::intersects on float boxes: closed intervals overlap in every direction
+    if (box[3] < tb[0] || box[0] > tb[3] || box[4] < tb[1] || box[1] > tb[4] || box[5] < tb[2] || box[2] > tb[5]) continue;
+    ++tested;
+    const int     quad = t >> 2, k = t & 3, kb = (k + 1) & 3;
+    const double* q    = p.quad_xyz + 15 * (int64_t)quad;
+    double        p1[3], p2[3], p3[3], u[3], v[3], w[3], n[3], cr[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) p1[d] = q[3 * k + d], p2[d] = q[3 * kb + d], p3[d] = q[12 + d];
+    // ContactManager::Projection (src/nimble_contact_manager.cc:1549-1620), tolerance 1.e-8
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      u[d] = p2[d] - p1[d];
+      v[d] = p3[d] - p1[d];
+      w[d] = pt[d] - p1[d];
+    }
+    contact_cross(u, v, n);
+    const double n_squared = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    contact_cross(u, w, cr);
+    const double alpha3 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
+    contact_cross(w, v, cr);
+    const double alpha2 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
+    const double alpha1 = 1.0 - alpha2 - alpha3;
+    const double tol = 1.e-8, tol2 = 1.0 + tol;
+    if (!((alpha1 > -tol && alpha1 < tol2) && (alpha2 > -tol && alpha2 < tol2) && (alpha3 > -tol && alpha3 < tol2))) continue;
+    const double xp = alpha1 * p1[0] + alpha2 * p2[0] + alpha3 * p3[0];
+    const double yp = alpha1 * p1[1] + alpha2 * p2[1] + alpha3 * p3[1];
+    const double zp = alpha1 * p1[2] + alpha2 * p2[2] + alpha3 * p3[2];
+    const double dx = pt[0] - xp, dy = pt[1] - yp, dz = pt[2] - zp;
+    const double sc = 1.0 / sqrt(n_squared);
+    const double nx = n[0] * sc, ny = n[1] * sc, nz = n[2] * sc;
+    const double gap = dx * nx + dy * ny + dz * nz;
+    if (!((gap < 0.0) && (gap > -p.quad_len[quad]))) continue;  // inside but not through
+    // PenaltyContactEnforcement::EnforceContact (src/nimble_contact_manager.h:94-128): facet first, then the node
+    ++enforced;
+    p.status[t] = 1, p.status[4 * p.n_quads + s] = 1;
+    const double scale = p.penalty * gap;
+    const double cf[3] = {scale * nx, scale * ny, scale * nz};
+    const int*   qn    = p.quad + 4 * (int64_t)quad;
+    contact_add3(p.fc, qn[k], alpha1 * cf[0], alpha1 * cf[1], alpha1 * cf[2]);
+    contact_add3(p.fc, qn[kb], alpha2 * cf[0], alpha2 * cf[1], alpha2 * cf[2]);
+    const double f3[3] = {(alpha3 * cf[0]) / 4.0, (alpha3 * cf[1]) / 4.0, (alpha3 * cf[2]) / 4.0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) contact_add3(p.fc, qn[i], f3[0], f3[1], f3[2]);
+    contact_add3(p.fc, nd, -cf[0], -cf[1], -cf[2]);
+  }
+  if (tested) atomicAdd(p.counters + 1, tested);
+  if (enforced) atomicAdd(p.counters, enforced);
+}
+
+// numActiveContactFaces / numActiveContactNodes (src/nimble_contact_manager.cc:692-714): entities whose contact_status
+// was set by the last evaluation
+__global__ void __launch_bounds__(256)
+contact_count_kernel(int64_t n_tri, int64_t n_sec, const unsigned char* status, unsigned long long* out /* [2] */)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool    f = t < n_tri && status[t];
+  const bool    n = t >= n_tri && t < n_tri + n_sec && status[t];
+  const unsigned bf = __ballot_sync(0xffffffffu, f), bn = __ballot_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0) {
+    if (bf) atomicAdd(out, (unsigned long long)__popc(bf));
+    if (bn) atomicAdd(out + 1, (unsigned long long)__popc(bn));
+  }
+}
+
+}  // namespace nsm

@@ -785,6 +785,7 @@ struct NodeArgs
   double*         a[3];
   double*         f[3];
   const double*   fext[3];   // nullptr: external force is identically zero (src/nimble_model_data.cc:609-618)
+  const double*   fcontact[3];  // nullptr: no contact; else a = (1/m)(f_int + f_ext + f_contact) (explicit_time_integrator.cc:243-249)
   const double*   mass;
   const int*      bc_of_dof[3];  // entry index or -1; nullptr when the deck has no kinematic BC
   const int*      bc_kind;
@@ -849,9 +850,11 @@ node_correct_kernel(const NodeArgs p, double hdt, int update_velocity)
   }
   if (!update_velocity) return;
   const double rm = 1.0 / p.mass[i];
-  const double a0 = rm * (f0 + (HAS_FEXT ? p.fext[0][i] : 0.0));
-  const double a1 = rm * (f1 + (HAS_FEXT ? p.fext[1][i] : 0.0));
-  const double a2 = rm * (f2 + (HAS_FEXT ? p.fext[2][i] : 0.0));
+  double       s0 = f0 + (HAS_FEXT ? p.fext[0][i] : 0.0), s1 = f1 + (HAS_FEXT ? p.fext[1][i] : 0.0), s2 = f2 + (HAS_FEXT ? p.fext[2][i] : 0.0);
+  if (p.fcontact[0]) s0 = s0 + p.fcontact[0][i], s1 = s1 + p.fcontact[1][i], s2 = s2 + p.fcontact[2][i];
+  const double a0 = rm * s0;
+  const double a1 = rm * s1;
+  const double a2 = rm * s2;
   p.a[0][i] = a0, p.a[1][i] = a1, p.a[2][i] = a2;
   p.v[0][i] = p.v[0][i] + hdt * a0;
   p.v[1][i] = p.v[1][i] + hdt * a1;
@@ -878,7 +881,9 @@ node_fused_kernel(const NodeArgs p, double hdt, double hdt_next, double dt_next)
   const double rm = 1.0 / p.mass[i];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double a = rm * (f[c] + (HAS_FEXT ? p.fext[c][i] : 0.0));
+    double sum = f[c] + (HAS_FEXT ? p.fext[c][i] : 0.0);
+    if (p.fcontact[0]) sum = sum + p.fcontact[c][i];
+    const double a = rm * sum;
     double       v = p.v[c][i];
     double       u = p.u[c][i];
     v              = v + hdt * a;

@@ -18,6 +18,7 @@
 #include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler is attached
 
 #include "../../include/nsm_b200.h"
+#include "contact.cuh"
 #include "hex8_kernels.cuh"
 #include "peer_exchange.cuh"
 
@@ -159,6 +160,29 @@ struct nsm_b200_ctx
     cudaEvent_t          ev_bc = nullptr;
   } pipe;
 
+  // penalty contact (nsm_b200_set_contact): entities, per-evaluation scratch, the nodal contact force
+  struct Contact
+  {
+    bool      active  = false;
+    double    penalty = 0.0;
+    int64_t   n_quads = 0, n_sec = 0;
+    int*      quad = nullptr;
+    double*   quad_len = nullptr;
+    int*      sec_node = nullptr;
+    double*   sec_len  = nullptr;
+    double*   quad_xyz = nullptr;
+    float*    tri_box  = nullptr;
+    long long* tri_cell = nullptr;
+    int*      next = nullptr;
+    int*      head = nullptr;
+    unsigned  table_mask = 0;
+    unsigned* red = nullptr;                  // [2][4], alternating by evaluation
+    unsigned long long* counters = nullptr;   // [4]: enforced, box-tested, active faces, active nodes
+    unsigned char* status = nullptr;
+    int       parity = 0;
+  } contact;
+  double* fc[3] = {nullptr, nullptr, nullptr};  // nodal contact force, SoA (allocated by nsm_b200_set_contact)
+
   PeerExchange comm;
   // overlap of the shared-node exchange with the interior elements (nsm_b200_step)
   cudaStream_t comm_stream = nullptr;
@@ -277,6 +301,7 @@ node_args(nsm_b200_ctx* c, int64_t bc_row = 0)
   for (int i = 0; i < 3; ++i) {
     p.u[i] = c->u[i], p.v[i] = c->v[i], p.a[i] = c->a[i], p.f[i] = c->f[i];
     p.fext[i]      = c->has_fext ? c->fext[i] : nullptr;
+    p.fcontact[i]  = c->contact.active ? c->fc[i] : nullptr;
     p.bc_of_dof[i] = c->bc_of_dof[i];
   }
   p.mass     = c->mass;
@@ -541,6 +566,35 @@ prof_resolve(nsm_b200_ctx* c)
   c->ev_used = 0;
 }
 
+// ContactManager::ComputeContactForce on the device displacement (csrc/contact.cuh): three launches, no host sync
+int
+enqueue_contact(nsm_b200_ctx* c)
+{
+  auto& k = c->contact;
+  if (!k.active) return NSM_OK;
+  NvtxRange   range("Contact");
+  ContactArgs p{};
+  p.n_quads = k.n_quads, p.n_sec = k.n_sec;
+  p.quad = k.quad, p.quad_len = k.quad_len, p.sec_node = k.sec_node, p.sec_len = k.sec_len;
+  for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.fc[i] = c->fc[i];
+  p.penalty  = k.penalty;
+  p.quad_xyz = k.quad_xyz, p.tri_box = k.tri_box, p.tri_cell = k.tri_cell, p.next = k.next, p.head = k.head;
+  p.table_mask = k.table_mask;
+  p.red = k.red + 4 * k.parity, p.red_next = k.red + 4 * (k.parity ^ 1);
+  p.counters = k.counters, p.status = k.status;
+  k.parity ^= 1;
+  const int64_t n_update = std::max<int64_t>(std::max(k.n_quads, k.n_sec), 32);
+  contact_update_kernel<<<grid_for(n_update, 256), 256, 0, c->stream>>>(p);
+  c->launches++;
+  if (k.n_quads > 0 && k.n_sec > 0) {
+    contact_bin_kernel<<<grid_for(4 * k.n_quads, 256), 256, 0, c->stream>>>(p);
+    contact_pair_kernel<<<grid_for(32 * k.n_sec, 256), 256, 0, c->stream>>>(p);
+    c->launches += 2;
+  }
+  NSM_CUDA(c, cudaGetLastError());
+  return NSM_OK;
+}
+
 // internal force of the current device displacement into the device force field (+ shared-node sum)
 int
 enqueue_internal_force(nsm_b200_ctx* c, bool store_ipt)
@@ -579,6 +633,10 @@ field_ptrs(nsm_b200_ctx* c, int field, double** p, int* ncomp)
     case NSM_FIELD_ACCELERATION: p[0] = c->a[0], p[1] = c->a[1], p[2] = c->a[2]; return NSM_OK;
     case NSM_FIELD_INTERNAL_FORCE: p[0] = c->f[0], p[1] = c->f[1], p[2] = c->f[2]; return NSM_OK;
     case NSM_FIELD_EXTERNAL_FORCE: p[0] = c->fext[0], p[1] = c->fext[1], p[2] = c->fext[2]; return NSM_OK;
+    case NSM_FIELD_CONTACT_FORCE:
+      if (!c->fc[0]) return fail(c, NSM_ERR_ARG, "contact_force: no contact entities on this context (nsm_b200_set_contact)");
+      p[0] = c->fc[0], p[1] = c->fc[1], p[2] = c->fc[2];
+      return NSM_OK;
   }
   return fail(c, NSM_ERR_ARG, "unknown field id %d", field);
 }
@@ -728,6 +786,12 @@ nsm_b200_destroy(nsm_b200_ctx* c)
     if (kv.second.conn_sched != kv.second.conn) fr(kv.second.conn_sched);
     fr(kv.second.conn), fr(kv.second.orig), fr(kv.second.group_bits), fr(kv.second.group_list);
     fr(kv.second.rec[0]), fr(kv.second.rec[1]);
+  }
+  {
+    auto& k = c->contact;
+    fr(k.quad), fr(k.quad_len), fr(k.sec_node), fr(k.sec_len), fr(k.quad_xyz), fr(k.tri_box), fr(k.tri_cell), fr(k.next), fr(k.head);
+    fr(k.red), fr(k.counters), fr(k.status);
+    for (int i = 0; i < 3; ++i) fr(c->fc[i]);
   }
   for (double* p : c->pipe.stage) fr(p);
   if (c->pipe.up) cudaStreamDestroy(c->pipe.up);
@@ -1533,6 +1597,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     }
     if (c->profiling) prof_event(c);
     mark_states_for_roll(c);
+    if ((rc = enqueue_contact(c))) return rc;  // explicit_time_integrator.cc:232-239, on the displacement of this step
     if (n > 0) {
       const NodeArgs na = node_args(c, s + 1);  // boundary-condition magnitudes of the step the fused pass opens
       if (c->comm.active()) {
@@ -1904,7 +1969,7 @@ nsm_b200_step_host(nsm_b200_ctx* c, double* time, double dt_user, double* displa
     int rc = build_host_pipe(c);
     if (rc) return rc;
   }
-  if (c->pipe.n_chunks >= 2 && c->bc_rows <= 1 && !c->comm.active())
+  if (c->pipe.n_chunks >= 2 && c->bc_rows <= 1 && !c->comm.active() && !c->contact.active)  // (contact needs the whole displacement)
     return step_host_pipelined(c, time, dt_user, displacement, velocity, acceleration, internal_force);
   const int64_t n = c->n_nodes;
   if (!c->io_stream) {
@@ -2211,6 +2276,109 @@ nsm_b200_comm_set_timeout(nsm_b200_ctx* c, double seconds)
 }
 
 // ---- measurement ------------------------------------------------------------------------------------
+int
+nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int32_t* face_nodes, const double* face_len, int64_t n_cn,
+                     const int32_t* cn_ids, const double* cn_len)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized, "set_contact: context not finalized");
+  NSM_REQUIRE(c, n_faces >= 0 && n_cn >= 0 && n_faces < ((int64_t)1 << 28) && n_cn < ((int64_t)1 << 31), "set_contact: entity count out of range");
+  NSM_REQUIRE(c, (n_faces == 0 || (face_nodes && face_len)) && (n_cn == 0 || (cn_ids && cn_len)), "set_contact: null argument");
+  NSM_REQUIRE(c, !c->comm.active(), "set_contact: contexts with a peer exchange are not supported (contact across partitions)");
+  auto& k = c->contact;
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  dev_release(c, k.quad), dev_release(c, k.quad_len), dev_release(c, k.sec_node), dev_release(c, k.sec_len), dev_release(c, k.quad_xyz);
+  dev_release(c, k.tri_box), dev_release(c, k.tri_cell), dev_release(c, k.next), dev_release(c, k.head), dev_release(c, k.status);
+  k.active = false, k.n_quads = k.n_sec = 0;
+  if (n_faces == 0 && n_cn == 0) {
+    if (c->fc[0])
+      for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->fc[i], 0, (size_t)std::max<int64_t>(c->n_nodes, 1) * sizeof(double), c->stream));
+    return NSM_OK;
+  }
+  // ComputeContactForce throws on a non-positive penalty (src/nimble_contact_manager.cc:398-400)
+  NSM_REQUIRE(c, penalty > 0.0, "Error in ComputeContactForce(), invalid penalty_parameter.");
+  std::vector<int> quads((size_t)n_faces * 4), nodes((size_t)n_cn);
+  for (int64_t i = 0; i < n_faces * 4; ++i) {
+    NSM_REQUIRE(c, face_nodes[i] >= 0 && face_nodes[i] < c->n_nodes, "set_contact: face node id out of range");
+    quads[(size_t)i] = c->node_perm_host.empty() ? face_nodes[i] : c->node_perm_host[face_nodes[i]];
+  }
+  for (int64_t i = 0; i < n_cn; ++i) {
+    NSM_REQUIRE(c, cn_ids[i] >= 0 && cn_ids[i] < c->n_nodes, "set_contact: contact node id out of range");
+    nodes[(size_t)i] = c->node_perm_host.empty() ? cn_ids[i] : c->node_perm_host[cn_ids[i]];
+  }
+  int rc;
+  const int64_t n_tri = 4 * n_faces;
+  unsigned      table = 1024;
+  while ((int64_t)table < 2 * n_tri) table <<= 1;
+  if ((rc = dev_alloc(c, &k.quad, n_faces * 4)) || (rc = dev_alloc(c, &k.quad_len, n_faces)) || (rc = dev_alloc(c, &k.sec_node, n_cn)) ||
+      (rc = dev_alloc(c, &k.sec_len, n_cn)) || (rc = dev_alloc(c, &k.quad_xyz, n_faces * 15)) || (rc = dev_alloc(c, &k.tri_box, n_tri * 6)) ||
+      (rc = dev_alloc(c, &k.tri_cell, n_tri * 3)) || (rc = dev_alloc(c, &k.next, n_tri)) || (rc = dev_alloc(c, &k.head, (int64_t)table)) ||
+      (rc = dev_alloc(c, &k.status, n_tri + n_cn)))
+    return rc;
+  if (!k.red && ((rc = dev_alloc(c, &k.red, 8)) || (rc = dev_alloc(c, &k.counters, 4)))) return rc;
+  for (int i = 0; i < 3; ++i)
+    if (!c->fc[i] && (rc = dev_alloc(c, &c->fc[i], c->n_nodes))) return rc;
+  for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->fc[i], 0, (size_t)std::max<int64_t>(c->n_nodes, 1) * sizeof(double), c->stream));
+  const unsigned red0[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u};
+  NSM_CUDA(c, cudaMemcpyAsync(k.red, red0, sizeof red0, cudaMemcpyHostToDevice, c->stream));
+  NSM_CUDA(c, cudaMemsetAsync(k.counters, 0, 4 * sizeof(unsigned long long), c->stream));
+  NSM_CUDA(c, cudaMemsetAsync(k.status, 0, (size_t)std::max<int64_t>(n_tri + n_cn, 1), c->stream));
+  if (n_faces) {
+    NSM_CUDA(c, cudaMemcpyAsync(k.quad, quads.data(), quads.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NSM_CUDA(c, cudaMemcpyAsync(k.quad_len, face_len, (size_t)n_faces * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (n_cn) {
+    NSM_CUDA(c, cudaMemcpyAsync(k.sec_node, nodes.data(), nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NSM_CUDA(c, cudaMemcpyAsync(k.sec_len, cn_len, (size_t)n_cn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  k.penalty = penalty, k.n_quads = n_faces, k.n_sec = n_cn, k.table_mask = table - 1, k.parity = 0;
+  k.active  = true;
+  return NSM_OK;
+}
+
+int
+nsm_b200_contact_force(nsm_b200_ctx* c)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized && c->contact.active, "contact_force: no contact entities on this context (nsm_b200_set_contact)");
+  int rc = enqueue_contact(c);
+  if (rc) return rc;
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
+nsm_b200_contact_force_host(nsm_b200_ctx* c, const double* displacement, double* contact_force)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, c->finalized && c->contact.active, "contact_force_host: no contact entities on this context (nsm_b200_set_contact)");
+  NSM_REQUIRE(c, contact_force != nullptr, "contact_force_host: null argument");
+  int rc;
+  if (displacement && (rc = upload_field(c, NSM_FIELD_DISPLACEMENT, displacement, false))) return rc;
+  if ((rc = enqueue_contact(c))) return rc;
+  return download_field(c, NSM_FIELD_CONTACT_FORCE, contact_force, true);
+}
+
+int
+nsm_b200_contact_stats(nsm_b200_ctx* c, int64_t stats[4])
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, stats != nullptr, "contact_stats: null argument");
+  stats[0] = stats[1] = stats[2] = stats[3] = 0;
+  auto& k = c->contact;
+  if (!k.active) return NSM_OK;
+  const int64_t n_tri = 4 * k.n_quads;
+  NSM_CUDA(c, cudaMemsetAsync(k.counters + 2, 0, 2 * sizeof(unsigned long long), c->stream));
+  contact_count_kernel<<<grid_for(std::max<int64_t>(n_tri + k.n_sec, 1), 256), 256, 0, c->stream>>>(n_tri, k.n_sec, k.status, k.counters + 2);
+  c->launches++;
+  unsigned long long h[4];
+  NSM_CUDA(c, cudaMemcpyAsync(h, k.counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 4; ++i) stats[i] = (int64_t)h[i];
+  return NSM_OK;
+}
+
 int
 nsm_b200_timer_start(nsm_b200_ctx* c)
 {

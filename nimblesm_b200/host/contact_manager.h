@@ -1,0 +1,117 @@
+// nimblesm_b200/host/contact_manager.h — nimble::ContactManager for the B200 build (src/nimble_contact_manager.{h,cc},
+// src/contact/serial/arborx_serial_contact_manager.cc): penalty contact between the skin of the primary blocks
+// (triangulated faces) and the skin nodes of the secondary blocks.
+//
+// Host side = what the reference does once, on the host, at start-up: parse the `contact:` deck line, skin the
+// blocks, list the contact nodes, measure the characteristic lengths (CreateContactEntities, :184-393).  The per-step
+// part -- coordinates, bounding boxes, search, projection, enforcement, scatter -- runs on the device behind
+// nsm_b200_set_contact / nsm_b200_contact_force (csrc/contact.cuh): a uniform hashed grid in place of the ArborX BVH,
+// the same accepted pairs, the same per-pair arithmetic.  Inside the fused step (ModelData::AdvanceOnDevice) the
+// contact force never leaves the device; ComputeContactForce keeps the reference's call shape for the call-by-call
+// sequence.  One rank only: contact across mesh partitions (the reference's ghost-face exchange,
+// src/contact/parallel) is outside this path and refused with a message.
+#pragma once
+#include <cstddef>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "view.h"
+
+namespace nimble_b200 {
+
+class DataManager;
+class GenesisMesh;
+class VectorCommunicator;
+
+// `contact:` line -> block names and penalty parameter; throws std::invalid_argument with the reference's messages
+// (ParseContactCommand, src/nimble_contact_manager.cc:95-149)
+void
+ParseContactCommand(std::string const& command, std::vector<std::string>& primary_block_names,
+                    std::vector<std::string>& secondary_block_names, double& penalty_parameter);
+
+// what CreateContactEntities builds on the host and sends to the device (mesh node ids)
+struct ContactEntityLists
+{
+  std::vector<int>    primary_face_nodes;  // [n_faces][4], Exodus face order
+  std::vector<int>    primary_face_entity_ids;
+  std::vector<double> primary_face_char_len;
+  std::vector<int>    contact_node_ids;
+  std::vector<double> contact_node_char_len;
+};
+
+class ContactManager
+{
+ public:
+  explicit ContactManager(DataManager& data_manager) : data_manager_(data_manager) {}
+  virtual ~ContactManager() = default;
+
+  bool
+  ContactEnabled() const
+  {
+    return contact_enabled_;
+  }
+  void
+  SetPenaltyParameter(double penalty_parameter)
+  {
+    penalty_parameter_ = penalty_parameter;
+  }
+  double
+  GetPenaltyForceParam() const noexcept
+  {
+    return penalty_parameter_;
+  }
+
+  // Skin faces of the listed blocks: faces met exactly once, each in the Exodus face order of its element, sorted by
+  // their sorted node lists (the reference's std::map order); entity id = (element global id + 1 + offset) << 5 |
+  // face ordinal << 2 (SkinBlocks, :788-934)
+  static void
+  SkinBlocks(GenesisMesh const& mesh, std::vector<int> const& block_ids, int entity_id_offset, std::vector<std::vector<int>>& skin_faces,
+             std::vector<int>& entity_ids);
+
+  // CreateContactEntities (:184-393): contact entities of this rank, sent to the device
+  void
+  CreateContactEntities(GenesisMesh const& mesh, VectorCommunicator& vector_communicator, std::vector<int> const& primary_block_ids,
+                        std::vector<int> const& secondary_block_ids);
+
+  // ComputeContactForce (:395-429): contact force of the displacement the device holds, into the caller's view
+  void
+  ComputeContactForce(int step, bool debug_output, Viewify<2> contact_force);
+
+  std::size_t
+  numContactFaces() const
+  {
+    return 4 * lists_.primary_face_char_len.size();
+  }
+  std::size_t
+  numContactNodes() const
+  {
+    return lists_.contact_node_ids.size();
+  }
+  std::size_t
+  numActiveContactFaces() const;
+  std::size_t
+  numActiveContactNodes() const;
+
+  ContactEntityLists const&
+  EntityLists() const
+  {
+    return lists_;
+  }
+  // everything CreateContactEntities does before the upload (no device involved)
+  static void
+  BuildEntityLists(GenesisMesh const& mesh, std::vector<int> const& primary_block_ids, std::vector<int> const& secondary_block_ids,
+                   ContactEntityLists& lists);
+
+ protected:
+  DataManager&       data_manager_;
+  bool               contact_enabled_   = false;
+  double             penalty_parameter_ = 0.0;
+  ContactEntityLists lists_;
+};
+
+// the reference's factory (GetContactManager, :151-171): nullptr when the deck has no `contact:` line
+std::shared_ptr<ContactManager>
+GetContactManager(DataManager& data_manager);
+
+}  // namespace nimble_b200

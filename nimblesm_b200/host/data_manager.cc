@@ -144,6 +144,7 @@ DataManager::Initialize(int device, int assembly, unsigned flags, std::shared_pt
   field_ids_.acceleration          = model_data_->AllocateNodeData(VECTOR, "acceleration", num_nodes);
   field_ids_.internal_force        = model_data_->AllocateNodeData(VECTOR, "internal_force", num_nodes);
   field_ids_.external_force        = model_data_->AllocateNodeData(VECTOR, "external_force", num_nodes);
+  field_ids_.contact_force         = model_data_->AllocateNodeData(VECTOR, "contact_force", num_nodes);
   model_data_->SetReferenceCoordinates(mesh_);
 }
 

@@ -252,6 +252,14 @@ GenesisMesh::GetElementType(int block_id) const
   throw std::invalid_argument("GenesisMesh::GetElementType(), unsupported element (nodes per element: " + numbered("", npe) + ")");
 }
 
+void
+GenesisMesh::BlockNamesToOnProcessorBlockIds(std::vector<std::string> const& block_names, std::vector<int>& block_ids) const
+{
+  block_ids.clear();
+  for (auto const& name : block_names)
+    if (HasBlock(name)) block_ids.push_back(GetBlockId(name));
+}
+
 int
 GenesisMesh::GetBlockId(std::string const& block_name) const
 {

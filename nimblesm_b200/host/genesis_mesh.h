@@ -122,6 +122,9 @@ class GenesisMesh
   }
   int
   GetBlockId(std::string const& block_name) const;
+  // ids of the named blocks that exist on this rank (src/nimble_genesis_mesh.cc:525-534)
+  void
+  BlockNamesToOnProcessorBlockIds(std::vector<std::string> const& block_names, std::vector<int>& block_ids) const;
   int
   GetDim() const
   {

@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "boundary_condition.h"
+#include "contact_manager.h"
 #include "data_manager.h"
 #include "exodus_output.h"
 #include "expression.h"
@@ -321,6 +322,37 @@ nsmh_bc_programs(const char* genesis_path, const char* deck_text, double t, char
     for (size_t k = 0; k < sv.size(); ++k) j << (k ? "," : "") << sv[k];
     j << "]}";
     return put(out, outlen, j.str(), err, errlen);
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
+// ContactManager's host side on a Genesis file + deck: the entity lists CreateContactEntities sends to the device
+// (no device involved).  Arrays may be null to query the counts: n[0] primary faces, n[1] contact nodes.
+int
+nsmh_contact_entities(const char* genesis_path, const char* deck_text, long long n[2], double* penalty, int* face_nodes, int* face_entity_ids,
+                      double* face_len, int* contact_nodes, double* contact_len, char* err, int errlen)
+{
+  try {
+    GenesisMesh m;
+    m.ReadFile(genesis_path);
+    Parser p;
+    p.InitializeFromString(deck_text);
+    if (!p.HasContact()) return fail(err, errlen, "the deck has no contact line");
+    std::vector<std::string> pn, sn;
+    ParseContactCommand(p.ContactString(), pn, sn, *penalty);
+    std::vector<int> pi, si;
+    m.BlockNamesToOnProcessorBlockIds(pn, pi);
+    m.BlockNamesToOnProcessorBlockIds(sn, si);
+    ContactEntityLists l;
+    ContactManager::BuildEntityLists(m, pi, si, l);
+    n[0] = (long long)l.primary_face_char_len.size(), n[1] = (long long)l.contact_node_ids.size();
+    if (face_nodes) std::copy(l.primary_face_nodes.begin(), l.primary_face_nodes.end(), face_nodes);
+    if (face_entity_ids) std::copy(l.primary_face_entity_ids.begin(), l.primary_face_entity_ids.end(), face_entity_ids);
+    if (face_len) std::copy(l.primary_face_char_len.begin(), l.primary_face_char_len.end(), face_len);
+    if (contact_nodes) std::copy(l.contact_node_ids.begin(), l.contact_node_ids.end(), contact_nodes);
+    if (contact_len) std::copy(l.contact_node_char_len.begin(), l.contact_node_char_len.end(), contact_len);
+    return 0;
   } catch (std::exception const& e) {
     return fail(err, errlen, e.what());
   }

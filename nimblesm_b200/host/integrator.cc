@@ -1,6 +1,8 @@
 // nimblesm_b200/host/integrator.cc — see integrator.h.
 #include "integrator.h"
 
+#include "contact_manager.h"
+
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -59,6 +61,23 @@ ExplicitTimeIntegrator::Integrate()
   auto internal_force = model_data->GetVectorNodeData("internal_force");
   auto external_force = model_data->GetVectorNodeData("external_force");
 
+  // contact entities (explicit_time_integrator.cc:66-99): block names of the `contact:` line -> ids on this rank ->
+  // skin faces / contact nodes, sent to the device once
+  auto       contact_manager = GetContactManager(data_manager);
+  const bool contact_enabled = parser.HasContact();
+  Viewify<2> contact_force;
+  if (contact_enabled) {
+    std::vector<std::string> contact_primary_block_names, contact_secondary_block_names;
+    double                   penalty_parameter = 0.0;
+    ParseContactCommand(parser.ContactString(), contact_primary_block_names, contact_secondary_block_names, penalty_parameter);
+    std::vector<int> contact_primary_block_ids, contact_secondary_block_ids;
+    Mesh().BlockNamesToOnProcessorBlockIds(contact_primary_block_names, contact_primary_block_ids);
+    Mesh().BlockNamesToOnProcessorBlockIds(contact_secondary_block_names, contact_secondary_block_ids);
+    contact_manager->SetPenaltyParameter(penalty_parameter);
+    contact_manager->CreateContactEntities(Mesh(), *data_manager.GetVectorCommunicator(), contact_primary_block_ids, contact_secondary_block_ids);
+    contact_force = model_data->GetVectorNodeData("contact_force");
+  }
+
   model_data->ComputeLumpedMass(data_manager);
   double critical_time_step = model_data->GetCriticalTimeStep();
   auto   group              = data_manager.GetVectorCommunicator()->Group();
@@ -95,7 +114,7 @@ ExplicitTimeIntegrator::Integrate()
 
   // the reference's timer regions (explicit_time_integrator.cc:172-279): host wall clock per region in the
   // call-by-call sequence; in the fused path the device reports the split of a run of steps (CUDA events)
-  double     total_dynamics_time = 0.0, total_force_time = 0.0, total_exodus_write_time = 0.0, total_vector_reduction_time = 0.0;
+  double     total_dynamics_time = 0.0, total_force_time = 0.0, total_exodus_write_time = 0.0, total_vector_reduction_time = 0.0, total_contact_time = 0.0;
   auto       seconds_since       = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
   const auto t0 = std::chrono::steady_clock::now();
   if (!reference_sequence_) {
@@ -144,9 +163,19 @@ ExplicitTimeIntegrator::Integrate()
       model_data->ComputeInternalForce(data_manager, time_previous, time_current, is_output_step, displacement, internal_force);
       total_force_time += seconds_since(t_region);
       t_region = std::chrono::steady_clock::now();
-      for (int i = 0; i < num_nodes; ++i) {
-        const double one_over_m = 1.0 / lumped_mass(i);
-        for (int c = 0; c < 3; ++c) acceleration(i, c) = one_over_m * (internal_force(i, c) + external_force(i, c));
+      if (contact_enabled) {  // :232-249
+        contact_manager->ComputeContactForce(step + 1, false, contact_force);
+        total_contact_time += seconds_since(t_region);
+        t_region = std::chrono::steady_clock::now();
+        for (int i = 0; i < num_nodes; ++i) {
+          const double one_over_m = 1.0 / lumped_mass(i);
+          for (int c = 0; c < 3; ++c) acceleration(i, c) = one_over_m * (internal_force(i, c) + external_force(i, c) + contact_force(i, c));
+        }
+      } else {
+        for (int i = 0; i < num_nodes; ++i) {
+          const double one_over_m = 1.0 / lumped_mass(i);
+          for (int c = 0; c < 3; ++c) acceleration(i, c) = one_over_m * (internal_force(i, c) + external_force(i, c));
+        }
       }
       axpy(velocity, half_delta_time, acceleration);
       model_data->UpdateWithNewVelocity(data_manager, half_delta_time);
@@ -176,7 +205,7 @@ ExplicitTimeIntegrator::Integrate()
     if (!fs.is_open())
       std::cerr << "Failed to open timing data file" << std::endl;
     else
-      fs << num_ranks << "\t" << step_loop_seconds_ << "\t" << total_force_time << "\t" << 0.0 << "\t" << total_exodus_write_time << "\t"
+      fs << num_ranks << "\t" << step_loop_seconds_ << "\t" << total_force_time << "\t" << total_contact_time << "\t" << total_exodus_write_time << "\t"
          << total_vector_reduction_time << "\n";
   }
   if (talk) {
@@ -186,6 +215,8 @@ ExplicitTimeIntegrator::Integrate()
     std::cout << "Total step time = " << step_loop_seconds_ << " s (" << upd << " element-updates/s on rank 0, output included)\n";
     std::cout << " --- Update A, V, U: " << total_dynamics_time << (reference_sequence_ ? "" : "  (device time; includes the shared-node exchange)") << '\n';
     std::cout << " --- Force: " << total_force_time << (reference_sequence_ ? "" : "  (device time of the element kernels)") << "\n";
+    if (contact_enabled)
+      std::cout << " --- Contact time: " << total_contact_time << (reference_sequence_ ? "" : "  (on the device, inside the update time)") << '\n';
     if (num_ranks > 1) std::cout << " --- Vector Reduction = " << total_vector_reduction_time << "  (on the device, inside the update time)\n";
     std::cout << " --- Exodus Write = " << total_exodus_write_time << "\n";
   }

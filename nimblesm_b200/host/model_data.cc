@@ -38,7 +38,7 @@ contains(const C& c, const T& v)
 }
 
 const char* const kDeviceFieldLabels[NSM_FIELD_COUNT] = {"lumped_mass",  "reference_coordinate", "displacement", "velocity",
-                                                         "acceleration", "internal_force",       "external_force"};
+                                                         "acceleration", "internal_force",       "external_force", "contact_force"};
 
 }  // namespace
 
@@ -350,9 +350,9 @@ void
 ModelData::PullNodalFields()
 {
   DeviceContext& d = *device_;
-  for (const char* label : {"displacement", "velocity", "acceleration", "internal_force"}) {
+  for (const char* label : {"displacement", "velocity", "acceleration", "internal_force", "contact_force"}) {
     const int id = GetFieldId(label);
-    if (id < 0) continue;
+    if (id < 0 || (std::string(label) == "contact_force" && !contact_on_device_)) continue;
     d.check(nsm_b200_download_field_async(d.get(), device_field(label), fields_[id].data), "ModelData::PullNodalFields");
   }
   d.check(nsm_b200_sync(d.get()), "ModelData::PullNodalFields (sync)");

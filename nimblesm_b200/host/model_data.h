@@ -213,6 +213,13 @@ class ModelData : public ModelDataBase
   {
     return device_update_seconds_;
   }
+  // contact entities were sent to the device (ContactManager::CreateContactEntities): the fused steps carry the contact
+  // term and PullNodalFields also brings the contact force home
+  void
+  SetContactOnDevice(bool on)
+  {
+    contact_on_device_ = on;
+  }
   void
   PushNodalFields();  // host mirrors (u, v, a) -> device
   void
@@ -246,6 +253,7 @@ class ModelData : public ModelDataBase
   std::vector<double>                   bc_slots_;
   bool                                  bc_table_sent_ = false, bc_programs_sent_ = false;
   int                                   num_nodes_     = 0;
+  bool                                  contact_on_device_ = false;
 };
 
 }  // namespace nimble_b200

@@ -81,6 +81,11 @@ class Parser
     return !contact_string_.empty();
   }
   std::string
+  ContactString() const
+  {
+    return contact_string_;
+  }
+  std::string
   GetModelMaterialParameters(int block_id) const;  // "none" for a block the deck does not list
   int
   GetBlockIdFromMaterial(const std::string& material_key) const;

@@ -1,0 +1,238 @@
+"""GPU tests of the penalty contact (second half): csrc/contact.cuh behind nsm_b200_set_contact /
+nsm_b200_contact_force / the contact term of nsm_b200_step, and the host ContactManager inside the NimbleSM_b200 driver.
+
+Checker: oracle/contact_oracle.c (pinned bit for bit to the reference's own ContactEntity objects and to the reference's
+gold files, tests/test_oracle.py).  Bars: contact force of a given displacement within 1e-12 (max-norm relative; each
+pair's force has the oracle's bits, only the order of the sum over pairs differs) with the SAME set of accepted pairs;
+fields after N steps within 1e-9 * max; the reference's gold files under the reference's exodiff rules."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, load_golden
+from tests.test_gpu_host_cpp import EXE, _run
+from tests.test_host_cpp import LIB as HOST_LIB
+from tests.test_host_cpp import host_contact_entities
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    s = np.abs(b).max()
+    return np.abs(a - b).max() / (s if s > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def host():
+    return C.CDLL(HOST_LIB)
+
+
+def _context(mesh, deck_obj, flags=0, assembly=None):
+    from nimblesm_b200 import capi
+
+    c = capi.Context(0)
+    c.set_nodes(mesh["x"], mesh["y"], mesh["z"])
+    for b in mesh["block_ids"]:
+        m = deck_obj.block_material(b)
+        c.add_block(b, mesh["conn"][b], m.model, m.bulk_modulus, m.shear_modulus, m.density)
+    c.finalize(capi.ASSEMBLY_ORDERED if assembly is None else assembly, flags)
+    return c
+
+
+@pytest.mark.parametrize("flags", [0, 8])
+def test_contact_force_vs_oracle(oracle, host, tmp_path, flags):
+    """One-shot evaluations on the cubes_contact mesh: entity lists from the C++ ContactManager, displacement fields in
+    contact, separated, and pushed through by more than the facets' characteristic length.  Same accepted pairs and
+    active entities as the oracle's all-pairs walk, force within 1e-12; also with the nodes renumbered inside the context."""
+    from nimblesm_b200.deck import parse_deck
+    from nimblesm_b200.exodus_py import write_genesis
+    from oracle.model import OracleModel
+
+    deck, mesh, *_ = load_golden("cubes_contact")
+    g = str(tmp_path / "c.g")
+    write_genesis(g, mesh)
+    ent = host_contact_entities(host, g, deck)
+    om = OracleModel(deck, mesh)
+    n = len(mesh["x"])
+    in_b1 = np.zeros(n, bool)
+    in_b1[np.unique(mesh["conn"][1])] = True
+    rng = np.random.default_rng(5)
+    total = 0
+    with _context(mesh, parse_deck(deck), flags) as c:
+        c.set_contact(ent["penalty"], ent["primary_quads"], ent["primary_char_len"], ent["contact_nodes"], ent["contact_node_char_len"])
+        for amp, shift in ((0.0, 0.0), (1e-4, 0.0), (1e-3, -2e-3), (1e-2, -0.02), (1e-3, 0.05), (0.0, -1.0), (1e-3, -3e-3)):
+            u = amp * (2.0 * rng.random((n, 3)) - 1.0)
+            u[in_b1, 2] += shift
+            want, pairs, status = om.contact.force(u, want_status=True)
+            got = c.contact_force_host(u)
+            st = c.contact_stats()
+            assert st["pairs"] == pairs, (amp, shift, st)
+            assert st["active_faces"] == int(status[:4 * len(ent["primary_quads"])].sum())
+            assert st["active_nodes"] == int(status[4 * len(ent["primary_quads"]):].sum())
+            assert st["box_tested"] >= pairs
+            if pairs:
+                assert _rel(got, want) <= 1e-12, (amp, shift, _rel(got, want))
+            else:
+                assert not got.any()
+            total += pairs
+            # the device-resident call gives the same field
+            c.upload("displacement", u)
+            c.contact_force()
+            assert _rel(c.download("contact_force"), want) <= 1e-12
+        # switching contact off clears the field
+        c.set_contact(0.0, np.zeros((0, 4), np.int32), np.zeros(0), np.zeros(0, np.int32), np.zeros(0))
+        assert not c.download("contact_force").any() and c.contact_stats()["pairs"] == 0
+    assert total > 100
+
+
+def test_contact_argument_errors(host, tmp_path):
+    from nimblesm_b200 import capi
+    from nimblesm_b200.deck import parse_deck
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, *_ = load_golden("cubes_contact")
+    g = str(tmp_path / "c.g")
+    write_genesis(g, mesh)
+    ent = host_contact_entities(host, g, deck)
+    with _context(mesh, parse_deck(deck)) as c:
+        with pytest.raises(capi.NsmError):  # no entities yet
+            c.contact_force()
+        with pytest.raises(capi.NsmError):
+            c.download("contact_force")
+        with pytest.raises(capi.NsmError) as e:  # ComputeContactForce: invalid penalty_parameter
+            c.set_contact(0.0, ent["primary_quads"], ent["primary_char_len"], ent["contact_nodes"], ent["contact_node_char_len"])
+        assert "penalty_parameter" in str(e.value)
+        bad = ent["primary_quads"].copy()
+        bad[3, 2] = len(mesh["x"])
+        with pytest.raises(capi.NsmError):
+            c.set_contact(1.0, bad, ent["primary_char_len"], ent["contact_nodes"], ent["contact_node_char_len"])
+
+
+@pytest.mark.parametrize("assembly", ["ordered", "atomic"])
+def test_contact_steps_vs_oracle(oracle, host, tmp_path, assembly):
+    """The explicit loop with the contact term on the device (nsm_b200_step: predict, elements, contact, correct) against
+    the oracle's loop on cubes_contact: 100 steps in runs of 1 / 7 / the rest, contact force and fields at 1e-9 * max
+    (measured ~1e-14), the same number of enforced pairs at the end."""
+    from nimblesm_b200 import capi
+    from nimblesm_b200.deck import parse_deck
+    from nimblesm_b200.exodus_py import write_genesis
+    from oracle.model import OracleModel
+
+    deck, mesh, *_ = load_golden("cubes_contact")
+    g = str(tmp_path / "c.g")
+    write_genesis(g, mesh)
+    ent = host_contact_entities(host, g, deck)
+    d = parse_deck(deck)
+    om = OracleModel(deck, mesh)
+    om.begin()
+    om.advance(100)
+    tn, tc, tv = [], [], []
+    v0 = np.zeros((len(mesh["x"]), 3))
+    for bc in d.boundary_conditions:
+        ns = mesh["node_sets"][bc.node_set_id]
+        if bc.kind == "initial_velocity":
+            v0[ns, bc.coordinate] = bc.magnitude
+        else:
+            tn.append(ns), tc.append(np.full(len(ns), bc.coordinate, np.int32)), tv.append(np.full(len(ns), bc.magnitude))
+    tn, tc, tv = np.concatenate(tn).astype(np.int32), np.concatenate(tc), np.concatenate(tv)
+    asm = capi.ASSEMBLY_ORDERED if assembly == "ordered" else capi.ASSEMBLY_ATOMIC
+    with _context(mesh, d, 2, asm) as c:
+        c.compute_lumped_mass()
+        c.set_contact(ent["penalty"], ent["primary_quads"], ent["primary_char_len"], ent["contact_nodes"], ent["contact_node_char_len"])
+        c.set_bc_table(tn, tc, np.zeros(len(tn), np.int32))
+        c.set_bc_values(tv)
+        for k in range(len(tn)):  # ApplyKinematicConditions at t = 0 (later entries win)
+            v0[tn[k], tc[k]] = tv[k]
+        c.upload("velocity", v0)
+        dt = (d.final_time - d.initial_time) / d.num_load_steps
+        t = c.step(1, 0.0, dt)
+        t = c.step(7, t, dt)
+        t = c.step(92, t, dt, store_ipt_last=True)  # the last step is an output step: boundary conditions once more
+        assert t == om.time
+        for lbl, want in (("displacement", om.u), ("velocity", om.v), ("acceleration", om.a), ("contact_force", om.fcontact)):
+            assert _rel(c.download(lbl), want) <= 1e-9, lbl
+        assert c.contact_stats()["pairs"] == om.contact_pairs > 0
+        # Forces on the SAME displacement (the 1e-12 bar).  The force of the oracle's own trajectory is a weaker check in
+        # this deck: x = X + u carries 1e-16 of rounding, the strain 1e-15, the stress K * 1e-15 = 1.6e-4 -- one ulp of u
+        # moves nodal forces by ~2e-4 of a maximum of 9e4 (2e-9), whoever computes them.
+        ug = c.download("displacement")
+        f_same = np.zeros_like(ug)
+        for b in sorted(mesh["block_ids"]):
+            m = d.block_material(b)
+            fb, _ed = oracle.internal_force(oracle.NEOHOOKEAN, m.bulk_modulus, m.shear_modulus, om.ref, ug, mesh["conn"][b], False)
+            f_same += fb
+        assert _rel(c.download("internal_force"), f_same) <= 1e-12
+        assert _rel(c.download("contact_force"), om.contact.force(ug)[0]) <= 1e-12
+        assert _rel(c.download("internal_force"), om.f) <= 1e-7
+        # the host-state step takes the plain schedule with contact and carries the same term
+        U, V, A, Fo = (c.download(l) for l in ("displacement", "velocity", "acceleration", "internal_force"))
+        t2 = c.step_host(t, dt, U, V, A, Fo)
+    om.advance(1)
+    assert t2 == om.time and _rel(U, om.u) <= 1e-9 and _rel(A, om.a) <= 1e-9
+
+
+@pytest.mark.parametrize("case", ["cubes_contact", "sphere_plate_contact", "sliding_contact"])
+@pytest.mark.parametrize("extra", [(), ("--assembly", "atomic"), ("--reference_sequence",)])
+def test_driver_runs_contact_decks(case, extra, tmp_path):
+    """NimbleSM_b200 on the reference's contact decks (the reference runs them only in its Kokkos + ArborX / BVH builds):
+    deck -> Genesis mesh -> ContactManager (skinning, entities) -> device steps with the contact term -> Exodus output.
+    The output is compared with the reference's gold file under the reference's exodiff rules and with snapshots of the
+    reference's serial code + ContactEntity objects (tests/golden) at 1e-9 * max, contact_force included; fused stepping,
+    ATOMIC assembly, and the call-by-call reference sequence (ComputeContactForce on host views)."""
+    from nimblesm_b200 import exodiff
+    from nimblesm_b200.exodus_py import read_results
+
+    if case == "sliding_contact" and extra:
+        pytest.skip("1000 steps of a 1149-element deck: one schedule is enough")
+    _deck, mesh, gold, ref, _pieces, out = _run(tmp_path, case, extra=extra)
+    res = read_results(out)
+    idx = ref["snapshot_index"] if "snapshot_index" in ref else np.arange(len(ref["times"]))
+    assert np.array_equal(res["times"][idx], ref["times"])
+    for lbl in ("displacement", "velocity", "internal_force", "contact_force"):
+        want = ref["node_" + lbl]
+        # internal force of a TRAJECTORY: one ulp of u moves it by K * eps * |X| (see test_contact_steps_vs_oracle); the
+        # tight bar for it is the same-displacement check below
+        bar = 1e-7 if lbl == "internal_force" else 1e-9
+        for i, comp in enumerate("xyz"):
+            key = "%s_%s" % (lbl, comp)
+            if key in res["nod"]:
+                assert np.abs(res["nod"][key][idx] - want[:, :, i]).max() <= bar * np.abs(want).max(), key
+    assert "contact_force_z" in res["nod"] and np.abs(res["nod"]["contact_force_x"]).max() > 0
+    # forces of the file's own displacement at the last output step, recomputed by the oracle: 1e-12
+    from nimblesm_b200.deck import parse_deck
+    from oracle import contact as contact_oracle
+    from oracle import hex8
+
+    d = parse_deck(_deck)
+    X = np.ascontiguousarray(np.stack([mesh["x"], mesh["y"], mesh["z"]], 1))
+    u_last = np.ascontiguousarray(np.stack([res["nod"]["displacement_" + comp][-1] for comp in "xyz"], 1))
+    prim, sec, penalty = contact_oracle.parse_contact_command(d.contact_string)
+    ids = lambda names: [int(nm.rsplit("_", 1)[1]) for nm in names]
+    fc_want, pairs = contact_oracle.ContactSetup(mesh, ids(prim), ids(sec), penalty).force(u_last)
+    fc_got = np.stack([res["nod"]["contact_force_" + comp][-1] for comp in "xyz"], 1)
+    assert np.abs(fc_got - fc_want).max() <= 1e-12 * max(np.abs(fc_want).max(), 1e-300) and (pairs > 0 or not fc_got.any())
+    if "internal_force_x" in res["nod"]:
+        f_want = np.zeros_like(X)
+        for b in sorted(mesh["block_ids"]):
+            m = d.block_material(b)
+            fb, _ed = hex8.internal_force(hex8.NEOHOOKEAN, m.bulk_modulus, m.shear_modulus, X, u_last, mesh["conn"][b], False)
+            f_want += fb
+        f_got = np.stack([res["nod"]["internal_force_" + comp][-1] for comp in "xyz"], 1)
+        assert np.abs(f_got - f_want).max() <= 1e-12 * np.abs(f_want).max()
+    if len(gold["times"]):
+        fails = exodiff.compare(gold["exodiff"], gold, res)
+        assert not fails, fails[:5]
+
+
+def test_driver_refuses_contact_across_partitions(tmp_path):
+    import subprocess
+
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, *_ = load_golden("cubes_contact")
+    write_genesis(str(tmp_path / "cubes_contact.g"), mesh)
+    (tmp_path / "case.in").write_text(deck)
+    r = subprocess.run([EXE, "--quiet", "--gpus", "2", "--devices", "0,0", "case.in"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "contact across mesh partitions" in r.stderr

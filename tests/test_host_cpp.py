@@ -352,3 +352,59 @@ def test_vector_communicator_tables_match_python(host, case, P):
         assert list(peers[:npeers.value]) == list(wp)
         assert list(poff[:npeers.value + 1]) == list(wo)
         assert list(pnodes[:poff[npeers.value]]) == list(wn)
+
+
+def host_contact_entities(host, genesis_path, deck):
+    """ContactManager::BuildEntityLists through the C shim -> dict (mesh node ids)."""
+    n = (C.c_longlong * 2)()
+    pen = C.c_double()
+    err = C.create_string_buffer(2048)
+    assert host.nsmh_contact_entities(genesis_path.encode(), deck.encode(), n, C.byref(pen), None, None, None, None, None, err, 2048) == 0, err.value
+    nf, nn = int(n[0]), int(n[1])
+    quads, ids, flen = np.zeros((nf, 4), np.int32), np.zeros(nf, np.int32), np.zeros(nf)
+    nodes, nlen = np.zeros(nn, np.int32), np.zeros(nn)
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    assert host.nsmh_contact_entities(genesis_path.encode(), deck.encode(), n, C.byref(pen), quads.ctypes.data_as(ip), ids.ctypes.data_as(ip),
+                                      flen.ctypes.data_as(dp), nodes.ctypes.data_as(ip), nlen.ctypes.data_as(dp), err, 2048) == 0, err.value
+    return {"penalty": pen.value, "primary_quads": quads, "primary_entity_ids": ids, "primary_char_len": flen, "contact_nodes": nodes,
+            "contact_node_char_len": nlen}
+
+
+@pytest.mark.parametrize("case", ["cubes_contact", "sphere_plate_contact", "sliding_contact"])
+def test_contact_manager_entity_lists(host, tmp_path, case):
+    """ContactManager::SkinBlocks / CreateContactEntities (host side, C++): the skin quads of the primary blocks in the
+    reference's std::map order, the contact nodes of the secondary blocks in order of first appearance, and both
+    characteristic lengths -- equal, value for value, to what the glue around the reference's own ContactEntity objects
+    built from the same deck (tests/golden, oracle/ref_contact.cc)."""
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, _gold, ref, _ = load_golden(case)
+    g = str(tmp_path / "c.g")
+    write_genesis(g, mesh)
+    got = host_contact_entities(host, g, deck)
+    assert got["penalty"] == float("0.33333333333333333333333333333e12")
+    for k in ("primary_quads", "contact_nodes", "primary_char_len", "contact_node_char_len"):
+        assert np.array_equal(got[k], ref["contact_" + k]), k
+    # entity ids: (element global id + 1 + largest node global id) << 5 | face ordinal << 2, unique per face
+    assert len(set(got["primary_entity_ids"].tolist())) == len(got["primary_quads"])
+    assert np.all((got["primary_entity_ids"] & 3) == 0) and np.all(((got["primary_entity_ids"] >> 2) & 7) < 6)
+
+
+def test_contact_command_errors(host, tmp_path):
+    """ParseContactCommand keeps the reference's error behaviour (src/nimble_contact_manager.cc:95-149)."""
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, *_ = load_golden("cubes_contact")
+    g = str(tmp_path / "c.g")
+    write_genesis(g, mesh)
+    n, pen, err = (C.c_longlong * 2)(), C.c_double(), C.create_string_buffer(2048)
+    base = "\n".join(l for l in deck.splitlines() if not l.startswith("contact:"))
+    for line, msg in (("contact: main_blocks block_2 secondary_blocks block_1 penalty_parameter 1.0", b"unknown key: main_blocks"),
+                      ("contact: primary_blocks block_2 penalty_parameter 1.0", b"secondary_blocks"),
+                      ("contact: primary_blocks block_2 secondary_blocks block_1", b"penalty_parameter")):
+        rc = host.nsmh_contact_entities(g.encode(), (base + "\n" + line + "\n").encode(), n, C.byref(pen), None, None, None, None, None, err, 2048)
+        assert rc == 1 and msg in err.value, err.value
+    # the deprecated spelling is still read
+    ok = base + "\ncontact: master_blocks block_2 slave_blocks block_1 penalty_parameter 2.5e11\n"
+    assert host.nsmh_contact_entities(g.encode(), ok.encode(), n, C.byref(pen), None, None, None, None, None, err, 2048) == 0, err.value
+    assert pen.value == 2.5e11 and n[0] == 384 and n[1] == 518
