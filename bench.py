@@ -389,10 +389,11 @@ def main():
     ap.add_argument("--material", default="neohookean", choices=["neohookean", "elastic", "j2_plasticity"],
                     help="j2_plasticity: the history-dependent model of the state-variable slot (yield 5e8, hardening 2e10); "
                          "its parity is pinned by tests/test_gpu_state.py, the bench line only measures it")
-    ap.add_argument("--workload", default="cube", choices=["cube", "twoblock"],
+    ap.add_argument("--workload", default="cube", choices=["cube", "twoblock", "contact"],
                     help="twoblock: BASELINE.json configs[4], every brick split at its mid-x plane into an elastic "
                          "block 1 and a neohookean block 2 (brick_with_fibers material_2 constants), prescribed "
-                         "velocity on both global x faces")
+                         "velocity on both global x faces; contact: two stacked bodies of EDGE x EDGE x EDGE/2 neohookean "
+                         "elements, the upper one falling onto the lower one (penalty contact, SURVEY §8 f-4); one GPU")
     ap.add_argument("--assembly", default="atomic", choices=["atomic", "ordered"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--flags", type=int, default=2, help="nsm_b200_finalize flags (2 = cache the reference Jacobians)")
@@ -410,6 +411,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "contact":
+        return run_contact(args)
 
     from nimblesm_b200 import capi
     from nimblesm_b200.mesh import brick_surface_gids, cube_partition, brick_grid, shared_node_tables
@@ -670,6 +673,154 @@ def main():
         bad.append("parity check failed: %r" % (parity,))
     if bad:
         sys.stderr.write("bench.py: " + "; ".join(bad) + "\n")
+        sys.exit(3)
+
+
+def contact_stack(n):
+    """Two bodies of n x n x n/2 unit-aspect elements (h = 1/n): block 2 (primary) fills z in [0, 1/2], block 1
+    (secondary) sits a thousandth of h above it, shifted by (0.37 h, 0.21 h) so that its bottom nodes meet the lower
+    body's top facets at generic positions.  Returns the mesh, the contact entities as ContactManager builds them for a
+    structured body (all six sides of each skin; Exodus face orders, outward normals) and the node sets."""
+    from nimblesm_b200.mesh import HEX_CORNERS
+
+    h, nz = 1.0 / n, n // 2
+    face_of_side = {"z-": (4, [0, 3, 2, 1]), "z+": (5, [4, 5, 6, 7]), "x-": (3, [0, 4, 7, 3]), "x+": (1, [1, 2, 6, 5]),
+                    "y-": (0, [0, 1, 5, 4]), "y+": (2, [2, 3, 7, 6])}
+
+    def body(origin, node_base):
+        nx = ny = n + 1
+        idx = np.arange(nx * ny * (nz + 1), dtype=np.int64)
+        i, j, k = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+        xyz = [origin[0] + i * h, origin[1] + j * h, origin[2] + k * h]
+        e = np.arange(n * n * nz, dtype=np.int64)
+        ei, ej, ek = e % n, (e // n) % n, e // (n * n)
+        conn = np.empty((len(e), 8), dtype=np.int32)
+        for c_, (di, dj, dk) in enumerate(HEX_CORNERS):
+            conn[:, c_] = node_base + (ei + di) + nx * ((ej + dj) + ny * (ek + dk))
+        sides = {"z-": ek == 0, "z+": ek == nz - 1, "x-": ei == 0, "x+": ei == n - 1, "y-": ej == 0, "y+": ej == n - 1}
+        quads = np.concatenate([conn[sel][:, face_of_side[sd][1]] for sd, sel in sides.items()])
+        return xyz, conn, quads, (i, j, k)
+
+    lo_xyz, lo_conn, lo_quads, lo_ijk = body((0.0, 0.0, 0.0), 0)
+    n_lo = len(lo_xyz[0])
+    up_xyz, up_conn, up_quads, _ = body((0.37 * h, 0.21 * h, 0.5 + 1.0e-3 * h), n_lo)
+    mesh = dict(x=np.concatenate([lo_xyz[0], up_xyz[0]]), y=np.concatenate([lo_xyz[1], up_xyz[1]]),
+                z=np.concatenate([lo_xyz[2], up_xyz[2]]), block_ids=[1, 2], conn={1: up_conn, 2: lo_conn},
+                node_sets={"bottom": np.flatnonzero(lo_ijk[2] == 0).astype(np.int32),
+                           "upper": np.arange(n_lo, n_lo + len(up_xyz[0]), dtype=np.int32)})
+    X = np.stack([mesh["x"], mesh["y"], mesh["z"]], 1)
+
+    def longest_edge(q):  # ContactManager::CreateContactEntities: longest edge of a skin face, model configuration
+        e = [np.sqrt(((X[q[:, (a + 1) % 4]] - X[q[:, a]]) ** 2).sum(1)) for a in range(4)]
+        return np.max(e, axis=0)
+
+    flat = up_quads.ravel()
+    _u, first = np.unique(flat, return_index=True)
+    contact_nodes = flat[np.sort(first)].astype(np.int32)
+    node_len = np.zeros(len(X))
+    np.maximum.at(node_len, up_quads.ravel(), np.repeat(longest_edge(up_quads), 4))
+    ent = dict(primary_quads=np.ascontiguousarray(lo_quads, dtype=np.int32), primary_char_len=longest_edge(lo_quads),
+               contact_nodes=contact_nodes, contact_node_char_len=node_len[contact_nodes])
+    return mesh, ent, h
+
+
+def run_contact(args):
+    """`--workload contact`: the explicit step WITH the contact term on one GPU.  Reports the step with
+    and without contact, the contact evaluation alone, the pair counters, and a parity block (contact force of a window
+    of contact nodes recomputed by the oracle on the device's own displacement)."""
+    from nimblesm_b200 import capi
+
+    n = args.n if args.n != 400 else 200
+    mesh, ent, h = contact_stack(n)
+    n_elem, n_nodes = sum(len(c_) for c_ in mesh["conn"].values()), len(mesh["x"])
+    c = capi.Context(0)
+    c.set_nodes(mesh["x"], mesh["y"], mesh["z"])
+    for b in (1, 2):
+        c.add_block(b, mesh["conn"][b], "neohookean", BULK, SHEAR, RHO)
+    c.finalize(capi.ASSEMBLY_ORDERED if args.assembly == "ordered" else capi.ASSEMBLY_ATOMIC, args.flags)
+    c.compute_lumped_mass()
+    dt_user = 0.2 * h / np.sqrt(BULK / RHO)
+    penalty = BULK * h  # the stiffness of one element face
+    bottom = mesh["node_sets"]["bottom"]
+    c.set_bc_table(np.repeat(bottom, 3), np.tile(np.arange(3, dtype=np.int32), len(bottom)), np.zeros(3 * len(bottom), np.int32))
+    c.set_bc_values(np.zeros(3 * len(bottom)))
+    v0 = np.zeros((n_nodes, 3))
+    v0[mesh["node_sets"]["upper"], 2] = -1000.0  # closes the 1e-3 h gap in the third step
+    results = {}
+    for mode in ("with_contact", "without_contact"):
+        if mode == "with_contact":
+            c.set_contact(penalty, ent["primary_quads"], ent["primary_char_len"], ent["contact_nodes"], ent["contact_node_char_len"])
+        else:
+            c.set_contact(0.0, np.zeros((0, 4), np.int32), np.zeros(0), np.zeros(0, np.int32), np.zeros(0))
+        c.upload("displacement", np.zeros((n_nodes, 3)))
+        c.upload("acceleration", np.zeros((n_nodes, 3)))
+        c.upload("velocity", v0)
+        t = c.step(max(args.warmup, 3), 0.0, dt_user)
+        sampler = ClockSampler(0)
+        sampler.start()
+        c.profile(True)
+        l0 = c.launch_count
+        c.sync()
+        sampler.mark_begin()
+        c.timer_start()
+        t = c.step(args.steps, t, dt_user)
+        ms = c.timer_stop()
+        sampler.mark_end()
+        clocks = sampler.stop()
+        elem_ms, node_ms, _np = c.profile_read()
+        c.profile(False)
+        results[mode] = {"ms_per_step": ms / args.steps, "element_kernels_ms": elem_ms, "node_side_ms": node_ms,
+                         "gpu_launches": int(c.launch_count - l0), "clocks": clocks}
+        if mode == "with_contact":
+            stats = c.contact_stats()
+            c.timer_start()
+            for _ in range(20):
+                c.contact_force()
+            eval_ms = c.timer_stop() / 20
+            # parity: a window of contact nodes around the middle of the interface, facets near them, oracle on the device's u
+            from oracle import contact as contact_oracle
+
+            u = c.download("displacement")
+            fc = c.download("contact_force")
+            X = np.stack([mesh["x"], mesh["y"], mesh["z"]], 1)
+            cn = ent["contact_nodes"]
+            cur = X[cn] + u[cn]
+            w = 8.0 * h
+            near = (np.abs(cur[:, 0] - 0.5) < w) & (np.abs(cur[:, 1] - 0.5) < w) & (np.abs(cur[:, 2] - 0.5) < w)
+            qc = (X[ent["primary_quads"]] + u[ent["primary_quads"]]).mean(1)
+            qsel = (np.abs(qc[:, 0] - 0.5) < w + 3 * h) & (np.abs(qc[:, 1] - 0.5) < w + 3 * h) & (np.abs(qc[:, 2] - 0.5) < w + 3 * h)
+            want = np.zeros_like(X)
+            L = contact_oracle._lib()
+            pairs_w = L.h8o_contact_force(penalty, n_nodes, np.ascontiguousarray(X), np.ascontiguousarray(u), int(qsel.sum()),
+                                          np.ascontiguousarray(ent["primary_quads"][qsel]).reshape(-1),
+                                          np.ascontiguousarray(ent["primary_char_len"][qsel]), int(near.sum()),
+                                          np.ascontiguousarray(cn[near]), np.ascontiguousarray(ent["contact_node_char_len"][near]),
+                                          want, None)
+            scale = np.abs(fc[cn]).max()
+            err = float(np.abs(fc[cn[near]] - want[cn[near]]).max() / scale) if scale > 0 else 0.0
+            parity = {"checked": True, "window_contact_nodes": int(near.sum()), "window_pairs": int(pairs_w), "max_rel_fc": err,
+                      "ok": bool(err <= 1e-12 and pairs_w > 0 and stats["pairs"] > 0),
+                      "what": "contact force on the contact nodes of a 16h window of the interface, oracle/contact_oracle.c on the "
+                              "device's own displacement; bar 1e-12 of the largest nodal contact force"}
+    wc, nc = results["with_contact"], results["without_contact"]
+    out = {"metric": "hex8 element-updates/sec per explicit step", "value": n_elem * 1e3 / wc["ms_per_step"], "unit": "element-updates/s",
+           "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wc["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "two stacked neohookean bodies of %d x %d x %d elements each (%d elements), the upper one falling "
+                                  "onto the lower one, penalty contact between all of the lower skin (%d triangles) and the upper "
+                                  "skin nodes (%d)" % (n, n, n // 2, n_elem, 4 * len(ent["primary_quads"]), len(ent["contact_nodes"])),
+                      "assembly": args.assembly, "penalty": penalty, "dt": dt_user},
+           "gpu_launches": wc["gpu_launches"], "clocks": wc["clocks"],
+           "contact": {"step_ms_with_contact": wc["ms_per_step"], "step_ms_without_contact": nc["ms_per_step"],
+                       "cost_of_contact_ms_per_step": wc["ms_per_step"] - nc["ms_per_step"],
+                       "contact_evaluation_alone_ms": eval_ms, "launches_per_evaluation": 3,
+                       "pairs_enforced": stats["pairs"], "pairs_box_tested": stats["box_tested"],
+                       "active_triangles": stats["active_faces"], "active_nodes": stats["active_nodes"],
+                       "node_side_ms_with": wc["node_side_ms"], "node_side_ms_without": nc["node_side_ms"]},
+           "parity": parity, "without_contact": nc}
+    print(json.dumps(out))
+    if not wc["clocks"].get("samples") or not parity["ok"]:
+        sys.stderr.write("bench.py: contact workload: invalid line (%r)\n" % ({"clocks": wc["clocks"], "parity": parity},))
         sys.exit(3)
 
 

@@ -17,18 +17,30 @@
 //                           triangles' inflated boxes (narrowed to float exactly as ArborX::Point does), a grid-wide
 //                           minimum corner and maximum box extent (warp reductions + one atomic per warp), contact
 //                           force of the touched nodes cleared, hash heads cleared
-//   contact_bin_kernel      thread per triangle: cell of the box's minimum corner on a uniform grid of pitch
-//                           h >= every box extent, pushed on the chain of its hash bucket (atomicExch, no scan)
+//   contact_bin_kernel      thread per QUAD (its four triangles share three quarters of their boxes): cell of the
+//                           minimum corner of the union box on a uniform grid of pitch h >= every box extent, pushed
+//                           on the chain of its hash bucket (atomicExch, no scan, no sort)
 //   contact_pair_kernel     one WARP per contact node, lane l < 27 walks the chain of neighbour cell l: a box of extent
-//                           <= h anchored in cell n can only meet boxes anchored in n + {-1,0,1}^3; float box test,
-//                           projection and enforcement in the reference's operation order (so each pair's force has the
-//                           oracle's bits), red.global.add.f64 into the nodal contact force (the order of the sum over
-//                           pairs is not fixed: noise ~1e-16, as in the reference's own Kokkos::atomic_add scatter)
+//                           <= h anchored in cell n can only meet boxes anchored in n + {-1,0,1}^3; per quad the four
+//                           triangles' float boxes are tested exactly as ArborX tests them, then projection and
+//                           enforcement in the reference's operation order (so each pair's force has the oracle's
+//                           bits), red.global.add.f64 into the nodal contact force (the order of the sum over pairs is
+//                           not fixed: noise ~1e-16, as in the reference's own Kokkos::atomic_add scatter).  The kernel
+//                           is a chain of dependent L2 round trips per warp (node id -> coordinates -> bucket head ->
+//                           chain entry -> boxes -> vertices); binning quads instead of triangles cut the chain from
+//                           ~7 entries per occupied cell to ~2 (r02n -> r02o: 544 -> see DESIGN §3.8)
 #pragma once
 #include <float.h>
 #include <stdint.h>
 
 namespace nsm {
+
+struct alignas(32) QuadBin
+{
+  long long cell[3];
+  int       next;
+  int       pad;
+};
 
 struct ContactArgs
 {
@@ -44,12 +56,12 @@ struct ContactArgs
   // per-evaluation scratch
   double*    quad_xyz;  // [n_quads][15]: the four corners and the centre, current configuration
   float*     tri_box;   // [4 n_quads][6]: lo xyz, hi xyz
-  long long* tri_cell;  // [4 n_quads][3]
-  int*       next;      // [4 n_quads] hash chain
+  QuadBin*   bin;       // [n_quads] cell of the quad's union box + next quad of the hash chain
   int*       head;      // [table_mask + 1]
   unsigned   table_mask;
-  unsigned*  red;       // [4] this evaluation: ordered-float min corner x, y, z; max box extent (float bits, >= 0)
-  unsigned*  red_next;  // [4] the next evaluation's, reset here
+  unsigned*  red;       // [8] this evaluation: ordered-float min corner x, y, z of the triangles' boxes; max extent of any
+                        //     box (float bits, >= 0); ordered-float max corner x, y, z of the triangles' boxes; pad
+  unsigned*  red_next;  // [8] the next evaluation's, reset here
   unsigned long long* counters;  // [0] enforced pairs, [1] pairs that passed the box test
   unsigned char*      status;    // [4 n_quads + n_sec] contact_status flags of this evaluation
 };
@@ -86,9 +98,9 @@ contact_update_kernel(const ContactArgs p)
   const int64_t t   = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = t; i <= (int64_t)p.table_mask; i += nth) p.head[i] = -1;
-  if (t < 4) p.red_next[t] = t < 3 ? 0xffffffffu : 0u;
+  if (t < 8) p.red_next[t] = t < 3 ? 0xffffffffu : 0u;
   if (t < 2) p.counters[t] = 0ull;
-  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ext = 0.0f;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, ext = 0.0f;
   if (t < p.n_quads) {
     // ContactManager::ApplyDisplacements (src/nimble_contact_manager.cc:750-786) + ContactEntity::SetCoordinates
     // (src/nimble_contact_entity.h:236-258): the third vertex of every triangle is the mean of the quad's nodes
@@ -132,10 +144,12 @@ contact_update_kernel(const ContactArgs p)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         lo[d] = fminf(lo[d], box[d]);
-        ext   = fmaxf(ext, box[3 + d] - box[d]);
+        hi[d] = fmaxf(hi[d], box[3 + d]);
       }
       p.status[4 * t + k] = 0;
     }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) ext = fmaxf(ext, hi[d] - lo[d]);  // the quad is binned by the union of its triangles' boxes
   }
   if (t < p.n_sec) {
     const int nd = p.sec_node[t];
@@ -148,21 +162,37 @@ contact_update_kernel(const ContactArgs p)
     float box[6];
     inflate_to_float(x, x, p.sec_len[t], box);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      lo[d] = fminf(lo[d], box[d]);
-      ext   = fmaxf(ext, box[3 + d] - box[d]);
-    }
+    for (int d = 0; d < 3; ++d) ext = fmaxf(ext, box[3 + d] - box[d]);  // (the grid is anchored at the triangles' boxes only)
     p.status[4 * p.n_quads + t] = 0;
   }
-  // grid-wide minimum corner and maximum extent: warp reduction, one atomic per warp and quantity
-  unsigned r[4] = {ordered_float(lo[0]), ordered_float(lo[1]), ordered_float(lo[2]), __float_as_uint(ext)};
+  // grid-wide corners of the triangles' boxes and maximum extent: warp reduction, then one atomic per CTA and quantity
+  unsigned r[7] = {ordered_float(lo[0]), ordered_float(lo[1]), ordered_float(lo[2]), __float_as_uint(ext),
+                   ordered_float(hi[0]), ordered_float(hi[1]), ordered_float(hi[2])};
 #pragma unroll
   for (int d = 0; d < 3; ++d) r[d] = __reduce_min_sync(0xffffffffu, r[d]);
-  r[3] = __reduce_max_sync(0xffffffffu, r[3]);
-  if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) atomicMin(p.red + d, r[d]);
-    atomicMax(p.red + 3, r[3]);
+  for (int d = 3; d < 7; ++d) r[d] = __reduce_max_sync(0xffffffffu, r[d]);
+  __shared__ unsigned part[8][7];
+  const int           warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < 7; ++d) part[warp][d] = r[d];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    unsigned v[7];
+#pragma unroll
+    for (int d = 0; d < 7; ++d) v[d] = lane < 8 ? part[lane][d] : (d < 3 ? 0xffffffffu : 0u);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v[d] = __reduce_min_sync(0xffffffffu, v[d]);
+#pragma unroll
+    for (int d = 3; d < 7; ++d) v[d] = __reduce_max_sync(0xffffffffu, v[d]);
+    if (lane == 0) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) atomicMin(p.red + d, v[d]);
+#pragma unroll
+      for (int d = 3; d < 7; ++d) atomicMax(p.red + d, v[d]);
+    }
   }
 }
 
@@ -194,14 +224,18 @@ contact_hash(long long cx, long long cy, long long cz)
 __global__ void __launch_bounds__(256)
 contact_bin_kernel(const ContactArgs p)
 {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 4 * p.n_quads) return;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.n_quads) return;
+  const float* tb = p.tri_box + 24 * q;
+  float        lo[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) lo[d] = fminf(fminf(tb[d], tb[6 + d]), fminf(tb[12 + d], tb[18 + d]));
   const double pitch = contact_pitch(p.red);
   long long    cell[3];
-  contact_cell(p.tri_box + 6 * t, p.red, pitch, cell);
-  p.tri_cell[3 * t] = cell[0], p.tri_cell[3 * t + 1] = cell[1], p.tri_cell[3 * t + 2] = cell[2];
-  const unsigned bucket = contact_hash(cell[0], cell[1], cell[2]) & p.table_mask;
-  p.next[t]             = atomicExch(p.head + bucket, (int)t);
+  contact_cell(lo, p.red, pitch, cell);
+  QuadBin& e = p.bin[q];
+  e.cell[0] = cell[0], e.cell[1] = cell[1], e.cell[2] = cell[2];
+  e.next = atomicExch(p.head + (contact_hash(cell[0], cell[1], cell[2]) & p.table_mask), (int)q);
 }
 
 __device__ __forceinline__ void
@@ -220,74 +254,100 @@ contact_add3(double* const fc[3], int node, double x, double y, double z)
   atomicAdd(fc[2] + node, z);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 contact_pair_kernel(const ContactArgs p)
 {
   const int64_t s    = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per contact node
   const int     lane = threadIdx.x & 31;
-  if (s >= p.n_sec || lane >= 27) return;
+  unsigned long long tested = 0, enforced = 0;
+  if (s < p.n_sec && lane < 27) {
   const int nd = p.sec_node[s];
   double    pt[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) pt[d] = p.X[d][nd] + p.u[d][nd];
   float box[6];
   inflate_to_float(pt, pt, p.sec_len[s], box);
+  // a node whose box misses the bounding box of all triangles meets none of them (most of a body's skin nodes)
+  bool near = true;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) near = near && !(box[3 + d] < float_of_ordered(p.red[d]) || box[d] > float_of_ordered(p.red[4 + d]));
+  if (near) {
   const double pitch = contact_pitch(p.red);
   long long    cell[3];
   contact_cell(box, p.red, pitch, cell);
   cell[0] += lane % 3 - 1, cell[1] += (lane / 3) % 3 - 1, cell[2] += lane / 9 - 1;
-  unsigned long long tested = 0, enforced = 0;
-  for (int t = p.head[contact_hash(cell[0], cell[1], cell[2]) & p.table_mask]; t >= 0; t = p.next[t]) {
-    const long long* tc = p.tri_cell + 3 * (int64_t)t;
-    if (tc[0] != cell[0] || tc[1] != cell[1] || tc[2] != cell[2]) continue;  // another cell of the same bucket
-    const float* tb = p.tri_box + 6 * (int64_t)t;
-    // ArborX::intersects on float boxes: closed intervals overlap in every direction
-    if (box[3] < tb[0] || box[0] > tb[3] || box[4] < tb[1] || box[1] > tb[4] || box[5] < tb[2] || box[2] > tb[5]) continue;
-    ++tested;
-    const int     quad = t >> 2, k = t & 3, kb = (k + 1) & 3;
-    const double* q    = p.quad_xyz + 15 * (int64_t)quad;
-    double        p1[3], p2[3], p3[3], u[3], v[3], w[3], n[3], cr[3];
+  for (int quad = p.head[contact_hash(cell[0], cell[1], cell[2]) & p.table_mask]; quad >= 0;) {
+    const QuadBin e = p.bin[quad];
+    const int     this_quad = quad;
+    quad                    = e.next;
+    if (e.cell[0] != cell[0] || e.cell[1] != cell[1] || e.cell[2] != cell[2]) continue;  // another cell of the same bucket
+    // ArborX::intersects on float boxes, triangle by triangle: closed intervals overlap in every direction
+    const float* tb  = p.tri_box + 24 * (int64_t)this_quad;
+    unsigned     hit = 0;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) p1[d] = q[3 * k + d], p2[d] = q[3 * kb + d], p3[d] = q[12 + d];
-    // ContactManager::Projection (src/nimble_contact_manager.cc:1549-1620), tolerance 1.e-8
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      u[d] = p2[d] - p1[d];
-      v[d] = p3[d] - p1[d];
-      w[d] = pt[d] - p1[d];
+    for (int k = 0; k < 4; ++k) {
+      const float b0 = tb[6 * k], b1 = tb[6 * k + 1], b2 = tb[6 * k + 2], b3 = tb[6 * k + 3], b4 = tb[6 * k + 4], b5 = tb[6 * k + 5];
+      if (!(box[3] < b0 || box[0] > b3 || box[4] < b1 || box[1] > b4 || box[5] < b2 || box[2] > b5)) hit |= 1u << k;
     }
-    contact_cross(u, v, n);
-    const double n_squared = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-    contact_cross(u, w, cr);
-    const double alpha3 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
-    contact_cross(w, v, cr);
-    const double alpha2 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
-    const double alpha1 = 1.0 - alpha2 - alpha3;
-    const double tol = 1.e-8, tol2 = 1.0 + tol;
-    if (!((alpha1 > -tol && alpha1 < tol2) && (alpha2 > -tol && alpha2 < tol2) && (alpha3 > -tol && alpha3 < tol2))) continue;
-    const double xp = alpha1 * p1[0] + alpha2 * p2[0] + alpha3 * p3[0];
-    const double yp = alpha1 * p1[1] + alpha2 * p2[1] + alpha3 * p3[1];
-    const double zp = alpha1 * p1[2] + alpha2 * p2[2] + alpha3 * p3[2];
-    const double dx = pt[0] - xp, dy = pt[1] - yp, dz = pt[2] - zp;
-    const double sc = 1.0 / sqrt(n_squared);
-    const double nx = n[0] * sc, ny = n[1] * sc, nz = n[2] * sc;
-    const double gap = dx * nx + dy * ny + dz * nz;
-    if (!((gap < 0.0) && (gap > -p.quad_len[quad]))) continue;  // inside but not through
-    // PenaltyContactEnforcement::EnforceContact (src/nimble_contact_manager.h:94-128): facet first, then the node
-    ++enforced;
-    p.status[t] = 1, p.status[4 * p.n_quads + s] = 1;
-    const double scale = p.penalty * gap;
-    const double cf[3] = {scale * nx, scale * ny, scale * nz};
-    const int*   qn    = p.quad + 4 * (int64_t)quad;
-    contact_add3(p.fc, qn[k], alpha1 * cf[0], alpha1 * cf[1], alpha1 * cf[2]);
-    contact_add3(p.fc, qn[kb], alpha2 * cf[0], alpha2 * cf[1], alpha2 * cf[2]);
-    const double f3[3] = {(alpha3 * cf[0]) / 4.0, (alpha3 * cf[1]) / 4.0, (alpha3 * cf[2]) / 4.0};
+    if (!hit) continue;
+    tested += __popc(hit);
+    const double* q   = p.quad_xyz + 15 * (int64_t)this_quad;
+    const int*    qn  = p.quad + 4 * (int64_t)this_quad;
+    const double  len   = p.quad_len[this_quad];
+    const double  p3[3] = {q[12], q[13], q[14]};
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {  // (a rolled loop: the vertices come from L1, the registers stay under the occupancy cap)
+      if (!(hit & (1u << k))) continue;
+      const int kb = (k + 1) & 3;
+      double    p1[3], p2[3], u[3], v[3], w[3], n[3], cr[3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) contact_add3(p.fc, qn[i], f3[0], f3[1], f3[2]);
-    contact_add3(p.fc, nd, -cf[0], -cf[1], -cf[2]);
+      for (int d = 0; d < 3; ++d) p1[d] = q[3 * k + d], p2[d] = q[3 * kb + d];
+      // ContactManager::Projection (src/nimble_contact_manager.cc:1549-1620), tolerance 1.e-8
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        u[d] = p2[d] - p1[d];
+        v[d] = p3[d] - p1[d];
+        w[d] = pt[d] - p1[d];
+      }
+      contact_cross(u, v, n);
+      const double n_squared = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+      contact_cross(u, w, cr);
+      const double alpha3 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
+      contact_cross(w, v, cr);
+      const double alpha2 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
+      const double alpha1 = 1.0 - alpha2 - alpha3;
+      const double tol = 1.e-8, tol2 = 1.0 + tol;
+      if (!((alpha1 > -tol && alpha1 < tol2) && (alpha2 > -tol && alpha2 < tol2) && (alpha3 > -tol && alpha3 < tol2))) continue;
+      const double xp = alpha1 * p1[0] + alpha2 * p2[0] + alpha3 * p3[0];
+      const double yp = alpha1 * p1[1] + alpha2 * p2[1] + alpha3 * p3[1];
+      const double zp = alpha1 * p1[2] + alpha2 * p2[2] + alpha3 * p3[2];
+      const double dx = pt[0] - xp, dy = pt[1] - yp, dz = pt[2] - zp;
+      const double sc = 1.0 / sqrt(n_squared);
+      const double nx = n[0] * sc, ny = n[1] * sc, nz = n[2] * sc;
+      const double gap = dx * nx + dy * ny + dz * nz;
+      if (!((gap < 0.0) && (gap > -len))) continue;  // inside but not through
+      // PenaltyContactEnforcement::EnforceContact (src/nimble_contact_manager.h:94-128): facet first, then the node
+      ++enforced;
+      p.status[4 * (int64_t)this_quad + k] = 1, p.status[4 * p.n_quads + s] = 1;
+      const double scale = p.penalty * gap;
+      const double cf[3] = {scale * nx, scale * ny, scale * nz};
+      contact_add3(p.fc, qn[k], alpha1 * cf[0], alpha1 * cf[1], alpha1 * cf[2]);
+      contact_add3(p.fc, qn[kb], alpha2 * cf[0], alpha2 * cf[1], alpha2 * cf[2]);
+      const double f3[3] = {(alpha3 * cf[0]) / 4.0, (alpha3 * cf[1]) / 4.0, (alpha3 * cf[2]) / 4.0};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) contact_add3(p.fc, qn[i], f3[0], f3[1], f3[2]);
+      contact_add3(p.fc, nd, -cf[0], -cf[1], -cf[2]);
+    }
   }
-  if (tested) atomicAdd(p.counters + 1, tested);
-  if (enforced) atomicAdd(p.counters, enforced);
+  }
+  }
+  // counters: one pair of global atomics per warp that tested anything
+  tested   = __reduce_add_sync(0xffffffffu, (unsigned)tested);
+  enforced = __reduce_add_sync(0xffffffffu, (unsigned)enforced);
+  if (lane == 0 && tested) {
+    atomicAdd(p.counters + 1, tested);
+    if (enforced) atomicAdd(p.counters, enforced);
+  }
 }
 
 // numActiveContactFaces / numActiveContactNodes (src/nimble_contact_manager.cc:692-714): entities whose contact_status

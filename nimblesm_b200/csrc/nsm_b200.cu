@@ -172,11 +172,10 @@ struct nsm_b200_ctx
     double*   sec_len  = nullptr;
     double*   quad_xyz = nullptr;
     float*    tri_box  = nullptr;
-    long long* tri_cell = nullptr;
-    int*      next = nullptr;
+    QuadBin*  bin  = nullptr;
     int*      head = nullptr;
     unsigned  table_mask = 0;
-    unsigned* red = nullptr;                  // [2][4], alternating by evaluation
+    unsigned* red = nullptr;                  // [2][8], alternating by evaluation
     unsigned long long* counters = nullptr;   // [4]: enforced, box-tested, active faces, active nodes
     unsigned char* status = nullptr;
     int       parity = 0;
@@ -578,16 +577,16 @@ enqueue_contact(nsm_b200_ctx* c)
   p.quad = k.quad, p.quad_len = k.quad_len, p.sec_node = k.sec_node, p.sec_len = k.sec_len;
   for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.fc[i] = c->fc[i];
   p.penalty  = k.penalty;
-  p.quad_xyz = k.quad_xyz, p.tri_box = k.tri_box, p.tri_cell = k.tri_cell, p.next = k.next, p.head = k.head;
+  p.quad_xyz = k.quad_xyz, p.tri_box = k.tri_box, p.bin = k.bin, p.head = k.head;
   p.table_mask = k.table_mask;
-  p.red = k.red + 4 * k.parity, p.red_next = k.red + 4 * (k.parity ^ 1);
+  p.red = k.red + 8 * k.parity, p.red_next = k.red + 8 * (k.parity ^ 1);
   p.counters = k.counters, p.status = k.status;
   k.parity ^= 1;
   const int64_t n_update = std::max<int64_t>(std::max(k.n_quads, k.n_sec), 32);
   contact_update_kernel<<<grid_for(n_update, 256), 256, 0, c->stream>>>(p);
   c->launches++;
   if (k.n_quads > 0 && k.n_sec > 0) {
-    contact_bin_kernel<<<grid_for(4 * k.n_quads, 256), 256, 0, c->stream>>>(p);
+    contact_bin_kernel<<<grid_for(k.n_quads, 256), 256, 0, c->stream>>>(p);
     contact_pair_kernel<<<grid_for(32 * k.n_sec, 256), 256, 0, c->stream>>>(p);
     c->launches += 2;
   }
@@ -789,7 +788,7 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   }
   {
     auto& k = c->contact;
-    fr(k.quad), fr(k.quad_len), fr(k.sec_node), fr(k.sec_len), fr(k.quad_xyz), fr(k.tri_box), fr(k.tri_cell), fr(k.next), fr(k.head);
+    fr(k.quad), fr(k.quad_len), fr(k.sec_node), fr(k.sec_len), fr(k.quad_xyz), fr(k.tri_box), fr(k.bin), fr(k.head);
     fr(k.red), fr(k.counters), fr(k.status);
     for (int i = 0; i < 3; ++i) fr(c->fc[i]);
   }
@@ -2288,7 +2287,7 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
   auto& k = c->contact;
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   dev_release(c, k.quad), dev_release(c, k.quad_len), dev_release(c, k.sec_node), dev_release(c, k.sec_len), dev_release(c, k.quad_xyz);
-  dev_release(c, k.tri_box), dev_release(c, k.tri_cell), dev_release(c, k.next), dev_release(c, k.head), dev_release(c, k.status);
+  dev_release(c, k.tri_box), dev_release(c, k.bin), dev_release(c, k.head), dev_release(c, k.status);
   k.active = false, k.n_quads = k.n_sec = 0;
   if (n_faces == 0 && n_cn == 0) {
     if (c->fc[0])
@@ -2309,17 +2308,17 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
   int rc;
   const int64_t n_tri = 4 * n_faces;
   unsigned      table = 1024;
-  while ((int64_t)table < 2 * n_tri) table <<= 1;
+  while ((int64_t)table < 2 * n_faces) table <<= 1;
   if ((rc = dev_alloc(c, &k.quad, n_faces * 4)) || (rc = dev_alloc(c, &k.quad_len, n_faces)) || (rc = dev_alloc(c, &k.sec_node, n_cn)) ||
       (rc = dev_alloc(c, &k.sec_len, n_cn)) || (rc = dev_alloc(c, &k.quad_xyz, n_faces * 15)) || (rc = dev_alloc(c, &k.tri_box, n_tri * 6)) ||
-      (rc = dev_alloc(c, &k.tri_cell, n_tri * 3)) || (rc = dev_alloc(c, &k.next, n_tri)) || (rc = dev_alloc(c, &k.head, (int64_t)table)) ||
+      (rc = dev_alloc(c, &k.bin, n_faces)) || (rc = dev_alloc(c, &k.head, (int64_t)table)) ||
       (rc = dev_alloc(c, &k.status, n_tri + n_cn)))
     return rc;
-  if (!k.red && ((rc = dev_alloc(c, &k.red, 8)) || (rc = dev_alloc(c, &k.counters, 4)))) return rc;
+  if (!k.red && ((rc = dev_alloc(c, &k.red, 16)) || (rc = dev_alloc(c, &k.counters, 4)))) return rc;
   for (int i = 0; i < 3; ++i)
     if (!c->fc[i] && (rc = dev_alloc(c, &c->fc[i], c->n_nodes))) return rc;
   for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->fc[i], 0, (size_t)std::max<int64_t>(c->n_nodes, 1) * sizeof(double), c->stream));
-  const unsigned red0[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u};
+  const unsigned red0[16] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
   NSM_CUDA(c, cudaMemcpyAsync(k.red, red0, sizeof red0, cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaMemsetAsync(k.counters, 0, 4 * sizeof(unsigned long long), c->stream));
   NSM_CUDA(c, cudaMemsetAsync(k.status, 0, (size_t)std::max<int64_t>(n_tri + n_cn, 1), c->stream));

@@ -46,42 +46,53 @@ ContactManager::SkinBlocks(GenesisMesh const& mesh, std::vector<int> const& bloc
 {
   // Exodus hex8 face ordinal -> local nodes
   static const int kFaceNodes[6][4] = {{0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {0, 4, 7, 3}, {0, 3, 2, 1}, {4, 5, 6, 7}};
-  struct Occurrence
+  // Every face of every element with its node ids sorted: faces that occur once are skin.  The reference counts them in
+  // a std::map keyed by the sorted ids and walks the map (src/nimble_contact_manager.cc:797-933), so its skin comes out
+  // in the lexicographic order of those keys, each face listed as the FIRST element that showed it lists it.  A sort of
+  // a flat array gives the same order without a node allocation per face (48 M faces for an 8 M-element block); the
+  // position in the array breaks ties so that "first" keeps its meaning.
+  struct Face
   {
-    int                times;
-    std::array<int, 4> nodes;  // as the first element that showed the face lists them
+    std::array<int, 4> key, nodes;
     int                element_id, ordinal;
+    long long          position;
   };
-  std::map<std::array<int, 4>, Occurrence> seen;  // keyed by the sorted node ids: the iteration order IS the output order
+  std::vector<Face> faces;
+  long long         total = 0;
+  for (int block_id : block_ids) total += 6LL * mesh.GetNumElementsInBlock(block_id);
+  faces.reserve((size_t)total);
   for (int block_id : block_ids) {
     const int        n_elem = mesh.GetNumElementsInBlock(block_id);
     const int        npe    = mesh.GetNumNodesPerElement(block_id);
     const int* const conn   = mesh.GetConnectivity(block_id);
     const auto&      gid    = mesh.GetElementGlobalIdsInBlock(block_id);
-    if (npe != 8) throw std::invalid_argument("\nError in ContactManager::SkinBlocks(), contact blocks must be hex8 blocks.\n");
+    if (n_elem > 0 && npe != 8) throw std::invalid_argument("\nError in ContactManager::SkinBlocks(), contact blocks must be hex8 blocks.\n");
     for (int e = 0; e < n_elem; ++e)
       for (int ordinal = 0; ordinal < 6; ++ordinal) {
-        std::array<int, 4> nodes;
-        for (int k = 0; k < 4; ++k) nodes[k] = conn[8 * e + kFaceNodes[ordinal][k]];
-        std::array<int, 4> key = nodes;
-        std::sort(key.begin(), key.end());
-        auto found = seen.find(key);
-        if (found == seen.end())
-          seen.emplace(key, Occurrence{1, nodes, gid[e] + 1, ordinal});  // 1-based element id, valid as an Exodus id
-        else
-          found->second.times += 1;
+        Face f;
+        for (int k = 0; k < 4; ++k) f.nodes[k] = conn[8 * e + kFaceNodes[ordinal][k]];
+        f.key = f.nodes;
+        std::sort(f.key.begin(), f.key.end());
+        f.element_id = gid[e] + 1;  // 1-based: a valid Exodus id in the contact visualisation output
+        f.ordinal    = ordinal;
+        f.position   = (long long)faces.size();
+        faces.push_back(f);
       }
   }
+  std::sort(faces.begin(), faces.end(), [](const Face& a, const Face& b) { return a.key != b.key ? a.key < b.key : a.position < b.position; });
   skin_faces.clear();
   entity_ids.clear();
-  for (auto const& entry : seen) {
-    const Occurrence& o = entry.second;
-    if (o.times == 1) {
+  for (size_t i = 0; i < faces.size();) {
+    size_t j = i + 1;
+    while (j < faces.size() && faces[j].key == faces[i].key) ++j;
+    const Face& o = faces[i];
+    if (j - i == 1) {
       skin_faces.emplace_back(o.nodes.begin(), o.nodes.end());
       entity_ids.push_back(((o.element_id + entity_id_offset) << 5) | (o.ordinal << 2));  // 2 low bits: triangle ordinal, set later
-    } else if (o.times != 2) {
+    } else if (j - i != 2) {
       throw std::runtime_error("Error in mesh skinning routine, face found more than two times!\n");
     }
+    i = j;
   }
 }
 
