@@ -149,6 +149,11 @@ struct nsm_b200_ctx
   struct HostPipe
   {
     int                  requested_chunks = -1;  // -1: automatic
+    // element-kernel CTA slots left to the copy-side kernels of the pipelined STEP (NSM_B200_PIPE_RESERVE).  Measured
+    // at 64 M elements (profiles/r02q_*): 0 -> 169 ms per step, 8 -> 157, 16 -> 152, 32 -> 148, 64 -> 147.  The
+    // force seam moves a third of the bytes and is bound by the elements, so it reserves nothing (47.2 ms; 51 ms at 32).
+    int                  reserve_ctas     = 32;
+    int                  reserve_now      = 0;   // what the ranged launches of the call in flight leave free
     bool                 built            = false;
     int                  n_chunks         = 0;
     std::vector<int64_t> node_end;                 // [C] end of node chunk c
@@ -379,6 +384,9 @@ groups_of(int64_t n_elem)
   return (n_elem + kElemsPerWarp - 1) / kElemsPerWarp;
 }
 
+// CTAs a ranged launch of the pipelined host paths leaves free (see enqueue_element_range); 0 everywhere else
+thread_local int t_reserve_ctas = 0;
+
 // Persistent launch: one wave of CTAs (SM count x resident CTAs per SM), fewer when the block is small.
 template <int MAT, bool ORDERED, int MODE>
 cudaError_t
@@ -404,7 +412,7 @@ launch_element(const ElemArgs& p, cudaStream_t s)
   }
   const int64_t positions = p.sched == kSchedList ? p.n_list : (p.n_range > 0 ? p.n_range : groups_of(p.n_elem));
   const int64_t need      = std::max<int64_t>((positions + kElemWarps * kTicketChunk - 1) / (kElemWarps * kTicketChunk), 1);
-  k<<<(unsigned)std::min<int64_t>(need, wave), kElemThreads, kElemSmemBytes, s>>>(p);
+  k<<<(unsigned)std::min<int64_t>(need, std::max(wave - t_reserve_ctas, 1)), kElemThreads, kElemSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -472,7 +480,13 @@ enqueue_element_range(nsm_b200_ctx* c, const Block& b, bool store_ipt, int g0, i
   int mode = (store_ipt ? kModeStoreIpt : 0) | (c->binv ? kModeReadBinv : 0);
   ElemArgs p    = elem_args(c, b, kSchedAll);
   p.group_begin = g0, p.n_range = g1 - g0;
-  NSM_CUDA(c, launch_element_any(p, b.material, c->assembly == NSM_ASSEMBLY_ORDERED, mode, s));
+  // The element kernel is persistent and fills every SM (2 CTAs x 128 registers x 256 threads = the whole register
+  // file): the small transpose / node kernels of the upload and download streams would wait for a whole ranged launch
+  // to drain before they get an SM, and the copy engines would idle behind them.  Leave a few CTA slots free.
+  t_reserve_ctas       = c->pipe.reserve_now;
+  const cudaError_t le = launch_element_any(p, b.material, c->assembly == NSM_ASSEMBLY_ORDERED, mode, s);
+  t_reserve_ctas       = 0;
+  NSM_CUDA(c, le);
   c->ticket_parity ^= 1;
   c->launches++;
   return NSM_OK;
@@ -1743,8 +1757,12 @@ build_host_pipe(nsm_b200_ctx* c)
     int rc = dev_alloc(c, &p, std::max<int64_t>(n * 3, 1));
     if (rc) return rc;
   }
-  NSM_CUDA(c, cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
-  NSM_CUDA(c, cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
+  // the copy-side streams outrank the element stream: their CTAs are dispatched first whenever a slot is free
+  int prio_least = 0, prio_greatest = 0;
+  NSM_CUDA(c, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  NSM_CUDA(c, cudaStreamCreateWithPriority(&P.up, cudaStreamNonBlocking, prio_greatest));
+  NSM_CUDA(c, cudaStreamCreateWithPriority(&P.down, cudaStreamNonBlocking, prio_greatest));
+  if (const char* e = getenv("NSM_B200_PIPE_RESERVE")) P.reserve_ctas = std::max(0, atoi(e));
   NSM_CUDA(c, cudaEventCreateWithFlags(&P.ev_bc, cudaEventDisableTiming));
   P.ev_up.resize(C), P.ev_elem.resize(C);
   for (int k = 0; k < C; ++k) {
@@ -1765,6 +1783,12 @@ step_host_pipelined(nsm_b200_ctx* c, double* time, double dt_user, double* displ
   const int     C       = P.n_chunks;
   const bool    ordered = c->assembly == NSM_ASSEMBLY_ORDERED;
   const bool    has_bc  = c->n_bc > 0;
+  struct Reserve  // the ranged element launches of this call leave CTA slots to the copy-side kernels
+  {
+    int& now;
+    Reserve(int& n, int v) : now(n) { now = v; }
+    ~Reserve() { now = 0; }
+  } reserve(P.reserve_now, P.reserve_ctas);
   const bool    store   = (c->flags_ & NSM_FLAG_STORE_IPT_EVERY_STEP) != 0;
   const double  t_prev  = *time;
   const double  t       = t_prev + dt_user;
