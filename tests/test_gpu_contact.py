@@ -236,3 +236,48 @@ def test_driver_refuses_contact_across_partitions(tmp_path):
     (tmp_path / "case.in").write_text(deck)
     r = subprocess.run([EXE, "--quiet", "--gpus", "2", "--devices", "0,0", "case.in"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "contact across mesh partitions" in r.stderr
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_contact_search_never_misses_a_pair(oracle, seed):
+    """The hashed-grid search against the oracle's all-pairs walk on random two-body configurations: body size, length
+    scale (1e-3 ... 1e3), position (negative coordinates, far from the origin), random and rigid displacements that open,
+    close and over-close the gap, so that cell pitch, grid anchor and hash buckets differ from case to case.  Same number
+    of accepted pairs, same active entities, force within 1e-12 -- every time."""
+    import bench
+    from nimblesm_b200 import capi
+    from oracle.contact import ContactSetup
+
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(2, 9)) * 2
+    mesh, _ent, h = bench.contact_stack(n)
+    scale = 10.0 ** rng.uniform(-3, 3)
+    shift = scale * rng.uniform(-50, 50, 3) * (rng.random(3) < 0.7)
+    for k, c_ in zip("xyz", range(3)):
+        mesh[k] = np.ascontiguousarray(mesh[k] * scale + shift[c_])
+    h *= scale
+    cs = ContactSetup(mesh, [2], [1], 1.0e9 * scale)  # entity lists (pinned to the host C++ lists in tests/test_host_cpp.py)
+    nn = len(mesh["x"])
+    upper = mesh["node_sets"]["upper"]
+    c = capi.Context(0)
+    c.set_nodes(mesh["x"], mesh["y"], mesh["z"])
+    for b in (1, 2):
+        c.add_block(b, mesh["conn"][b], "elastic", 1.6e12, 0.8e12, 7.8)
+    c.finalize(capi.ASSEMBLY_ATOMIC, 0)
+    c.set_contact(cs.penalty, cs.primary_quads, cs.primary_char_len, cs.contact_nodes, cs.contact_node_char_len)
+    total = 0
+    for trial in range(8):
+        u = h * 10.0 ** rng.uniform(-4, -0.5) * (2.0 * rng.random((nn, 3)) - 1.0)
+        u[upper] += h * np.array([rng.uniform(-1.5, 1.5), rng.uniform(-1.5, 1.5), rng.choice([-0.3, -0.05, -0.004, 0.0, 0.2, -1.4, -2.5])])
+        want, pairs, status = cs.force(u, want_status=True)
+        got = c.contact_force_host(u)
+        st = c.contact_stats()
+        assert st["pairs"] == pairs, (seed, trial, st, pairs)
+        assert st["active_faces"] == int(status[:4 * len(cs.primary_quads)].sum()) and st["active_nodes"] == int(status[4 * len(cs.primary_quads):].sum())
+        if pairs:
+            assert _rel(got, want) <= 1e-12, (seed, trial)
+        else:
+            assert not got.any()
+        total += pairs
+    c.close()
+    assert total > 0
