@@ -276,8 +276,10 @@ int nsm_b200_set_host_step_chunks(nsm_b200_ctx* ctx, int n_chunks);
  * lengths, and the contact nodes of the secondary blocks with theirs (the host layer's ContactManager computes both
  * lists as the reference does, :184-330).  From then on every step evaluates the contact force after the internal
  * force and the acceleration is (1/m)(f_int + f_ext + f_contact).  n_primary_faces == 0 && n_contact_nodes == 0
- * switches contact off again.  Contexts with a peer exchange are refused (the reference's ghost-face exchange across
- * ranks, src/contact/parallel, is outside this path). */
+ * switches contact off again.  Contexts with a peer exchange are refused: for contact across mesh partitions the host
+ * layer replicates the contact surface in a second, element-free context (n_blocks == 0, nodes = the surface nodes of
+ * all ranks) and calls nsm_b200_contact_force_host on it with the pooled displacements (host/contact_manager.cc,
+ * ContactManager::BuildReplicatedSubModel). */
 int nsm_b200_set_contact(nsm_b200_ctx* ctx, double penalty_parameter, int64_t n_primary_faces, const int32_t* primary_face_nodes,
                          const double* primary_face_char_len, int64_t n_contact_nodes, const int32_t* contact_node_ids,
                          const double* contact_node_char_len);

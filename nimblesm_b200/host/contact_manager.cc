@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstring>
 #include <iostream>
 #include <limits>
 #include <map>
@@ -96,33 +97,27 @@ ContactManager::SkinBlocks(GenesisMesh const& mesh, std::vector<int> const& bloc
   }
 }
 
+namespace {
+
+// Entity lists from skin faces (node ids of any numbering) and a coordinate lookup: characteristic lengths in the
+// reference's operation order (src/nimble_contact_manager.cc:288-330, 1062-1077), contact nodes in the order the
+// secondary faces first show them, each with the largest length of its faces.
+template <class Coord>
 void
-ContactManager::BuildEntityLists(GenesisMesh const& mesh, std::vector<int> const& primary_block_ids, std::vector<int> const& secondary_block_ids,
-                                 ContactEntityLists& lists)
+lists_from_faces(std::vector<std::vector<int>> const& primary, std::vector<std::vector<int>> const& secondary, Coord const& xyz,
+                 ContactEntityLists& lists)
 {
-  auto& primary_face_nodes_      = lists.primary_face_nodes;
-  auto& primary_face_entity_ids_ = lists.primary_face_entity_ids;
-  auto& primary_face_char_len_   = lists.primary_face_char_len;
-  auto& contact_node_ids_        = lists.contact_node_ids;
-  auto& contact_node_char_len_   = lists.contact_node_char_len;
-  const double* x = mesh.GetCoordinatesX();
-  const double* y = mesh.GetCoordinatesY();
-  const double* z = mesh.GetCoordinatesZ();
-  std::vector<std::vector<int>> primary, secondary;
-  std::vector<int>              secondary_entity_ids;
-  const int                     offset = mesh.GetMaxNodeGlobalId();  // no entity id is shared by a node and a face
-  SkinBlocks(mesh, primary_block_ids, offset, primary, primary_face_entity_ids_);
-  SkinBlocks(mesh, secondary_block_ids, offset, secondary, secondary_entity_ids);
-  // squared edge length in the model configuration, summed x, y, z as the reference does (:295-302, :1066-1073)
-  auto edge2 = [&](int a, int b) { return (x[b] - x[a]) * (x[b] - x[a]) + (y[b] - y[a]) * (y[b] - y[a]) + (z[b] - z[a]) * (z[b] - z[a]); };
-  primary_face_nodes_.clear(), primary_face_char_len_.clear(), contact_node_ids_.clear(), contact_node_char_len_.clear();
+  auto edge2 = [&](int a, int b) {
+    const double *pa = xyz(a), *pb = xyz(b);
+    return (pb[0] - pa[0]) * (pb[0] - pa[0]) + (pb[1] - pa[1]) * (pb[1] - pa[1]) + (pb[2] - pa[2]) * (pb[2] - pa[2]);
+  };
+  lists.primary_face_nodes.clear(), lists.primary_face_char_len.clear(), lists.contact_node_ids.clear(), lists.contact_node_char_len.clear();
   for (auto const& face : primary) {
     double longest = std::numeric_limits<double>::lowest();
     for (int i = 0; i < 4; ++i) longest = std::max(longest, std::sqrt(edge2(face[i], face[(i + 1) % 4])));
-    primary_face_nodes_.insert(primary_face_nodes_.end(), face.begin(), face.end());
-    primary_face_char_len_.push_back(longest);
+    lists.primary_face_nodes.insert(lists.primary_face_nodes.end(), face.begin(), face.end());
+    lists.primary_face_char_len.push_back(longest);
   }
-  // contact nodes in the order the secondary faces first show them; a node keeps the largest length of its faces
   std::map<int, std::size_t> position;
   for (auto const& face : secondary) {
     double longest2 = std::numeric_limits<double>::lowest();
@@ -131,28 +126,167 @@ ContactManager::BuildEntityLists(GenesisMesh const& mesh, std::vector<int> const
     for (int node : face) {
       auto at = position.find(node);
       if (at == position.end()) {
-        position[node] = contact_node_ids_.size();
-        contact_node_ids_.push_back(node);
-        contact_node_char_len_.push_back(len);
-      } else if (contact_node_char_len_[at->second] < len) {
-        contact_node_char_len_[at->second] = len;
+        position[node] = lists.contact_node_ids.size();
+        lists.contact_node_ids.push_back(node);
+        lists.contact_node_char_len.push_back(len);
+      } else if (lists.contact_node_char_len[at->second] < len) {
+        lists.contact_node_char_len[at->second] = len;
       }
     }
   }
+}
+
+}  // namespace
+
+void
+ContactManager::BuildEntityLists(GenesisMesh const& mesh, std::vector<int> const& primary_block_ids, std::vector<int> const& secondary_block_ids,
+                                 ContactEntityLists& lists)
+{
+  const double* x = mesh.GetCoordinatesX();
+  const double* y = mesh.GetCoordinatesY();
+  const double* z = mesh.GetCoordinatesZ();
+  std::vector<std::vector<int>> primary, secondary;
+  std::vector<int>              secondary_entity_ids;
+  const int                     offset = mesh.GetMaxNodeGlobalId();  // no entity id is shared by a node and a face
+  SkinBlocks(mesh, primary_block_ids, offset, primary, lists.primary_face_entity_ids);
+  SkinBlocks(mesh, secondary_block_ids, offset, secondary, secondary_entity_ids);
+  std::vector<double> point(3 * (size_t)mesh.GetNumNodes());
+  for (size_t i = 0; i < (size_t)mesh.GetNumNodes(); ++i) point[3 * i] = x[i], point[3 * i + 1] = y[i], point[3 * i + 2] = z[i];
+  lists_from_faces(primary, secondary, [&](int n) { return point.data() + 3 * (size_t)n; }, lists);
+}
+
+// Contact across mesh partitions: the REPLICATED sub-model.  The reference exchanges ghost faces between ranks and
+// searches a distributed tree (src/contact/parallel/arborx_parallel_contact_manager.cc).  A contact surface is small
+// (two-dimensional), so here every rank learns the whole of it once -- its own skin faces with global node ids and
+// coordinates travel through the rank group, faces that two ranks list are partition cuts and drop out
+// (RemoveInternalSkinFaces, src/nimble_contact_manager.cc:937-1041), the rest is sorted by global ids, which is the
+// order a serial run's skin has -- and rank 0 owns a second, element-free device context whose nodes are the surface
+// nodes.  Per step the ranks pool the displacement of the surface nodes they hold, rank 0 evaluates the contact force
+// of the whole surface on its GPU, and every rank picks the entries of its own nodes: all holders of a shared node get
+// the SAME bits (one evaluation), which is what the reference's clique all-reduce of contact_force guarantees.
+void
+ContactManager::BuildReplicatedSubModel(GenesisMesh const& mesh, VectorCommunicator& vc, std::vector<int> const& primary_block_ids,
+                                        std::vector<int> const& secondary_block_ids)
+{
+  struct Wire  // one skin face on the wire
+  {
+    int    gid[4];
+    int    secondary;
+    double xyz[12];
+  };
+  const int*    gid = mesh.GetNodeGlobalIds();
+  const double* x   = mesh.GetCoordinatesX();
+  const double* y   = mesh.GetCoordinatesY();
+  const double* z   = mesh.GetCoordinatesZ();
+  std::vector<Wire> mine;
+  for (int side = 0; side < 2; ++side) {
+    std::vector<std::vector<int>> faces;
+    std::vector<int>              ids;
+    SkinBlocks(mesh, side ? secondary_block_ids : primary_block_ids, 0, faces, ids);
+    for (auto const& f : faces) {
+      Wire w;
+      w.secondary = side;
+      for (int k = 0; k < 4; ++k) {
+        w.gid[k] = gid[f[k]];
+        w.xyz[3 * k] = x[f[k]], w.xyz[3 * k + 1] = y[f[k]], w.xyz[3 * k + 2] = z[f[k]];
+      }
+      mine.push_back(w);
+    }
+  }
+  std::vector<char> blob(mine.size() * sizeof(Wire));
+  if (!mine.empty()) memcpy(blob.data(), mine.data(), blob.size());
+  const auto all = vc.Group()->AllGather(vc.Rank(), blob);
+  struct Merged
+  {
+    std::array<int, 4> key;
+    Wire               w;
+  };
+  std::vector<Merged> merged;
+  for (auto const& b : all) {
+    const size_t n = b.size() / sizeof(Wire);
+    for (size_t i = 0; i < n; ++i) {
+      Merged m;
+      memcpy(&m.w, b.data() + i * sizeof(Wire), sizeof(Wire));
+      for (int k = 0; k < 4; ++k) m.key[k] = m.w.gid[k];
+      std::sort(m.key.begin(), m.key.end());
+      merged.push_back(m);
+    }
+  }
+  std::stable_sort(merged.begin(), merged.end(), [](const Merged& a, const Merged& b) {
+    return a.w.secondary != b.w.secondary ? a.w.secondary < b.w.secondary : a.key < b.key;
+  });
+  // surface nodes = nodes of the faces that survive, ascending global id
+  std::map<int, std::array<double, 3>> node_xyz;
+  std::vector<const Merged*>           kept;
+  for (size_t i = 0; i < merged.size();) {
+    size_t j = i + 1;
+    while (j < merged.size() && merged[j].w.secondary == merged[i].w.secondary && merged[j].key == merged[i].key) ++j;
+    if (j - i == 1) {
+      kept.push_back(&merged[i]);
+      for (int k = 0; k < 4; ++k) node_xyz[merged[i].w.gid[k]] = {merged[i].w.xyz[3 * k], merged[i].w.xyz[3 * k + 1], merged[i].w.xyz[3 * k + 2]};
+    } else if (j - i != 2) {
+      throw std::runtime_error("Error in mesh skinning routine, face found more than two times!\n");
+    }
+    i = j;
+  }
+  std::map<int, int> surface_of_gid;
+  surface_xyz_.clear();
+  for (auto const& kv : node_xyz) {
+    surface_of_gid[kv.first] = (int)surface_of_gid.size();
+    surface_xyz_.insert(surface_xyz_.end(), kv.second.begin(), kv.second.end());
+  }
+  std::vector<std::vector<int>> primary, secondary;
+  for (const Merged* m : kept) {
+    std::vector<int> f(4);
+    for (int k = 0; k < 4; ++k) f[k] = surface_of_gid.at(m->w.gid[k]);
+    (m->w.secondary ? secondary : primary).push_back(f);
+  }
+  lists_from_faces(primary, secondary, [&](int n) { return surface_xyz_.data() + 3 * (size_t)n; }, lists_);
+  lists_.primary_face_entity_ids.assign(primary.size(), 0);
+  // the surface nodes this rank holds: (local node, surface index)
+  held_local_.clear(), held_surface_.clear();
+  for (int i = 0; i < (int)mesh.GetNumNodes(); ++i) {
+    auto at = surface_of_gid.find(gid[i]);
+    if (at != surface_of_gid.end()) held_local_.push_back(i), held_surface_.push_back(at->second);
+  }
+  replicated_ = true;
 }
 
 void
 ContactManager::CreateContactEntities(GenesisMesh const& mesh, VectorCommunicator& vector_communicator, std::vector<int> const& primary_block_ids,
                                       std::vector<int> const& secondary_block_ids)
 {
-  if (vector_communicator.NumRanks() > 1)
-    throw std::invalid_argument(
-        "\nError: contact across mesh partitions (the reference's ghost-face exchange, src/contact/parallel) is outside the B200 "
-        "hex8 path; run decks with a `contact:` line on one GPU.\n");
-  BuildEntityLists(mesh, primary_block_ids, secondary_block_ids, lists_);
-  contact_enabled_ = true;
   auto* model_data = dynamic_cast<ModelData*>(data_manager_.GetModelData().get());
   if (!model_data) throw std::runtime_error("ContactManager needs a nimble_b200::ModelData");
+  if (vector_communicator.NumRanks() > 1) {
+    group_ = vector_communicator.Group();
+    rank_  = vector_communicator.Rank();
+    BuildReplicatedSubModel(mesh, vector_communicator, primary_block_ids, secondary_block_ids);
+    contact_enabled_ = true;
+    if (rank_ == 0) {
+      // the contact sub-model on rank 0's GPU: surface nodes, no elements
+      const size_t        n = surface_xyz_.size() / 3;
+      std::vector<double> sx(n), sy(n), sz(n);
+      for (size_t i = 0; i < n; ++i) sx[i] = surface_xyz_[3 * i], sy[i] = surface_xyz_[3 * i + 1], sz[i] = surface_xyz_[3 * i + 2];
+      sub_model_.reset(new DeviceContext(model_data->DeviceIndex()));
+      DeviceContext& d = *sub_model_;
+      d.check(nsm_b200_set_nodes(d.get(), (int64_t)n, sx.data(), sy.data(), sz.data()), "ContactManager (contact sub-model nodes)");
+      d.check(nsm_b200_finalize(d.get(), NSM_ASSEMBLY_ATOMIC, 0), "ContactManager (contact sub-model)");
+      d.check(nsm_b200_set_contact(d.get(), penalty_parameter_, (int64_t)lists_.primary_face_char_len.size(), lists_.primary_face_nodes.data(),
+                                   lists_.primary_face_char_len.data(), (int64_t)lists_.contact_node_ids.size(), lists_.contact_node_ids.data(),
+                                   lists_.contact_node_char_len.data()),
+              "ContactManager::CreateContactEntities (contact sub-model)");
+      std::cout << "Contact initialization:" << std::endl;
+      std::cout << "  number of triangular contact facets (primary blocks): " << numContactFaces() << std::endl;
+      std::cout << "  number of contact nodes (secondary blocks): " << numContactNodes() << std::endl;
+      std::cout << "  " << vector_communicator.NumRanks() << " ranks: the contact surface (" << n
+                << " nodes) is replicated and evaluated on rank 0's GPU\n"
+                << std::endl;
+    }
+    return;
+  }
+  BuildEntityLists(mesh, primary_block_ids, secondary_block_ids, lists_);
+  contact_enabled_ = true;
   DeviceContext& d = model_data->Device();
   d.check(nsm_b200_set_contact(d.get(), penalty_parameter_, (int64_t)lists_.primary_face_char_len.size(), lists_.primary_face_nodes.data(),
                                lists_.primary_face_char_len.data(), (int64_t)lists_.contact_node_ids.size(), lists_.contact_node_ids.data(),
@@ -170,8 +304,41 @@ void
 ContactManager::ComputeContactForce(int, bool, Viewify<2> contact_force)
 {
   if (penalty_parameter_ <= 0.0) throw std::invalid_argument("\nError in ComputeContactForce(), invalid penalty_parameter.\n");
-  auto*          model_data = dynamic_cast<ModelData*>(data_manager_.GetModelData().get());
-  DeviceContext& d          = model_data->Device();
+  auto* model_data = dynamic_cast<ModelData*>(data_manager_.GetModelData().get());
+  if (replicated_) {
+    // pool the displacement of the surface nodes (replicas of a shared node carry the same bits: any holder may write)
+    Viewify<2>        displacement = model_data->GetVectorNodeData("displacement");
+    const size_t      n_held = held_local_.size(), n_surface = surface_xyz_.size() / 3;
+    std::vector<char> blob(n_held * (sizeof(int) + 3 * sizeof(double)));
+    for (size_t i = 0; i < n_held; ++i) {
+      char* at = blob.data() + i * (sizeof(int) + 3 * sizeof(double));
+      memcpy(at, &held_surface_[i], sizeof(int));
+      const double u[3] = {displacement(held_local_[i], 0), displacement(held_local_[i], 1), displacement(held_local_[i], 2)};
+      memcpy(at + sizeof(int), u, sizeof u);
+    }
+    const auto        pooled = group_->AllGather(rank_, blob);
+    std::vector<char> force_blob;
+    if (rank_ == 0) {
+      std::vector<double> u(3 * n_surface, 0.0);
+      for (auto const& b : pooled)
+        for (size_t at = 0; at + sizeof(int) + 3 * sizeof(double) <= b.size(); at += sizeof(int) + 3 * sizeof(double)) {
+          int idx;
+          memcpy(&idx, b.data() + at, sizeof(int));
+          memcpy(&u[3 * (size_t)idx], b.data() + at + sizeof(int), 3 * sizeof(double));
+        }
+      force_blob.resize(3 * n_surface * sizeof(double));
+      sub_model_->check(nsm_b200_contact_force_host(sub_model_->get(), u.data(), reinterpret_cast<double*>(force_blob.data())),
+                        "ContactManager::ComputeContactForce (contact sub-model)");
+    }
+    const auto    forces = group_->AllGather(rank_, force_blob);
+    const double* fc     = reinterpret_cast<const double*>(forces[0].data());
+    const int     n_local = contact_force.size()[0];
+    for (int i = 0; i < n_local; ++i) contact_force(i, 0) = contact_force(i, 1) = contact_force(i, 2) = 0.0;
+    for (size_t i = 0; i < n_held; ++i)
+      for (int c = 0; c < 3; ++c) contact_force(held_local_[i], c) = fc[3 * (size_t)held_surface_[i] + c];
+    return;
+  }
+  DeviceContext& d = model_data->Device();
   // the displacement reached the device through ModelData::UpdateWithNewDisplacement, as in the reference
   d.check(nsm_b200_contact_force_host(d.get(), nullptr, contact_force.data()), "ContactManager::ComputeContactForce");
 }
@@ -181,6 +348,10 @@ ContactManager::numActiveContactFaces() const
 {
   auto*   model_data = dynamic_cast<ModelData*>(data_manager_.GetModelData().get());
   int64_t st[4]      = {0, 0, 0, 0};
+  if (replicated_) {
+    if (sub_model_) sub_model_->check(nsm_b200_contact_stats(sub_model_->get(), st), "ContactManager::numActiveContactFaces");
+    return (std::size_t)st[2];
+  }
   model_data->Device().check(nsm_b200_contact_stats(model_data->Device().get(), st), "ContactManager::numActiveContactFaces");
   return (std::size_t)st[2];
 }
@@ -190,6 +361,10 @@ ContactManager::numActiveContactNodes() const
 {
   auto*   model_data = dynamic_cast<ModelData*>(data_manager_.GetModelData().get());
   int64_t st[4]      = {0, 0, 0, 0};
+  if (replicated_) {
+    if (sub_model_) sub_model_->check(nsm_b200_contact_stats(sub_model_->get(), st), "ContactManager::numActiveContactNodes");
+    return (std::size_t)st[3];
+  }
   model_data->Device().check(nsm_b200_contact_stats(model_data->Device().get(), st), "ContactManager::numActiveContactNodes");
   return (std::size_t)st[3];
 }

@@ -8,20 +8,23 @@
 // nsm_b200_set_contact / nsm_b200_contact_force (csrc/contact.cuh): a uniform hashed grid in place of the ArborX BVH,
 // the same accepted pairs, the same per-pair arithmetic.  Inside the fused step (ModelData::AdvanceOnDevice) the
 // contact force never leaves the device; ComputeContactForce keeps the reference's call shape for the call-by-call
-// sequence.  One rank only: contact across mesh partitions (the reference's ghost-face exchange,
-// src/contact/parallel) is outside this path and refused with a message.
+// sequence.  Several ranks (mesh partitions): the contact surface is replicated -- every rank learns the whole skin
+// once, rank 0 evaluates the contact force of the whole surface on its GPU each step from the pooled displacements and
+// every rank picks its nodes' entries (see BuildReplicatedSubModel); such runs take the call-by-call sequence.
 #pragma once
 #include <cstddef>
 #include <memory>
 #include <string>
 #include <vector>
 
+#include "device.h"
 #include "view.h"
 
 namespace nimble_b200 {
 
 class DataManager;
 class GenesisMesh;
+class RankGroup;
 class VectorCommunicator;
 
 // `contact:` line -> block names and penalty parameter; throws std::invalid_argument with the reference's messages
@@ -98,6 +101,12 @@ class ContactManager
   {
     return lists_;
   }
+  // contact across partitions: the replicated sub-model is in use (the integrator then sequences the steps call by call)
+  bool
+  Replicated() const
+  {
+    return replicated_;
+  }
   // everything CreateContactEntities does before the upload (no device involved)
   static void
   BuildEntityLists(GenesisMesh const& mesh, std::vector<int> const& primary_block_ids, std::vector<int> const& secondary_block_ids,
@@ -108,6 +117,16 @@ class ContactManager
   bool               contact_enabled_   = false;
   double             penalty_parameter_ = 0.0;
   ContactEntityLists lists_;
+  // several ranks: the replicated contact sub-model (surface numbering = ascending global node id)
+  void
+  BuildReplicatedSubModel(GenesisMesh const& mesh, VectorCommunicator& vector_communicator, std::vector<int> const& primary_block_ids,
+                          std::vector<int> const& secondary_block_ids);
+  bool                           replicated_ = false;
+  std::shared_ptr<RankGroup>     group_;
+  int                            rank_ = 0;
+  std::vector<double>            surface_xyz_;                  // [n_surface][3] model coordinates
+  std::vector<int>               held_local_, held_surface_;    // surface nodes this rank holds: local id, surface index
+  std::unique_ptr<DeviceContext> sub_model_;                    // rank 0: the element-free context of the surface nodes
 };
 
 // the reference's factory (GetContactManager, :151-171): nullptr when the deck has no `contact:` line

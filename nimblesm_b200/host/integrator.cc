@@ -117,7 +117,12 @@ ExplicitTimeIntegrator::Integrate()
   double     total_dynamics_time = 0.0, total_force_time = 0.0, total_exodus_write_time = 0.0, total_vector_reduction_time = 0.0, total_contact_time = 0.0;
   auto       seconds_since       = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
   const auto t0 = std::chrono::steady_clock::now();
-  if (!reference_sequence_) {
+  // contact across partitions pools the surface displacements on the host every step (ContactManager, replicated
+  // sub-model): those runs are sequenced call by call
+  const bool call_by_call = reference_sequence_ || (contact_enabled && contact_manager->Replicated());
+  if (talk && call_by_call && !reference_sequence_)
+    std::cout << "(contact across " << (group ? group->NumRanks() : 1) << " mesh partitions: steps are sequenced call by call)" << std::endl;
+  if (!call_by_call) {
     // ---- fused: one device call per run of steps that ends at an output step (or at a 10 % progress mark)
     int step = 0;
     while (step < num_load_steps) {
@@ -213,10 +218,10 @@ ExplicitTimeIntegrator::Integrate()
     const double upd = (double)Mesh().GetNumElements() * num_load_steps / (step_loop_seconds_ > 0 ? step_loop_seconds_ : 1.0);
     std::cout << "======== Timing data: ========\n";
     std::cout << "Total step time = " << step_loop_seconds_ << " s (" << upd << " element-updates/s on rank 0, output included)\n";
-    std::cout << " --- Update A, V, U: " << total_dynamics_time << (reference_sequence_ ? "" : "  (device time; includes the shared-node exchange)") << '\n';
-    std::cout << " --- Force: " << total_force_time << (reference_sequence_ ? "" : "  (device time of the element kernels)") << "\n";
+    std::cout << " --- Update A, V, U: " << total_dynamics_time << (call_by_call ? "" : "  (device time; includes the shared-node exchange)") << '\n';
+    std::cout << " --- Force: " << total_force_time << (call_by_call ? "" : "  (device time of the element kernels)") << "\n";
     if (contact_enabled)
-      std::cout << " --- Contact time: " << total_contact_time << (reference_sequence_ ? "" : "  (on the device, inside the update time)") << '\n';
+      std::cout << " --- Contact time: " << total_contact_time << (call_by_call ? "" : "  (on the device, inside the update time)") << '\n';
     if (num_ranks > 1) std::cout << " --- Vector Reduction = " << total_vector_reduction_time << "  (on the device, inside the update time)\n";
     std::cout << " --- Exodus Write = " << total_exodus_write_time << "\n";
   }

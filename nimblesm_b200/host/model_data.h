@@ -192,6 +192,11 @@ class ModelData : public ModelDataBase
   {
     return *device_;
   }
+  int
+  DeviceIndex() const
+  {
+    return device_index_;
+  }
   std::map<int, std::shared_ptr<Block>>&
   GetBlocks()
   {

@@ -244,8 +244,10 @@ def main():
             if sub == "contact" and not k.startswith(("stress_xx", "deformation_gradient_xx")):
                 continue  # the contact .exodiff files compare nodal variables only; keep the fixture small
             out["gold_elem_%s_eb%d" % (k, b)] = a
-        for p in sorted(glob.glob(os.path.join(base, g + ".g.*.*"))) if sub != "contact" else []:
+        for p in sorted(glob.glob(os.path.join(base, g + ".g.*.*"))):
             tag = p.split(".g.")[1]
+            if sub == "contact" and int(tag.split(".")[0]) > 4:
+                continue  # (the np8 pieces of sphere_plate_contact: keep the fixture small)
             pack_mesh("piece_%s_" % tag, read_genesis(p), out)
         # reference-code snapshots at the deck's output steps (tight oracle when /root/reference is absent)
         run = refdrive.RefRun(str(out["deck"]), mesh, keep_snapshots=True)
