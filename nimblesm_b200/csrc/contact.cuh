@@ -20,7 +20,8 @@
 //   contact_bin_kernel      thread per QUAD (its four triangles share three quarters of their boxes): cell of the
 //                           minimum corner of the union box on a uniform grid of pitch h >= every box extent, pushed
 //                           on the chain of its hash bucket (atomicExch, no scan, no sort)
-//   contact_pair_kernel     one WARP per contact node, lane l < 27 walks the chain of neighbour cell l: a box of extent
+//   (contact_bin_kernel also compacts the contact nodes whose box meets the triangles' bounding box into a list)
+//   contact_pair_kernel     one WARP per listed contact node, lane l < 27 walks the chain of neighbour cell l: a box of extent
 //                           <= h anchored in cell n can only meet boxes anchored in n + {-1,0,1}^3; per quad the four
 //                           triangles' float boxes are tested exactly as ArborX tests them, then projection and
 //                           enforcement in the reference's operation order (so each pair's force has the oracle's
@@ -62,7 +63,8 @@ struct ContactArgs
   unsigned*  red;       // [8] this evaluation: ordered-float min corner x, y, z of the triangles' boxes; max extent of any
                         //     box (float bits, >= 0); ordered-float max corner x, y, z of the triangles' boxes; pad
   unsigned*  red_next;  // [8] the next evaluation's, reset here
-  unsigned long long* counters;  // [0] enforced pairs, [1] pairs that passed the box test
+  int*       near_list; // [n_sec] contact nodes whose box meets the bounding box of all triangles (this evaluation)
+  unsigned long long* counters;  // [0] enforced pairs, [1] pairs that passed the box test, [4] length of near_list
   unsigned char*      status;    // [4 n_quads + n_sec] contact_status flags of this evaluation
 };
 
@@ -100,6 +102,7 @@ contact_update_kernel(const ContactArgs p)
   for (int64_t i = t; i <= (int64_t)p.table_mask; i += nth) p.head[i] = -1;
   if (t < 8) p.red_next[t] = t < 3 ? 0xffffffffu : 0u;
   if (t < 2) p.counters[t] = 0ull;
+  if (t == 2) p.counters[4] = 0ull;
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, ext = 0.0f;
   if (t < p.n_quads) {
     // ContactManager::ApplyDisplacements (src/nimble_contact_manager.cc:750-786) + ContactEntity::SetCoordinates
@@ -225,17 +228,42 @@ __global__ void __launch_bounds__(256)
 contact_bin_kernel(const ContactArgs p)
 {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= p.n_quads) return;
-  const float* tb = p.tri_box + 24 * q;
-  float        lo[3];
+  if (q < p.n_quads) {
+    const float* tb = p.tri_box + 24 * q;
+    float        lo[3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) lo[d] = fminf(fminf(tb[d], tb[6 + d]), fminf(tb[12 + d], tb[18 + d]));
-  const double pitch = contact_pitch(p.red);
-  long long    cell[3];
-  contact_cell(lo, p.red, pitch, cell);
-  QuadBin& e = p.bin[q];
-  e.cell[0] = cell[0], e.cell[1] = cell[1], e.cell[2] = cell[2];
-  e.next = atomicExch(p.head + (contact_hash(cell[0], cell[1], cell[2]) & p.table_mask), (int)q);
+    for (int d = 0; d < 3; ++d) lo[d] = fminf(fminf(tb[d], tb[6 + d]), fminf(tb[12 + d], tb[18 + d]));
+    const double pitch = contact_pitch(p.red);
+    long long    cell[3];
+    contact_cell(lo, p.red, pitch, cell);
+    QuadBin& e = p.bin[q];
+    e.cell[0] = cell[0], e.cell[1] = cell[1], e.cell[2] = cell[2];
+    e.next = atomicExch(p.head + (contact_hash(cell[0], cell[1], cell[2]) & p.table_mask), (int)q);
+  }
+  // The contact nodes worth a search: those whose box meets the bounding box of all triangles (most skin nodes of a
+  // body do not).  They are COMPACTED into a list, so that the pair kernel's CTAs hold eight working warps each: with
+  // one warp per contact node of the whole skin, a CTA lived as long as its one or two interface nodes and kept six
+  // idle warp slots occupied (r02p -> r02v).
+  bool near = false;
+  if (q < p.n_sec) {
+    const int nd = p.sec_node[q];
+    double    x[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = p.X[d][nd] + p.u[d][nd];
+    float box[6];
+    inflate_to_float(x, x, p.sec_len[q], box);
+    near = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) near = near && !(box[3 + d] < float_of_ordered(p.red[d]) || box[d] > float_of_ordered(p.red[4 + d]));
+  }
+  const unsigned vote = __ballot_sync(0xffffffffu, near);
+  if (vote) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(p.counters + 4, (unsigned long long)__popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (near) p.near_list[base + __popc(vote & ((1u << lane) - 1u))] = (int)q;
+  }
 }
 
 __device__ __forceinline__ void
@@ -254,99 +282,127 @@ contact_add3(double* const fc[3], int node, double x, double y, double z)
   atomicAdd(fc[2] + node, z);
 }
 
-__global__ void __launch_bounds__(256, 3)
+// One accepted-or-not (node, triangle) pair: ContactManager::Projection (src/nimble_contact_manager.cc:1549-1620,
+// tolerance 1.e-8) and, for a node inside the facet that has not gone through it,
+// PenaltyContactEnforcement::EnforceContact (src/nimble_contact_manager.h:94-128): facet first, then the node.
+__device__ __forceinline__ bool
+contact_pair(const ContactArgs& p, int64_t s, int nd, const double pt[3], int quad, int k)
+{
+  const double* q  = p.quad_xyz + 15 * (int64_t)quad;
+  const int     kb = (k + 1) & 3;
+  double        p1[3], p2[3], p3[3], u[3], v[3], w[3], n[3], cr[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) p1[d] = q[3 * k + d], p2[d] = q[3 * kb + d], p3[d] = q[12 + d];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    u[d] = p2[d] - p1[d];
+    v[d] = p3[d] - p1[d];
+    w[d] = pt[d] - p1[d];
+  }
+  contact_cross(u, v, n);
+  const double n_squared = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+  contact_cross(u, w, cr);
+  const double alpha3 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
+  contact_cross(w, v, cr);
+  const double alpha2 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
+  const double alpha1 = 1.0 - alpha2 - alpha3;
+  const double tol = 1.e-8, tol2 = 1.0 + tol;
+  if (!((alpha1 > -tol && alpha1 < tol2) && (alpha2 > -tol && alpha2 < tol2) && (alpha3 > -tol && alpha3 < tol2))) return false;
+  const double xp = alpha1 * p1[0] + alpha2 * p2[0] + alpha3 * p3[0];
+  const double yp = alpha1 * p1[1] + alpha2 * p2[1] + alpha3 * p3[1];
+  const double zp = alpha1 * p1[2] + alpha2 * p2[2] + alpha3 * p3[2];
+  const double dx = pt[0] - xp, dy = pt[1] - yp, dz = pt[2] - zp;
+  const double sc = 1.0 / sqrt(n_squared);
+  const double nx = n[0] * sc, ny = n[1] * sc, nz = n[2] * sc;
+  const double gap = dx * nx + dy * ny + dz * nz;
+  if (!((gap < 0.0) && (gap > -p.quad_len[quad]))) return false;  // inside but not through
+  p.status[4 * (int64_t)quad + k] = 1, p.status[4 * p.n_quads + s] = 1;
+  const double scale = p.penalty * gap;
+  const double cf[3] = {scale * nx, scale * ny, scale * nz};
+  const int*   qn    = p.quad + 4 * (int64_t)quad;
+  contact_add3(p.fc, qn[k], alpha1 * cf[0], alpha1 * cf[1], alpha1 * cf[2]);
+  contact_add3(p.fc, qn[kb], alpha2 * cf[0], alpha2 * cf[1], alpha2 * cf[2]);
+  const double f3[3] = {(alpha3 * cf[0]) / 4.0, (alpha3 * cf[1]) / 4.0, (alpha3 * cf[2]) / 4.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) contact_add3(p.fc, qn[i], f3[0], f3[1], f3[2]);
+  contact_add3(p.fc, nd, -cf[0], -cf[1], -cf[2]);
+  return true;
+}
+
+// One WARP per listed contact node, in rounds: (1) lane l < 27 advances along the hash chain of neighbour cell l until it
+// holds a quad with at least one triangle whose float box meets the node's (ArborX::intersects, closed intervals);
+// (2) the lanes' finds are compacted into the warp's list; (3) ALL 32 lanes share out the (quad, triangle) items of the
+// list -- projection and enforcement run side by side instead of one triangle after another on the few lanes whose
+// cells are occupied (a contact surface fills ~9 of a node's 27 neighbour cells).  (Filing the whole chains in one pass
+// through a shared counter was measured slower, 116 vs 105 us: the overflow path costs the hot loop its registers.)
+#ifndef NSM_CONTACT_MIN_BLOCKS
+#define NSM_CONTACT_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, NSM_CONTACT_MIN_BLOCKS)
 contact_pair_kernel(const ContactArgs p)
 {
-  const int64_t s    = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per contact node
-  const int     lane = threadIdx.x & 31;
-  unsigned long long tested = 0, enforced = 0;
-  if (s < p.n_sec && lane < 27) {
-  const int nd = p.sec_node[s];
+  __shared__ unsigned found[8][32];  // quad << 4 | mask of its triangles that passed the box test (never 0)
+  const int        warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t    n_near = (int64_t)p.counters[4], n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  unsigned         tested = 0, enforced = 0;
+  for (int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < n_near; slot += n_warps) {  // (whole warps)
+  const int64_t s  = p.near_list[slot];
+  const int     nd = p.sec_node[s];
   double    pt[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) pt[d] = p.X[d][nd] + p.u[d][nd];
   float box[6];
   inflate_to_float(pt, pt, p.sec_len[s], box);
-  // a node whose box misses the bounding box of all triangles meets none of them (most of a body's skin nodes)
-  bool near = true;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) near = near && !(box[3 + d] < float_of_ordered(p.red[d]) || box[d] > float_of_ordered(p.red[4 + d]));
-  if (near) {
-  const double pitch = contact_pitch(p.red);
-  long long    cell[3];
-  contact_cell(box, p.red, pitch, cell);
-  cell[0] += lane % 3 - 1, cell[1] += (lane / 3) % 3 - 1, cell[2] += lane / 9 - 1;
-  for (int quad = p.head[contact_hash(cell[0], cell[1], cell[2]) & p.table_mask]; quad >= 0;) {
-    const QuadBin e = p.bin[quad];
-    const int     this_quad = quad;
-    quad                    = e.next;
-    if (e.cell[0] != cell[0] || e.cell[1] != cell[1] || e.cell[2] != cell[2]) continue;  // another cell of the same bucket
-    // ArborX::intersects on float boxes, triangle by triangle: closed intervals overlap in every direction
-    const float* tb  = p.tri_box + 24 * (int64_t)this_quad;
-    unsigned     hit = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float b0 = tb[6 * k], b1 = tb[6 * k + 1], b2 = tb[6 * k + 2], b3 = tb[6 * k + 3], b4 = tb[6 * k + 4], b5 = tb[6 * k + 5];
-      if (!(box[3] < b0 || box[0] > b3 || box[4] < b1 || box[1] > b4 || box[5] < b2 || box[2] > b5)) hit |= 1u << k;
-    }
-    if (!hit) continue;
-    tested += __popc(hit);
-    const double* q   = p.quad_xyz + 15 * (int64_t)this_quad;
-    const int*    qn  = p.quad + 4 * (int64_t)this_quad;
-    const double  len   = p.quad_len[this_quad];
-    const double  p3[3] = {q[12], q[13], q[14]};
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {  // (a rolled loop: the vertices come from L1, the registers stay under the occupancy cap)
-      if (!(hit & (1u << k))) continue;
-      const int kb = (k + 1) & 3;
-      double    p1[3], p2[3], u[3], v[3], w[3], n[3], cr[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) p1[d] = q[3 * k + d], p2[d] = q[3 * kb + d];
-      // ContactManager::Projection (src/nimble_contact_manager.cc:1549-1620), tolerance 1.e-8
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        u[d] = p2[d] - p1[d];
-        v[d] = p3[d] - p1[d];
-        w[d] = pt[d] - p1[d];
-      }
-      contact_cross(u, v, n);
-      const double n_squared = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-      contact_cross(u, w, cr);
-      const double alpha3 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
-      contact_cross(w, v, cr);
-      const double alpha2 = (cr[0] * n[0] + cr[1] * n[1] + cr[2] * n[2]) / n_squared;
-      const double alpha1 = 1.0 - alpha2 - alpha3;
-      const double tol = 1.e-8, tol2 = 1.0 + tol;
-      if (!((alpha1 > -tol && alpha1 < tol2) && (alpha2 > -tol && alpha2 < tol2) && (alpha3 > -tol && alpha3 < tol2))) continue;
-      const double xp = alpha1 * p1[0] + alpha2 * p2[0] + alpha3 * p3[0];
-      const double yp = alpha1 * p1[1] + alpha2 * p2[1] + alpha3 * p3[1];
-      const double zp = alpha1 * p1[2] + alpha2 * p2[2] + alpha3 * p3[2];
-      const double dx = pt[0] - xp, dy = pt[1] - yp, dz = pt[2] - zp;
-      const double sc = 1.0 / sqrt(n_squared);
-      const double nx = n[0] * sc, ny = n[1] * sc, nz = n[2] * sc;
-      const double gap = dx * nx + dy * ny + dz * nz;
-      if (!((gap < 0.0) && (gap > -len))) continue;  // inside but not through
-      // PenaltyContactEnforcement::EnforceContact (src/nimble_contact_manager.h:94-128): facet first, then the node
-      ++enforced;
-      p.status[4 * (int64_t)this_quad + k] = 1, p.status[4 * p.n_quads + s] = 1;
-      const double scale = p.penalty * gap;
-      const double cf[3] = {scale * nx, scale * ny, scale * nz};
-      contact_add3(p.fc, qn[k], alpha1 * cf[0], alpha1 * cf[1], alpha1 * cf[2]);
-      contact_add3(p.fc, qn[kb], alpha2 * cf[0], alpha2 * cf[1], alpha2 * cf[2]);
-      const double f3[3] = {(alpha3 * cf[0]) / 4.0, (alpha3 * cf[1]) / 4.0, (alpha3 * cf[2]) / 4.0};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) contact_add3(p.fc, qn[i], f3[0], f3[1], f3[2]);
-      contact_add3(p.fc, nd, -cf[0], -cf[1], -cf[2]);
-    }
+  long long cell[3];
+  contact_cell(box, p.red, contact_pitch(p.red), cell);
+  int quad = -1;
+  if (lane < 27) {
+    cell[0] += lane % 3 - 1, cell[1] += (lane / 3) % 3 - 1, cell[2] += lane / 9 - 1;
+    quad = p.head[contact_hash(cell[0], cell[1], cell[2]) & p.table_mask];
   }
+  for (;;) {
+    // (1) every lane advances along its chain to its next quad with a box hit
+    unsigned mine = 0u;
+    while (quad >= 0) {
+      const QuadBin e  = p.bin[quad];
+      const int     at = quad;
+      quad             = e.next;
+      if (e.cell[0] != cell[0] || e.cell[1] != cell[1] || e.cell[2] != cell[2]) continue;  // another cell of the same bucket
+      const float* tb  = p.tri_box + 24 * (int64_t)at;
+      unsigned     hit = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float b0 = tb[6 * k], b1 = tb[6 * k + 1], b2 = tb[6 * k + 2], b3 = tb[6 * k + 3], b4 = tb[6 * k + 4], b5 = tb[6 * k + 5];
+        if (!(box[3] < b0 || box[0] > b3 || box[4] < b1 || box[1] > b4 || box[5] < b2 || box[2] > b5)) hit |= 1u << k;
+      }
+      if (hit) {
+        mine = ((unsigned)at << 4) | hit;
+        tested += __popc(hit);
+        break;
+      }
+    }
+    // (2) the lanes' finds, compacted
+    const unsigned have = __ballot_sync(0xffffffffu, mine != 0u);
+    if (!have) break;
+    if (mine != 0u) found[warp][__popc(have & ((1u << lane) - 1u))] = mine;
+    __syncwarp();
+    // (3) all 32 lanes share out the (quad, triangle) items
+    const int n_items = 4 * __popc(have);
+    for (int item = lane; item < n_items; item += 32) {
+      const unsigned f = found[warp][item >> 2];
+      const int      k = item & 3;
+      if ((f >> k) & 1u)
+        if (contact_pair(p, s, nd, pt, (int)(f >> 4), k)) ++enforced;
+    }
+    __syncwarp();
   }
   }
   // counters: one pair of global atomics per warp that tested anything
-  tested   = __reduce_add_sync(0xffffffffu, (unsigned)tested);
-  enforced = __reduce_add_sync(0xffffffffu, (unsigned)enforced);
+  tested   = __reduce_add_sync(0xffffffffu, tested);
+  enforced = __reduce_add_sync(0xffffffffu, enforced);
   if (lane == 0 && tested) {
-    atomicAdd(p.counters + 1, tested);
-    if (enforced) atomicAdd(p.counters, enforced);
+    atomicAdd(p.counters + 1, (unsigned long long)tested);
+    if (enforced) atomicAdd(p.counters, (unsigned long long)enforced);
   }
 }
 

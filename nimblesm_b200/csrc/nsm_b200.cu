@@ -181,7 +181,8 @@ struct nsm_b200_ctx
     int*      head = nullptr;
     unsigned  table_mask = 0;
     unsigned* red = nullptr;                  // [2][8], alternating by evaluation
-    unsigned long long* counters = nullptr;   // [4]: enforced, box-tested, active faces, active nodes
+    unsigned long long* counters = nullptr;   // [8]: enforced, box-tested, active faces, active nodes, near-list length
+    int*      near_list = nullptr;
     unsigned char* status = nullptr;
     int       parity = 0;
   } contact;
@@ -594,14 +595,15 @@ enqueue_contact(nsm_b200_ctx* c)
   p.quad_xyz = k.quad_xyz, p.tri_box = k.tri_box, p.bin = k.bin, p.head = k.head;
   p.table_mask = k.table_mask;
   p.red = k.red + 8 * k.parity, p.red_next = k.red + 8 * (k.parity ^ 1);
-  p.counters = k.counters, p.status = k.status;
+  p.counters = k.counters, p.status = k.status, p.near_list = k.near_list;
   k.parity ^= 1;
   const int64_t n_update = std::max<int64_t>(std::max(k.n_quads, k.n_sec), 32);
   contact_update_kernel<<<grid_for(n_update, 256), 256, 0, c->stream>>>(p);
   c->launches++;
   if (k.n_quads > 0 && k.n_sec > 0) {
-    contact_bin_kernel<<<grid_for(k.n_quads, 256), 256, 0, c->stream>>>(p);
-    contact_pair_kernel<<<grid_for(32 * k.n_sec, 256), 256, 0, c->stream>>>(p);
+    contact_bin_kernel<<<grid_for(std::max(k.n_quads, k.n_sec), 256), 256, 0, c->stream>>>(p);
+    // a grid that fills the device once; its warps stride over the list of near nodes (whose length only the device knows)
+    contact_pair_kernel<<<(unsigned)std::min<int64_t>(grid_for(32 * k.n_sec, 256), 148 * 3 * 2), 256, 0, c->stream>>>(p);
     c->launches += 2;
   }
   NSM_CUDA(c, cudaGetLastError());
@@ -803,7 +805,7 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   {
     auto& k = c->contact;
     fr(k.quad), fr(k.quad_len), fr(k.sec_node), fr(k.sec_len), fr(k.quad_xyz), fr(k.tri_box), fr(k.bin), fr(k.head);
-    fr(k.red), fr(k.counters), fr(k.status);
+    fr(k.red), fr(k.counters), fr(k.status), fr(k.near_list);
     for (int i = 0; i < 3; ++i) fr(c->fc[i]);
   }
   for (double* p : c->pipe.stage) fr(p);
@@ -2311,7 +2313,7 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
   auto& k = c->contact;
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   dev_release(c, k.quad), dev_release(c, k.quad_len), dev_release(c, k.sec_node), dev_release(c, k.sec_len), dev_release(c, k.quad_xyz);
-  dev_release(c, k.tri_box), dev_release(c, k.bin), dev_release(c, k.head), dev_release(c, k.status);
+  dev_release(c, k.tri_box), dev_release(c, k.bin), dev_release(c, k.head), dev_release(c, k.status), dev_release(c, k.near_list);
   k.active = false, k.n_quads = k.n_sec = 0;
   if (n_faces == 0 && n_cn == 0) {
     if (c->fc[0])
@@ -2336,15 +2338,15 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
   if ((rc = dev_alloc(c, &k.quad, n_faces * 4)) || (rc = dev_alloc(c, &k.quad_len, n_faces)) || (rc = dev_alloc(c, &k.sec_node, n_cn)) ||
       (rc = dev_alloc(c, &k.sec_len, n_cn)) || (rc = dev_alloc(c, &k.quad_xyz, n_faces * 15)) || (rc = dev_alloc(c, &k.tri_box, n_tri * 6)) ||
       (rc = dev_alloc(c, &k.bin, n_faces)) || (rc = dev_alloc(c, &k.head, (int64_t)table)) ||
-      (rc = dev_alloc(c, &k.status, n_tri + n_cn)))
+      (rc = dev_alloc(c, &k.status, n_tri + n_cn)) || (rc = dev_alloc(c, &k.near_list, n_cn)))
     return rc;
-  if (!k.red && ((rc = dev_alloc(c, &k.red, 16)) || (rc = dev_alloc(c, &k.counters, 4)))) return rc;
+  if (!k.red && ((rc = dev_alloc(c, &k.red, 16)) || (rc = dev_alloc(c, &k.counters, 8)))) return rc;
   for (int i = 0; i < 3; ++i)
     if (!c->fc[i] && (rc = dev_alloc(c, &c->fc[i], c->n_nodes))) return rc;
   for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->fc[i], 0, (size_t)std::max<int64_t>(c->n_nodes, 1) * sizeof(double), c->stream));
   const unsigned red0[16] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
   NSM_CUDA(c, cudaMemcpyAsync(k.red, red0, sizeof red0, cudaMemcpyHostToDevice, c->stream));
-  NSM_CUDA(c, cudaMemsetAsync(k.counters, 0, 4 * sizeof(unsigned long long), c->stream));
+  NSM_CUDA(c, cudaMemsetAsync(k.counters, 0, 8 * sizeof(unsigned long long), c->stream));
   NSM_CUDA(c, cudaMemsetAsync(k.status, 0, (size_t)std::max<int64_t>(n_tri + n_cn, 1), c->stream));
   if (n_faces) {
     NSM_CUDA(c, cudaMemcpyAsync(k.quad, quads.data(), quads.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
