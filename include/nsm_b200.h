@@ -170,9 +170,10 @@ int nsm_b200_internal_force_host(nsm_b200_ctx* ctx, const double* displacement, 
 /* ---- stress seam (replaces BlockMaterialInterface::ComputeStress, the MDRange(elem, ipt) loop of
  *      src/nimble_kokkos_block_material_interface.cc:65-119 -> Material::GetStress,
  *      src/nimble_material.cc:95-126, 252-310) ----------------------------------------------------- */
-/* Host arrays: def_grad [n_points][9] -> stress [n_points][6], evaluated on the device.  PARITY / PLUG-IN SEAM, not a
- * performance path: it allocates, copies and frees per call (the reference re-creates and calls this seam every step,
- * src/nimble_kokkos_model_data.cc:1230-1234; here the step itself never leaves the device). */
+/* Host arrays: def_grad [n_points][9] -> stress [n_points][6], evaluated on the device.  PARITY / PLUG-IN SEAM: the
+ * reference re-creates and calls this seam every step (src/nimble_kokkos_model_data.cc:1230-1234); here the step itself
+ * never leaves the device, and a caller who does cross the seam pays two copies and a launch per call (the device
+ * scratch is kept and only grows). */
 int nsm_b200_compute_stress(nsm_b200_ctx* ctx, int material_kind, double bulk_modulus, double shear_modulus,
                             int64_t n_points, const double* def_grad, double* stress);
 

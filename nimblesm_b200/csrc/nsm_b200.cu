@@ -188,6 +188,12 @@ struct nsm_b200_ctx
   } contact;
   double* fc[3] = {nullptr, nullptr, nullptr};  // nodal contact force, SoA (allocated by nsm_b200_set_contact)
 
+  // scratch of the stress seam (nsm_b200_compute_stress / _state): grow-only, so that a caller who crosses the seam
+  // every step -- as the reference re-creates and calls it every step, src/nimble_kokkos_model_data.cc:1230-1234 --
+  // pays two copies and a launch, not an allocation
+  double* seam      = nullptr;
+  size_t  seam_cap  = 0;  // doubles
+
   PeerExchange comm;
   // overlap of the shared-node exchange with the interior elements (nsm_b200_step)
   cudaStream_t comm_stream = nullptr;
@@ -610,6 +616,22 @@ enqueue_contact(nsm_b200_ctx* c)
   return NSM_OK;
 }
 
+// the stress seam's device scratch, at least `doubles` long
+int
+seam_scratch(nsm_b200_ctx* c, size_t doubles, double** out)
+{
+  if (c->seam_cap < doubles) {
+    NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+    dev_release(c, c->seam);
+    c->seam_cap = 0;
+    int rc = dev_alloc(c, &c->seam, (int64_t)doubles);
+    if (rc) return rc;
+    c->seam_cap = doubles;
+  }
+  *out = c->seam;
+  return NSM_OK;
+}
+
 // internal force of the current device displacement into the device force field (+ shared-node sum)
 int
 enqueue_internal_force(nsm_b200_ctx* c, bool store_ipt)
@@ -792,6 +814,7 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   for (int i = 0; i < 3; ++i) {
     fr(c->X[i]), fr(c->u[i]), fr(c->v[i]), fr(c->a[i]), fr(c->f[i]), fr(c->fext[i]), fr(c->bc_of_dof[i]);
   }
+  fr(c->seam);
   fr(c->node_perm), fr(c->mass), fr(c->staging), fr(c->staging_u), fr(c->ipt), fr(c->binv), fr(c->ef), fr(c->adj_off), fr(c->adj_slot);
   if (c->io_stream) cudaStreamDestroy(c->io_stream);
   if (c->ev_u_staged) cudaEventDestroy(c->ev_u_staged);
@@ -1284,9 +1307,10 @@ nsm_b200_compute_stress(nsm_b200_ctx* c, int material_kind, double bulk, double 
   if (material_kind != NSM_MAT_ELASTIC && material_kind != NSM_MAT_NEOHOOKEAN)
     return fail(c, NSM_ERR_MATERIAL, "unknown material kind %d", material_kind);
   if (n_points == 0) return NSM_OK;
-  double *dF = nullptr, *dS = nullptr;
-  NSM_CUDA(c, cudaMalloc((void**)&dF, (size_t)n_points * 9 * sizeof(double)));
-  NSM_CUDA(c, cudaMalloc((void**)&dS, (size_t)n_points * 6 * sizeof(double)));
+  double* dF = nullptr;
+  int     rc = seam_scratch(c, (size_t)n_points * 15, &dF);
+  if (rc) return rc;
+  double* dS = dF + (size_t)n_points * 9;
   NSM_CUDA(c, cudaMemcpyAsync(dF, def_grad, (size_t)n_points * 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (material_kind == NSM_MAT_ELASTIC)
     stress_kernel<0><<<grid_for(n_points, 128), 128, 0, c->stream>>>(n_points, dF, dS, bulk, shear);
@@ -1296,8 +1320,6 @@ nsm_b200_compute_stress(nsm_b200_ctx* c, int material_kind, double bulk, double 
   NSM_CUDA(c, cudaGetLastError());
   NSM_CUDA(c, cudaMemcpyAsync(stress, dS, (size_t)n_points * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaFree(dF);
-  cudaFree(dS);
   return NSM_OK;
 }
 
@@ -1320,7 +1342,8 @@ nsm_b200_compute_stress_state(nsm_b200_ctx* c, int material_kind, int n_params, 
   // one device buffer: F_n 9, F_np1 9, sigma_n 6, state_n ns | sigma_np1 6, state_np1 ns
   const size_t n = (size_t)n_points;
   double*      d = nullptr;
-  NSM_CUDA(c, cudaMalloc((void**)&d, n * (size_t)(30 + 2 * ns) * sizeof(double)));
+  int          rc_s = seam_scratch(c, n * (size_t)(30 + 2 * ns), &d);
+  if (rc_s) return rc_s;
   double *dFn = d, *dF = dFn + 9 * n, *dsn = dF + 9 * n, *dstn = dsn + 6 * n, *ds = dstn + ns * n, *dst = ds + 6 * n;
   cudaError_t e = cudaMemcpyAsync(dFn, def_grad_n, 9 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dF, def_grad_np1, 9 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
@@ -1335,7 +1358,6 @@ nsm_b200_compute_stress_state(nsm_b200_ctx* c, int material_kind, int n_params, 
   if (e == cudaSuccess) e = cudaMemcpyAsync(stress_np1, ds, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(state_np1, dst, ns * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(d);
   if (e != cudaSuccess) return fail(c, NSM_ERR_CUDA, "compute_stress_state: %s", cudaGetErrorString(e));
   return NSM_OK;
 }
