@@ -799,13 +799,15 @@ def run_contact(args):
             scale = np.abs(fc[cn]).max()
             err = float(np.abs(fc[cn[near]] - want[cn[near]]).max() / scale) if scale > 0 else 0.0
             # size-independent property of the WHOLE surface: action = reaction, the contact forces sum to zero
-            resid = float(np.abs(fc.sum(0)).max() / scale) if scale > 0 else 0.0
+            # (summed in extended precision: the facet side is all of one sign and comes first in the numbering, so a
+            # double-precision running sum carries ~1e-9 of rounding of its own before the node side cancels it)
+            resid = float(np.abs(fc.astype(np.longdouble).sum(0)).max() / scale) if scale > 0 else 0.0
             parity = {"checked": True, "window_contact_nodes": int(near.sum()), "window_pairs": int(pairs_w), "max_rel_fc": err,
                       "sum_of_contact_forces_over_largest": resid,
-                      "ok": bool(err <= 1e-12 and pairs_w > 0 and stats["pairs"] > 0 and resid <= 1e-9),
+                      "ok": bool(err <= 1e-12 and pairs_w > 0 and stats["pairs"] > 0 and resid <= 1e-10),
                       "what": "contact force on the contact nodes of a 16h window of the interface, oracle/contact_oracle.c on the "
                               "device's own displacement; bar 1e-12 of the largest nodal contact force.  Whole surface: the contact "
-                              "forces sum to zero (action = reaction), bar 1e-9 of the largest"}
+                              "forces sum to zero (action = reaction), bar 1e-10 of the largest"}
     wc, nc = results["with_contact"], results["without_contact"]
     out = {"metric": "hex8 element-updates/sec per explicit step", "value": n_elem * 1e3 / wc["ms_per_step"], "unit": "element-updates/s",
            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wc["ms_per_step"], "higher_is_better": True,
