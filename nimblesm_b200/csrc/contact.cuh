@@ -14,22 +14,22 @@
 // Execution plan (B200): the contact surfaces are 2-D, so the work is tiny next to the element kernel and latency, not
 // bandwidth, is what counts -- three launches per evaluation, no host synchronisation, no sort:
 //   contact_update_kernel   thread per quad / per contact node: current coordinates (X + u), the quad's centre, the four
-//                           triangles' inflated boxes (narrowed to float exactly as ArborX::Point does), a grid-wide
-//                           minimum corner and maximum box extent (warp reductions + one atomic per warp), contact
-//                           force of the touched nodes cleared, hash heads cleared
+//                           triangles' inflated boxes (narrowed to float exactly as ArborX::Point does), the grid-wide
+//                           bounding box of the triangles and the largest box extent (warp -> CTA -> one atomic per
+//                           quantity), contact force of the touched nodes cleared, hash heads cleared
 //   contact_bin_kernel      thread per QUAD (its four triangles share three quarters of their boxes): cell of the
 //                           minimum corner of the union box on a uniform grid of pitch h >= every box extent, pushed
-//                           on the chain of its hash bucket (atomicExch, no scan, no sort)
-//   (contact_bin_kernel also compacts the contact nodes whose box meets the triangles' bounding box into a list)
-//   contact_pair_kernel     one WARP per listed contact node, lane l < 27 walks the chain of neighbour cell l: a box of extent
-//                           <= h anchored in cell n can only meet boxes anchored in n + {-1,0,1}^3; per quad the four
-//                           triangles' float boxes are tested exactly as ArborX tests them, then projection and
-//                           enforcement in the reference's operation order (so each pair's force has the oracle's
-//                           bits), red.global.add.f64 into the nodal contact force (the order of the sum over pairs is
-//                           not fixed: noise ~1e-16, as in the reference's own Kokkos::atomic_add scatter).  The kernel
-//                           is a chain of dependent L2 round trips per warp (node id -> coordinates -> bucket head ->
-//                           chain entry -> boxes -> vertices); binning quads instead of triangles cut the chain from
-//                           ~7 entries per occupied cell to ~2 (r02n -> r02o: 544 -> see DESIGN §3.8)
+//                           on the chain of its hash bucket (atomicExch, no scan, no sort); thread per contact node:
+//                           the nodes whose box meets the triangles' bounding box are compacted into a list
+//   contact_pair_kernel     one WARP per LISTED contact node (a device-filling grid strides over the list), in rounds:
+//                           lane l < 27 advances along the chain of neighbour cell l -- a box of extent <= h anchored
+//                           in cell n can only meet boxes anchored in n + {-1,0,1}^3 -- to its next quad with a float-box
+//                           hit, tested triangle by triangle exactly as ArborX tests them; the finds are compacted and
+//                           all 32 lanes share out the (quad, triangle) items: projection and enforcement in the
+//                           reference's operation order (so each pair's force has the oracle's bits),
+//                           red.global.add.f64 into the nodal contact force (the order of the sum over pairs is not
+//                           fixed: noise ~1e-16, as in the reference's own Kokkos::atomic_add scatter).
+// What bounds it and what each step of the above bought (544 -> 106 us at 640 k triangles / 160 k nodes): DESIGN.md §3.8.
 #pragma once
 #include <float.h>
 #include <stdint.h>
