@@ -242,9 +242,10 @@ int nsm_b200_set_bc_slots_steps(nsm_b200_ctx* ctx, int n_rows, int n_slots, cons
 int nsm_b200_apply_kinematic_bc(nsm_b200_ctx* ctx, double time_current, double time_previous);
 
 /* ---- the explicit step (replaces the loop body of ExplicitTimeIntegrator::Integrate,
- *      src/integrators/explicit_time_integrator.cc:177-278, contact disabled) ----------------------
+ *      src/integrators/explicit_time_integrator.cc:177-278, the contact branch :232-249 included once
+ *      nsm_b200_set_contact has been called) -------------------------------------------------------
  * Advances n_steps steps from *time (in/out): per step t_prev = t; t += dt_user; dt = t - t_prev;
- * v += dt/2 a; BC; u += dt v; BC; f_int(u); a = (1/m)(f_int + f_ext); v += dt/2 a.
+ * v += dt/2 a; BC; u += dt v; BC; f_int(u); [f_contact(u);] a = (1/m)(f_int + f_ext [+ f_contact]); v += dt/2 a.
  * BC magnitudes: the row of the last nsm_b200_set_bc_values call; for time-dependent expressions either one
  * host-evaluated row per step (nsm_b200_set_bc_values_steps) or device programs with per-step slots
  * (nsm_b200_set_bc_programs + nsm_b200_set_bc_slots_steps).  store_ipt_last != 0 writes F/sigma on the final step and re-applies the BCs after
@@ -260,8 +261,8 @@ int nsm_b200_step(nsm_b200_ctx* ctx, int n_steps, double* time, double dt_user, 
  * The dependency ranges come from the connectivity, so the overlap is as good as the mesh numbering is local (lattice
  * or Morton order: a diagonal pipeline; random order: the plain upload -> step -> download schedule).  Per-node and
  * per-element arithmetic and the ORDERED summation order are those of nsm_b200_step, hence the same bits.  Use pinned
- * buffers (nsm_b200_host_alloc).  Contexts with a peer exchange, an internal node renumbering or per-step
- * boundary-condition rows take the plain schedule. */
+ * buffers (nsm_b200_host_alloc).  Contexts with a peer exchange, an internal node renumbering, per-step
+ * boundary-condition rows or contact entities (the search needs the whole displacement) take the plain schedule. */
 int nsm_b200_step_host(nsm_b200_ctx* ctx, double* time, double dt_user, double* displacement, double* velocity,
                        double* acceleration, double* internal_force);
 
