@@ -318,3 +318,23 @@ def test_contact_search_never_misses_a_pair(oracle, seed):
         total += pairs
     c.close()
     assert total > 0
+
+
+def test_contact_workload_of_the_bench_checks_itself():
+    """`bench.py --workload contact` at a size the suite affords (2 x 96 x 96 x 48 elements, 147 k contact triangles): the
+    line's own parity block -- a window of contact nodes against the oracle on the device's displacement (1e-12), the
+    whole surface's action = reaction (1e-10) -- must hold, and the step with contact must not cost more than a third
+    over the step without."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "contact", "--n", "96", "--steps", "5"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-1000:] + r.stderr[-2000:]
+    d = json.loads(lines[-1])
+    assert d["parity"]["ok"] and d["parity"]["max_rel_fc"] <= 1e-12 and d["parity"]["window_pairs"] > 0, d["parity"]
+    assert d["contact"]["pairs_enforced"] > 1000
+    assert d["contact"]["step_ms_with_contact"] < 1.34 * d["contact"]["step_ms_without_contact"], d["contact"]
+    assert r.returncode in (0, 3), r.stderr[-2000:]  # (3: no nvidia-smi clock sample fell inside a 5-step timed region)
