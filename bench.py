@@ -564,6 +564,19 @@ def main():
                "what": "per step: nsm_b200_step_host on pinned host [n][3] views = upload u,v,a, one explicit step, download "
                        "u,v,a,f_int, pipelined over node chunks (upload, element kernels and download overlap); host wall "
                        "clock, max over ranks"}
+        # the same call when the caller does not ask for the internal force (the integrator reads it on output steps only)
+        if world == 1:
+            t = c.step_host(t, dt_user, pin["u"].array, pin["v"].array, pin["a"].array, None)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                t = c.step_host(t, dt_user, pin["u"].array, pin["v"].array, pin["a"].array, None)
+            barrier()
+            dt_state = time.perf_counter() - t0
+            e2e["without_force_download"] = {"value": total_elems * k_e2e / dt_state, "unit": "element-updates/s",
+                                             "ms_per_step": dt_state / k_e2e * 1e3, "h2d_bytes_per_step": h2d,
+                                             "d2h_bytes_per_step": int(3 * 24 * n_nodes),
+                                             "what": "nsm_b200_step_host with internal_force = NULL (a non-output step): u, v, a up and down"}
         # second figure: the reference's own crossing pattern.  Its Kokkos path keeps the integrator's axpys on the host
         # and crosses once per step at ModelData::ComputeInternalForce (displacement up, internal force down;
         # src/nimble_kokkos_model_data.cc:1730-1740, 1282) -- here nsm_b200_internal_force_host on the same pinned views,

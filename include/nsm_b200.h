@@ -253,7 +253,9 @@ int nsm_b200_apply_kinematic_bc(nsm_b200_ctx* ctx, double time_current, double t
 int nsm_b200_step(nsm_b200_ctx* ctx, int n_steps, double* time, double dt_user, int store_ipt_last);
 /* The same loop body on HOST-resident state, i.e. on the reference's Viewify<2> views as ExplicitTimeIntegrator holds
  * them (src/integrators/explicit_time_integrator.cc:131-160): uploads displacement, velocity, acceleration
- * ([n_nodes][3]), advances one step, returns displacement, velocity, acceleration and internal_force in place.
+ * ([n_nodes][3]), advances one step, returns displacement, velocity, acceleration and internal_force in place
+ * (internal_force may be NULL: the integrator reads it on output steps only, and a step that does not ask for it moves
+ * 6 instead of 7 fields across the bus).
  * The call is PIPELINED over chunks of consecutive node ids (32 by default on meshes of a million nodes or more): chunk
  * c is uploaded and integrated (first half of the step) while chunk c-1's elements run -- every 4-element group whose
  * nodes all lie in the chunks uploaded so far -- and every chunk whose elements have all run is corrected and sent

@@ -384,10 +384,10 @@ class Context:
     def step_host(self, time, dt_user, displacement, velocity, acceleration, internal_force) -> float:
         """One explicit step on host-resident [n][3] float64 arrays, updated in place (pinned arrays overlap copies)."""
         for a in (displacement, velocity, acceleration, internal_force):
-            assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n_nodes, 3)
+            assert a is None or (a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n_nodes, 3))
         t = C.c_double(time)
         self._ck(self._L.nsm_b200_step_host(self._h, C.byref(t), dt_user, displacement.ctypes.data, velocity.ctypes.data,
-                                             acceleration.ctypes.data, internal_force.ctypes.data))
+                                             acceleration.ctypes.data, internal_force.ctypes.data if internal_force is not None else None))
         return t.value
 
     def element_data(self, block_id, previous=False):

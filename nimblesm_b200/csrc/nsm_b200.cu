@@ -1896,6 +1896,7 @@ step_host_pipelined(nsm_b200_ctx* c, double* time, double dt_user, double* displ
         // upload was consumed on the up stream before ev_up of the chunk)
         const int fields[3] = {3, 1, 2};
         for (int f : fields) {
+          if (!host[f]) continue;  // (internal_force == NULL: the caller does not want the force back this step)
           soa_to_aos_range_kernel<<<g2, 256, 0, P.down>>>(j0, mm, dev[f][0], dev[f][1], dev[f][2], P.stage[f]);
           NSM_CUDA(c, cudaMemcpyAsync(host[f] + 3 * j0, P.stage[f] + 3 * j0, (size_t)mm * 3 * sizeof(double), cudaMemcpyDeviceToHost, P.down));
         }
@@ -2013,7 +2014,7 @@ nsm_b200_step_host(nsm_b200_ctx* c, double* time, double dt_user, double* displa
 {
   NSM_ENTER(c);
   NSM_REQUIRE(c, c->finalized, "step_host: context not finalized");
-  NSM_REQUIRE(c, time && displacement && velocity && acceleration && internal_force, "step_host: null argument");
+  NSM_REQUIRE(c, time && displacement && velocity && acceleration, "step_host: null argument");
   if (!c->pipe.built) {
     int rc = build_host_pipe(c);
     if (rc) return rc;
@@ -2038,7 +2039,7 @@ nsm_b200_step_host(nsm_b200_ctx* c, double* time, double dt_user, double* displa
     cudaStreamSynchronize(c->io_stream);
     return rc;
   }
-  if ((rc = download_field(c, NSM_FIELD_INTERNAL_FORCE, internal_force, false))) return rc;
+  if (internal_force && (rc = download_field(c, NSM_FIELD_INTERNAL_FORCE, internal_force, false))) return rc;
   if ((rc = download_field(c, NSM_FIELD_VELOCITY, velocity, false))) return rc;
   if ((rc = download_field(c, NSM_FIELD_ACCELERATION, acceleration, false))) return rc;
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -608,6 +608,13 @@ def test_step_host_equals_upload_step_download():
         assert t2 == t
         for got, want in ((U, u), (V, v), (A, a), (Fo, f)):
             assert np.array_equal(np.asarray(got).view(np.int64), want.view(np.int64))
+        # a step that does not ask for the force (internal_force = NULL) advances the state alike and leaves Fo alone
+        Fo_before = np.array(Fo)
+        U2, V2, A2 = (np.array(x) for x in (U, V, A))
+        t3 = c.step_host(t2, dt, U2, V2, A2, None)
+        t4 = c.step_host(t2, dt, U, V, A, Fo)
+        assert t3 == t4 and all(np.array_equal(x.view(np.int64), np.asarray(y).view(np.int64)) for x, y in ((U2, U), (V2, V), (A2, A)))
+        assert not np.array_equal(np.asarray(Fo), Fo_before)
         c.close()
         if pinned:
             for b in bufs:
