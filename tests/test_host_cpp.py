@@ -408,3 +408,37 @@ def test_contact_command_errors(host, tmp_path):
     ok = base + "\ncontact: master_blocks block_2 slave_blocks block_1 penalty_parameter 2.5e11\n"
     assert host.nsmh_contact_entities(g.encode(), ok.encode(), n, C.byref(pen), None, None, None, None, None, err, 2048) == 0, err.value
     assert pen.value == 2.5e11 and n[0] == 384 and n[1] == 518
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_skin_blocks_on_random_block_assignments(host, tmp_path, seed):
+    """ContactManager::SkinBlocks (sort-based) against the oracle's independent skinner on cubes whose elements are dealt
+    at random to a primary block, a secondary block and a bystander block -- ragged skins, interfaces between blocks that
+    share nodes, faces inside a block: same quads in the same order, same contact nodes, same characteristic lengths."""
+    from nimblesm_b200.exodus_py import write_genesis
+    from nimblesm_b200.mesh import structured_cube
+    from oracle.contact import ContactSetup
+
+    rng = np.random.default_rng(40 + seed)
+    n = int(rng.integers(3, 7))
+    lab = rng.integers(1, 4, size=(n, n, n))
+    mesh = structured_cube(n, block_of_element=lambda i, j, k: lab[i, j, k])
+    if len(mesh["block_ids"]) < 3:
+        pytest.skip("a block came out empty")
+    # distort the lattice so that edge lengths differ
+    for c in "xyz":
+        mesh[c] = mesh[c] + 0.2 / n * (rng.random(len(mesh[c])) - 0.5)
+    mesh["node_gid"] = np.arange(len(mesh["x"]), dtype=np.int32)
+    g = str(tmp_path / "r.g")
+    write_genesis(g, mesh)
+    deck = ("genesis input file: r.g\nexodus output file: r.e\nfinal time: 1.0\nnumber of load steps: 1\n"
+            "material parameters: m neohookean density 7.8 bulk_modulus 1.6e12 shear_modulus 0.8e12\n"
+            "element block: block_1 m\nelement block: block_2 m\nelement block: block_3 m\n"
+            "contact: primary_blocks block_2 secondary_blocks block_1 penalty_parameter 1.0e9\n")
+    got = host_contact_entities(host, g, deck)
+    want = ContactSetup(mesh, [2], [1], 1.0e9)
+    assert np.array_equal(got["primary_quads"], want.primary_quads)
+    assert np.array_equal(got["contact_nodes"], want.contact_nodes)
+    assert np.array_equal(got["primary_char_len"], want.primary_char_len)
+    assert np.array_equal(got["contact_node_char_len"], want.contact_node_char_len)
+    assert len(got["primary_quads"]) > 0 and len(got["contact_nodes"]) > 0
