@@ -174,13 +174,14 @@ def test_contact_steps_vs_oracle(oracle, host, tmp_path, assembly):
 
 
 @pytest.mark.parametrize("case", ["cubes_contact", "sphere_plate_contact", "sliding_contact"])
-@pytest.mark.parametrize("extra", [(), ("--assembly", "atomic"), ("--reference_sequence",)])
+@pytest.mark.parametrize("extra", [(), ("--assembly", "atomic"), ("--reference_sequence",), ("--flags", "14")])
 def test_driver_runs_contact_decks(case, extra, tmp_path):
     """NimbleSM_b200 on the reference's contact decks (the reference runs them only in its Kokkos + ArborX / BVH builds):
     deck -> Genesis mesh -> ContactManager (skinning, entities) -> device steps with the contact term -> Exodus output.
     The output is compared with the reference's gold file under the reference's exodiff rules and with snapshots of the
     reference's serial code + ContactEntity objects (tests/golden) at 1e-9 * max, contact_force included; fused stepping,
-    ATOMIC assembly, and the call-by-call reference sequence (ComputeContactForce on host views)."""
+    ATOMIC assembly, the call-by-call reference sequence (ComputeContactForce on host views), and with the elements
+    walked and the nodes numbered along Morton curves inside the context (--flags 14: the entity lists keep the caller's ids)."""
     from nimblesm_b200 import exodiff
     from nimblesm_b200.exodus_py import read_results
 
