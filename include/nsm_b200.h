@@ -369,6 +369,9 @@ int64_t nsm_b200_launch_count(const nsm_b200_ctx* ctx);
  * with CUDA events around each launch when profiling is switched on. */
 int nsm_b200_profile(nsm_b200_ctx* ctx, int enable);
 int nsm_b200_profile_read(nsm_b200_ctx* ctx, double* elem_kernel_ms_avg, double* node_kernel_ms_avg, int64_t* n_launches);
+/* the contact evaluation's share of the same profiled steps (the reference times it as its own region "Contact",
+ * src/integrators/explicit_time_integrator.cc:233-236); node_kernel_ms_avg above does not include it */
+int nsm_b200_profile_read_contact(nsm_b200_ctx* ctx, double* contact_ms_avg);
 /* Integration points that left the branch-free arithmetic window since creation and were recomputed with the
  * plain IEEE operators (same bits, slower; see csrc/hex8_math.cuh).  Wraps at 2^32. */
 int64_t nsm_b200_cold_points(nsm_b200_ctx* ctx);

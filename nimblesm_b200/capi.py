@@ -48,6 +48,7 @@ SYMBOLS = [
     "nsm_b200_set_element_data", "nsm_b200_set_bc_entry_constants", "nsm_b200_comm_set_host_barrier",
     "nsm_b200_set_host_step_chunks", "nsm_b200_effective_flags", "nsm_b200_fp64_peak_sustained",
     "nsm_b200_set_contact", "nsm_b200_contact_force", "nsm_b200_contact_force_host", "nsm_b200_contact_stats",
+    "nsm_b200_profile_read_contact",
 ]
 
 
@@ -143,6 +144,7 @@ def lib():
         "nsm_b200_contact_force": (i32, [vp]),
         "nsm_b200_contact_force_host": (i32, [vp, vp, vp]),
         "nsm_b200_contact_stats": (i32, [vp, lp]),
+        "nsm_b200_profile_read_contact": (i32, [vp, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -476,6 +478,12 @@ class Context:
         e, n, k = C.c_double(), C.c_double(), C.c_int64()
         self._ck(self._L.nsm_b200_profile_read(self._h, C.byref(e), C.byref(n), C.byref(k)))
         return e.value, n.value, k.value
+
+    def profile_read_contact(self):
+        """average device time of the contact evaluation per profiled step, ms"""
+        m = C.c_double()
+        self._ck(self._L.nsm_b200_profile_read_contact(self._h, C.byref(m)))
+        return m.value
 
     @property
     def cold_points(self):

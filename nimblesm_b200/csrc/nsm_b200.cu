@@ -141,7 +141,7 @@ struct nsm_b200_ctx
   bool                     profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t                   ev_used = 0;
-  double                   prof_elem_ms = 0, prof_node_ms = 0;
+  double                   prof_elem_ms = 0, prof_node_ms = 0, prof_contact_ms = 0;
   int64_t                  prof_steps   = 0;
 
   // pipelined nsm_b200_step_host: node chunks travel up, are integrated, their elements run and the finished chunks
@@ -573,14 +573,17 @@ prof_event(nsm_b200_ctx* c)
 void
 prof_resolve(nsm_b200_ctx* c)
 {
-  // events come in triples: before the element kernels, after them, after the node-side work of the step
+  // events come in fours: before the element kernels, after them, after the contact evaluation (nothing in between
+  // without contact entities), after the node-side work of the step
   cudaStreamSynchronize(c->stream);
-  for (size_t i = 0; i + 2 < c->ev_used; i += 3) {
-    float m1 = 0, m2 = 0;
+  for (size_t i = 0; i + 3 < c->ev_used; i += 4) {
+    float m1 = 0, m2 = 0, m3 = 0;
     cudaEventElapsedTime(&m1, c->ev_pool[i], c->ev_pool[i + 1]);
     cudaEventElapsedTime(&m2, c->ev_pool[i + 1], c->ev_pool[i + 2]);
+    cudaEventElapsedTime(&m3, c->ev_pool[i + 2], c->ev_pool[i + 3]);
     c->prof_elem_ms += m1;
-    c->prof_node_ms += m2;
+    c->prof_contact_ms += m2;
+    c->prof_node_ms += m3;
     c->prof_steps++;
   }
   c->ev_used = 0;
@@ -1635,6 +1638,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     if (c->profiling) prof_event(c);
     mark_states_for_roll(c);
     if ((rc = enqueue_contact(c))) return rc;  // explicit_time_integrator.cc:232-239, on the displacement of this step
+    if (c->profiling) prof_event(c);
     if (n > 0) {
       const NodeArgs na = node_args(c, s + 1);  // boundary-condition magnitudes of the step the fused pass opens
       if (c->comm.active()) {
@@ -1693,7 +1697,7 @@ nsm_b200_step(nsm_b200_ctx* c, int n_steps, double* time, double dt_user, int st
     }
     if (c->profiling) {
       prof_event(c);
-      if (c->ev_used >= 3 * 256) prof_resolve(c);
+      if (c->ev_used >= 4 * 256) prof_resolve(c);
     }
     NSM_CUDA(c, cudaGetLastError());
   }
@@ -2460,7 +2464,7 @@ nsm_b200_profile(nsm_b200_ctx* c, int enable)
 {
   NSM_REQUIRE(c, c != nullptr, "null context");
   c->profiling    = enable != 0;
-  c->prof_elem_ms = c->prof_node_ms = 0;
+  c->prof_elem_ms = c->prof_node_ms = c->prof_contact_ms = 0;
   c->prof_steps   = 0;
   c->ev_used      = 0;
   return NSM_OK;
@@ -2475,6 +2479,16 @@ nsm_b200_profile_read(nsm_b200_ctx* c, double* elem_ms, double* node_ms, int64_t
   if (elem_ms) *elem_ms = c->prof_elem_ms * k;
   if (node_ms) *node_ms = c->prof_node_ms * k;
   if (n) *n = c->prof_steps;
+  return NSM_OK;
+}
+
+int
+nsm_b200_profile_read_contact(nsm_b200_ctx* c, double* contact_ms)
+{
+  NSM_ENTER(c);
+  NSM_REQUIRE(c, contact_ms != nullptr, "profile_read_contact: null argument");
+  prof_resolve(c);
+  *contact_ms = c->prof_steps ? c->prof_contact_ms / (double)c->prof_steps : 0.0;
   return NSM_OK;
 }
 

@@ -147,6 +147,7 @@ ExplicitTimeIntegrator::Integrate()
     model_data->PullNodalFields();
     total_force_time    = model_data->DeviceForceSeconds();
     total_dynamics_time = model_data->DeviceUpdateSeconds();
+    total_contact_time  = model_data->DeviceContactSeconds();
   } else {
     // ---- reference sequence (explicit_time_integrator.cc:177-278), host-sequenced through the ModelData virtuals
     for (int step = 0; step < num_load_steps; ++step) {
@@ -221,7 +222,7 @@ ExplicitTimeIntegrator::Integrate()
     std::cout << " --- Update A, V, U: " << total_dynamics_time << (call_by_call ? "" : "  (device time; includes the shared-node exchange)") << '\n';
     std::cout << " --- Force: " << total_force_time << (call_by_call ? "" : "  (device time of the element kernels)") << "\n";
     if (contact_enabled)
-      std::cout << " --- Contact time: " << total_contact_time << (call_by_call ? "" : "  (on the device, inside the update time)") << '\n';
+      std::cout << " --- Contact time: " << total_contact_time << (call_by_call ? "" : "  (device time of the contact kernels)") << '\n';
     if (num_ranks > 1) std::cout << " --- Vector Reduction = " << total_vector_reduction_time << "  (on the device, inside the update time)\n";
     std::cout << " --- Exodus Write = " << total_exodus_write_time << "\n";
   }

@@ -426,6 +426,11 @@ ModelData::AdvanceOnDevice(DataManager& data_manager, int n_steps, double& time_
   d.check(nsm_b200_profile_read(d.get(), &elem_ms, &node_ms, &n_prof), "ModelData::AdvanceOnDevice (profile)");
   device_force_seconds_ += 1e-3 * elem_ms * (double)n_prof;
   device_update_seconds_ += 1e-3 * node_ms * (double)n_prof;
+  if (contact_on_device_) {
+    double contact_ms = 0.0;
+    d.check(nsm_b200_profile_read_contact(d.get(), &contact_ms), "ModelData::AdvanceOnDevice (profile)");
+    device_contact_seconds_ += 1e-3 * contact_ms * (double)n_prof;
+  }
   enter_exchange_call(data_manager);
 }
 

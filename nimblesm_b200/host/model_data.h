@@ -218,6 +218,11 @@ class ModelData : public ModelDataBase
   {
     return device_update_seconds_;
   }
+  double
+  DeviceContactSeconds() const
+  {
+    return device_contact_seconds_;
+  }
   // contact entities were sent to the device (ContactManager::CreateContactEntities): the fused steps carry the contact
   // term and PullNodalFields also brings the contact force home
   void
@@ -253,7 +258,7 @@ class ModelData : public ModelDataBase
   std::map<int, std::shared_ptr<Block>> blocks_;
   std::vector<int>                      block_ids_;
   std::map<int, std::vector<double>>    element_data_np1_;
-  double                                device_force_seconds_ = 0.0, device_update_seconds_ = 0.0;
+  double                                device_force_seconds_ = 0.0, device_update_seconds_ = 0.0, device_contact_seconds_ = 0.0;
   std::vector<double>                   bc_values_;
   std::vector<double>                   bc_slots_;
   bool                                  bc_table_sent_ = false, bc_programs_sent_ = false;

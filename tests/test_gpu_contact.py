@@ -339,3 +339,29 @@ def test_contact_workload_of_the_bench_checks_itself():
     assert d["contact"]["pairs_enforced"] > 1000
     assert d["contact"]["step_ms_with_contact"] < 1.34 * d["contact"]["step_ms_without_contact"], d["contact"]
     assert r.returncode in (0, 3), r.stderr[-2000:]  # (3: no nvidia-smi clock sample fell inside a 5-step timed region)
+
+
+def test_driver_reports_contact_time(tmp_path):
+    """The reference times contact as its own region and writes it into the timing log
+    (src/integrators/explicit_time_integrator.cc:233-236, 301, 312-316; src/nimble_timing_utils.cc:70-94): the driver's
+    closing summary and nimble_timing_data_*.log carry the device time of the contact kernels."""
+    import glob
+    import re
+    import subprocess
+
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, *_ = load_golden("cubes_contact")
+    deck = re.sub(r"\n*$", "\n", deck) + "write timing data file: on\n"
+    write_genesis(str(tmp_path / "cubes_contact.g"), mesh)
+    (tmp_path / "case.in").write_text(deck)
+    r = subprocess.run([EXE, "case.in"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    m = re.search(r" --- Contact time: ([0-9.eE+-]+)", r.stdout)
+    assert m and float(m.group(1)) > 0.0, r.stdout[-1500:]
+    assert "number of triangular contact facets (primary blocks): 1536" in r.stdout
+    logs = glob.glob(str(tmp_path / "nimble_timing_data_n1_*.log"))
+    assert len(logs) == 1
+    cols = open(logs[0]).read().split()
+    sim, force, contact = float(cols[1]), float(cols[2]), float(cols[3])
+    assert 0.0 < contact < sim and force > 0.0
