@@ -26,6 +26,19 @@ namespace nsm {
 #endif
 constexpr int kElemThreads   = NSM_ELEM_THREADS;  // 8 warps; a warp owns 4 elements ("group") per pass
 constexpr int kElemWarps     = kElemThreads / 32;
+// CTA shape of the element kernel per material.  16 warps per SM either way (the register file is full at 128 registers
+// per thread); the elastic instance, whose passes are half as long, runs 2 % faster as four CTAs of four warps than as
+// two of eight (2.588 vs 2.642 ms at 8 M elements, profiles/r02b_kernel_variants.txt `t128b4`), the others do not care.
+#ifndef NSM_ELEM_THREADS_ELASTIC
+#define NSM_ELEM_THREADS_ELASTIC 128
+#endif
+template <int MAT>
+struct ElemShape
+{
+  static constexpr int threads    = MAT == 0 ? NSM_ELEM_THREADS_ELASTIC : NSM_ELEM_THREADS;
+  static constexpr int warps      = threads / 32;
+  static constexpr int min_blocks = (NSM_ELEM_THREADS * NSM_ELEM_MIN_BLOCKS) / threads;
+};
 constexpr int kElemsPerWarp  = 4;
 #ifndef NSM_TICKET_CHUNK
 #define NSM_TICKET_CHUNK 8
@@ -382,7 +395,7 @@ stage_gather(const ElemArgs& p, double* st, int node, int q, int ew)
 #ifdef NSM_ELEM_MAXREG  // A/B builds: an explicit register cap instead of the one __launch_bounds__ derives
 #define NSM_ELEM_BOUNDS __maxnreg__(NSM_ELEM_MAXREG)
 #else
-#define NSM_ELEM_BOUNDS __launch_bounds__(kElemThreads, NSM_ELEM_MIN_BLOCKS)
+#define NSM_ELEM_BOUNDS __launch_bounds__(ElemShape<MAT>::threads, ElemShape<MAT>::min_blocks)
 #endif
 template <int MAT, bool ORDERED, int MODE>
 __global__ void NSM_ELEM_BOUNDS

@@ -402,7 +402,8 @@ launch_element(const ElemArgs& p, cudaStream_t s)
   // function attributes and occupancy are per device: a process may drive several GPUs (one thread each)
   static int wave_of_device[64] = {0};
   auto       k                  = element_force_kernel<MAT, ORDERED, MODE>;
-  constexpr size_t kElemSmemBytes = (size_t)kElemWarps * warp_smem_doubles<MAT, MODE>() * sizeof(double);
+  constexpr int    kThreads = ElemShape<MAT>::threads, kWarps = ElemShape<MAT>::warps;
+  constexpr size_t kElemSmemBytes = (size_t)kWarps * warp_smem_doubles<MAT, MODE>() * sizeof(double);
   int        dev                = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -413,13 +414,15 @@ launch_element(const ElemArgs& p, cudaStream_t s)
     if (e != cudaSuccess) return e;
     int sms = 0, per_sm = 0;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kElemThreads, kElemSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, kElemSmemBytes)) != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     wave = wave_of_device[dev] = sms * per_sm;
   }
   const int64_t positions = p.sched == kSchedList ? p.n_list : (p.n_range > 0 ? p.n_range : groups_of(p.n_elem));
-  const int64_t need      = std::max<int64_t>((positions + kElemWarps * kTicketChunk - 1) / (kElemWarps * kTicketChunk), 1);
-  k<<<(unsigned)std::min<int64_t>(need, std::max(wave - t_reserve_ctas, 1)), kElemThreads, kElemSmemBytes, s>>>(p);
+  const int64_t need      = std::max<int64_t>((positions + kWarps * kTicketChunk - 1) / (kWarps * kTicketChunk), 1);
+  // (the reservation is counted in CTAs of NSM_ELEM_THREADS threads)
+  const int     reserve   = t_reserve_ctas * (kElemThreads / kThreads);
+  k<<<(unsigned)std::min<int64_t>(need, std::max(wave - reserve, 1)), kThreads, kElemSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
 
