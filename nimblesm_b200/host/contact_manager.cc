@@ -166,8 +166,12 @@ ContactManager::BuildEntityLists(GenesisMesh const& mesh, std::vector<int> const
 // the SAME bits (one evaluation), which is what the reference's clique all-reduce of contact_force guarantees.
 void
 ContactManager::BuildReplicatedSubModel(GenesisMesh const& mesh, VectorCommunicator& vc, std::vector<int> const& primary_block_ids,
-                                        std::vector<int> const& secondary_block_ids)
+                                        std::vector<int> const& secondary_block_ids, ReplicatedContactSubModel& out)
 {
+  auto& surface_xyz_  = out.surface_xyz;
+  auto& held_local_   = out.held_local;
+  auto& held_surface_ = out.held_surface;
+  auto& lists_        = out.lists;
   struct Wire  // one skin face on the wire
   {
     int    gid[4];
@@ -231,7 +235,9 @@ ContactManager::BuildReplicatedSubModel(GenesisMesh const& mesh, VectorCommunica
   }
   std::map<int, int> surface_of_gid;
   surface_xyz_.clear();
+  out.surface_gid.clear();
   for (auto const& kv : node_xyz) {
+    out.surface_gid.push_back(kv.first);
     surface_of_gid[kv.first] = (int)surface_of_gid.size();
     surface_xyz_.insert(surface_xyz_.end(), kv.second.begin(), kv.second.end());
   }
@@ -249,7 +255,6 @@ ContactManager::BuildReplicatedSubModel(GenesisMesh const& mesh, VectorCommunica
     auto at = surface_of_gid.find(gid[i]);
     if (at != surface_of_gid.end()) held_local_.push_back(i), held_surface_.push_back(at->second);
   }
-  replicated_ = true;
 }
 
 void
@@ -261,7 +266,13 @@ ContactManager::CreateContactEntities(GenesisMesh const& mesh, VectorCommunicato
   if (vector_communicator.NumRanks() > 1) {
     group_ = vector_communicator.Group();
     rank_  = vector_communicator.Rank();
-    BuildReplicatedSubModel(mesh, vector_communicator, primary_block_ids, secondary_block_ids);
+    ReplicatedContactSubModel sub;
+    BuildReplicatedSubModel(mesh, vector_communicator, primary_block_ids, secondary_block_ids, sub);
+    lists_        = std::move(sub.lists);
+    surface_xyz_  = std::move(sub.surface_xyz);
+    held_local_   = std::move(sub.held_local);
+    held_surface_ = std::move(sub.held_surface);
+    replicated_      = true;
     contact_enabled_ = true;
     if (rank_ == 0) {
       // the contact sub-model on rank 0's GPU: surface nodes, no elements

@@ -43,6 +43,16 @@ struct ContactEntityLists
   std::vector<double> contact_node_char_len;
 };
 
+// the replicated contact sub-model of a multi-rank run (ContactManager::BuildReplicatedSubModel): identical on every
+// rank except for the `held_*` lists
+struct ReplicatedContactSubModel
+{
+  ContactEntityLists  lists;          // node ids = surface indices
+  std::vector<double> surface_xyz;    // [n_surface][3] model coordinates
+  std::vector<int>    surface_gid;    // [n_surface] global node id, ascending
+  std::vector<int>    held_local, held_surface;  // surface nodes this rank holds: local node id, surface index
+};
+
 class ContactManager
 {
  public:
@@ -107,6 +117,11 @@ class ContactManager
   {
     return replicated_;
   }
+  // several ranks: the replicated contact sub-model (surface numbering = ascending global node id); collective over the
+  // ranks of the communicator's group, no device involved
+  static void
+  BuildReplicatedSubModel(GenesisMesh const& mesh, VectorCommunicator& vector_communicator, std::vector<int> const& primary_block_ids,
+                          std::vector<int> const& secondary_block_ids, ReplicatedContactSubModel& out);
   // everything CreateContactEntities does before the upload (no device involved)
   static void
   BuildEntityLists(GenesisMesh const& mesh, std::vector<int> const& primary_block_ids, std::vector<int> const& secondary_block_ids,
@@ -117,10 +132,6 @@ class ContactManager
   bool               contact_enabled_   = false;
   double             penalty_parameter_ = 0.0;
   ContactEntityLists lists_;
-  // several ranks: the replicated contact sub-model (surface numbering = ascending global node id)
-  void
-  BuildReplicatedSubModel(GenesisMesh const& mesh, VectorCommunicator& vector_communicator, std::vector<int> const& primary_block_ids,
-                          std::vector<int> const& secondary_block_ids);
   bool                           replicated_ = false;
   std::shared_ptr<RankGroup>     group_;
   int                            rank_ = 0;

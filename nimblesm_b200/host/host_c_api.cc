@@ -358,6 +358,83 @@ nsmh_contact_entities(const char* genesis_path, const char* deck_text, long long
   }
 }
 
+// ContactManager::BuildReplicatedSubModel on `n_ranks` threads, one Genesis piece each (paths separated by '\n'): the
+// sub-model every rank ends up with, as JSON {n_surface, surface_gid, primary_quads_gid, contact_nodes_gid,
+// primary_char_len, contact_node_char_len, held: [per rank count], identical: true when all ranks built the same lists}
+int
+nsmh_contact_replicated(const char* piece_paths, const char* deck_text, int n_ranks, char* out, int outlen, char* err, int errlen)
+{
+  try {
+    std::vector<std::string> paths;
+    {
+      std::istringstream in(piece_paths);
+      std::string        line;
+      while (std::getline(in, line))
+        if (!line.empty()) paths.push_back(line);
+    }
+    if ((int)paths.size() != n_ranks) return fail(err, errlen, "one piece path per rank expected");
+    Parser p;
+    p.InitializeFromString(deck_text);
+    std::vector<std::string> pn, sn;
+    double                   penalty = 0.0;
+    ParseContactCommand(p.ContactString(), pn, sn, penalty);
+    auto                                   group = std::make_shared<RankGroup>(n_ranks);
+    std::vector<ReplicatedContactSubModel> subs(n_ranks);
+    std::vector<std::string>               errors(n_ranks);
+    std::vector<std::thread>               threads;
+    for (int r = 0; r < n_ranks; ++r)
+      threads.emplace_back([&, r] {
+        try {
+          GenesisMesh m;
+          m.ReadFile(paths[r]);
+          VectorCommunicator vc(m.GetDim(), m.GetNumNodes(), group, r);
+          std::vector<int>   gids(m.GetNodeGlobalIds(), m.GetNodeGlobalIds() + m.GetNumNodes());
+          vc.Initialize(gids);
+          std::vector<int> pi, si;
+          m.BlockNamesToOnProcessorBlockIds(pn, pi);
+          m.BlockNamesToOnProcessorBlockIds(sn, si);
+          ContactManager::BuildReplicatedSubModel(m, vc, pi, si, subs[r]);
+        } catch (std::exception const& e) {
+          errors[r] = e.what();
+        }
+      });
+    for (auto& t : threads) t.join();
+    for (auto const& e : errors)
+      if (!e.empty()) return fail(err, errlen, e);
+    bool same = true;
+    for (int r = 1; r < n_ranks; ++r)
+      same = same && subs[r].surface_gid == subs[0].surface_gid && subs[r].lists.primary_face_nodes == subs[0].lists.primary_face_nodes &&
+             subs[r].lists.contact_node_ids == subs[0].lists.contact_node_ids &&
+             subs[r].lists.primary_face_char_len == subs[0].lists.primary_face_char_len &&
+             subs[r].lists.contact_node_char_len == subs[0].lists.contact_node_char_len && subs[r].surface_xyz == subs[0].surface_xyz;
+    const auto&        s0 = subs[0];
+    std::ostringstream j;
+    j.precision(17);
+    auto ints = [&](const char* key, const std::vector<int>& v, bool to_gid) {
+      j << "\"" << key << "\":[";
+      for (size_t i = 0; i < v.size(); ++i) j << (i ? "," : "") << (to_gid ? s0.surface_gid[v[i]] : v[i]);
+      j << "],";
+    };
+    auto dbls = [&](const char* key, const std::vector<double>& v) {
+      j << "\"" << key << "\":[";
+      for (size_t i = 0; i < v.size(); ++i) j << (i ? "," : "") << v[i];
+      j << "],";
+    };
+    j << "{\"n_surface\":" << s0.surface_gid.size() << ",";
+    ints("surface_gid", s0.surface_gid, false);
+    ints("primary_quads_gid", s0.lists.primary_face_nodes, true);
+    ints("contact_nodes_gid", s0.lists.contact_node_ids, true);
+    dbls("primary_char_len", s0.lists.primary_face_char_len);
+    dbls("contact_node_char_len", s0.lists.contact_node_char_len);
+    j << "\"held\":[";
+    for (int r = 0; r < n_ranks; ++r) j << (r ? "," : "") << subs[r].held_local.size();
+    j << "],\"identical\":" << (same ? "true" : "false") << "}";
+    return put(out, outlen, j.str(), err, errlen);
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
 // VectorCommunicator::Initialize on `n_ranks` threads: rank r holds global ids gids[off[r] .. off[r+1]).
 // Returns, for rank `query_rank`, its peers and shared local node lists (flattened).
 int

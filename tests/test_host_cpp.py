@@ -442,3 +442,38 @@ def test_skin_blocks_on_random_block_assignments(host, tmp_path, seed):
     assert np.array_equal(got["primary_char_len"], want.primary_char_len)
     assert np.array_equal(got["contact_node_char_len"], want.contact_node_char_len)
     assert len(got["primary_quads"]) > 0 and len(got["contact_nodes"]) > 0
+
+
+@pytest.mark.parametrize("case,P", [("sphere_plate_contact", 2), ("sphere_plate_contact", 4), ("sliding_contact", 4)])
+def test_replicated_contact_sub_model_on_rank_threads(host, tmp_path, case, P):
+    """Contact across mesh partitions, host side (ContactManager::BuildReplicatedSubModel on P rank threads, one Nemesis
+    piece each, no device): every rank ends up with the SAME sub-model, and that sub-model is the serial one -- the same
+    skin quads (partition cuts dropped), the same contact nodes, the same characteristic lengths as the glue around the
+    reference's own ContactEntity objects built from the undecomposed mesh (tests/golden), all in global node ids."""
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, _gold, ref, pieces = load_golden(case)
+    paths = []
+    for r in range(P):
+        path = str(tmp_path / ("p.g.%d.%d" % (P, r)))
+        write_genesis(path, pieces[(P, r)])
+        paths.append(path)
+    j = _call_json(host.nsmh_contact_replicated, "\n".join(paths).encode(), deck.encode(), P)
+    assert j["identical"] is True
+    gid = np.asarray(mesh["node_gid"])
+    quads_want = gid[ref["contact_primary_quads"]]
+    quads_got = np.array(j["primary_quads_gid"]).reshape(-1, 4)
+    # same set of faces, each with the same cyclic orientation (the owning element may list it from another corner)
+    key = lambda q: tuple(sorted(q))
+    want = {key(q): list(q) for q in quads_want.tolist()}
+    assert len(quads_got) == len(quads_want) and {key(q) for q in quads_got.tolist()} == set(want)
+    for q in quads_got.tolist():
+        w = want[key(q)]
+        i = w.index(q[0])
+        assert w[i:] + w[:i] == q
+    len_want = {key(q): l for q, l in zip(quads_want.tolist(), ref["contact_primary_char_len"])}
+    assert all(len_want[key(q)] == l for q, l in zip(quads_got.tolist(), j["primary_char_len"]))
+    nodes_want = dict(zip(gid[ref["contact_contact_nodes"]].tolist(), ref["contact_contact_node_char_len"]))
+    assert dict(zip(j["contact_nodes_gid"], j["contact_node_char_len"])) == nodes_want
+    assert j["n_surface"] == len(set(quads_want.ravel().tolist()) | set(gid[np.unique(ref["contact_secondary_quads"])].tolist()))
+    assert sum(j["held"]) >= j["n_surface"] and all(h > 0 for h in j["held"])
