@@ -279,7 +279,8 @@ int nsm_b200_set_host_step_chunks(nsm_b200_ctx* ctx, int n_chunks);
  * becomes four triangles around its centre, src/nimble_contact_manager.cc:1043-1190) with their characteristic
  * lengths, and the contact nodes of the secondary blocks with theirs (the host layer's ContactManager computes both
  * lists as the reference does, :184-330).  From then on every step evaluates the contact force after the internal
- * force and the acceleration is (1/m)(f_int + f_ext + f_contact).  n_primary_faces == 0 && n_contact_nodes == 0
+ * force and the acceleration is (1/m)(f_int + f_ext + f_contact).  The sum over pairs is atomic (order not fixed, noise
+ * ~1e-16) in ATOMIC assembly and ordered like the serial walk in ORDERED assembly.  n_primary_faces == 0 && n_contact_nodes == 0
  * switches contact off again.  Contexts with a peer exchange are refused: for contact across mesh partitions the host
  * layer replicates the contact surface in a second, element-free context (n_blocks == 0, nodes = the surface nodes of
  * all ranks) and calls nsm_b200_contact_force_host on it with the pooled displacements (host/contact_manager.cc,
@@ -294,8 +295,11 @@ int nsm_b200_contact_force(nsm_b200_ctx* ctx);
  * reached the device): uploads displacement [n][3] when it is non-null, evaluates, downloads contact_force [n][3]. */
 int nsm_b200_contact_force_host(nsm_b200_ctx* ctx, const double* displacement, double* contact_force);
 /* Counters of the last evaluation: stats[0] node-face pairs enforced, [1] pairs that passed the bounding-box test,
- * [2] triangles in contact (numActiveContactFaces, :692-702), [3] nodes in contact (numActiveContactNodes). */
-int nsm_b200_contact_stats(nsm_b200_ctx* ctx, int64_t stats[4]);
+ * [2] triangles in contact (numActiveContactFaces, :692-702), [3] nodes in contact (numActiveContactNodes), [4] ORDERED
+ * assembly only: pairs that did not fit the ordered lists (room for four pairs per contact node) and were added
+ * atomically -- 0 means the contact force was summed in the serial order (contact nodes ascending, triangles ascending,
+ * facet nodes before the node) and is bit-reproducible. */
+int nsm_b200_contact_stats(nsm_b200_ctx* ctx, int64_t stats[5]);
 
 /* ---- element data / derived output (replaces ModelData::GetElementDataNew + Block::ComputeDerivedElementData,
  *      src/nimble_block.cc:438-497; HexElement::ComputeVolumeAverage, src/nimble_element.h:343-392) --- */

@@ -325,9 +325,10 @@ class Context:
 
     def contact_stats(self):
         """-> dict of the last evaluation's counters (pairs enforced / box-tested, active faces / nodes)"""
-        st = np.zeros(4, np.int64)
+        st = np.zeros(5, np.int64)
         self._ck(self._L.nsm_b200_contact_stats(self._h, st.ctypes.data_as(C.POINTER(C.c_int64))))
-        return {"pairs": int(st[0]), "box_tested": int(st[1]), "active_faces": int(st[2]), "active_nodes": int(st[3])}
+        return {"pairs": int(st[0]), "box_tested": int(st[1]), "active_faces": int(st[2]), "active_nodes": int(st[3]),
+                "ordered_overflow_pairs": int(st[4])}
 
     def compute_stress(self, material, bulk_modulus, shear_modulus, def_grad):
         kind = MATERIAL_KINDS[material] if isinstance(material, str) else int(material)

@@ -66,6 +66,15 @@ struct ContactArgs
   int*       near_list; // [n_sec] contact nodes whose box meets the bounding box of all triangles (this evaluation)
   unsigned long long* counters;  // [0] enforced pairs, [1] pairs that passed the box test, [4] length of near_list
   unsigned char*      status;    // [4 n_quads + n_sec] contact_status flags of this evaluation
+  // ORDERED assembly: the seven nodal contributions of every accepted pair are FILED with their place in the serial
+  // order (contact node, triangle, slot) instead of being added atomically; contact_ordered_sum_kernel adds them per
+  // target node in that order, so the contact force has the serial walk's bits (counters[5] = contributions filed,
+  // counters[6] = pairs that did not fit and were added atomically)
+  int                 ordered;
+  long long           contrib_cap;
+  unsigned long long* contrib_key;     // [cap] contact node << 33 | triangle << 3 | slot
+  int*                contrib_target;  // [cap]
+  double*             contrib_val;     // [cap][3]
 };
 
 __device__ __forceinline__ unsigned
@@ -103,6 +112,7 @@ contact_update_kernel(const ContactArgs p)
   if (t < 8) p.red_next[t] = t < 3 ? 0xffffffffu : 0u;
   if (t < 2) p.counters[t] = 0ull;
   if (t == 2) p.counters[4] = 0ull;
+  if (t == 3) p.counters[5] = p.counters[6] = 0ull;
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, ext = 0.0f;
   if (t < p.n_quads) {
     // ContactManager::ApplyDisplacements (src/nimble_contact_manager.cc:750-786) + ContactEntity::SetCoordinates
@@ -320,9 +330,27 @@ contact_pair(const ContactArgs& p, int64_t s, int nd, const double pt[3], int qu
   const double scale = p.penalty * gap;
   const double cf[3] = {scale * nx, scale * ny, scale * nz};
   const int*   qn    = p.quad + 4 * (int64_t)quad;
+  const double f3[3] = {(alpha3 * cf[0]) / 4.0, (alpha3 * cf[1]) / 4.0, (alpha3 * cf[2]) / 4.0};
+  if (p.ordered) {
+    const unsigned long long at = atomicAdd(p.counters + 5, 7ull);
+    if ((long long)at + 7 <= p.contrib_cap) {
+      const unsigned long long key = ((unsigned long long)s << 33) | ((unsigned long long)(4 * quad + k) << 3);
+      const int    target[7] = {qn[k], qn[kb], qn[0], qn[1], qn[2], qn[3], nd};
+      const double value[7][3] = {{alpha1 * cf[0], alpha1 * cf[1], alpha1 * cf[2]}, {alpha2 * cf[0], alpha2 * cf[1], alpha2 * cf[2]},
+                                  {f3[0], f3[1], f3[2]}, {f3[0], f3[1], f3[2]}, {f3[0], f3[1], f3[2]}, {f3[0], f3[1], f3[2]},
+                                  {-cf[0], -cf[1], -cf[2]}};
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        p.contrib_key[at + i]    = key | (unsigned long long)i;
+        p.contrib_target[at + i] = target[i];
+        p.contrib_val[3 * (at + i)] = value[i][0], p.contrib_val[3 * (at + i) + 1] = value[i][1], p.contrib_val[3 * (at + i) + 2] = value[i][2];
+      }
+      return true;
+    }
+    atomicAdd(p.counters + 6, 1ull);  // the lists are full: this pair goes the atomic way
+  }
   contact_add3(p.fc, qn[k], alpha1 * cf[0], alpha1 * cf[1], alpha1 * cf[2]);
   contact_add3(p.fc, qn[kb], alpha2 * cf[0], alpha2 * cf[1], alpha2 * cf[2]);
-  const double f3[3] = {(alpha3 * cf[0]) / 4.0, (alpha3 * cf[1]) / 4.0, (alpha3 * cf[2]) / 4.0};
 #pragma unroll
   for (int i = 0; i < 4; ++i) contact_add3(p.fc, qn[i], f3[0], f3[1], f3[2]);
   contact_add3(p.fc, nd, -cf[0], -cf[1], -cf[2]);
@@ -404,6 +432,40 @@ contact_pair_kernel(const ContactArgs p)
     atomicAdd(p.counters + 1, (unsigned long long)tested);
     if (enforced) atomicAdd(p.counters, (unsigned long long)enforced);
   }
+}
+
+// ORDERED assembly, after the contributions have been sorted by (target node; contact node, triangle, slot): the thread
+// at the head of a target's run adds the run in order -- PenaltyContactEnforcement::EnforceContact's scatter order inside a
+// pair (facet node 1, facet node 2, the quad's four nodes, the contact node), pairs node-major with triangles ascending,
+// which is the order of the serial walk (oracle/contact_oracle.c) -- and adds the sum to the (cleared) contact force.
+__global__ void __launch_bounds__(256)
+contact_gather_targets_kernel(long long n, const unsigned* __restrict__ order, const int* __restrict__ target, unsigned* out)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (unsigned)target[order[i]];
+}
+
+__global__ void __launch_bounds__(256)
+contact_ordered_sum_kernel(long long n, const unsigned* __restrict__ sorted_target, const unsigned* __restrict__ order,
+                           const double* __restrict__ val, double* f0, double* f1, double* f2)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned t = sorted_target[i];
+  if (i > 0 && sorted_target[i - 1] == t) return;
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (long long j = i; j < n && sorted_target[j] == t; ++j) {
+    const double* v = val + 3 * (long long)order[j];
+    a += v[0], b += v[1], c += v[2];
+  }
+  f0[t] = f0[t] + a, f1[t] = f1[t] + b, f2[t] = f2[t] + c;
+}
+
+__global__ void __launch_bounds__(256)
+contact_iota_kernel(long long n, unsigned* out)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (unsigned)i;
 }
 
 // numActiveContactFaces / numActiveContactNodes (src/nimble_contact_manager.cc:692-714): entities whose contact_status

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler is attached
 
@@ -185,6 +186,15 @@ struct nsm_b200_ctx
     int*      near_list = nullptr;
     unsigned char* status = nullptr;
     int       parity = 0;
+    // ORDERED assembly: filed contributions and the scratch of their two stable sorts
+    long long           contrib_cap = 0;
+    unsigned long long *contrib_key = nullptr, *key_sorted = nullptr;
+    int*                contrib_target = nullptr;
+    double*             contrib_val    = nullptr;
+    unsigned *          iota = nullptr, *order1 = nullptr, *order2 = nullptr, *target1 = nullptr, *target2 = nullptr;
+    void*               sort_tmp = nullptr;
+    size_t              sort_tmp_bytes = 0;
+    long long           ordered_overflow_pairs = 0;  // of the last evaluation
   } contact;
   double* fc[3] = {nullptr, nullptr, nullptr};  // nodal contact force, SoA (allocated by nsm_b200_set_contact)
 
@@ -608,6 +618,8 @@ enqueue_contact(nsm_b200_ctx* c)
   p.table_mask = k.table_mask;
   p.red = k.red + 8 * k.parity, p.red_next = k.red + 8 * (k.parity ^ 1);
   p.counters = k.counters, p.status = k.status, p.near_list = k.near_list;
+  p.ordered = k.contrib_cap > 0 ? 1 : 0, p.contrib_cap = k.contrib_cap;
+  p.contrib_key = k.contrib_key, p.contrib_target = k.contrib_target, p.contrib_val = k.contrib_val;
   k.parity ^= 1;
   const int64_t n_update = std::max<int64_t>(std::max(k.n_quads, k.n_sec), 32);
   contact_update_kernel<<<grid_for(n_update, 256), 256, 0, c->stream>>>(p);
@@ -617,6 +629,25 @@ enqueue_contact(nsm_b200_ctx* c)
     // a grid that fills the device once; its warps stride over the list of near nodes (whose length only the device knows)
     contact_pair_kernel<<<(unsigned)std::min<int64_t>(grid_for(32 * k.n_sec, 256), 148 * 3 * 2), 256, 0, c->stream>>>(p);
     c->launches += 2;
+    if (p.ordered) {
+      // ORDERED assembly: sort the filed contributions by their place in the serial order, then (stably) by target node,
+      // and add every target's run in order (csrc/contact.cuh).  The number of contributions is read back: one small
+      // synchronisation per evaluation, in the mode whose point is reproducibility.
+      unsigned long long filed[2] = {0, 0};
+      NSM_CUDA(c, cudaMemcpyAsync(filed, k.counters + 5, sizeof filed, cudaMemcpyDeviceToHost, c->stream));
+      NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+      k.ordered_overflow_pairs = (long long)filed[1];
+      const long long n        = std::min<long long>((long long)filed[0], k.contrib_cap / 7 * 7);
+      if (n > 0) {
+        size_t tmp = k.sort_tmp_bytes;
+        NSM_CUDA(c, cub::DeviceRadixSort::SortPairs(k.sort_tmp, tmp, k.contrib_key, k.key_sorted, k.iota, k.order1, (int)n, 0, 64, c->stream));
+        contact_gather_targets_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, k.order1, k.contrib_target, k.target1);
+        tmp = k.sort_tmp_bytes;
+        NSM_CUDA(c, cub::DeviceRadixSort::SortPairs(k.sort_tmp, tmp, k.target1, k.target2, k.order1, k.order2, (int)n, 0, 32, c->stream));
+        contact_ordered_sum_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(n, k.target2, k.order2, k.contrib_val, c->fc[0], c->fc[1], c->fc[2]);
+        c->launches += 2;
+      }
+    }
   }
   NSM_CUDA(c, cudaGetLastError());
   return NSM_OK;
@@ -835,6 +866,8 @@ nsm_b200_destroy(nsm_b200_ctx* c)
     auto& k = c->contact;
     fr(k.quad), fr(k.quad_len), fr(k.sec_node), fr(k.sec_len), fr(k.quad_xyz), fr(k.tri_box), fr(k.bin), fr(k.head);
     fr(k.red), fr(k.counters), fr(k.status), fr(k.near_list);
+    fr(k.contrib_key), fr(k.key_sorted), fr(k.contrib_target), fr(k.contrib_val), fr(k.iota), fr(k.order1), fr(k.order2), fr(k.target1),
+        fr(k.target2), fr(k.sort_tmp);
     for (int i = 0; i < 3; ++i) fr(c->fc[i]);
   }
   for (double* p : c->pipe.stage) fr(p);
@@ -2373,6 +2406,27 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
       (rc = dev_alloc(c, &k.status, n_tri + n_cn)) || (rc = dev_alloc(c, &k.near_list, n_cn)))
     return rc;
   if (!k.red && ((rc = dev_alloc(c, &k.red, 16)) || (rc = dev_alloc(c, &k.counters, 8)))) return rc;
+  dev_release(c, k.contrib_key), dev_release(c, k.key_sorted), dev_release(c, k.contrib_target), dev_release(c, k.contrib_val);
+  dev_release(c, k.iota), dev_release(c, k.order1), dev_release(c, k.order2), dev_release(c, k.target1), dev_release(c, k.target2);
+  if (k.sort_tmp) cudaFree(k.sort_tmp), k.sort_tmp = nullptr;
+  k.contrib_cap = 0;
+  if (c->assembly == NSM_ASSEMBLY_ORDERED && n_cn > 0 && n_faces > 0) {
+    // room for four accepted pairs per contact node (a node on a facet vertex meets the facets around it) + slack; pairs
+    // beyond it are added atomically and counted (nsm_b200_contact_stats)
+    const long long cap = std::min<long long>(7 * (4 * n_cn + 4096), 2147483647LL / 7 * 7);
+    if ((rc = dev_alloc(c, &k.contrib_key, cap)) || (rc = dev_alloc(c, &k.key_sorted, cap)) || (rc = dev_alloc(c, &k.contrib_target, cap)) ||
+        (rc = dev_alloc(c, &k.contrib_val, 3 * cap)) || (rc = dev_alloc(c, &k.iota, cap)) || (rc = dev_alloc(c, &k.order1, cap)) ||
+        (rc = dev_alloc(c, &k.order2, cap)) || (rc = dev_alloc(c, &k.target1, cap)) || (rc = dev_alloc(c, &k.target2, cap)))
+      return rc;
+    size_t t64 = 0, t32 = 0;
+    NSM_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, t64, k.contrib_key, k.key_sorted, k.iota, k.order1, (int)cap, 0, 64, c->stream));
+    NSM_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, t32, k.target1, k.target2, k.order1, k.order2, (int)cap, 0, 32, c->stream));
+    k.sort_tmp_bytes = std::max(t64, t32);
+    NSM_CUDA(c, cudaMalloc(&k.sort_tmp, k.sort_tmp_bytes));
+    contact_iota_kernel<<<grid_for(cap, 256), 256, 0, c->stream>>>(cap, k.iota);
+    c->launches++;
+    k.contrib_cap = cap;
+  }
   for (int i = 0; i < 3; ++i)
     if (!c->fc[i] && (rc = dev_alloc(c, &c->fc[i], c->n_nodes))) return rc;
   for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->fc[i], 0, (size_t)std::max<int64_t>(c->n_nodes, 1) * sizeof(double), c->stream));
@@ -2418,11 +2472,11 @@ nsm_b200_contact_force_host(nsm_b200_ctx* c, const double* displacement, double*
 }
 
 int
-nsm_b200_contact_stats(nsm_b200_ctx* c, int64_t stats[4])
+nsm_b200_contact_stats(nsm_b200_ctx* c, int64_t stats[5])
 {
   NSM_ENTER(c);
   NSM_REQUIRE(c, stats != nullptr, "contact_stats: null argument");
-  stats[0] = stats[1] = stats[2] = stats[3] = 0;
+  stats[0] = stats[1] = stats[2] = stats[3] = stats[4] = 0;
   auto& k = c->contact;
   if (!k.active) return NSM_OK;
   const int64_t n_tri = 4 * k.n_quads;
@@ -2433,6 +2487,7 @@ nsm_b200_contact_stats(nsm_b200_ctx* c, int64_t stats[4])
   NSM_CUDA(c, cudaMemcpyAsync(h, k.counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < 4; ++i) stats[i] = (int64_t)h[i];
+  stats[4] = (int64_t)k.ordered_overflow_pairs;
   return NSM_OK;
 }
 

@@ -282,7 +282,8 @@ ContactManager::CreateContactEntities(GenesisMesh const& mesh, VectorCommunicato
       sub_model_.reset(new DeviceContext(model_data->DeviceIndex()));
       DeviceContext& d = *sub_model_;
       d.check(nsm_b200_set_nodes(d.get(), (int64_t)n, sx.data(), sy.data(), sz.data()), "ContactManager (contact sub-model nodes)");
-      d.check(nsm_b200_finalize(d.get(), NSM_ASSEMBLY_ATOMIC, 0), "ContactManager (contact sub-model)");
+      // (the model's assembly mode: ORDERED sums the contact force in the serial order, bit-reproducible)
+      d.check(nsm_b200_finalize(d.get(), model_data->Assembly(), 0), "ContactManager (contact sub-model)");
       d.check(nsm_b200_set_contact(d.get(), penalty_parameter_, (int64_t)lists_.primary_face_char_len.size(), lists_.primary_face_nodes.data(),
                                    lists_.primary_face_char_len.data(), (int64_t)lists_.contact_node_ids.size(), lists_.contact_node_ids.data(),
                                    lists_.contact_node_char_len.data()),
@@ -358,7 +359,7 @@ std::size_t
 ContactManager::numActiveContactFaces() const
 {
   auto*   model_data = dynamic_cast<ModelData*>(data_manager_.GetModelData().get());
-  int64_t st[4]      = {0, 0, 0, 0};
+  int64_t st[5]      = {0, 0, 0, 0, 0};
   if (replicated_) {
     if (sub_model_) sub_model_->check(nsm_b200_contact_stats(sub_model_->get(), st), "ContactManager::numActiveContactFaces");
     return (std::size_t)st[2];
@@ -371,7 +372,7 @@ std::size_t
 ContactManager::numActiveContactNodes() const
 {
   auto*   model_data = dynamic_cast<ModelData*>(data_manager_.GetModelData().get());
-  int64_t st[4]      = {0, 0, 0, 0};
+  int64_t st[5]      = {0, 0, 0, 0, 0};
   if (replicated_) {
     if (sub_model_) sub_model_->check(nsm_b200_contact_stats(sub_model_->get(), st), "ContactManager::numActiveContactNodes");
     return (std::size_t)st[3];

@@ -197,6 +197,11 @@ class ModelData : public ModelDataBase
   {
     return device_index_;
   }
+  int
+  Assembly() const
+  {
+    return assembly_;
+  }
   std::map<int, std::shared_ptr<Block>>&
   GetBlocks()
   {

@@ -41,11 +41,13 @@ def _context(mesh, deck_obj, flags=0, assembly=None):
     return c
 
 
-@pytest.mark.parametrize("flags", [0, 8])
-def test_contact_force_vs_oracle(oracle, host, tmp_path, flags):
+@pytest.mark.parametrize("flags,ordered", [(0, False), (8, False), (0, True), (8, True)])
+def test_contact_force_vs_oracle(oracle, host, tmp_path, flags, ordered):
     """One-shot evaluations on the cubes_contact mesh: entity lists from the C++ ContactManager, displacement fields in
     contact, separated, and pushed through by more than the facets' characteristic length.  Same accepted pairs and
-    active entities as the oracle's all-pairs walk, force within 1e-12; also with the nodes renumbered inside the context."""
+    active entities as the oracle's all-pairs walk, force within 1e-12; also with the nodes renumbered inside the context.
+    ORDERED assembly files the pairs' contributions and adds them in the serial order: the force is then BIT-IDENTICAL to
+    the oracle's (and to the walk over the reference's own ContactEntity objects, which the oracle equals bit for bit)."""
     from nimblesm_b200.deck import parse_deck
     from nimblesm_b200.exodus_py import write_genesis
     from oracle.model import OracleModel
@@ -60,7 +62,9 @@ def test_contact_force_vs_oracle(oracle, host, tmp_path, flags):
     in_b1[np.unique(mesh["conn"][1])] = True
     rng = np.random.default_rng(5)
     total = 0
-    with _context(mesh, parse_deck(deck), flags) as c:
+    from nimblesm_b200 import capi
+
+    with _context(mesh, parse_deck(deck), flags, capi.ASSEMBLY_ORDERED if ordered else capi.ASSEMBLY_ATOMIC) as c:
         c.set_contact(ent["penalty"], ent["primary_quads"], ent["primary_char_len"], ent["contact_nodes"], ent["contact_node_char_len"])
         for amp, shift in ((0.0, 0.0), (1e-4, 0.0), (1e-3, -2e-3), (1e-2, -0.02), (1e-3, 0.05), (0.0, -1.0), (1e-3, -3e-3)):
             u = amp * (2.0 * rng.random((n, 3)) - 1.0)
@@ -76,6 +80,9 @@ def test_contact_force_vs_oracle(oracle, host, tmp_path, flags):
                 assert _rel(got, want) <= 1e-12, (amp, shift, _rel(got, want))
             else:
                 assert not got.any()
+            if ordered:
+                assert st["ordered_overflow_pairs"] == 0
+                assert np.array_equal(got.view(np.int64), want.view(np.int64)), "ORDERED contact force must be bit-identical"
             total += pairs
             # the device-resident call gives the same field
             c.upload("displacement", u)
@@ -166,6 +173,11 @@ def test_contact_steps_vs_oracle(oracle, host, tmp_path, assembly):
         assert _rel(c.download("internal_force"), f_same) <= 1e-12
         assert _rel(c.download("contact_force"), om.contact.force(ug)[0]) <= 1e-12
         assert _rel(c.download("internal_force"), om.f) <= 1e-7
+        if assembly == "ordered":  # internal and contact forces both summed in the serial order: the same trajectory, bit for bit
+            for lbl, want in (("displacement", om.u), ("velocity", om.v), ("acceleration", om.a), ("internal_force", om.f),
+                              ("contact_force", om.fcontact)):
+                assert np.array_equal(c.download(lbl).view(np.int64), want.view(np.int64)), lbl
+            assert c.contact_stats()["ordered_overflow_pairs"] == 0
         # the host-state step takes the plain schedule with contact and carries the same term
         U, V, A, Fo = (c.download(l) for l in ("displacement", "velocity", "acceleration", "internal_force"))
         t2 = c.step_host(t, dt, U, V, A, Fo)
@@ -201,6 +213,14 @@ def test_driver_runs_contact_decks(case, extra, tmp_path):
             if key in res["nod"]:
                 assert np.abs(res["nod"][key][idx] - want[:, :, i]).max() <= bar * np.abs(want).max(), key
     assert "contact_force_z" in res["nod"] and np.abs(res["nod"]["contact_force_x"]).max() > 0
+    if "atomic" not in extra:
+        # ORDERED assembly (the driver's default): internal force summed in the serial element order, contact force in the
+        # serial pair order -- every nodal field the file holds is BIT-IDENTICAL to the serial reference-entity run
+        for lbl in ("displacement", "velocity", "internal_force", "contact_force"):
+            for i, comp in enumerate("xyz"):
+                key = "%s_%s" % (lbl, comp)
+                if key in res["nod"]:
+                    assert np.array_equal(res["nod"][key][idx].view(np.int64), ref["node_" + lbl][:, :, i].view(np.int64)), key
     # forces of the file's own displacement at the last output step, recomputed by the oracle: 1e-12
     from nimblesm_b200.deck import parse_deck
     from oracle import contact as contact_oracle
