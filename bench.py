@@ -743,6 +743,10 @@ def run_contact(args):
     of contact nodes recomputed by the oracle on the device's own displacement)."""
     from nimblesm_b200 import capi
 
+    if env_int("WORLD_SIZE", 1) > 1 or args.gpus > 1:
+        sys.stderr.write("bench.py: --workload contact is a single-GPU line (contact across partitions runs through the C++ "
+                         "driver, tests/test_gpu_contact.py)\n")
+        sys.exit(2)
     n = args.n if args.n != 400 else 200
     mesh, ent, h = contact_stack(n)
     n_elem, n_nodes = sum(len(c_) for c_ in mesh["conn"].values()), len(mesh["x"])
