@@ -284,3 +284,38 @@ def test_bench_parity_block(world, corrupt, ok):
     if corrupt is None:
         assert res["max_rel_f"] <= 1e-13
     assert got.get(1) is None
+
+
+def test_bench_contact_stack_entities_match_the_generic_skinner():
+    """bench.py builds the contact entities of its two-body workload analytically (six sides per body, Exodus face orders);
+    they must be the skin the oracle's generic skinner finds -- same quads with the same cyclic orientation (outward
+    normals), same contact nodes, same characteristic lengths."""
+    import bench
+    from oracle.contact import ContactSetup
+
+    mesh, ent, h = bench.contact_stack(10)
+    cs = ContactSetup(mesh, [2], [1], 1.0)
+    want = {tuple(sorted(q)): list(q) for q in cs.primary_quads.tolist()}
+    assert len(ent["primary_quads"]) == len(want)
+    for q, l in zip(ent["primary_quads"].tolist(), ent["primary_char_len"]):
+        w = want[tuple(sorted(q))]
+        i = w.index(q[0])
+        assert w[i:] + w[:i] == q
+        assert l == cs.primary_char_len[[tuple(sorted(x)) for x in cs.primary_quads.tolist()].index(tuple(sorted(q)))]
+    assert dict(zip(ent["contact_nodes"].tolist(), ent["contact_node_char_len"])) == dict(zip(cs.contact_nodes.tolist(), cs.contact_node_char_len))
+    assert abs(h - 0.1) < 1e-15
+
+
+def test_exodiff_rounding_floor():
+    """An absolute tolerance far below the rounding of the data (the contact decks ask for 2e-4 on forces of 3e8) can be
+    floored at a multiple of the variable's magnitude; relative tolerances and honest absolute ones are untouched."""
+    from nimblesm_b200 import exodiff
+
+    spec = "NODAL VARIABLES relative 1.e-6 floor 0.0\n\tf_x absolute 2.0e-4\n\tu_x absolute 1.0e-8\n"
+    gold = {"times": np.array([0.0, 1.0]), "nod": {"f_x": np.array([[0.0, 3.0e8], [1.0e8, 2.0e8]]), "u_x": np.array([[0.0, 1.0e-5], [0.0, 2.0e-5]])}, "elem": {}}
+    test = {"times": gold["times"].copy(), "nod": {"f_x": gold["nod"]["f_x"] + 3.0e-4, "u_x": gold["nod"]["u_x"] + 5.0e-9}, "elem": {}}
+    assert exodiff.compare(spec, gold, test)  # 3e-4 > 2e-4
+    assert not exodiff.compare(spec, gold, test, rounding_floor=1e-11)  # 3e-4 < 1e-11 * 3e8 = 3e-3
+    test["nod"]["u_x"] = gold["nod"]["u_x"] + 2.0e-8
+    fails = exodiff.compare(spec, gold, test, rounding_floor=1e-11)
+    assert len(fails) == 1 and "u_x" in fails[0]  # (1e-11 * 2e-5 is far below the 1e-8 the file asks for)
