@@ -50,6 +50,8 @@ struct ContactArgs
   const double* quad_len;  // [n_quads] characteristic length (largest edge in the model configuration)
   const int*    sec_node;  // [n_sec]
   const double* sec_len;   // [n_sec]
+  int64_t       n_surf;    // nodes of the contact sub-model (of the quads and the contact nodes), each once
+  const int*    surf_node; // [n_surf]
   const double* X[3];
   const double* u[3];
   double*       fc[3];     // nodal contact force, SoA
@@ -106,36 +108,48 @@ inflate_to_float(const double lo[3], const double hi[3], double char_len, float*
 __global__ void __launch_bounds__(256)
 contact_update_kernel(const ContactArgs p)
 {
+  // The per-quad records leave through shared memory: a thread's 15 doubles / 24 floats are 120 / 96 bytes apart from
+  // its neighbour's, and stored lane by lane every instruction touched 32 sectors -- the load/store unit's queue was
+  // where this kernel waited (ncu: lg_throttle 40 of 90 stall cycles per issue, profiles/r02S_*).  Staged, the CTA
+  // writes its 256 records as contiguous runs.
+  __shared__ double   stage[256 * 15];
+  __shared__ unsigned part[8][7];
   const int64_t t   = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  const int     l   = threadIdx.x;
   for (int64_t i = t; i <= (int64_t)p.table_mask; i += nth) p.head[i] = -1;
+  // the contact force of every node of the contact sub-model, once (the quads share their nodes four ways)
+  for (int64_t i = t; i < p.n_surf; i += nth) {
+    const int nd = p.surf_node[i];
+    p.fc[0][nd] = 0.0, p.fc[1][nd] = 0.0, p.fc[2][nd] = 0.0;
+  }
+  for (int64_t i = t; i < 4 * p.n_quads + p.n_sec; i += nth) p.status[i] = 0;
   if (t < 8) p.red_next[t] = t < 3 ? 0xffffffffu : 0u;
   if (t < 2) p.counters[t] = 0ull;
   if (t == 2) p.counters[4] = 0ull;
   if (t == 3) p.counters[5] = p.counters[6] = 0ull;
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, ext = 0.0f;
+  float box[4][6];
+  const int64_t block_base = (int64_t)blockIdx.x * blockDim.x;
+  const int     n_here     = (int)max((int64_t)0, min((int64_t)blockDim.x, p.n_quads - block_base));  // quads of this CTA
   if (t < p.n_quads) {
     // ContactManager::ApplyDisplacements (src/nimble_contact_manager.cc:750-786) + ContactEntity::SetCoordinates
     // (src/nimble_contact_entity.h:236-258): the third vertex of every triangle is the mean of the quad's nodes
     double c[4][3], ctr[3];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int nd = p.quad[4 * t + k];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        c[k][d]      = p.X[d][nd] + p.u[d][nd];
-        p.fc[d][nd]  = 0.0;
-      }
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) ctr[d] = (c[0][d] + c[1][d] + c[2][d] + c[3][d]) / 4.0;
-    double* q = p.quad_xyz + 15 * t;
+    const int4 qn = *reinterpret_cast<const int4*>(p.quad + 4 * t);
+    const int  node[4] = {qn.x, qn.y, qn.z, qn.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int d = 0; d < 3; ++d) q[3 * k + d] = c[k][d];
+      for (int d = 0; d < 3; ++d) c[k][d] = p.X[d][node[k]] + p.u[d][node[k]];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) q[12 + d] = ctr[d];
+    for (int d = 0; d < 3; ++d) ctr[d] = (c[0][d] + c[1][d] + c[2][d] + c[3][d]) / 4.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) stage[15 * l + 3 * k + d] = c[k][d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) stage[15 * l + 12 + d] = ctr[d];
     const double len = p.quad_len[t];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -149,34 +163,37 @@ contact_update_kernel(const ContactArgs p)
         if (ctr[d] < blo[d]) blo[d] = ctr[d];
         if (ctr[d] > bhi[d]) bhi[d] = ctr[d];
       }
-      float box[6];
-      inflate_to_float(blo, bhi, len, box);
-      float* o = p.tri_box + 6 * (4 * t + k);
-#pragma unroll
-      for (int d = 0; d < 6; ++d) o[d] = box[d];
+      inflate_to_float(blo, bhi, len, box[k]);
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        lo[d] = fminf(lo[d], box[d]);
-        hi[d] = fmaxf(hi[d], box[3 + d]);
+        lo[d] = fminf(lo[d], box[k][d]);
+        hi[d] = fmaxf(hi[d], box[k][3 + d]);
       }
-      p.status[4 * t + k] = 0;
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) ext = fmaxf(ext, hi[d] - lo[d]);  // the quad is binned by the union of its triangles' boxes
   }
+  __syncthreads();
+  for (int i = l; i < 15 * n_here; i += blockDim.x) p.quad_xyz[15 * block_base + i] = stage[i];
+  __syncthreads();
+  float* fstage = reinterpret_cast<float*>(stage);
+  if (t < p.n_quads) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int d = 0; d < 6; ++d) fstage[24 * l + 6 * k + d] = box[k][d];
+  }
+  __syncthreads();
+  for (int i = l; i < 24 * n_here; i += blockDim.x) p.tri_box[24 * block_base + i] = fstage[i];
   if (t < p.n_sec) {
     const int nd = p.sec_node[t];
     double    x[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      x[d]        = p.X[d][nd] + p.u[d][nd];
-      p.fc[d][nd] = 0.0;
-    }
-    float box[6];
-    inflate_to_float(x, x, p.sec_len[t], box);
+    for (int d = 0; d < 3; ++d) x[d] = p.X[d][nd] + p.u[d][nd];
+    float nbox[6];
+    inflate_to_float(x, x, p.sec_len[t], nbox);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) ext = fmaxf(ext, box[3 + d] - box[d]);  // (the grid is anchored at the triangles' boxes only)
-    p.status[4 * p.n_quads + t] = 0;
+    for (int d = 0; d < 3; ++d) ext = fmaxf(ext, nbox[3 + d] - nbox[d]);  // (the grid is anchored at the triangles' boxes only)
   }
   // grid-wide corners of the triangles' boxes and maximum extent: warp reduction, then one atomic per CTA and quantity
   unsigned r[7] = {ordered_float(lo[0]), ordered_float(lo[1]), ordered_float(lo[2]), __float_as_uint(ext),
@@ -185,8 +202,7 @@ contact_update_kernel(const ContactArgs p)
   for (int d = 0; d < 3; ++d) r[d] = __reduce_min_sync(0xffffffffu, r[d]);
 #pragma unroll
   for (int d = 3; d < 7; ++d) r[d] = __reduce_max_sync(0xffffffffu, r[d]);
-  __shared__ unsigned part[8][7];
-  const int           warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) {
 #pragma unroll
     for (int d = 0; d < 7; ++d) part[warp][d] = r[d];

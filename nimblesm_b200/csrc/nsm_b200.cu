@@ -176,6 +176,8 @@ struct nsm_b200_ctx
     double*   quad_len = nullptr;
     int*      sec_node = nullptr;
     double*   sec_len  = nullptr;
+    int64_t   n_surf    = 0;
+    int*      surf_node = nullptr;
     double*   quad_xyz = nullptr;
     float*    tri_box  = nullptr;
     QuadBin*  bin  = nullptr;
@@ -612,6 +614,7 @@ enqueue_contact(nsm_b200_ctx* c)
   ContactArgs p{};
   p.n_quads = k.n_quads, p.n_sec = k.n_sec;
   p.quad = k.quad, p.quad_len = k.quad_len, p.sec_node = k.sec_node, p.sec_len = k.sec_len;
+  p.n_surf = k.n_surf, p.surf_node = k.surf_node;
   for (int i = 0; i < 3; ++i) p.X[i] = c->X[i], p.u[i] = c->u[i], p.fc[i] = c->fc[i];
   p.penalty  = k.penalty;
   p.quad_xyz = k.quad_xyz, p.tri_box = k.tri_box, p.bin = k.bin, p.head = k.head;
@@ -865,7 +868,7 @@ nsm_b200_destroy(nsm_b200_ctx* c)
   {
     auto& k = c->contact;
     fr(k.quad), fr(k.quad_len), fr(k.sec_node), fr(k.sec_len), fr(k.quad_xyz), fr(k.tri_box), fr(k.bin), fr(k.head);
-    fr(k.red), fr(k.counters), fr(k.status), fr(k.near_list);
+    fr(k.red), fr(k.counters), fr(k.status), fr(k.near_list), fr(k.surf_node);
     fr(k.contrib_key), fr(k.key_sorted), fr(k.contrib_target), fr(k.contrib_val), fr(k.iota), fr(k.order1), fr(k.order2), fr(k.target1),
         fr(k.target2), fr(k.sort_tmp);
     for (int i = 0; i < 3; ++i) fr(c->fc[i]);
@@ -2379,6 +2382,8 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
   dev_release(c, k.quad), dev_release(c, k.quad_len), dev_release(c, k.sec_node), dev_release(c, k.sec_len), dev_release(c, k.quad_xyz);
   dev_release(c, k.tri_box), dev_release(c, k.bin), dev_release(c, k.head), dev_release(c, k.status), dev_release(c, k.near_list);
+  dev_release(c, k.surf_node);
+  k.n_surf = 0;
   k.active = false, k.n_quads = k.n_sec = 0;
   if (n_faces == 0 && n_cn == 0) {
     if (c->fc[0])
@@ -2396,6 +2401,11 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
     NSM_REQUIRE(c, cn_ids[i] >= 0 && cn_ids[i] < c->n_nodes, "set_contact: contact node id out of range");
     nodes[(size_t)i] = c->node_perm_host.empty() ? cn_ids[i] : c->node_perm_host[cn_ids[i]];
   }
+  // nodes of the contact sub-model, each once (the update kernel clears their contact force)
+  std::vector<int> surf(quads);
+  surf.insert(surf.end(), nodes.begin(), nodes.end());
+  std::sort(surf.begin(), surf.end());
+  surf.erase(std::unique(surf.begin(), surf.end()), surf.end());
   int rc;
   const int64_t n_tri = 4 * n_faces;
   unsigned      table = 1024;
@@ -2403,7 +2413,8 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
   if ((rc = dev_alloc(c, &k.quad, n_faces * 4)) || (rc = dev_alloc(c, &k.quad_len, n_faces)) || (rc = dev_alloc(c, &k.sec_node, n_cn)) ||
       (rc = dev_alloc(c, &k.sec_len, n_cn)) || (rc = dev_alloc(c, &k.quad_xyz, n_faces * 15)) || (rc = dev_alloc(c, &k.tri_box, n_tri * 6)) ||
       (rc = dev_alloc(c, &k.bin, n_faces)) || (rc = dev_alloc(c, &k.head, (int64_t)table)) ||
-      (rc = dev_alloc(c, &k.status, n_tri + n_cn)) || (rc = dev_alloc(c, &k.near_list, n_cn)))
+      (rc = dev_alloc(c, &k.status, n_tri + n_cn)) || (rc = dev_alloc(c, &k.near_list, n_cn)) ||
+      (rc = dev_alloc(c, &k.surf_node, (int64_t)surf.size())))
     return rc;
   if (!k.red && ((rc = dev_alloc(c, &k.red, 16)) || (rc = dev_alloc(c, &k.counters, 8)))) return rc;
   dev_release(c, k.contrib_key), dev_release(c, k.key_sorted), dev_release(c, k.contrib_target), dev_release(c, k.contrib_val);
@@ -2442,7 +2453,9 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
     NSM_CUDA(c, cudaMemcpyAsync(k.sec_node, nodes.data(), nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     NSM_CUDA(c, cudaMemcpyAsync(k.sec_len, cn_len, (size_t)n_cn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
+  if (!surf.empty()) NSM_CUDA(c, cudaMemcpyAsync(k.surf_node, surf.data(), surf.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  k.n_surf  = (int64_t)surf.size();
   k.penalty = penalty, k.n_quads = n_faces, k.n_sec = n_cn, k.table_mask = table - 1, k.parity = 0;
   k.active  = true;
   return NSM_OK;
