@@ -385,7 +385,10 @@ contact_pair(const ContactArgs& p, int64_t s, int nd, const double pt[3], int qu
 __global__ void __launch_bounds__(256, NSM_CONTACT_MIN_BLOCKS)
 contact_pair_kernel(const ContactArgs p)
 {
-  __shared__ unsigned found[8][32];  // quad << 4 | mask of its triangles that passed the box test (never 0)
+  constexpr int kCand = 64;  // candidate quads per round (a node's 27 cells normally hold ~20)
+  __shared__ int      cand[8][kCand];
+  __shared__ unsigned items[8][4 * kCand];  // quad << 2 | triangle, box test passed
+  __shared__ int      n_cand[8], n_items[8];
   const int        warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t    n_near = (int64_t)p.counters[4], n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   unsigned         tested = 0, enforced = 0;
@@ -405,13 +408,24 @@ contact_pair_kernel(const ContactArgs p)
     quad = p.head[contact_hash(cell[0], cell[1], cell[2]) & p.table_mask];
   }
   for (;;) {
-    // (1) every lane advances along its chain to its next quad with a box hit
-    unsigned mine = 0u;
+    if (lane == 0) n_cand[warp] = 0, n_items[warp] = 0;
+    __syncwarp();
+    // (1) the divergent part, kept thin: each lane walks its chain and lists the quads of its cell
     while (quad >= 0) {
-      const QuadBin e  = p.bin[quad];
-      const int     at = quad;
-      quad             = e.next;
-      if (e.cell[0] != cell[0] || e.cell[1] != cell[1] || e.cell[2] != cell[2]) continue;  // another cell of the same bucket
+      const QuadBin e = p.bin[quad];
+      if (e.cell[0] == cell[0] && e.cell[1] == cell[1] && e.cell[2] == cell[2]) {  // (else another cell of the same bucket)
+        const int at = atomicAdd(&n_cand[warp], 1);
+        if (at >= kCand) break;  // list full: this quad waits for the next round
+        cand[warp][at] = quad;
+      }
+      quad = e.next;
+    }
+    __syncwarp();
+    const int nc = min(n_cand[warp], kCand);
+    if (nc == 0) break;
+    // (2) box tests, one candidate quad per lane
+    for (int c = lane; c < nc; c += 32) {
+      const int    at  = cand[warp][c];
       const float* tb  = p.tri_box + 24 * (int64_t)at;
       unsigned     hit = 0;
 #pragma unroll
@@ -420,23 +434,20 @@ contact_pair_kernel(const ContactArgs p)
         if (!(box[3] < b0 || box[0] > b3 || box[4] < b1 || box[1] > b4 || box[5] < b2 || box[2] > b5)) hit |= 1u << k;
       }
       if (hit) {
-        mine = ((unsigned)at << 4) | hit;
-        tested += __popc(hit);
-        break;
+        const int nh = __popc(hit);
+        tested += nh;
+        int at_item = atomicAdd(&n_items[warp], nh);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if ((hit >> k) & 1u) items[warp][at_item++] = ((unsigned)at << 2) | (unsigned)k;
       }
     }
-    // (2) the lanes' finds, compacted
-    const unsigned have = __ballot_sync(0xffffffffu, mine != 0u);
-    if (!have) break;
-    if (mine != 0u) found[warp][__popc(have & ((1u << lane) - 1u))] = mine;
     __syncwarp();
     // (3) all 32 lanes share out the (quad, triangle) items
-    const int n_items = 4 * __popc(have);
-    for (int item = lane; item < n_items; item += 32) {
-      const unsigned f = found[warp][item >> 2];
-      const int      k = item & 3;
-      if ((f >> k) & 1u)
-        if (contact_pair(p, s, nd, pt, (int)(f >> 4), k)) ++enforced;
+    const int ni = n_items[warp];
+    for (int item = lane; item < ni; item += 32) {
+      const unsigned f = items[warp][item];
+      if (contact_pair(p, s, nd, pt, (int)(f >> 2), (int)(f & 3u))) ++enforced;
     }
     __syncwarp();
   }
