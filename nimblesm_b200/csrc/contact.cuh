@@ -422,6 +422,7 @@ contact_pair_kernel(const ContactArgs p)
     }
     __syncwarp();
     const int nc = min(n_cand[warp], kCand);
+    __syncwarp();  // (everyone has read the count before lane 0 of the next node resets it)
     if (nc == 0) break;
     // (2) box tests, one candidate quad per lane
     for (int c = lane; c < nc; c += 32) {
