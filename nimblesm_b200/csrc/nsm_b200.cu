@@ -194,7 +194,7 @@ struct nsm_b200_ctx
     int*                contrib_target = nullptr;
     double*             contrib_val    = nullptr;
     unsigned *          iota = nullptr, *order1 = nullptr, *order2 = nullptr, *target1 = nullptr, *target2 = nullptr;
-    void*               sort_tmp = nullptr;
+    unsigned char*      sort_tmp = nullptr;
     size_t              sort_tmp_bytes = 0;
     long long           ordered_overflow_pairs = 0;  // of the last evaluation
   } contact;
@@ -2378,20 +2378,9 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
   NSM_REQUIRE(c, n_faces >= 0 && n_cn >= 0 && n_faces < ((int64_t)1 << 28) && n_cn < ((int64_t)1 << 31), "set_contact: entity count out of range");
   NSM_REQUIRE(c, (n_faces == 0 || (face_nodes && face_len)) && (n_cn == 0 || (cn_ids && cn_len)), "set_contact: null argument");
   NSM_REQUIRE(c, !c->comm.active(), "set_contact: contexts with a peer exchange are not supported (contact across partitions)");
-  auto& k = c->contact;
-  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
-  dev_release(c, k.quad), dev_release(c, k.quad_len), dev_release(c, k.sec_node), dev_release(c, k.sec_len), dev_release(c, k.quad_xyz);
-  dev_release(c, k.tri_box), dev_release(c, k.bin), dev_release(c, k.head), dev_release(c, k.status), dev_release(c, k.near_list);
-  dev_release(c, k.surf_node);
-  k.n_surf = 0;
-  k.active = false, k.n_quads = k.n_sec = 0;
-  if (n_faces == 0 && n_cn == 0) {
-    if (c->fc[0])
-      for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->fc[i], 0, (size_t)std::max<int64_t>(c->n_nodes, 1) * sizeof(double), c->stream));
-    return NSM_OK;
-  }
-  // ComputeContactForce throws on a non-positive penalty (src/nimble_contact_manager.cc:398-400)
-  NSM_REQUIRE(c, penalty > 0.0, "Error in ComputeContactForce(), invalid penalty_parameter.");
+  // every argument is checked before the entities in place are touched: a refused call leaves the context as it was
+  // (ComputeContactForce throws on a non-positive penalty, src/nimble_contact_manager.cc:398-400)
+  NSM_REQUIRE(c, (n_faces == 0 && n_cn == 0) || penalty > 0.0, "Error in ComputeContactForce(), invalid penalty_parameter.");
   std::vector<int> quads((size_t)n_faces * 4), nodes((size_t)n_cn);
   for (int64_t i = 0; i < n_faces * 4; ++i) {
     NSM_REQUIRE(c, face_nodes[i] >= 0 && face_nodes[i] < c->n_nodes, "set_contact: face node id out of range");
@@ -2400,6 +2389,22 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
   for (int64_t i = 0; i < n_cn; ++i) {
     NSM_REQUIRE(c, cn_ids[i] >= 0 && cn_ids[i] < c->n_nodes, "set_contact: contact node id out of range");
     nodes[(size_t)i] = c->node_perm_host.empty() ? cn_ids[i] : c->node_perm_host[cn_ids[i]];
+  }
+  auto& k = c->contact;
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  dev_release(c, k.quad), dev_release(c, k.quad_len), dev_release(c, k.sec_node), dev_release(c, k.sec_len), dev_release(c, k.quad_xyz);
+  dev_release(c, k.tri_box), dev_release(c, k.bin), dev_release(c, k.head), dev_release(c, k.status), dev_release(c, k.near_list);
+  dev_release(c, k.surf_node);
+  dev_release(c, k.contrib_key), dev_release(c, k.key_sorted), dev_release(c, k.contrib_target), dev_release(c, k.contrib_val);
+  dev_release(c, k.iota), dev_release(c, k.order1), dev_release(c, k.order2), dev_release(c, k.target1), dev_release(c, k.target2);
+  dev_release(c, k.sort_tmp);
+  k.contrib_cap = 0, k.sort_tmp_bytes = 0, k.ordered_overflow_pairs = 0;
+  k.n_surf = 0;
+  k.active = false, k.n_quads = k.n_sec = 0;
+  if (n_faces == 0 && n_cn == 0) {
+    if (c->fc[0])
+      for (int i = 0; i < 3; ++i) NSM_CUDA(c, cudaMemsetAsync(c->fc[i], 0, (size_t)std::max<int64_t>(c->n_nodes, 1) * sizeof(double), c->stream));
+    return NSM_OK;
   }
   // nodes of the contact sub-model, each once (the update kernel clears their contact force)
   std::vector<int> surf(quads);
@@ -2417,10 +2422,6 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
       (rc = dev_alloc(c, &k.surf_node, (int64_t)surf.size())))
     return rc;
   if (!k.red && ((rc = dev_alloc(c, &k.red, 16)) || (rc = dev_alloc(c, &k.counters, 8)))) return rc;
-  dev_release(c, k.contrib_key), dev_release(c, k.key_sorted), dev_release(c, k.contrib_target), dev_release(c, k.contrib_val);
-  dev_release(c, k.iota), dev_release(c, k.order1), dev_release(c, k.order2), dev_release(c, k.target1), dev_release(c, k.target2);
-  if (k.sort_tmp) cudaFree(k.sort_tmp), k.sort_tmp = nullptr;
-  k.contrib_cap = 0;
   if (c->assembly == NSM_ASSEMBLY_ORDERED && n_cn > 0 && n_faces > 0) {
     // room for four accepted pairs per contact node (a node on a facet vertex meets the facets around it) + slack; pairs
     // beyond it are added atomically and counted (nsm_b200_contact_stats)
@@ -2433,7 +2434,7 @@ nsm_b200_set_contact(nsm_b200_ctx* c, double penalty, int64_t n_faces, const int
     NSM_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, t64, k.contrib_key, k.key_sorted, k.iota, k.order1, (int)cap, 0, 64, c->stream));
     NSM_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, t32, k.target1, k.target2, k.order1, k.order2, (int)cap, 0, 32, c->stream));
     k.sort_tmp_bytes = std::max(t64, t32);
-    NSM_CUDA(c, cudaMalloc(&k.sort_tmp, k.sort_tmp_bytes));
+    if ((rc = dev_alloc(c, &k.sort_tmp, (int64_t)k.sort_tmp_bytes))) return rc;
     contact_iota_kernel<<<grid_for(cap, 256), 256, 0, c->stream>>>(cap, k.iota);
     c->launches++;
     k.contrib_cap = cap;

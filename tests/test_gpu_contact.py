@@ -115,6 +115,22 @@ def test_contact_argument_errors(host, tmp_path):
         bad[3, 2] = len(mesh["x"])
         with pytest.raises(capi.NsmError):
             c.set_contact(1.0, bad, ent["primary_char_len"], ent["contact_nodes"], ent["contact_node_char_len"])
+        # a refused call leaves the entities in place as they were; replacing and dropping them returns their memory
+        bare = c.device_bytes
+        args = (ent["primary_quads"], ent["primary_char_len"], ent["contact_nodes"], ent["contact_node_char_len"])
+        c.set_contact(1.0e5, *args)
+        c.contact_force()
+        with_contact, fc = c.device_bytes, c.download("contact_force")
+        for refused in ((0.0,) + args, (1.0, bad) + args[1:]):
+            with pytest.raises(capi.NsmError):
+                c.set_contact(*refused)
+            c.contact_force()
+            assert np.array_equal(c.download("contact_force"), fc) and c.device_bytes == with_contact
+        c.set_contact(2.0e5, *args)
+        assert c.device_bytes == with_contact
+        c.set_contact(0.0, args[0][:0], args[1][:0], args[2][:0], args[3][:0])
+        fc_bytes = 3 * 8 * len(mesh["x"])  # the nodal contact-force field stays (zeroed) once it exists
+        assert c.device_bytes <= bare + fc_bytes + 256 and not c.download("contact_force").any()
 
 
 @pytest.mark.parametrize("assembly", ["ordered", "atomic"])
