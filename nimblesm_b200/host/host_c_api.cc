@@ -129,6 +129,55 @@ nsmh_deck_summary(const char* deck_text, const int* block_ids, int n_blocks, cha
   }
 }
 
+// MaterialFactoryBase::ParseMaterialParametersString through a factory that registers extra parameter names, as the
+// TestMaterialFactory of the reference's unit test does (unit_tests/test_nimble_material_params.cc:63-90):
+// material string -> JSON {"name", "doubles": {...}, "strings": {...}}; names are blank-separated lists (may be empty)
+int
+nsmh_material_params(const char* material_string, const char* extra_double_names, const char* extra_string_names, char* out, int outlen,
+                     char* err, int errlen)
+{
+  struct TestFactory : MaterialFactoryBase
+  {
+    std::shared_ptr<MaterialParameters>
+    parse_string(const char* params) const
+    {
+      return ParseMaterialParametersString(params);
+    }
+    void
+    create() override
+    {
+    }
+  };
+  try {
+    TestFactory        factory;
+    std::istringstream dn(extra_double_names ? extra_double_names : ""), sn(extra_string_names ? extra_string_names : "");
+    for (std::string w; dn >> w;) factory.add_valid_double_parameter_name(w.c_str());
+    for (std::string w; sn >> w;) factory.add_valid_string_parameter_name(w.c_str());
+    auto               params = factory.parse_string(material_string);
+    std::ostringstream j;
+    j.precision(17);
+    j << "{\"name\":\"" << params->GetMaterialName(false) << "\",\"upper\":\"" << params->GetMaterialName(true)
+      << "\",\"n_doubles\":" << params->GetNumParameters() << ",\"n_strings\":" << params->GetNumStringParameters() << ",\"doubles\":{";
+    bool first = true;
+    for (auto const& kv : params->GetParameters()) {
+      if (!params->IsParameter(kv.first.c_str())) return fail(err, errlen, "IsParameter denies a listed parameter");
+      j << (first ? "" : ",") << "\"" << kv.first << "\":" << params->GetParameterValue(kv.first.c_str());
+      first = false;
+    }
+    j << "},\"strings\":{";
+    first = true;
+    for (auto const& kv : params->GetStringParameters()) {
+      if (!params->IsStringParameter(kv.first.c_str())) return fail(err, errlen, "IsStringParameter denies a listed parameter");
+      j << (first ? "" : ",") << "\"" << kv.first << "\":\"" << params->GetStringParameterValue(kv.first.c_str()) << "\"";
+      first = false;
+    }
+    j << "}}";
+    return put(out, outlen, j.str(), err, errlen);
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
 // Genesis file -> JSON summary (counts, id maps, checksums) for comparison with an independent reader
 int
 nsmh_mesh_summary(const char* path, char* out, int outlen, char* err, int errlen)

@@ -27,6 +27,17 @@ MaterialParameters::GetParameterValue(const char* name) const
   return it->second;
 }
 
+const std::string&
+MaterialParameters::GetStringParameterValue(const char* name) const
+{
+  auto it = string_params_.find(name);
+  if (it == string_params_.end()) {
+    std::string msg = "Error in GetStringParameterValue() for material " + material_name_ + "; parameter '" + name + "' not found";
+    throw std::invalid_argument(msg);
+  }
+  return it->second;
+}
+
 Material::Material(const MaterialParameters& params, nsm_material_kind kind) : params_(params), kind_(kind)
 {
   // src/nimble_material.cc:52-60, 210-218
@@ -72,16 +83,24 @@ MaterialFactoryBase::ParseMaterialParametersString(const std::string& material_p
   std::vector<std::string> tokens;
   for (std::string t; in >> t;) tokens.push_back(t);
   if (tokens.size() < 2) throw std::invalid_argument("material string needs a model name and parameters: '" + material_parameters + "'");
-  std::map<std::string, double> doubles;
+  // key-value pairs after the model name; a key is a double parameter, a string parameter, or an error
+  // (src/nimble_material_factory_base.cc:62-98; the first occurrence of a key wins, as std::map::insert there)
+  std::map<std::string, double>      doubles;
+  std::map<std::string, std::string> strings;
   for (size_t i = 1; i < tokens.size(); i += 2) {
-    const std::string& key = tokens[i];
-    if (std::find(valid_double_parameter_names_.begin(), valid_double_parameter_names_.end(), key) ==
-        valid_double_parameter_names_.end())
-      throw std::invalid_argument("Invalid material parameter encountered: '" + key + "'");
+    const std::string& key       = tokens[i];
+    const bool         is_double = std::find(valid_double_parameter_names_.begin(), valid_double_parameter_names_.end(), key) !=
+                           valid_double_parameter_names_.end();
+    const bool is_string = !is_double && std::find(valid_string_parameter_names_.begin(), valid_string_parameter_names_.end(), key) !=
+                                             valid_string_parameter_names_.end();
+    if (!is_double && !is_string) throw std::invalid_argument("Invalid material parameter encountered: '" + key + "'");
     if (i + 1 >= tokens.size()) throw std::invalid_argument("material parameter '" + key + "' has no value");
-    doubles[key] = std::stod(tokens[i + 1]);
+    if (is_double)
+      doubles.insert(std::make_pair(key, std::stod(tokens[i + 1])));
+    else
+      strings.insert(std::make_pair(key, tokens[i + 1]));
   }
-  return std::make_shared<MaterialParameters>(tokens.front(), std::map<std::string, std::string>(), doubles, num_material_points);
+  return std::make_shared<MaterialParameters>(tokens.front(), strings, doubles, num_material_points);
 }
 
 void

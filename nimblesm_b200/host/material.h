@@ -35,10 +35,20 @@ class MaterialParameters
   {
     double_params_[name] = value;
   }
+  void
+  AddStringParameter(const char* name, const char* value)
+  {
+    string_params_[name] = value;
+  }
   bool
   IsParameter(const char* name) const
   {
     return double_params_.count(name) != 0;
+  }
+  bool
+  IsStringParameter(const char* name) const
+  {
+    return string_params_.count(name) != 0;
   }
   std::string
   GetMaterialName(bool upper_case = false) const;
@@ -49,10 +59,22 @@ class MaterialParameters
   }
   double
   GetParameterValue(const char* name) const;  // throws std::invalid_argument when absent
+  int
+  GetNumStringParameters() const
+  {
+    return (int)string_params_.size();
+  }
+  const std::string&
+  GetStringParameterValue(const char* name) const;  // throws std::invalid_argument when absent
   const std::map<std::string, double>&
   GetParameters() const
   {
     return double_params_;
+  }
+  const std::map<std::string, std::string>&
+  GetStringParameters() const
+  {
+    return string_params_;
   }
   int
   GetNumMaterialPoints() const
@@ -180,6 +202,13 @@ class MaterialFactoryBase
         valid_double_parameter_names_.end())
       valid_double_parameter_names_.push_back(name);
   }
+  void
+  add_valid_string_parameter_name(const char* name)
+  {
+    if (std::find(valid_string_parameter_names_.begin(), valid_string_parameter_names_.end(), name) ==
+        valid_string_parameter_names_.end())
+      valid_string_parameter_names_.push_back(name);
+  }
   virtual std::shared_ptr<Material>
   get_material() const
   {
@@ -212,6 +241,7 @@ class MaterialFactoryBase
 
  private:
   std::vector<std::string> valid_double_parameter_names_;
+  std::vector<std::string> valid_string_parameter_names_;
 };
 
 class MaterialFactory : public MaterialFactoryBase

@@ -28,8 +28,20 @@ def _lib():
         L.h8o_contact_force.restype = C.c_long
         L.h8o_contact_force.argtypes = [C.c_double, C.c_long, _dp, _dp, C.c_long, _ip, _dp, C.c_long, _ip, _dp, _dp, C.c_void_p]
         L.h8o_accel_contact.argtypes = [C.c_long, _dp, _dp, C.c_void_p, _dp, _dp]
+        L.h8o_contact_projection.restype = C.c_int
+        L.h8o_contact_projection.argtypes = [_dp, _dp, C.c_double, _dp, _dp, _dp]
         _bound = True
     return L
+
+
+def projection(node, tri, char_len):
+    """ContactManager::Projection (src/nimble_contact_manager.cc:1549-1620) of one node on one triangular facet ->
+    (in, gap, normal[3], barycentric[3]); the last three are NaN when the projection falls outside the facet (the
+    reference leaves its outputs untouched there)."""
+    gap, normal, bary = np.full(1, np.nan), np.full(3, np.nan), np.full(3, np.nan)
+    inside = _lib().h8o_contact_projection(np.ascontiguousarray(node, dtype=np.float64), np.ascontiguousarray(tri, dtype=np.float64).reshape(-1),
+                                          float(char_len), gap, normal, bary)
+    return bool(inside), float(gap[0]), normal, bary
 
 
 def parse_contact_command(command: str):
@@ -90,6 +102,18 @@ class ContactSetup:
         _lib().h8o_contact_char_lengths(self.ref, len(self.primary_quads), self.primary_quads.reshape(-1), self.primary_char_len,
                                         len(self.secondary_quads), self.secondary_quads.reshape(-1), n, node_len)
         self.contact_node_char_len = np.ascontiguousarray(node_len[self.contact_nodes])
+
+    def entity_vertices(self, coord):
+        """The coordinates the contact entities hold for the nodal coordinates `coord` [n,3], in the order of the
+        reference's contact visualisation database (src/nimble_contact_manager.cc:515-563): three vertices per
+        triangular facet (node k, node k+1, the fictitious node at the mean of the face's four nodes,
+        CreateContactNodesAndFaces :1083-1088 and ContactEntity::SetCoordinates), then the contact nodes."""
+        c = np.asarray(coord)[self.primary_quads]  # [nf,4,3]
+        centre = (((0.0 + c[:, 0]) + c[:, 1]) + c[:, 2] + c[:, 3]) / 4
+        tri = np.empty((len(c), 4, 3, 3))
+        for k in range(4):
+            tri[:, k, 0], tri[:, k, 1], tri[:, k, 2] = c[:, k], c[:, (k + 1) % 4], centre
+        return np.vstack([tri.reshape(-1, 3), np.asarray(coord)[self.contact_nodes]])
 
     def force(self, disp, want_status=False):
         """-> (contact force [n,3], enforced pairs[, status flags of the 4*nf triangles then the contact nodes])"""

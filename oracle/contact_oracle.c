@@ -125,6 +125,19 @@ projection(const double* p, const Tri* t, double* gap, double* normal, double* b
   return (*gap < 0.0) && (*gap > -t->char_len); /* inside but not through */
 }
 
+/* The projection alone, for the known answers of the reference's unit test (unit_tests/projection_node_to_face.cc:146-279):
+ * node[3], tri[9] = the facet's three vertices; gap / normal[3] / bary[3] are written only when the projection falls
+ * inside the facet's barycentric window, as in the reference; returns the reference's `in` flag. */
+int
+h8o_contact_projection(const double* node, const double* tri, double char_len, double* gap, double* normal, double* bary)
+{
+  Tri t;
+  memset(&t, 0, sizeof t);
+  for (int d = 0; d < 3; ++d) t.p1[d] = tri[d], t.p2[d] = tri[3 + d], t.p3[d] = tri[6 + d];
+  t.char_len = char_len;
+  return projection(node, &t, gap, normal, bary);
+}
+
 /* One evaluation of the contact force.
  *   ref, disp, contact_force: [n_nodes][3]; contact_force is overwritten (zero away from the contact surfaces,
  *     ContactManager::GetForces, src/nimble_contact_manager.cc:732-748)

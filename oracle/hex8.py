@@ -29,6 +29,8 @@ def lib():
         L.h8o_stress_elastic.argtypes = [d, d, _dp, _dp]
         L.h8o_stress_neohookean.argtypes = [d, d, _dp, _dp]
         L.h8o_polar_left_stretch.argtypes = [_dp, _dp]
+        L.h8o_invert_full33.restype = d
+        L.h8o_invert_full33.argtypes = [_dp, _dp]
         L.h8o_nodal_forces.argtypes = [_dp, _dp, _dp]
         L.h8o_lumped_mass.argtypes = [d, _dp, _dp]
         L.h8o_char_length.restype = d

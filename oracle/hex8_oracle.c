@@ -342,12 +342,10 @@ h8o_eigen_sym33(const double A[6], double eval[3], double v0[3], double v1[3], d
   }
 }
 
-/* Left stretch V of F = V R as computed by Polar_Decomp (src/nimble_utils.h:859-908) through
- * Invert_Full33 (:523-551) and Square_Full33T_Full33 (:194-205): eigen-decompose (F^-1)^T (F^-1) = V^-2
- * and rebuild V = sum_i v_i v_i^T / (sqrt(lambda_i) |v_i|^2).  The rotation product of :907 only feeds a
- * debug check in the caller and is not part of any result. */
-void
-h8o_polar_left_stretch(const double F[9], double V[6])
+/* Invert_Full33 (src/nimble_utils.h:523-551): cofactors over the determinant, the signs applied as "-1.0 * minor / det";
+ * returns the determinant.  Known answers: unit_tests/test_nimble_utils.cc:47-93 (tests/test_oracle.py). */
+double
+h8o_invert_full33(const double F[9], double G[9])
 {
   const double m0  = F[FYY] * F[FZZ] - F[FYZ] * F[FZY];
   const double m1  = F[FYX] * F[FZZ] - F[FYZ] * F[FZX];
@@ -359,7 +357,6 @@ h8o_polar_left_stretch(const double F[9], double V[6])
   const double m7  = F[FXX] * F[FYZ] - F[FXZ] * F[FYX];
   const double m8  = F[FXX] * F[FYY] - F[FXY] * F[FYX];
   const double det = F[FXX] * m0 - F[FXY] * m1 + F[FXZ] * m2;
-  double       G[9];
   G[FXX] = m0 / det;
   G[FXY] = -1.0 * m3 / det;
   G[FXZ] = m6 / det;
@@ -369,6 +366,18 @@ h8o_polar_left_stretch(const double F[9], double V[6])
   G[FZX] = m2 / det;
   G[FZY] = -1.0 * m5 / det;
   G[FZZ] = m8 / det;
+  return det;
+}
+
+/* Left stretch V of F = V R as computed by Polar_Decomp (src/nimble_utils.h:859-908) through
+ * Invert_Full33 (:523-551) and Square_Full33T_Full33 (:194-205): eigen-decompose (F^-1)^T (F^-1) = V^-2
+ * and rebuild V = sum_i v_i v_i^T / (sqrt(lambda_i) |v_i|^2).  The rotation product of :907 only feeds a
+ * debug check in the caller and is not part of any result. */
+void
+h8o_polar_left_stretch(const double F[9], double V[6])
+{
+  double G[9];
+  h8o_invert_full33(F, G);
 
   double C[6]; /* G^T G */
   C[SXX] = G[FXX] * G[FXX] + G[FYX] * G[FYX] + G[FZX] * G[FZX];

@@ -40,6 +40,10 @@ CONTACT_CASES = [
     ("cubes_contact", "cubes_contact", "cubes_contact"),
     ("sphere_plate_contact", "sphere_plate_contact", "sphere_plate_contact"),
     ("sliding_contact", "sliding_contact", "sliding_contact"),
+    # five blocks, two primary and two secondary; its gold file is the reference's CONTACT VISUALISATION database (one
+    # triangle element per contact facet with its own three nodes, one sphere element per contact node, the entities'
+    # displacement): the reference's own record of which entities CreateContactEntities makes, in which order
+    ("contact_entity_creation", "contact_entity_creation", "contact_entity_creation"),
 ]
 
 
@@ -145,6 +149,7 @@ def load_case(name):
     z = np.load(os.path.join(HERE, name + ".npz"), allow_pickle=False)
     mesh = unpack_mesh("mesh_", z)
     gold = {"times": z["gold_times"], "nod": {}, "elem": {}}
+    gold["vis"] = {k[len("gold_vis_"):]: z[k] for k in z.files if k.startswith("gold_vis_")}  # contact visualisation database
     for k in z.files:
         if k.startswith("gold_nod_"):
             gold["nod"][k[len("gold_nod_"):]] = z[k]
@@ -225,7 +230,8 @@ def main():
         return
 
     cases = [("dynamics",) + c for c in CASES] if "--contact-only" not in sys.argv else []
-    for sub, d, deck, g in cases + [("contact",) + c for c in CONTACT_CASES]:
+    contact_cases = [c for c in CONTACT_CASES if "--entity-creation-only" not in sys.argv or c[0] == "contact_entity_creation"]
+    for sub, d, deck, g in ([] if "--entity-creation-only" in sys.argv else cases) + [("contact",) + c for c in contact_cases]:
         base = os.path.join(refroot, "test", sub, d)
         out = {}
         mesh = read_genesis(os.path.join(base, g + ".g"))
@@ -238,6 +244,11 @@ def main():
         else:
             times, nod, elem = np.zeros(0), {}, {}
         out["gold_times"] = times
+        if nod and len(next(iter(nod.values()))[0]) != len(mesh["x"]):
+            # not a results file of the mesh: the contact visualisation database (src/nimble_contact_manager.cc:431-590)
+            f = netcdf_file(os.path.join(base, deck + ".gold.e"), "r", mmap=False)
+            for k in ("coordx", "coordy", "coordz", "elem_num_map", "node_num_map", "connect1", "connect2"):
+                out["gold_vis_" + k] = np.array(f.variables[k].data)
         for k, a in nod.items():
             out["gold_nod_" + k] = a
         for (k, b), a in elem.items():

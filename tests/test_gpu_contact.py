@@ -263,6 +263,38 @@ def test_driver_runs_contact_decks(case, extra, tmp_path):
         assert not fails, fails[:5]
 
 
+@pytest.mark.parametrize("extra", [(), ("--assembly", "atomic")])
+def test_driver_runs_contact_entity_creation_deck(extra, tmp_path):
+    """test/contact/contact_entity_creation through NimbleSM_b200: five blocks of three materials, primary block_1 block_2,
+    secondary block_3 block_5, block_4 outside the contact definition, `contact visualization` parsed and not written.
+    Blocks 1 and 5 fly at 1e7 for 2e-9 s and meet nothing: the contact force stays zero, the nodal fields equal the
+    reference-entity snapshots (bit for bit in ORDERED assembly), and the displacement the contact ENTITIES see at the end
+    -- facet vertices, fictitious face-centre nodes, contact nodes, in the reference's entity order -- meets the last
+    record of the reference's gold visualisation database under contact_entity_creation.exodiff (2e-8 / 1e-12 / 1e-12)."""
+    from nimblesm_b200.deck import parse_deck
+    from nimblesm_b200.exodus_py import read_results
+    from oracle import contact as contact_oracle
+
+    deck, mesh, gold, ref, _pieces, out = _run(tmp_path, "contact_entity_creation", extra=extra)
+    res = read_results(out)
+    assert np.array_equal(res["times"], ref["times"])
+    for i, comp in enumerate("xyz"):
+        got, want = res["nod"]["displacement_" + comp], ref["node_displacement"][:, :, i]
+        assert np.abs(got - want).max() <= 1e-9 * np.abs(ref["node_displacement"]).max()
+        if "atomic" not in extra:
+            assert np.array_equal(got.view(np.int64), want.view(np.int64))
+        assert not res["nod"]["contact_force_" + comp].any()
+    prim, sec, penalty = contact_oracle.parse_contact_command(parse_deck(deck).contact_string)
+    ids = lambda names: [int(nm.rsplit("_", 1)[1]) for nm in names]
+    cs = contact_oracle.ContactSetup(mesh, ids(prim), ids(sec), penalty)
+    u_last = np.stack([res["nod"]["displacement_" + comp][-1] for comp in "xyz"], 1)
+    seen = cs.entity_vertices(cs.ref + u_last) - cs.entity_vertices(cs.ref)
+    assert len(seen) == len(gold["vis"]["coordx"]) == 6778
+    for i, (comp, tol) in enumerate(zip("xyz", (2.0e-8, 1.0e-12, 1.0e-12))):
+        assert np.abs(seen[:, i] - gold["nod"]["displacement_" + comp][-1]).max() <= tol, comp
+    assert np.abs(seen[:, 0]).max() == pytest.approx(0.02, rel=1e-9)
+
+
 def _check_contact_run(mesh, gold, ref, res):
     from nimblesm_b200 import exodiff
 

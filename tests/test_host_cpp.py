@@ -103,6 +103,34 @@ def test_expression_programs_reproduce_host_evaluation(host):
     assert len(slots) == 1
 
 
+def test_material_params_known_answers_of_the_reference_unit_test(host):
+    """unit_tests/test_nimble_material_params.cc:53-147 on the host MaterialParameters / MaterialFactoryBase: an unknown key
+    throws, the three doubles of a neohookean string parse, extra double and string parameter names can be registered."""
+
+    def parse(text, doubles=b"", strings=b""):
+        out, err = C.create_string_buffer(4096), C.create_string_buffer(2048)
+        rc = host.nsmh_material_params(text.encode(), doubles, strings, out, len(out), err, len(err))
+        return (json.loads(out.value.decode()) if rc == 0 else None), err.value.decode()
+
+    # invalid_parameter_throws
+    got, err = parse("neohookean some_stuff 1.0e6 stuff 0.27 density 1.0e3")
+    assert got is None and "Invalid material parameter encountered: 'some_stuff'" in err
+    # parse_double_parameters
+    got, err = parse("neohookean bulk_modulus 1.0e6 shear_modulus 5.e5 density 1.0e3")
+    assert got["name"] == "neohookean" and got["upper"] == "NEOHOOKEAN" and got["n_doubles"] == 3 and got["n_strings"] == 0
+    assert got["doubles"] == {"bulk_modulus": 1.0e6, "shear_modulus": 5.0e5, "density": 1.0e3} and "testParam" not in got["doubles"]
+    # register_new_test_property / register_new_test_string_property
+    text = "neohookean bulk_modulus 1.0e6 shear_modulus 5.e5 density 1.0e3 test_property "
+    assert parse(text + "2.0")[0] is None  # not registered: refused
+    got, err = parse(text + "2.0", doubles=b"test_property")
+    assert got["doubles"]["test_property"] == 2.0 and got["n_doubles"] == 4
+    got, err = parse(text + "custom_property_val", strings=b"test_property")
+    assert got["strings"] == {"test_property": "custom_property_val"} and got["n_strings"] == 1 and got["n_doubles"] == 3
+    # (src/nimble_material_factory_base.cc:85: std::map::insert keeps the first value of a repeated key)
+    assert parse("elastic density 1 density 2 bulk_modulus 3 shear_modulus 4")[0]["doubles"]["density"] == 1.0
+    assert parse("elastic density")[0] is None and parse("elastic")[0] is None
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_parser_and_material_factory_on_reference_decks(host, case):
     from nimblesm_b200.deck import parse_deck
@@ -370,7 +398,7 @@ def host_contact_entities(host, genesis_path, deck):
             "contact_node_char_len": nlen}
 
 
-@pytest.mark.parametrize("case", ["cubes_contact", "sphere_plate_contact", "sliding_contact"])
+@pytest.mark.parametrize("case", ["cubes_contact", "sphere_plate_contact", "sliding_contact", "contact_entity_creation"])
 def test_contact_manager_entity_lists(host, tmp_path, case):
     """ContactManager::SkinBlocks / CreateContactEntities (host side, C++): the skin quads of the primary blocks in the
     reference's std::map order, the contact nodes of the secondary blocks in order of first appearance, and both
@@ -382,12 +410,43 @@ def test_contact_manager_entity_lists(host, tmp_path, case):
     g = str(tmp_path / "c.g")
     write_genesis(g, mesh)
     got = host_contact_entities(host, g, deck)
-    assert got["penalty"] == float("0.33333333333333333333333333333e12")
+    assert got["penalty"] == (1.0e13 if case == "contact_entity_creation" else float("0.33333333333333333333333333333e12"))
     for k in ("primary_quads", "contact_nodes", "primary_char_len", "contact_node_char_len"):
         assert np.array_equal(got[k], ref["contact_" + k]), k
     # entity ids: (element global id + 1 + largest node global id) << 5 | face ordinal << 2, unique per face
     assert len(set(got["primary_entity_ids"].tolist())) == len(got["primary_quads"])
     assert np.all((got["primary_entity_ids"] & 3) == 0) and np.all(((got["primary_entity_ids"] >> 2) & 7) < 6)
+
+
+def test_contact_manager_entities_equal_the_reference_visualisation_database(host, tmp_path):
+    """The reference's own record of CreateContactEntities: the gold file of test/contact/contact_entity_creation is the
+    contact visualisation database (src/nimble_contact_manager.cc:431-590) -- every facet with its three vertices and
+    every contact node, in entity order, with the entity ids as Exodus maps.  The C++ ContactManager of this repository
+    (five blocks: primary block_1 block_2, secondary block_3 block_5) makes the same entities: 6 778 vertex coordinates
+    bit for bit in the same order, the same entity id per triangle ((element id + offset) << 5 | face ordinal << 2 |
+    triangle ordinal, :924-927, :1106-1176), the same ids for the visualisation nodes (:525-535) and contact nodes (:321)."""
+    from nimblesm_b200.exodus_py import write_genesis
+
+    deck, mesh, gold, _ref, _ = load_golden("contact_entity_creation")
+    vis = gold["vis"]
+    g = str(tmp_path / "c.g")
+    write_genesis(g, mesh)
+    ent = host_contact_entities(host, g, deck)
+    n_tri = 4 * len(ent["primary_quads"])
+    assert (n_tri, len(ent["contact_nodes"])) == (len(vis["connect1"]), len(vis["connect2"])) == (2112, 442)
+    X = np.stack([mesh["x"], mesh["y"], mesh["z"]], 1)
+    c = X[ent["primary_quads"]]
+    centre = (((0.0 + c[:, 0]) + c[:, 1]) + c[:, 2] + c[:, 3]) / 4
+    tri = np.stack([np.stack([c[:, k], c[:, (k + 1) % 4], centre], 1) for k in range(4)], 1)  # [nf,4,3,3]
+    got = np.vstack([tri.reshape(-1, 3), X[ent["contact_nodes"]]])
+    want = np.stack([vis["coordx"], vis["coordy"], vis["coordz"]], 1)
+    assert np.array_equal(got.view(np.int64), want.astype(np.float64).view(np.int64))
+    tri_ids = np.repeat(ent["primary_entity_ids"], 4) | np.tile(np.arange(4, dtype=np.int32), len(ent["primary_quads"]))
+    node_ids = np.asarray(mesh["node_gid"])[ent["contact_nodes"]] + 1
+    assert np.array_equal(vis["elem_num_map"], np.concatenate([tri_ids, node_ids]) + 1)  # (Exodus maps are written 1-based)
+    top = max(tri_ids.max(), node_ids.max())
+    vis_nodes = np.stack([3 * tri_ids + top + 9, 3 * tri_ids + top + 10, 3 * tri_ids + top + 11], 1).ravel()
+    assert np.array_equal(vis["node_num_map"], np.concatenate([vis_nodes, node_ids]) + 1)
 
 
 def test_contact_command_errors(host, tmp_path):
@@ -444,7 +503,8 @@ def test_skin_blocks_on_random_block_assignments(host, tmp_path, seed):
     assert len(got["primary_quads"]) > 0 and len(got["contact_nodes"]) > 0
 
 
-@pytest.mark.parametrize("case,P", [("sphere_plate_contact", 2), ("sphere_plate_contact", 4), ("sliding_contact", 4)])
+@pytest.mark.parametrize("case,P", [("sphere_plate_contact", 2), ("sphere_plate_contact", 4), ("sliding_contact", 4),
+                                    ("contact_entity_creation", 2), ("contact_entity_creation", 3), ("contact_entity_creation", 4)])
 def test_replicated_contact_sub_model_on_rank_threads(host, tmp_path, case, P):
     """Contact across mesh partitions, host side (ContactManager::BuildReplicatedSubModel on P rank threads, one Nemesis
     piece each, no device): every rank ends up with the SAME sub-model, and that sub-model is the serial one -- the same
