@@ -300,6 +300,11 @@ int nsm_b200_contact_force_host(nsm_b200_ctx* ctx, const double* displacement, d
  * atomically -- 0 means the contact force was summed in the serial order (contact nodes ascending, triangles ascending,
  * facet nodes before the node) and is bit-reproducible. */
 int nsm_b200_contact_stats(nsm_b200_ctx* ctx, int64_t stats[5]);
+/* ContactEntity::contact_status() of every entity after the last evaluation (what ContactVisualizationWriteStep copies
+ * back with its entities, src/nimble_contact_manager.cc:596-602, 640-668): face_status [4 * n_faces], triangle k of
+ * face f at 4 f + k (the entity order of CreateContactNodesAndFaces, :1043-1190), node_status [n_contact_nodes] in
+ * the order of set_contact; 1 = in contact.  Either pointer may be NULL.  All zero before the first evaluation. */
+int nsm_b200_contact_status(nsm_b200_ctx* ctx, unsigned char* face_status, unsigned char* node_status);
 
 /* ---- element data / derived output (replaces ModelData::GetElementDataNew + Block::ComputeDerivedElementData,
  *      src/nimble_block.cc:438-497; HexElement::ComputeVolumeAverage, src/nimble_element.h:343-392) --- */

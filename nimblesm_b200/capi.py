@@ -48,7 +48,7 @@ SYMBOLS = [
     "nsm_b200_set_element_data", "nsm_b200_set_bc_entry_constants", "nsm_b200_comm_set_host_barrier",
     "nsm_b200_set_host_step_chunks", "nsm_b200_effective_flags", "nsm_b200_fp64_peak_sustained",
     "nsm_b200_set_contact", "nsm_b200_contact_force", "nsm_b200_contact_force_host", "nsm_b200_contact_stats",
-    "nsm_b200_profile_read_contact",
+    "nsm_b200_profile_read_contact", "nsm_b200_contact_status",
 ]
 
 
@@ -144,6 +144,7 @@ def lib():
         "nsm_b200_contact_force": (i32, [vp]),
         "nsm_b200_contact_force_host": (i32, [vp, vp, vp]),
         "nsm_b200_contact_stats": (i32, [vp, lp]),
+        "nsm_b200_contact_status": (i32, [vp, vp, vp]),
         "nsm_b200_profile_read_contact": (i32, [vp, dp]),
     }
     for name, (res, args) in sig.items():
@@ -329,6 +330,12 @@ class Context:
         self._ck(self._L.nsm_b200_contact_stats(self._h, st.ctypes.data_as(C.POINTER(C.c_int64))))
         return {"pairs": int(st[0]), "box_tested": int(st[1]), "active_faces": int(st[2]), "active_nodes": int(st[3]),
                 "ordered_overflow_pairs": int(st[4])}
+
+    def contact_status(self, n_faces, n_contact_nodes):
+        """-> (status of the 4 * n_faces triangles, status of the contact nodes) after the last evaluation (uint8, 1 = in contact)"""
+        face, node = np.zeros(4 * int(n_faces), np.uint8), np.zeros(int(n_contact_nodes), np.uint8)
+        self._ck(self._L.nsm_b200_contact_status(self._h, face.ctypes.data, node.ctypes.data))
+        return face, node
 
     def compute_stress(self, material, bulk_modulus, shear_modulus, def_grad):
         kind = MATERIAL_KINDS[material] if isinstance(material, str) else int(material)

@@ -2506,6 +2506,19 @@ nsm_b200_contact_stats(nsm_b200_ctx* c, int64_t stats[5])
 }
 
 int
+nsm_b200_contact_status(nsm_b200_ctx* c, unsigned char* face_status, unsigned char* node_status)
+{
+  NSM_ENTER(c);
+  auto& k = c->contact;
+  NSM_REQUIRE(c, c->finalized && k.active, "contact_status: no contact entities on this context (nsm_b200_set_contact)");
+  const int64_t n_tri = 4 * k.n_quads;
+  if (face_status && n_tri > 0) NSM_CUDA(c, cudaMemcpyAsync(face_status, k.status, (size_t)n_tri, cudaMemcpyDeviceToHost, c->stream));
+  if (node_status && k.n_sec > 0) NSM_CUDA(c, cudaMemcpyAsync(node_status, k.status + n_tri, (size_t)k.n_sec, cudaMemcpyDeviceToHost, c->stream));
+  NSM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NSM_OK;
+}
+
+int
 nsm_b200_timer_start(nsm_b200_ctx* c)
 {
   NSM_ENTER(c);

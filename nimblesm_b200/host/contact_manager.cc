@@ -298,6 +298,7 @@ ContactManager::CreateContactEntities(GenesisMesh const& mesh, VectorCommunicato
     return;
   }
   BuildEntityLists(mesh, primary_block_ids, secondary_block_ids, lists_);
+  mesh_            = &mesh;
   contact_enabled_ = true;
   DeviceContext& d = model_data->Device();
   d.check(nsm_b200_set_contact(d.get(), penalty_parameter_, (int64_t)lists_.primary_face_char_len.size(), lists_.primary_face_nodes.data(),
@@ -353,6 +354,127 @@ ContactManager::ComputeContactForce(int, bool, Viewify<2> contact_force)
   DeviceContext& d = model_data->Device();
   // the displacement reached the device through ModelData::UpdateWithNewDisplacement, as in the reference
   d.check(nsm_b200_contact_force_host(d.get(), nullptr, contact_force.data()), "ContactManager::ComputeContactForce");
+}
+
+void
+ContactVisualizationDatabase::EntityVertices(const double* displacement, std::vector<double>& x, std::vector<double>& y, std::vector<double>& z) const
+{
+  const double* const mx[3] = {model_mesh_.GetCoordinatesX(), model_mesh_.GetCoordinatesY(), model_mesh_.GetCoordinatesZ()};
+  const size_t        n_faces = lists_.primary_face_char_len.size(), n_cn = lists_.contact_node_ids.size();
+  std::vector<double>* const out[3] = {&x, &y, &z};
+  for (int d = 0; d < 3; ++d) {
+    out[d]->resize(12 * n_faces + n_cn);
+    auto at = [&](int node) { return displacement ? mx[d][node] + displacement[3 * (size_t)node + d] : mx[d][node]; };
+    size_t k = 0;
+    for (size_t f = 0; f < n_faces; ++f) {
+      const int*   q      = &lists_.primary_face_nodes[4 * f];
+      const double centre = (at(q[0]) + at(q[1]) + at(q[2]) + at(q[3])) / 4.0;
+      for (int t = 0; t < 4; ++t) {
+        (*out[d])[k++] = at(q[t]);
+        (*out[d])[k++] = at(q[(t + 1) % 4]);
+        (*out[d])[k++] = centre;
+      }
+    }
+    for (size_t i = 0; i < n_cn; ++i) (*out[d])[k++] = at(lists_.contact_node_ids[i]);
+  }
+}
+
+void
+ContactManager::InitializeContactVisualization(std::string const& contact_visualization_exodus_file_name)
+{
+  if (replicated_ || !mesh_) {
+    if (rank_ == 0)
+      std::cout << "(contact visualization: written by single-rank runs only; skipped for the replicated contact surface)" << std::endl;
+    return;
+  }
+  visualization_.reset(new ContactVisualizationDatabase(*mesh_, lists_, contact_visualization_exodus_file_name));
+}
+
+ContactVisualizationDatabase::ContactVisualizationDatabase(GenesisMesh const& model_mesh, ContactEntityLists const& lists,
+                                                           std::string const& contact_visualization_exodus_file_name)
+    : model_mesh_(model_mesh), lists_(lists)
+{
+  const size_t n_faces = lists_.primary_face_char_len.size(), n_cn = lists_.contact_node_ids.size();
+  // entity ids (src/nimble_contact_manager.cc:924-927, 1106-1176, 321): facet = skin entity id | triangle ordinal,
+  // contact node = global node id + 1
+  std::vector<int> face_ids(4 * n_faces), node_ids(n_cn);
+  int              max_contact_entity_id = 0;
+  for (size_t f = 0; f < n_faces; ++f)
+    for (int t = 0; t < 4; ++t) {
+      face_ids[4 * f + t]   = lists_.primary_face_entity_ids[f] | t;
+      max_contact_entity_id = std::max(max_contact_entity_id, face_ids[4 * f + t]);
+    }
+  const int* const gid = model_mesh_.GetNodeGlobalIds();
+  for (size_t i = 0; i < n_cn; ++i) {
+    node_ids[i]           = gid[lists_.contact_node_ids[i]] + 1;
+    max_contact_entity_id = std::max(max_contact_entity_id, node_ids[i]);
+  }
+  std::vector<int>                node_global_id, elem_global_id, block_ids = {1, 2};
+  std::vector<double>             node_x, node_y, node_z;
+  std::map<int, std::string>      block_names              = {{1, "contact_faces"}, {2, "contact_nodes"}};
+  std::map<int, std::vector<int>> block_elem_global_ids    = {{1, {}}, {2, {}}};
+  std::map<int, int>              block_num_nodes_per_elem = {{1, 3}, {2, 1}};
+  std::map<int, std::vector<int>> block_elem_connectivity  = {{1, {}}, {2, {}}};
+  EntityVertices(nullptr, node_x, node_y, node_z);
+  int node_index = 0;
+  for (size_t i = 0; i < 4 * n_faces; ++i) {
+    for (int v = 0; v < 3; ++v) {
+      node_global_id.push_back(3 * face_ids[i] + max_contact_entity_id + 9 + v);  // :525-535
+      block_elem_connectivity[1].push_back(node_index++);
+    }
+    elem_global_id.push_back(face_ids[i]);
+  }
+  for (size_t i = 0; i < n_cn; ++i) {
+    node_global_id.push_back(node_ids[i]);
+    block_elem_connectivity[2].push_back(node_index++);
+    elem_global_id.push_back(node_ids[i]);
+  }
+  GenesisMesh&  mesh = mesh_;
+  ExodusOutput& out  = out_;
+  mesh.Initialize("contact_visualization", node_global_id, node_x, node_y, node_z, elem_global_id, block_ids, block_names, block_elem_global_ids,
+                  block_num_nodes_per_elem, block_elem_connectivity);
+  out.Initialize(contact_visualization_exodus_file_name, mesh);
+  std::map<int, std::vector<std::string>> no_elem_data = {{1, {}}, {2, {}}};
+  out.InitializeDatabase(mesh, {"num_contacts"}, {"displacement_x", "displacement_y", "displacement_z", "contact_status"}, no_elem_data, no_elem_data);
+}
+
+void
+ContactVisualizationDatabase::WriteStep(double t, const double* displacement, const unsigned char* face_status, const unsigned char* node_status)
+{
+  const GenesisMesh&  mesh    = mesh_;
+  const size_t        n_faces = lists_.primary_face_char_len.size(), n_cn = lists_.contact_node_ids.size();
+  const double* const model[3] = {mesh.GetCoordinatesX(), mesh.GetCoordinatesY(), mesh.GetCoordinatesZ()};
+  std::vector<std::vector<double>> node_data(4);
+  EntityVertices(displacement, node_data[0], node_data[1], node_data[2]);
+  for (int d = 0; d < 3; ++d)
+    for (size_t i = 0; i < node_data[d].size(); ++i) node_data[d][i] -= model[d][i];  // (:644-668)
+  node_data[3].assign(12 * n_faces + n_cn, 0.0);
+  double num_contacts = 0.0;
+  for (size_t i = 0; i < 4 * n_faces; ++i) {
+    const double status = face_status && face_status[i] ? 1.0 : 0.0;
+    num_contacts += status;  // numActiveContactFaces (:692-702)
+    for (int v = 0; v < 3; ++v) node_data[3][3 * i + v] = status;
+  }
+  for (size_t i = 0; i < n_cn; ++i) node_data[3][12 * n_faces + i] = node_status && node_status[i] ? 1.0 : 0.0;
+  std::map<int, std::vector<std::string>>         no_labels = {{1, {}}, {2, {}}};
+  std::map<int, std::vector<std::vector<double>>> no_data   = {{1, {}}, {2, {}}};
+  out_.WriteStep(t, {num_contacts}, node_data, no_labels, no_data, no_labels, no_data);
+}
+
+void
+ContactManager::ContactVisualizationWriteStep(double time_current, bool evaluated)
+{
+  if (!visualization_) return;
+  if (!evaluated) {
+    visualization_->WriteStep(time_current, nullptr, nullptr, nullptr);
+    return;
+  }
+  auto*                      model_data = dynamic_cast<ModelData*>(data_manager_.GetModelData().get());
+  Viewify<2>                 displacement = model_data->GetVectorNodeData("displacement");
+  std::vector<unsigned char> face_status(numContactFaces()), node_status(numContactNodes());
+  DeviceContext&             d = model_data->Device();
+  d.check(nsm_b200_contact_status(d.get(), face_status.data(), node_status.data()), "ContactManager::ContactVisualizationWriteStep");
+  visualization_->WriteStep(time_current, displacement.data(), face_status.data(), node_status.data());
 }
 
 std::size_t

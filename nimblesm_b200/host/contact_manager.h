@@ -18,12 +18,13 @@
 #include <vector>
 
 #include "device.h"
+#include "exodus_output.h"
+#include "genesis_mesh.h"
 #include "view.h"
 
 namespace nimble_b200 {
 
 class DataManager;
-class GenesisMesh;
 class RankGroup;
 class VectorCommunicator;
 
@@ -51,6 +52,38 @@ struct ReplicatedContactSubModel
   std::vector<double> surface_xyz;    // [n_surface][3] model coordinates
   std::vector<int>    surface_gid;    // [n_surface] global node id, ascending
   std::vector<int>    held_local, held_surface;  // surface nodes this rank holds: local node id, surface index
+};
+
+// The contact visualisation database (InitializeContactVisualization / WriteVisualizationData,
+// src/nimble_contact_manager.cc:431-678), device-free: a second Exodus file with one triangle element per contact facet
+// (its own three nodes: two face nodes and the fictitious node at the face centre), one single-node element per contact
+// node, the entities' displacement and contact_status as nodal variables and num_contacts as a global one.  Entity ids
+// as in the reference: element id = contact_entity_global_id_ (facet: skin entity id | triangle ordinal; contact node:
+// global node id + 1), facet nodes 3 id + max id + 9 / 10 / 11.
+class ContactVisualizationDatabase
+{
+ public:
+  ContactVisualizationDatabase(GenesisMesh const& mesh, ContactEntityLists const& lists, std::string const& exodus_file_name);
+  // displacement [n_nodes][3] of the mesh nodes (nullptr = entities at their model coordinates), status flags per
+  // triangle and per contact node (nullptr = 0)
+  void
+  WriteStep(double t, const double* displacement, const unsigned char* face_status, const unsigned char* node_status);
+  // coordinates of the visualisation nodes for nodal coordinates model + displacement: per facet node 1, node 2,
+  // (c0 + c1 + c2 + c3) / 4 of its face (ContactEntity::SetCoordinates, src/nimble_contact_entity.h:236-258), then the
+  // contact nodes
+  void
+  EntityVertices(const double* displacement, std::vector<double>& x, std::vector<double>& y, std::vector<double>& z) const;
+  void
+  Close()
+  {
+    out_.Close();
+  }
+
+ private:
+  GenesisMesh const&        model_mesh_;
+  ContactEntityLists const& lists_;
+  GenesisMesh               mesh_;  // genesis_mesh_for_contact_visualization_
+  ExodusOutput              out_;   // exodus_output_for_contact_visualization_
 };
 
 class ContactManager
@@ -106,6 +139,15 @@ class ContactManager
   std::size_t
   numActiveContactNodes() const;
 
+  // InitializeContactVisualization / ContactVisualizationWriteStep (src/nimble_contact_manager.cc:431-602): the database
+  // above, fed with the displacement of the model data and the contact_status flags of the device.  Written by
+  // single-rank runs (with the replicated sub-model of a multi-rank run the request is reported and skipped).
+  void
+  InitializeContactVisualization(std::string const& contact_visualization_exodus_file_name);
+  // `evaluated` = false writes the entities at their model coordinates (the initial write, before any evaluation)
+  void
+  ContactVisualizationWriteStep(double time_current, bool evaluated = true);
+
   ContactEntityLists const&
   EntityLists() const
   {
@@ -138,6 +180,9 @@ class ContactManager
   std::vector<double>            surface_xyz_;                  // [n_surface][3] model coordinates
   std::vector<int>               held_local_, held_surface_;    // surface nodes this rank holds: local id, surface index
   std::unique_ptr<DeviceContext> sub_model_;                    // rank 0: the element-free context of the surface nodes
+  // contact visualisation
+  const GenesisMesh*                            mesh_ = nullptr;  // the mesh the entity lists refer to (single rank)
+  std::unique_ptr<ContactVisualizationDatabase> visualization_;
 };
 
 // the reference's factory (GetContactManager, :151-171): nullptr when the deck has no `contact:` line

@@ -245,11 +245,15 @@ std::string
 GenesisMesh::GetElementType(int block_id) const
 {
   // src/nimble_genesis_mesh.cc:480-505: the type string of the file is ignored, nodes per element decide
+  // (SPHERE and TRIANGLE are the blocks of the contact visualisation database; "TRIANGLE:" in 2D is the reference's spelling)
   const int npe = block_num_nodes_per_elem_.at(block_id);
-  if (dim_ == 2 && npe == 4) return "QUAD4";
-  if (dim_ == 3 && npe == 4) return "TET";
+  if (dim_ == 2 && npe == 3) return "TRIANGLE:";
+  if (dim_ == 2 && npe == 4) return "QUAD";
+  if (dim_ == 3 && npe == 1) return "SPHERE";
+  if (dim_ == 3 && npe == 3) return "TRIANGLE";
+  if (dim_ == 3 && npe == 4) return "TETRA";
   if (dim_ == 3 && npe == 8) return "HEX";
-  throw std::invalid_argument("GenesisMesh::GetElementType(), unsupported element (nodes per element: " + numbered("", npe) + ")");
+  throw std::invalid_argument("Error processing input mesh, unknown element type.");
 }
 
 void

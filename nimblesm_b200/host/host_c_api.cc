@@ -407,6 +407,37 @@ nsmh_contact_entities(const char* genesis_path, const char* deck_text, long long
   }
 }
 
+// The contact visualisation database of a Genesis file + deck (ContactVisualizationDatabase, no device involved):
+// n_times time planes; displacement [n_times][n_nodes][3] of the mesh nodes; plane k is written "unevaluated" (entities
+// at their model coordinates) when evaluated[k] == 0; status flags all zero.
+int
+nsmh_contact_visualization(const char* genesis_path, const char* deck_text, const char* out_path, int n_times, const double* times,
+                           const double* displacement, const int* evaluated, char* err, int errlen)
+{
+  try {
+    GenesisMesh m;
+    m.ReadFile(genesis_path);
+    Parser p;
+    p.InitializeFromString(deck_text);
+    if (!p.HasContact() || !p.ContactVisualization()) return fail(err, errlen, "the deck asks for no contact visualization");
+    std::vector<std::string> pn, sn;
+    double                   penalty = 0.0;
+    ParseContactCommand(p.ContactString(), pn, sn, penalty);
+    std::vector<int> pi, si;
+    m.BlockNamesToOnProcessorBlockIds(pn, pi);
+    m.BlockNamesToOnProcessorBlockIds(sn, si);
+    ContactEntityLists l;
+    ContactManager::BuildEntityLists(m, pi, si, l);
+    ContactVisualizationDatabase db(m, l, out_path);
+    const size_t                 plane = 3 * m.GetNumNodes();
+    for (int k = 0; k < n_times; ++k) db.WriteStep(times[k], evaluated[k] ? displacement + plane * (size_t)k : nullptr, nullptr, nullptr);
+    db.Close();
+    return 0;
+  } catch (std::exception const& e) {
+    return fail(err, errlen, e.what());
+  }
+}
+
 // ContactManager::BuildReplicatedSubModel on `n_ranks` threads, one Genesis piece each (paths separated by '\n'): the
 // sub-model every rank ends up with, as JSON {n_surface, surface_gid, primary_quads_gid, contact_nodes_gid,
 // primary_char_len, contact_node_char_len, held: [per rank count], identical: true when all ranks built the same lists}

@@ -76,7 +76,10 @@ ExplicitTimeIntegrator::Integrate()
     contact_manager->SetPenaltyParameter(penalty_parameter);
     contact_manager->CreateContactEntities(Mesh(), *data_manager.GetVectorCommunicator(), contact_primary_block_ids, contact_secondary_block_ids);
     contact_force = model_data->GetVectorNodeData("contact_force");
+    if (parser.ContactVisualization())  // explicit_time_integrator.cc:93-98
+      contact_manager->InitializeContactVisualization(IOFileName(parser.ContactVisualizationFileName(), "e", "out", my_rank, App().Options().num_ranks));
   }
+  const bool contact_visualization = contact_enabled && parser.ContactVisualization();
 
   model_data->ComputeLumpedMass(data_manager);
   double critical_time_step = model_data->GetCriticalTimeStep();
@@ -95,6 +98,7 @@ ExplicitTimeIntegrator::Integrate()
   model_data->ApplyKinematicConditions(data_manager, 0.0, 0.0);
   model_data->PushNodalFields();
   data_manager.WriteOutput(time_current);
+  if (contact_visualization) contact_manager->ContactVisualizationWriteStep(time_current, false);  // (:152: entities at model coordinates)
 
   if (talk) {
     std::cout << "\nUser specified time step:              " << user_specified_time_step << std::endl;
@@ -141,6 +145,7 @@ ExplicitTimeIntegrator::Integrate()
         const auto t_out = std::chrono::steady_clock::now();
         model_data->PullNodalFields();
         data_manager.WriteOutput(time_current);
+        if (contact_visualization) contact_manager->ContactVisualizationWriteStep(time_current);
         total_exodus_write_time += seconds_since(t_out);
       }
     }
@@ -190,6 +195,7 @@ ExplicitTimeIntegrator::Integrate()
         const auto t_out = std::chrono::steady_clock::now();
         model_data->ApplyKinematicConditions(data_manager, time_current, time_previous);
         data_manager.WriteOutput(time_current);
+        if (contact_visualization) contact_manager->ContactVisualizationWriteStep(time_current);  // :273
         total_exodus_write_time += seconds_since(t_out);
       }
       model_data->UpdateStates(data_manager);

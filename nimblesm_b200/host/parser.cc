@@ -119,6 +119,17 @@ Parser::ParseKeyValue(const std::string& key, const std::string& value)
     contact_backend_string_ = value;
   } else if (key == "contact visualization") {
     contact_visualization_string_ = value;
+    std::istringstream       ss(value);
+    std::vector<std::string> vals;
+    for (std::string val; ss >> val;) vals.push_back(val);
+    if (vals.size() != 6 || vals[0] != "visualize_contact_entities" || (vals[1] != "on" && vals[1] != "off") ||
+        vals[2] != "visualize_bounding_boxes" || (vals[3] != "on" && vals[3] != "off") || vals[4] != "file_name")
+      throw std::invalid_argument(
+          "\n**** Error in Parser::ReadFile(), unexpected value for \"contact visualization\"\n"
+          "**** Allowable syntax is \"visualize_contact_entities <on/off> visualize_bounding_boxes <on/off> file_name <file_name.e>\"\n");
+    visualize_contact_entities_       = vals[1] == "on";
+    visualize_contact_bounding_boxes_ = vals[3] == "on";
+    contact_visualization_file_name_  = vals[5];
   } else if (key == "material parameters") {
     const size_t space              = value.find(' ');
     material_strings_[value.substr(0, space)] = space == std::string::npos ? std::string() : value.substr(space + 1);

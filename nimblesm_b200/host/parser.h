@@ -85,6 +85,18 @@ class Parser
   {
     return contact_string_;
   }
+  // `contact visualization: visualize_contact_entities <on/off> visualize_bounding_boxes <on/off> file_name <name.e>`
+  // (src/nimble_parser.cc:293-316, src/nimble_parser.h:195-206)
+  bool
+  ContactVisualization() const
+  {
+    return visualize_contact_entities_ || visualize_contact_bounding_boxes_;
+  }
+  std::string
+  ContactVisualizationFileName() const
+  {
+    return contact_visualization_file_name_;
+  }
   std::string
   GetModelMaterialParameters(int block_id) const;  // "none" for a block the deck does not list
   int
@@ -137,6 +149,8 @@ class Parser
   double                                 initial_time_{0.0}, final_time_{0.0};
   int                                    num_load_steps_{0}, output_frequency_{1};
   std::string                            contact_string_, contact_backend_string_, contact_visualization_string_;
+  bool                                   visualize_contact_entities_ = false, visualize_contact_bounding_boxes_ = false;
+  std::string                            contact_visualization_file_name_ = "none";
   std::map<std::string, std::string>     material_strings_;
   std::map<int, BlockProperties>         model_blocks_;
   std::vector<std::string>               boundary_condition_strings_;

@@ -76,6 +76,9 @@ def test_contact_force_vs_oracle(oracle, host, tmp_path, flags, ordered):
             assert st["active_faces"] == int(status[:4 * len(ent["primary_quads"])].sum())
             assert st["active_nodes"] == int(status[4 * len(ent["primary_quads"]):].sum())
             assert st["box_tested"] >= pairs
+            # contact_status of every entity, in the entity order of the reference (triangle k of face f at 4 f + k)
+            face_status, node_status = c.contact_status(len(ent["primary_quads"]), len(ent["contact_nodes"]))
+            assert np.array_equal(np.concatenate([face_status, node_status]), status)
             if pairs:
                 assert _rel(got, want) <= 1e-12, (amp, shift, _rel(got, want))
             else:
@@ -293,6 +296,14 @@ def test_driver_runs_contact_entity_creation_deck(extra, tmp_path):
     for i, (comp, tol) in enumerate(zip("xyz", (2.0e-8, 1.0e-12, 1.0e-12))):
         assert np.abs(seen[:, i] - gold["nod"]["displacement_" + comp][-1]).max() <= tol, comp
     assert np.abs(seen[:, 0]).max() == pytest.approx(0.02, rel=1e-9)
+    # ... and the reference's own contract for this test (run_exodiff_test.py): the contact visualisation database the
+    # deck asks for, <file_name>.out.e, against contact_entity_creation.gold.e under contact_entity_creation.exodiff
+    from nimblesm_b200 import exodiff
+
+    vis = read_results(str(tmp_path / "contact_entity_creation.out.e"))
+    fails = exodiff.compare(gold["exodiff"], gold, vis)
+    assert not fails, fails[:5]
+    assert np.array_equal(vis["nod"]["displacement_x"][-1], seen[:, 0]) and not vis["nod"]["contact_status"].any()
 
 
 def _check_contact_run(mesh, gold, ref, res):

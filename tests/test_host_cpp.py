@@ -449,6 +449,58 @@ def test_contact_manager_entities_equal_the_reference_visualisation_database(hos
     assert np.array_equal(vis["node_num_map"], np.concatenate([vis_nodes, node_ids]) + 1)
 
 
+def test_contact_visualisation_database_meets_the_reference_gold_file(host, tmp_path):
+    """The reference's own contract for test/contact/contact_entity_creation (run_exodiff_test.py: exodiff -f
+    contact_entity_creation.exodiff contact_entity_creation.gold.e contact_entity_creation.out.e): the file named by the
+    deck's `contact visualization` line.  The host ContactVisualizationDatabase, fed with the oracle's displacement at
+    the reference's output steps, writes that file: same Exodus mesh (coordinates bit for bit, connectivity, both id
+    maps, block layout), time planes and nodal displacement within the reference's exodiff rules."""
+    from scipy.io import netcdf_file
+
+    from nimblesm_b200 import exodiff
+    from nimblesm_b200.exodus_py import read_results, write_genesis
+    from oracle.model import OracleModel
+
+    deck, mesh, gold, ref, _ = load_golden("contact_entity_creation")
+    g = str(tmp_path / "c.g")
+    write_genesis(g, mesh)
+    m = OracleModel(deck, mesh)
+    m.begin()
+    planes, at = [], 0
+    for step in (0, 1, 21, 41, 60):
+        m.advance(step - at)
+        at = step
+        planes.append(m.u.copy())
+    disp = np.ascontiguousarray(np.stack(planes))
+    times = np.ascontiguousarray(ref["times"], dtype=np.float64)
+    evaluated = np.array([0, 1, 1, 1, 1], np.int32)
+    out, err = str(tmp_path / "contact_entity_creation.out.e"), C.create_string_buffer(2048)
+    rc = host.nsmh_contact_visualization(g.encode(), deck.encode(), out.encode(), 5, times.ctypes.data_as(C.POINTER(C.c_double)),
+                                         disp.ctypes.data_as(C.POINTER(C.c_double)), evaluated.ctypes.data_as(C.POINTER(C.c_int)), err, 2048)
+    assert rc == 0, err.value
+    f = netcdf_file(out, "r", mmap=False)
+    vis = gold["vis"]
+    for k in ("coordx", "coordy", "coordz"):
+        assert np.array_equal(np.array(f.variables[k].data, dtype=np.float64).view(np.int64), vis[k].astype(np.float64).view(np.int64)), k
+    for k in ("connect1", "connect2", "elem_num_map", "node_num_map"):
+        assert np.array_equal(np.array(f.variables[k].data), vis[k]), k
+    assert f.dimensions["num_el_blk"] == 2 and f.dimensions["num_nod_per_el1"] == 3 and f.dimensions["num_nod_per_el2"] == 1
+    names = [b"".join(r).split(b"\x00")[0].decode().strip() for r in f.variables["name_nod_var"].data]
+    assert names == ["displacement_x", "displacement_y", "displacement_z", "contact_status"]
+    f.close()
+    res = read_results(out)
+    fails = exodiff.compare(gold["exodiff"], gold, res)
+    assert not fails, fails[:5]
+    assert np.abs(res["nod"]["displacement_x"][-1]).max() == pytest.approx(0.02, rel=1e-12) and not res["nod"]["contact_status"].any()
+    # a deck without the line is refused; a malformed line keeps the reference's parser error
+    rc = host.nsmh_contact_visualization(g.encode(), "\n".join(l for l in deck.splitlines() if not l.startswith("contact visualization")).encode(),
+                                         out.encode(), 0, None, None, None, err, 2048)
+    assert rc != 0 and b"no contact visualization" in err.value
+    rc = host.nsmh_contact_visualization(g.encode(), deck.replace("visualize_bounding_boxes off", "visualize_boxes off").encode(), out.encode(),
+                                         0, None, None, None, err, 2048)
+    assert rc != 0 and b'unexpected value for "contact visualization"' in err.value
+
+
 def test_contact_command_errors(host, tmp_path):
     """ParseContactCommand keeps the reference's error behaviour (src/nimble_contact_manager.cc:95-149)."""
     from nimblesm_b200.exodus_py import write_genesis
