@@ -269,7 +269,7 @@ def test_driver_runs_contact_decks(case, extra, tmp_path):
 @pytest.mark.parametrize("extra", [(), ("--assembly", "atomic")])
 def test_driver_runs_contact_entity_creation_deck(extra, tmp_path):
     """test/contact/contact_entity_creation through NimbleSM_b200: five blocks of three materials, primary block_1 block_2,
-    secondary block_3 block_5, block_4 outside the contact definition, `contact visualization` parsed and not written.
+    secondary block_3 block_5, block_4 outside the contact definition, `contact visualization` on.
     Blocks 1 and 5 fly at 1e7 for 2e-9 s and meet nothing: the contact force stays zero, the nodal fields equal the
     reference-entity snapshots (bit for bit in ORDERED assembly), and the displacement the contact ENTITIES see at the end
     -- facet vertices, fictitious face-centre nodes, contact nodes, in the reference's entity order -- meets the last
